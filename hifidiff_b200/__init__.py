@@ -1,0 +1,14 @@
+"""hifidiff_b200 — B200-native (sm_100a) implementation of HifiDiff's reverse-sampling hot path.
+
+Drop-in for the reference's module API (`Denoiser`, `FusedDenoiser`, `FacialRefiner`,
+`UNet2DOutput`, the `ddim_sample` loop); all per-timestep work runs in hand-written CUDA behind
+the C ABI in `include/hifidiff_b200.h`.  See DESIGN.md.
+"""
+from .modules import Denoiser, FusedDenoiser, UNet2DOutput
+from .conditioning import FacialPriorGuidance, FacialRefiner, ResNet50
+from .schedulers import DDIMScheduler, DDPMScheduler
+from .sampler import ddim_sample, ddpm_sample, sample, sample_sharded, shard_bounds
+
+__all__ = ["Denoiser", "FusedDenoiser", "UNet2DOutput", "FacialPriorGuidance", "FacialRefiner", "ResNet50",
+           "DDIMScheduler", "DDPMScheduler", "ddim_sample", "ddpm_sample", "sample", "sample_sharded",
+           "shard_bounds"]

@@ -1,0 +1,465 @@
+// Bandwidth-bound kernels of the denoiser step (NHWC activations, channel-contiguous rows).
+// Reference anchors are given per kernel; paths are relative to the reference tree.
+#pragma once
+
+#include "common.cuh"
+
+namespace hd {
+
+// Per-step state living in device memory so that a captured CUDA graph can be replayed for every
+// timestep: kernels read the current step from here instead of from launch parameters.
+struct StepState {
+  int step;  // index into the time-modulation table and the coefficient array
+};
+
+struct StepCoef {  // mirrors hd_step_coef
+  float timestep, sqrt_beta_prod, sqrt_alpha_prod, clip, k_x0, k_eps, k_x, k_noise;
+};
+
+// Where a kernel finds the AdaLN vectors of the face it is working on.
+struct ModRef {
+  const float* table;    // [rows][stride]
+  const int* row_idx;    // per-face table row (hd_denoise_step: face -> its t; sampler: all = current step)
+  int stride;            // floats per table row (124928 for the 32 blocks)
+  __device__ __forceinline__ const float* row(int face) const {
+    return table + static_cast<size_t>(row_idx[face]) * stride;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// intro: 3x3 conv 4 -> 128, NCHW fp32 latents -> NHWC fp32 residual stream (model.py:159-167,235)
+// grid (S, B), block 128 (one thread per output channel)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) intro_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ out,
+                                                         int S) {
+  extern __shared__ float s_in[];  // [4][3][S+2]
+  const int h = blockIdx.x, b = blockIdx.y, o = threadIdx.x;
+  const int W2 = S + 2;
+  for (int i = threadIdx.x; i < 4 * 3 * W2; i += blockDim.x) {
+    const int c = i / (3 * W2), r = (i / W2) % 3, col = i % W2;
+    const int hh = h + r - 1, ww = col - 1;
+    float v = 0.f;
+    if (hh >= 0 && hh < S && ww >= 0 && ww < S) v = x[((static_cast<size_t>(b) * 4 + c) * S + hh) * S + ww];
+    s_in[i] = v;
+  }
+  float wr[36];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) wr[i] = w[o * 36 + i];
+  const float bo = bias[o];
+  __syncthreads();
+  for (int col = 0; col < S; ++col) {
+    float acc = bo;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) acc = fmaf(s_in[(c * 3 + r) * W2 + col + kx], wr[(c * 3 + r) * 3 + kx], acc);
+    out[((static_cast<size_t>(b) * S + h) * S + col) * 128 + o] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm2d + AdaLN modulation (utils.py:16-24, conditional_naf.py:114-115,126-127)
+//   y = (x - mu) / sqrt(var + eps) ; y = w*y + b ; out = y*(scale+1) + shift
+// one warp per pixel row; fp32 residual in, T out.  C in {128,...,2048}
+// ------------------------------------------------------------------------------------------------
+template <int C, typename TOut>
+__global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x, const float* __restrict__ lw,
+                                                     const float* __restrict__ lb, TOut* __restrict__ out, int rows,
+                                                     int rows_per_face, ModRef mod, int shift_off, int scale_off,
+                                                     int has_mod) {
+  constexpr int PER = C / 32;  // elements per lane, in chunks of 4
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + static_cast<size_t>(row) * C;
+  float v[PER];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER / 4; ++i) {
+    const float4 q = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+    v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+    s += q.x + q.y + q.z + q.w;
+  }
+  const float mu = warp_sum(s) * (1.f / C);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { const float d = v[i] - mu; ss = fmaf(d, d, ss); }
+  const float var = warp_sum(ss) * (1.f / C);
+  const float denom = sqrtf(var + 1e-6f);
+  const float* mrow = has_mod ? mod.row(row / rows_per_face) : nullptr;
+  TOut* orow = out + static_cast<size_t>(row) * C;
+#pragma unroll
+  for (int i = 0; i < PER / 4; ++i) {
+    const int c0 = (i * 32 + lane) * 4;
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(lw + c0));
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(lb + c0));
+    float y[4];
+    y[0] = w4.x * ((v[4 * i] - mu) / denom) + b4.x;
+    y[1] = w4.y * ((v[4 * i + 1] - mu) / denom) + b4.y;
+    y[2] = w4.z * ((v[4 * i + 2] - mu) / denom) + b4.z;
+    y[3] = w4.w * ((v[4 * i + 3] - mu) / denom) + b4.w;
+    if (has_mod) {
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(mrow + scale_off + c0));
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(mrow + shift_off + c0));
+      y[0] = y[0] * (sc.x + 1.f) + sh.x;
+      y[1] = y[1] * (sc.y + 1.f) + sh.y;
+      y[2] = y[2] * (sc.z + 1.f) + sh.z;
+      y[3] = y[3] * (sc.w + 1.f) + sh.w;
+    }
+    if (sizeof(TOut) == 4) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(orow) + c0) = make_float4(y[0], y[1], y[2], y[3]);
+    } else {
+      uint2 p;
+      p.x = pack_bf16x2(y[0], y[1]);
+      p.y = pack_bf16x2(y[2], y[3]);
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(orow) + c0) = p;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise 3x3 (pad 1, bias) + SimpleGate + global average pool (conditional_naf.py:117-119, 54-65)
+//   in  h [B, sp, sp, 2c]   (x1 = channels [0,c), x2 = channels [c,2c))
+//   out g [B, sp, sp, c] = dw(x1) * dw(x2) ;  pooled[B, c] = mean_hw(g)
+// grid (c/64, B), block 256 = 8 channel-threads (8 channels each) x 32 pixel-threads
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv_gate_pool_kernel(const T* __restrict__ h, const float* __restrict__ w9,
+                                                               const float* __restrict__ bias, T* __restrict__ g,
+                                                               T* __restrict__ pooled, int sp, int c) {
+  __shared__ float s_w[9][2][64];
+  __shared__ float s_b[2][64];
+  __shared__ float s_red[32][65];
+  const int j0 = blockIdx.x * 64;
+  const int face = blockIdx.y;
+  const int ct = threadIdx.x & 7, pt = threadIdx.x >> 3;
+  const int C2 = 2 * c;
+  for (int i = threadIdx.x; i < 9 * 2 * 64; i += blockDim.x) {
+    const int tap = i / 128, half = (i / 64) & 1, ch = i & 63;
+    s_w[tap][half][ch] = w9[tap * C2 + half * c + j0 + ch];
+  }
+  if (threadIdx.x < 128) s_b[threadIdx.x >> 6][threadIdx.x & 63] = bias[(threadIdx.x >> 6) * c + j0 + (threadIdx.x & 63)];
+  __syncthreads();
+
+  float psum[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) psum[i] = 0.f;
+  const T* hf = h + static_cast<size_t>(face) * sp * sp * C2;
+  const int npix = sp * sp;
+  for (int p = pt; p < npix; p += 32) {
+    const int py = p / sp, px = p - py * sp;
+    float a1[8], a2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a1[i] = s_b[0][ct * 8 + i]; a2[i] = s_b[1][ct * 8 + i]; }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+      if (yy < 0 || yy >= sp || xx < 0 || xx >= sp) continue;
+      const T* src = hf + static_cast<size_t>(yy * sp + xx) * C2 + j0 + ct * 8;
+      float v1[8], v2[8];
+      load8(src, v1);
+      load8(src + c, v2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        a1[i] = fmaf(v1[i], s_w[tap][0][ct * 8 + i], a1[i]);
+        a2[i] = fmaf(v2[i], s_w[tap][1][ct * 8 + i], a2[i]);
+      }
+    }
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[i] = a1[i] * a2[i]; psum[i] += o[i]; }
+    store8(g + (static_cast<size_t>(face) * npix + p) * c + j0 + ct * 8, o);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s_red[pt][ct * 8 + i] = psum[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) s += s_red[r][threadIdx.x];
+    pooled[static_cast<size_t>(face) * c + j0 + threadIdx.x] = from_f32<T>(s / static_cast<float>(npix));
+  }
+}
+
+// g[m, k] *= s[face(m), k]   (the SCA channel scale, conditional_naf.py:119)
+template <typename T>
+__global__ void __launch_bounds__(256) scale_rows_kernel(T* __restrict__ g, const float* __restrict__ s, size_t total8,
+                                                         int c, int rows_per_face) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const size_t e = i * 8;
+  const size_t row = e / c;
+  const int k = static_cast<int>(e - row * c);
+  const int face = static_cast<int>(row / rows_per_face);
+  float v[8], sc[8];
+  load8(g + e, v);
+  load8(s + static_cast<size_t>(face) * c + k, sc);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] *= sc[j];
+  store8(g + e, v);
+}
+
+// SimpleGate on an unpacked [R, 2H] fp32 matrix (time path: model.py:49, conditional_naf.py:19)
+__global__ void gate_split_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int H) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(R) * H) return;
+  const size_t r = i / H;
+  const int j = static_cast<int>(i - r * H);
+  out[i] = in[r * 2 * H + j] * in[r * 2 * H + H + j];
+}
+
+// SimpleGate on the gate-packed conv4 output (fp32 mode): 128-column groups [x1(64) | x2(64)]
+template <typename TOut>
+__global__ void gate_packed_kernel(const float* __restrict__ in, TOut* __restrict__ out, size_t rows, int c) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * c) return;
+  const size_t r = i / c;
+  const int j = static_cast<int>(i - r * c);
+  const int grp = j >> 6, k = j & 63;
+  const float* src = in + r * 2 * c + grp * 128;
+  out[i] = from_f32<TOut>(src[k] * src[64 + k]);
+}
+
+// space-to-depth for the 2x2 stride-2 down conv (model.py:86): [B,n,n,c] fp32 -> [B,(n/2)^2, (i,j,c)] T
+template <typename T>
+__global__ void __launch_bounds__(256) s2d_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int n, int c) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int n2 = n >> 1;
+  const size_t total8 = static_cast<size_t>(B) * n2 * n2 * 4 * c / 8;
+  if (i >= total8) return;
+  const size_t e = i * 8;
+  const int K = 4 * c;
+  const size_t orow = e / K;
+  const int k = static_cast<int>(e - orow * K);
+  const int q = k / c, ch = k - q * c;
+  const int face = static_cast<int>(orow / (n2 * n2));
+  const int rem = static_cast<int>(orow - static_cast<size_t>(face) * n2 * n2);
+  const int h2 = rem / n2, w2 = rem - h2 * n2;
+  const size_t irow = (static_cast<size_t>(face) * n + (2 * h2 + (q >> 1))) * n + (2 * w2 + (q & 1));
+  float v[8];
+  load8(x + irow * c + ch, v);
+  store8(out + e, v);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ x, T* __restrict__ out, size_t total8) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  float v[8];
+  load8(x + i * 8, v);
+  store8(out + i * 8, v);
+}
+
+// HCA gate application (hca.py:28): f_o = f_d + w_c*f_d + w_s*f_d, optionally after adding the
+// hoisted idc_conv(identity) vector to f_d (model.py:245-246, level 0 only).
+template <typename T>
+__global__ void __launch_bounds__(256) hca_apply_kernel(const float* __restrict__ fd, const float* __restrict__ wc,
+                                                        const float* __restrict__ ws, const float* __restrict__ idc,
+                                                        T* __restrict__ out, size_t total8, int c, int rows_per_face) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const size_t e = i * 8;
+  const size_t row = e / c;
+  const int k = static_cast<int>(e - row * c);
+  const int face = static_cast<int>(row / rows_per_face);
+  float v[8], g[8];
+  load8(fd + e, v);
+  load8(wc + static_cast<size_t>(face) * c + k, g);
+  if (idc != nullptr) {
+    float a[8];
+    load8(idc + static_cast<size_t>(face) * c + k, a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += a[j];
+  }
+  const float s = ws[row];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = v[j] + g[j] * v[j] + s * v[j];
+  store8(out + e, v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ending: 3x3 conv 128 -> 4 (model.py:168-176,261-262), NHWC in, NCHW fp32 epsilon out.
+// one warp per pixel; weights [4][9][128] in shared memory
+// ------------------------------------------------------------------------------------------------
+template <typename TIn>
+__global__ void __launch_bounds__(256) ending_conv_kernel(const TIn* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ eps,
+                                                          int B, int S) {
+  __shared__ float s_w[4 * 9 * 128];
+  for (int i = threadIdx.x; i < 4 * 9 * 128; i += blockDim.x) s_w[i] = w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const size_t pix = static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t npix = static_cast<size_t>(B) * S * S;
+  if (pix >= npix) return;
+  const int face = static_cast<int>(pix / (S * S));
+  const int rem = static_cast<int>(pix - static_cast<size_t>(face) * S * S);
+  const int py = rem / S, px = rem - py * S;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+    if (yy < 0 || yy >= S || xx < 0 || xx >= S) continue;
+    const TIn* src = x + ((static_cast<size_t>(face) * S + yy) * S + xx) * 128 + lane * 4;
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = to_f32(src[i]);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const float* wr = s_w + (o * 9 + tap) * 128 + lane * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[o] = fmaf(v[i], wr[i], acc[o]);
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 4; ++o) acc[o] = warp_sum(acc[o]);
+  if (lane < 4) {
+    const float r = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+    eps[((static_cast<size_t>(face) * 4 + lane) * S + py) * S + px] = r + bias[lane];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// x_{t-1} update (diffusers DDIMScheduler.step / DDPMScheduler.step; reference call site
+// train_refiner.py:120) with Philox4x32-10 + Box-Muller noise keyed by (seed, face, step, group).
+// One thread = 4 consecutive elements = one Philox group.  Pure streaming: 12-16 B/element.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    if (r > 0) { k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+  }
+}
+__device__ __forceinline__ float philox_unit(uint32_t r) {
+  return (static_cast<float>(r >> 9) + 0.5f) * 1.1920928955078125e-07f;  // 2^-23
+}
+
+__global__ void __launch_bounds__(256) sampler_update_kernel(float* __restrict__ x, const float* __restrict__ eps,
+                                                             const StepCoef* __restrict__ coefs,
+                                                             const StepState* __restrict__ state, int fixed_step,
+                                                             const float* __restrict__ noise, unsigned long long seed,
+                                                             long long first_face, int batch, int elems_per_face) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int groups = elems_per_face >> 2;
+  if (i >= static_cast<size_t>(batch) * groups) return;
+  const int step = state != nullptr ? state->step : fixed_step;
+  const StepCoef cf = coefs[step];
+  const int face = static_cast<int>(i / groups);
+  const int grp = static_cast<int>(i - static_cast<size_t>(face) * groups);
+  const float4 xv = *reinterpret_cast<const float4*>(x + i * 4);
+  const float4 ev = *reinterpret_cast<const float4*>(eps + i * 4);
+  float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+  const float es[4] = {ev.x, ev.y, ev.z, ev.w};
+  float z[4] = {0.f, 0.f, 0.f, 0.f};
+  if (cf.k_noise != 0.f) {
+    if (noise != nullptr) {
+      const float4 nv = *reinterpret_cast<const float4*>(noise + (static_cast<size_t>(step) * batch * groups + i) * 4);
+      z[0] = nv.x; z[1] = nv.y; z[2] = nv.z; z[3] = nv.w;
+    } else {
+      uint32_t c[4] = {static_cast<uint32_t>(grp), static_cast<uint32_t>(first_face + face),
+                       static_cast<uint32_t>(step), 0x48494644u};
+      philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+      const float r0 = sqrtf(-2.f * logf(philox_unit(c[0])));
+      const float a0 = 6.283185307179586f * philox_unit(c[1]);
+      const float r1 = sqrtf(-2.f * logf(philox_unit(c[2])));
+      const float a1 = 6.283185307179586f * philox_unit(c[3]);
+      z[0] = r0 * cosf(a0); z[1] = r0 * sinf(a0);
+      z[2] = r1 * cosf(a1); z[3] = r1 * sinf(a1);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float x0 = (xs[j] - cf.sqrt_beta_prod * es[j]) / cf.sqrt_alpha_prod;
+    if (cf.clip > 0.f) x0 = fminf(fmaxf(x0, -cf.clip), cf.clip);
+    float r = cf.k_x0 * x0;
+    if (cf.k_eps != 0.f) r += cf.k_eps * es[j];
+    if (cf.k_x != 0.f) r += cf.k_x * xs[j];
+    if (cf.k_noise != 0.f) r += cf.k_noise * z[j];
+    xs[j] = r;
+  }
+  *reinterpret_cast<float4*>(x + i * 4) = make_float4(xs[0], xs[1], xs[2], xs[3]);
+}
+
+// end of a sampler step: step += 1 and point every face at the next table row (single block)
+__global__ void advance_rows_kernel(StepState* st, int* __restrict__ row_idx, int n) {
+  const int next = st->step + 1;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) row_idx[i] = next;
+  if (threadIdx.x == 0) st->step = next;
+}
+__global__ void set_step_kernel(StepState* st, int v) { st->step = v; }
+
+// sinusoidal embedding (model.py:22-29): emb[r, i] = sin(t_r f_i), emb[r, 64+i] = cos(t_r f_i)
+__global__ void time_embed_kernel(const float* __restrict__ t, const float* __restrict__ freqs, float* __restrict__ emb,
+                                  int R) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * 64) return;
+  const int r = i >> 6, j = i & 63;
+  const float a = t[r] * freqs[j];
+  emb[r * 128 + j] = sinf(a);
+  emb[r * 128 + 64 + j] = cosf(a);
+}
+
+// layout conversion at the boundary and for taps
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, int HW) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * C * HW) return;
+  const int c = static_cast<int>(i % C);
+  const size_t r = i / C;
+  const int p = static_cast<int>(r % HW);
+  const int b = static_cast<int>(r / HW);
+  out[i] = in[(static_cast<size_t>(b) * C + c) * HW + p];
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int B, int C, int HW, int ld) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * C * HW) return;
+  const int p = static_cast<int>(i % HW);
+  const size_t r = i / HW;
+  const int c = static_cast<int>(r % C);
+  const int b = static_cast<int>(r / C);
+  out[i] = to_f32(in[(static_cast<size_t>(b) * HW + p) * ld + c]);
+}
+
+// avg-pool + max-pool over pixels of an NHWC fp32 tensor (hca.py:34-36): out[b,c] = mean + max
+__global__ void pool_avgmax_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int HW, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  float s = 0.f, mx = -INFINITY;
+  for (int p = 0; p < HW; ++p) {
+    const float v = in[(static_cast<size_t>(b) * HW + p) * C + c];
+    s += v;
+    mx = fmaxf(mx, v);
+  }
+  out[i] = s / static_cast<float>(HW) + mx;
+}
+
+// weight repack: dst[n, kd] = rs[n] * src[perm[n]][kmap(kd)]
+//   taps == 1: src is [N_src, K];  taps > 1: src is OIHW [N_src, C, taps], kd = tap*C + c
+template <typename TDst>
+__global__ void pack_rows_kernel(const float* __restrict__ src, TDst* __restrict__ dst, const int* __restrict__ perm,
+                                 const float* __restrict__ rs, int N, int Kd, int taps) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(N) * Kd) return;
+  const int n = static_cast<int>(i / Kd), kd = static_cast<int>(i - static_cast<size_t>(n) * Kd);
+  const int sn = perm != nullptr ? perm[n] : n;
+  int sk = kd;
+  if (taps > 1) {
+    const int C = Kd / taps;
+    const int tap = kd / C, c = kd - tap * C;
+    sk = c * taps + tap;
+  }
+  float v = src[static_cast<size_t>(sn) * Kd + sk];
+  if (rs != nullptr) v *= rs[n];
+  dst[i] = from_f32<TDst>(v);
+}
+
+}  // namespace hd

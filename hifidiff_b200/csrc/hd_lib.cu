@@ -1,0 +1,1317 @@
+// hifidiff_b200 host side: handle, weight repacking, per-batch launch plan, C ABI (include/hifidiff_b200.h).
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/hifidiff_b200.h"
+#include "common.cuh"
+#include "elem_kernels.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+
+using namespace hd;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+std::string fmt(const char* f, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof(buf), f, ap);
+  va_end(ap);
+  return std::string(buf);
+}
+
+struct HdError {
+  int code;
+  std::string msg;
+};
+
+#define HD_THROW(code, ...) throw HdError{code, fmt(__VA_ARGS__)}
+#define CUDA_CHECK(expr)                                                                              \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      HD_THROW(HD_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+  } while (0)
+
+constexpr int kNumLevels = 5;
+constexpr int kEncBlocks[4] = {2, 2, 4, 8};  // models/denoiser/model.py:80
+constexpr int kMidBlocks = 8;                // model.py:89-91
+constexpr int kDecBlocks[4] = {2, 2, 2, 2};  // model.py:93
+constexpr int kWidth = 128;                  // model.py:36
+constexpr int kTimeDim = 512;                // model.py:44
+constexpr float kBnEps = 1e-5f;
+
+inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// chunked bump allocator for everything the library owns on the device
+// ------------------------------------------------------------------------------------------------
+struct Arena {
+  std::vector<void*> chunks;
+  char* cur = nullptr;
+  size_t left = 0;
+  size_t total = 0;
+  size_t chunk_bytes = size_t(256) << 20;
+  void* alloc(size_t bytes) {
+    bytes = (bytes + 255) & ~size_t(255);
+    if (bytes > left) {
+      size_t sz = std::max(bytes, chunk_bytes);
+      void* p = nullptr;
+      CUDA_CHECK(cudaMalloc(&p, sz));
+      CUDA_CHECK(cudaMemset(p, 0, sz));
+      chunks.push_back(p);
+      cur = static_cast<char*>(p);
+      left = sz;
+      total += sz;
+    }
+    void* r = cur;
+    cur += bytes;
+    left -= bytes;
+    return r;
+  }
+  template <typename T> T* get(size_t n) { return static_cast<T*>(alloc(n * sizeof(T))); }
+  void release() {
+    for (void* p : chunks) cudaFree(p);
+    chunks.clear();
+    cur = nullptr;
+    left = total = 0;
+  }
+};
+
+struct BlockW {
+  std::string prefix;
+  int level = 0, c = 0, mod_off = 0;
+  float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr;
+  void *w1 = nullptr, *wsca = nullptr, *w3 = nullptr, *w4 = nullptr, *w5 = nullptr;
+  float *b1 = nullptr, *bsca = nullptr, *b3 = nullptr, *b4 = nullptr, *b5 = nullptr;
+  float *dw_w = nullptr, *dw_b = nullptr;
+};
+
+struct HcaW {
+  int d = 0, sp = 0;
+  void* wf = nullptr;  // [d, 9d] fused 3x3, BN folded
+  float* bf = nullptr;
+  float *c0w = nullptr, *c0b = nullptr, *c2w = nullptr, *c2b = nullptr;  // channel_mlp
+  float *s0w = nullptr, *s0b = nullptr, *s3w = nullptr, *s3b = nullptr;  // spatial_mlp, BN folded
+  float *wc = nullptr, *ws = nullptr;                                    // per-face gates (set_condition)
+};
+
+struct TapInfo {
+  const void* ptr = nullptr;
+  int dtype = DT_F32, C = 0, HW = 0, ld = 0;
+};
+
+struct Op {
+  std::function<void(cudaStream_t)> fn;
+  std::string tap;
+  TapInfo info;
+};
+
+struct Plan {
+  int batch = 0;
+  std::vector<Op> ops;
+  cudaGraphExec_t graph = nullptr;  // one sampler step (plan + x_{t-1} update + advance), see hd_sample
+  uint64_t graph_seed = 0;
+  int64_t graph_first = 0;
+  const float* graph_noise = nullptr;
+  double flops_per_face = 0;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct SrcTensor {
+  const void* data;
+  int dtype;
+  std::vector<int64_t> shape;
+  size_t numel;
+};
+
+}  // namespace
+
+struct hd_handle {
+  hd_config cfg{};
+  std::string err;
+  bool fused = false, bf16 = true, weights_loaded = false, condition_set = false;
+  int S = 16, Bcap = 0, max_steps = 0, sm_count = 0, sm_major = 0, sm_minor = 0;
+  int c[kNumLevels], sp[kNumLevels];
+  int mod_stride = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  EncodeTiledFn encode = nullptr;
+  Arena arena;
+  DeviceStatus* d_status = nullptr;
+
+  // weights
+  std::vector<BlockW> blocks;  // execution order
+  HcaW hca[kNumLevels];
+  void *down_w[4] = {}, *up_w[4] = {};
+  float* down_b[4] = {};
+  float *intro_w = nullptr, *intro_b = nullptr, *end_w = nullptr, *end_b = nullptr;
+  float *tm1_w = nullptr, *tm1_b = nullptr, *tm3_w = nullptr, *tm3_b = nullptr, *mlp_w = nullptr, *mlp_b = nullptr;
+  float *idc_w = nullptr, *idc_b = nullptr, *freqs = nullptr;
+  int64_t weight_elems_step = 0;
+
+  // workspace
+  float* resid[kNumLevels] = {};
+  void *act_a = nullptr, *act_h = nullptr, *act_g = nullptr, *hca_out = nullptr, *pooled = nullptr;
+  float *sca_s = nullptr, *gate_tmp = nullptr;
+  float *x_state = nullptr, *eps_buf = nullptr, *x_stage = nullptr;
+  float *t_vals = nullptr, *t_emb = nullptr, *t_h1 = nullptr, *t_g1 = nullptr, *t_temb = nullptr, *t_g2 = nullptr,
+        *mod_table = nullptr;
+  int* row_idx = nullptr;
+  StepCoef* coefs = nullptr;
+  StepState* state = nullptr;
+  float *idc_add = nullptr, *cond_nhwc = nullptr, *cond_pool = nullptr, *cond_h = nullptr, *cond_hs = nullptr,
+        *cond_stage = nullptr;
+  std::vector<float> table_key;  // timesteps currently held by mod_table rows
+  const float* cur_x = nullptr;
+  float* cur_eps = nullptr;
+  std::map<int, std::unique_ptr<Plan>> plans;
+  size_t workspace_bytes = 0;
+
+  // transient during load
+  std::map<std::string, SrcTensor> src;
+  std::vector<void*> temp_dev;
+};
+
+namespace {
+
+size_t esize(int dt) { return dt == DT_BF16 ? 2 : 4; }
+
+// ------------------------------------------------------------------------------------------------
+// GEMM dispatch
+// ------------------------------------------------------------------------------------------------
+template <typename TA, typename TW, typename TOut>
+void launch_simt_typed(const GemmDesc& d, cudaStream_t st) {
+  simt::SimtArgs g;
+  g.M = d.M; g.N = d.N; g.K = d.K;
+  g.A = d.A; g.lda = d.lda; g.a_mode = d.a_mode; g.sp = d.sp; g.C = d.C;
+  g.W = d.W; g.ldw = d.ldw; g.bias = d.bias;
+  g.out = d.out; g.ldo = d.ldo; g.resid = d.resid; g.ldr = d.ldr;
+  dim3 grid(cdiv(d.M, simt::TM), cdiv(d.N, simt::TN));
+  switch (d.epi) {
+    case EPI_BIAS: simt::gemm_simt_kernel<TA, TW, TOut, EPI_BIAS><<<grid, 256, 0, st>>>(g); break;
+    case EPI_RELU: simt::gemm_simt_kernel<TA, TW, TOut, EPI_RELU><<<grid, 256, 0, st>>>(g); break;
+    case EPI_SIGMOID: simt::gemm_simt_kernel<TA, TW, TOut, EPI_SIGMOID><<<grid, 256, 0, st>>>(g); break;
+    case EPI_RESID: simt::gemm_simt_kernel<TA, TW, TOut, EPI_RESID><<<grid, 256, 0, st>>>(g); break;
+    case EPI_PIXSHUF: simt::gemm_simt_kernel<TA, TW, TOut, EPI_PIXSHUF><<<grid, 256, 0, st>>>(g); break;
+    default: break;
+  }
+}
+
+void launch_simt(const GemmDesc& d, cudaStream_t st) {
+  const bool abf = d.a_dtype == DT_BF16, wbf = d.w_dtype == DT_BF16, obf = d.out_dtype == DT_BF16;
+  if (!abf && !wbf && !obf) launch_simt_typed<float, float, float>(d, st);
+  else if (abf && wbf && obf) launch_simt_typed<bf16, bf16, bf16>(d, st);
+  else if (abf && wbf && !obf) launch_simt_typed<bf16, bf16, float>(d, st);
+  else if (!abf && !wbf && obf) launch_simt_typed<float, float, bf16>(d, st);
+  else launch_simt_typed<float, float, float>(d, st);  // unreachable by construction (checked in add_gemm)
+}
+
+struct TcLaunch {
+  CUtensorMap mapA, mapB;
+  tc::TcArgs args;
+  dim3 grid;
+  int epi, a_mode, out_dtype;
+};
+
+template <int EPI, int AMODE, typename TOut>
+void launch_tc_inst(const TcLaunch& L, cudaStream_t st) {
+  auto kern = tc::gemm_tc_kernel<128, EPI, AMODE, TOut>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TileCfg<128>::SMEM_BYTES);
+    configured = true;
+  }
+  kern<<<L.grid, tc::NUM_THREADS, tc::TileCfg<128>::SMEM_BYTES, st>>>(L.mapA, L.mapB, L.args);
+}
+
+void launch_tc(const TcLaunch& L, cudaStream_t st) {
+  const bool obf = L.out_dtype == DT_BF16;
+  if (L.a_mode == A_CONV3) {
+    if (L.epi == EPI_RELU && obf) launch_tc_inst<EPI_RELU, A_CONV3, bf16>(L, st);
+    return;
+  }
+  switch (L.epi) {
+    case EPI_BIAS:
+      if (obf) launch_tc_inst<EPI_BIAS, A_PLAIN, bf16>(L, st);
+      else launch_tc_inst<EPI_BIAS, A_PLAIN, float>(L, st);
+      break;
+    case EPI_RELU: launch_tc_inst<EPI_RELU, A_PLAIN, bf16>(L, st); break;
+    case EPI_RESID: launch_tc_inst<EPI_RESID, A_PLAIN, float>(L, st); break;
+    case EPI_GATE: launch_tc_inst<EPI_GATE, A_PLAIN, bf16>(L, st); break;
+    case EPI_PIXSHUF: launch_tc_inst<EPI_PIXSHUF, A_PLAIN, float>(L, st); break;
+    default: break;
+  }
+}
+
+void encode_map(hd_handle* h, CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
+                const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = h->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) HD_THROW(HD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+}
+
+// rows_alloc: number of valid rows in the A allocation (>= M, multiple of 128)
+TcLaunch build_tc(hd_handle* h, const GemmDesc& d, long long a_rows_alloc) {
+  TcLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.epi = d.epi; L.a_mode = d.a_mode; L.out_dtype = d.out_dtype;
+  tc::TcArgs& a = L.args;
+  a.M = d.M; a.N = d.N; a.num_kb = d.K / tc::BK;
+  a.bias = d.bias; a.out = d.out; a.ldo = d.ldo; a.resid = d.resid; a.ldr = d.ldr;
+  a.sp = d.sp; a.kb_per_tap = 1; a.conv_bh = 1; a.conv_bb = 1;
+  a.status = h->d_status;
+  if (d.a_mode == A_CONV3) {
+    const int n = d.sp, C = d.C;
+    if (128 % n != 0 || (n * n < 128 && 128 % (n * n) != 0)) HD_THROW(HD_ERR_UNSUPPORTED, "conv tile: spatial %d", n);
+    int bh, bb;
+    if (n * n >= 128) { bh = 128 / n; bb = 1; } else { bh = n; bb = 128 / (n * n); }
+    a.kb_per_tap = C / tc::BK; a.conv_bh = bh; a.conv_bb = bb;
+    const long long faces_alloc = a_rows_alloc / (n * n);
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)n, (cuuint64_t)n, (cuuint64_t)faces_alloc};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)n * C * 2, (cuuint64_t)n * n * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)n, (cuuint32_t)bh, (cuuint32_t)bb};
+    encode_map(h, &L.mapA, d.A, 4, dims, strides, box);
+  } else {
+    cuuint64_t dims[2] = {(cuuint64_t)d.K, (cuuint64_t)a_rows_alloc};
+    cuuint64_t strides[1] = {(cuuint64_t)d.lda * 2};
+    cuuint32_t box[2] = {64, 128};
+    encode_map(h, &L.mapA, d.A, 2, dims, strides, box);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d.K, (cuuint64_t)d.N};
+    cuuint64_t strides[1] = {(cuuint64_t)d.ldw * 2};
+    cuuint32_t box[2] = {64, 128};
+    encode_map(h, &L.mapB, d.W, 2, dims, strides, box);
+  }
+  L.grid = dim3(cdiv(d.M, 128), d.N / 128);
+  return L;
+}
+
+bool tc_eligible(const hd_handle* h, const GemmDesc& d) {
+  if (!h->bf16) return false;
+  if (d.a_dtype != DT_BF16 || d.w_dtype != DT_BF16) return false;
+  if (d.K % 64 != 0 || d.N % 128 != 0) return false;
+  if (d.a_mode == A_CONV3 && (d.C % 64 != 0)) return false;
+  if (d.epi == EPI_SIGMOID) return false;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight loading
+// ------------------------------------------------------------------------------------------------
+const SrcTensor& need(hd_handle* h, const std::string& name, std::initializer_list<int64_t> shape) {
+  auto it = h->src.find(name);
+  if (it == h->src.end()) HD_THROW(HD_ERR_INVALID, "missing tensor '%s'", name.c_str());
+  const SrcTensor& t = it->second;
+  size_t n = 1;
+  for (int64_t s : shape) n *= static_cast<size_t>(s);
+  if (t.dtype != 0) HD_THROW(HD_ERR_INVALID, "tensor '%s' must be fp32", name.c_str());
+  if (t.numel != n) HD_THROW(HD_ERR_INVALID, "tensor '%s' has %zu elements, expected %zu", name.c_str(), t.numel, n);
+  return t;
+}
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// device view of a source tensor (uploads host memory into a temporary)
+const float* dev_src(hd_handle* h, const SrcTensor& t) {
+  if (is_device_ptr(t.data)) return static_cast<const float*>(t.data);
+  void* p = nullptr;
+  CUDA_CHECK(cudaMalloc(&p, t.numel * 4));
+  h->temp_dev.push_back(p);
+  CUDA_CHECK(cudaMemcpy(p, t.data, t.numel * 4, cudaMemcpyHostToDevice));
+  return static_cast<const float*>(p);
+}
+
+std::vector<float> host_vec(hd_handle* h, const SrcTensor& t) {
+  std::vector<float> v(t.numel);
+  CUDA_CHECK(cudaMemcpy(v.data(), t.data, t.numel * 4, cudaMemcpyDefault));
+  return v;
+}
+
+float* upload_f32(hd_handle* h, const std::vector<float>& v) {
+  float* d = h->arena.get<float>(v.size());
+  CUDA_CHECK(cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+  return d;
+}
+int* upload_i32(hd_handle* h, const std::vector<int>& v) {
+  int* d = h->arena.get<int>(v.size());
+  CUDA_CHECK(cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+  return d;
+}
+
+// dst[n, kd] = rs[n] * src[perm[n]][kmap(kd)]  into a freshly allocated arena matrix of dtype dt
+void* pack_matrix(hd_handle* h, const SrcTensor& t, int N, int Kd, int taps, const std::vector<int>* perm,
+                  const std::vector<float>* rs, int dt, void* dst_override = nullptr) {
+  const float* src = dev_src(h, t);
+  void* dst = dst_override ? dst_override : h->arena.alloc(static_cast<size_t>(N) * Kd * esize(dt));
+  const int* dperm = perm ? upload_i32(h, *perm) : nullptr;
+  const float* drs = rs ? upload_f32(h, *rs) : nullptr;
+  const size_t total = static_cast<size_t>(N) * Kd;
+  const int blocks = cdiv(total, 256);
+  if (dt == DT_BF16)
+    pack_rows_kernel<bf16><<<blocks, 256, 0, h->stream>>>(src, static_cast<bf16*>(dst), dperm, drs, N, Kd, taps);
+  else
+    pack_rows_kernel<float><<<blocks, 256, 0, h->stream>>>(src, static_cast<float*>(dst), dperm, drs, N, Kd, taps);
+  CUDA_CHECK(cudaGetLastError());
+  return dst;
+}
+
+std::vector<float> bn_scale(hd_handle* h, const std::string& p, int n, std::vector<float>* shift_out,
+                            const std::vector<float>& conv_bias) {
+  // eval-mode BatchNorm folded into the preceding conv: y = rs * (conv + b - mean) + beta
+  auto w = host_vec(h, need(h, p + "weight", {n}));
+  auto b = host_vec(h, need(h, p + "bias", {n}));
+  auto mu = host_vec(h, need(h, p + "running_mean", {n}));
+  auto var = host_vec(h, need(h, p + "running_var", {n}));
+  std::vector<float> rs(n);
+  shift_out->resize(n);
+  for (int i = 0; i < n; ++i) {
+    rs[i] = w[i] / std::sqrt(var[i] + kBnEps);
+    (*shift_out)[i] = (conv_bias[i] - mu[i]) * rs[i] + b[i];
+  }
+  return rs;
+}
+
+void load_block(hd_handle* h, BlockW& bw, int wdt) {
+  const std::string& p = bw.prefix;
+  const int c = bw.c;
+  bw.ln1_w = upload_f32(h, host_vec(h, need(h, p + "norm1.weight", {c})));
+  bw.ln1_b = upload_f32(h, host_vec(h, need(h, p + "norm1.bias", {c})));
+  bw.ln2_w = upload_f32(h, host_vec(h, need(h, p + "norm2.weight", {c})));
+  bw.ln2_b = upload_f32(h, host_vec(h, need(h, p + "norm2.bias", {c})));
+  auto beta = host_vec(h, need(h, p + "beta", {c}));
+  auto gamma = host_vec(h, need(h, p + "gamma", {c}));
+
+  bw.w1 = pack_matrix(h, need(h, p + "conv1.weight", {2 * c, c}), 2 * c, c, 1, nullptr, nullptr, wdt);
+  bw.b1 = upload_f32(h, host_vec(h, need(h, p + "conv1.bias", {2 * c})));
+
+  {  // depthwise 3x3: [2c,1,3,3] -> [9][2c]
+    auto w = host_vec(h, need(h, p + "conv2.weight", {2 * c, 9}));
+    std::vector<float> t(static_cast<size_t>(18) * c);
+    for (int ch = 0; ch < 2 * c; ++ch)
+      for (int tap = 0; tap < 9; ++tap) t[static_cast<size_t>(tap) * 2 * c + ch] = w[static_cast<size_t>(ch) * 9 + tap];
+    bw.dw_w = upload_f32(h, t);
+    bw.dw_b = upload_f32(h, host_vec(h, need(h, p + "conv2.bias", {2 * c})));
+  }
+  bw.wsca = pack_matrix(h, need(h, p + "sca.1.weight", {c, c}), c, c, 1, nullptr, nullptr, wdt);
+  bw.bsca = upload_f32(h, host_vec(h, need(h, p + "sca.1.bias", {c})));
+
+  {  // conv3 with beta folded: y = inp + beta * (W3 x + b3)
+    auto b3 = host_vec(h, need(h, p + "conv3.bias", {c}));
+    for (int i = 0; i < c; ++i) b3[i] *= beta[i];
+    bw.w3 = pack_matrix(h, need(h, p + "conv3.weight", {c, c}), c, c, 1, nullptr, &beta, wdt);
+    bw.b3 = upload_f32(h, b3);
+  }
+  {  // conv4, gate-packed: 128-row groups [64 x1 rows | 64 matching x2 rows]
+    std::vector<int> perm(2 * c);
+    for (int n = 0; n < 2 * c; ++n) {
+      const int g = n / 128, r = n % 128;
+      perm[n] = r < 64 ? g * 64 + r : c + g * 64 + (r - 64);
+    }
+    auto b4 = host_vec(h, need(h, p + "conv4.bias", {2 * c}));
+    std::vector<float> b4p(2 * c);
+    for (int n = 0; n < 2 * c; ++n) b4p[n] = b4[perm[n]];
+    bw.w4 = pack_matrix(h, need(h, p + "conv4.weight", {2 * c, c}), 2 * c, c, 1, &perm, nullptr, wdt);
+    bw.b4 = upload_f32(h, b4p);
+  }
+  {  // conv5 with gamma folded
+    auto b5 = host_vec(h, need(h, p + "conv5.bias", {c}));
+    for (int i = 0; i < c; ++i) b5[i] *= gamma[i];
+    bw.w5 = pack_matrix(h, need(h, p + "conv5.weight", {c, c}), c, c, 1, nullptr, &gamma, wdt);
+    bw.b5 = upload_f32(h, b5);
+  }
+  // per-block time MLP rows go into the concatenated [mod_stride, 256] matrix
+  pack_matrix(h, need(h, p + "mlp.1.weight", {4 * c, 256}), 4 * c, 256, 1, nullptr, nullptr, DT_F32,
+              h->mlp_w + static_cast<size_t>(bw.mod_off) * 256);
+  {
+    const SrcTensor& t = need(h, p + "mlp.1.bias", {4 * c});
+    CUDA_CHECK(cudaMemcpy(h->mlp_b + bw.mod_off, t.data, static_cast<size_t>(4) * c * 4, cudaMemcpyDefault));
+  }
+  h->weight_elems_step += static_cast<int64_t>(c) * c * 7 + 18 * c;
+}
+
+void load_weights_impl(hd_handle* h) {
+  const int wdt = h->bf16 ? DT_BF16 : DT_F32;
+  h->weight_elems_step = 0;
+  h->mlp_w = h->arena.get<float>(static_cast<size_t>(h->mod_stride) * 256);
+  h->mlp_b = h->arena.get<float>(h->mod_stride);
+  for (auto& b : h->blocks) load_block(h, b, wdt);
+
+  h->tm1_w = upload_f32(h, host_vec(h, need(h, "time_mlp.1.weight", {2 * kTimeDim, kWidth})));
+  h->tm1_b = upload_f32(h, host_vec(h, need(h, "time_mlp.1.bias", {2 * kTimeDim})));
+  h->tm3_w = upload_f32(h, host_vec(h, need(h, "time_mlp.3.weight", {kTimeDim, kTimeDim})));
+  h->tm3_b = upload_f32(h, host_vec(h, need(h, "time_mlp.3.bias", {kTimeDim})));
+  h->intro_w = upload_f32(h, host_vec(h, need(h, "intro.weight", {kWidth, 36})));
+  h->intro_b = upload_f32(h, host_vec(h, need(h, "intro.bias", {kWidth})));
+  h->end_w = static_cast<float*>(pack_matrix(h, need(h, "ending.weight", {4, kWidth, 9}), 4, 9 * kWidth, 9, nullptr,
+                                             nullptr, DT_F32));
+  h->end_b = upload_f32(h, host_vec(h, need(h, "ending.bias", {4})));
+  h->weight_elems_step += 128 * 36 + 4 * 9 * 128;
+
+  for (int l = 0; l < 4; ++l) {
+    const int c = h->c[l];
+    const std::string p = "downs." + std::to_string(l) + ".";
+    h->down_w[l] = pack_matrix(h, need(h, p + "weight", {2 * c, c, 4}), 2 * c, 4 * c, 4, nullptr, nullptr, wdt);
+    h->down_b[l] = upload_f32(h, host_vec(h, need(h, p + "bias", {2 * c})));
+    h->weight_elems_step += static_cast<int64_t>(8) * c * c;
+  }
+  for (int L = 0; L < 4; ++L) {
+    const int cin = h->c[4 - L];  // 2048, 1024, 512, 256
+    const int N = 2 * cin, quarter = N / 4;
+    std::vector<int> perm(N);
+    for (int n = 0; n < N; ++n) perm[n] = 4 * (n % quarter) + n / quarter;  // packed row q*quarter+k <- 4k+q
+    h->up_w[L] = pack_matrix(h, need(h, "ups." + std::to_string(L) + ".0.weight", {N, cin}), N, cin, 1, &perm,
+                             nullptr, wdt);
+    h->weight_elems_step += static_cast<int64_t>(N) * cin;
+  }
+  if (h->fused) {
+    const int idc_out = 2048 * (h->S / 16) * (h->S / 16);
+    h->idc_w = upload_f32(h, host_vec(h, need(h, "idc_conv.weight", {idc_out, 2048})));
+    h->idc_b = upload_f32(h, host_vec(h, need(h, "idc_conv.bias", {idc_out})));
+    for (int j = 0; j < kNumLevels; ++j) {
+      HcaW& w = h->hca[j];
+      const int d = w.d;
+      const std::string p = "hcas." + std::to_string(j) + ".";
+      w.c0w = upload_f32(h, host_vec(h, need(h, p + "channel_mlp.0.weight", {d, d})));
+      w.c0b = upload_f32(h, host_vec(h, need(h, p + "channel_mlp.0.bias", {d})));
+      w.c2w = upload_f32(h, host_vec(h, need(h, p + "channel_mlp.2.weight", {d, d})));
+      w.c2b = upload_f32(h, host_vec(h, need(h, p + "channel_mlp.2.bias", {d})));
+      {
+        std::vector<float> shift;
+        auto cb = host_vec(h, need(h, p + "spatial_mlp.0.bias", {d / 2}));
+        auto rs = bn_scale(h, p + "spatial_mlp.1.", d / 2, &shift, cb);
+        w.s0w = static_cast<float*>(pack_matrix(h, need(h, p + "spatial_mlp.0.weight", {d / 2, d}), d / 2, d, 1,
+                                                nullptr, &rs, DT_F32));
+        w.s0b = upload_f32(h, shift);
+      }
+      {
+        std::vector<float> shift;
+        auto cb = host_vec(h, need(h, p + "spatial_mlp.3.bias", {1}));
+        auto rs = bn_scale(h, p + "spatial_mlp.4.", 1, &shift, cb);
+        w.s3w = static_cast<float*>(pack_matrix(h, need(h, p + "spatial_mlp.3.weight", {1, d / 2}), 1, d / 2, 1,
+                                                nullptr, &rs, DT_F32));
+        w.s3b = upload_f32(h, shift);
+      }
+      {
+        std::vector<float> shift;
+        auto cb = host_vec(h, need(h, p + "fused_mlp.0.bias", {d}));
+        auto rs = bn_scale(h, p + "fused_mlp.1.", d, &shift, cb);
+        w.wf = pack_matrix(h, need(h, p + "fused_mlp.0.weight", {d, d, 9}), d, 9 * d, 9, nullptr, &rs, wdt);
+        w.bf = upload_f32(h, shift);
+      }
+      // taps that can touch a real pixel: all 9 unless the level is 1x1 (centre tap only)
+      h->weight_elems_step += static_cast<int64_t>(d) * d * (w.sp == 1 ? 1 : 9);
+    }
+  }
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  for (void* p : h->temp_dev) cudaFree(p);
+  h->temp_dev.clear();
+  h->src.clear();
+  h->weights_loaded = true;
+  h->table_key.clear();
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan construction
+// ------------------------------------------------------------------------------------------------
+void add_op(Plan& P, std::function<void(cudaStream_t)> fn, const std::string& tap = std::string(),
+            TapInfo info = TapInfo()) {
+  Op op;
+  op.fn = std::move(fn);
+  op.tap = tap;
+  op.info = info;
+  P.ops.push_back(std::move(op));
+}
+
+void add_gemm(hd_handle* h, Plan& P, GemmDesc d, long long a_rows_alloc, const std::string& tap = std::string(),
+              TapInfo info = TapInfo()) {
+  const long long taps_exec = d.a_mode == A_CONV3 ? 1 : 1;
+  (void)taps_exec;
+  P.flops_per_face += 2.0 * d.M * static_cast<double>(d.N) * d.K / P.batch;
+  if (tc_eligible(h, d)) {
+    TcLaunch L = build_tc(h, d, a_rows_alloc);
+    add_op(P, [L](cudaStream_t st) { launch_tc(L, st); }, tap, info);
+    return;
+  }
+  if (d.epi == EPI_GATE) {
+    // fp32 mode: bias epilogue into a packed fp32 buffer, then the SimpleGate kernel
+    GemmDesc g = d;
+    g.epi = EPI_BIAS;
+    g.out = h->gate_tmp;
+    g.ldo = d.N;
+    g.out_dtype = DT_F32;
+    const int c = d.N / 2;
+    void* out = d.out;
+    const int odt = d.out_dtype;
+    const size_t rows = d.M;
+    float* tmp = h->gate_tmp;
+    add_op(P, [g](cudaStream_t st) { launch_simt(g, st); });
+    add_op(P, [=](cudaStream_t st) {
+      const int blocks = cdiv(rows * c, 256);
+      if (odt == DT_BF16) gate_packed_kernel<bf16><<<blocks, 256, 0, st>>>(tmp, static_cast<bf16*>(out), rows, c);
+      else gate_packed_kernel<float><<<blocks, 256, 0, st>>>(tmp, static_cast<float*>(out), rows, c);
+    }, tap, info);
+    return;
+  }
+  const bool abf = d.a_dtype == DT_BF16, wbf = d.w_dtype == DT_BF16;
+  if (abf != wbf) HD_THROW(HD_ERR_INVALID, "mixed-precision operands reached the FFMA GEMM");
+  add_op(P, [d](cudaStream_t st) { launch_simt(d, st); }, tap, info);
+}
+
+template <typename T>
+void launch_ln(int c, const float* x, const float* lw, const float* lb, T* out, int rows, int rpf, ModRef mod,
+               int shift_off, int scale_off, int has_mod, cudaStream_t st) {
+  const int grid = cdiv(rows, 8);
+  switch (c) {
+    case 128: ln_mod_kernel<128, T><<<grid, 256, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
+    case 256: ln_mod_kernel<256, T><<<grid, 256, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
+    case 512: ln_mod_kernel<512, T><<<grid, 256, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
+    case 1024: ln_mod_kernel<1024, T><<<grid, 256, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
+    case 2048: ln_mod_kernel<2048, T><<<grid, 256, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
+    default: break;
+  }
+}
+
+void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapname) {
+  const int B = P.batch, l = bw.level, c = bw.c, sp = h->sp[l];
+  const int rows = B * sp * sp, rpf = sp * sp;
+  const long long rows_alloc = static_cast<long long>(h->Bcap) * rpf;
+  const int adt = h->bf16 ? DT_BF16 : DT_F32;
+  float* resid = h->resid[l];
+  ModRef mod{h->mod_table, h->row_idx, h->mod_stride};
+  const bool bf = h->bf16;
+  void *act_a = h->act_a, *act_h = h->act_h, *act_g = h->act_g, *pooled = h->pooled;
+  float* sca_s = h->sca_s;
+
+  auto ln = [=](const float* lw, const float* lb, int shift_off, int scale_off) {
+    return [=](cudaStream_t st) {
+      if (bf) launch_ln<bf16>(c, resid, lw, lb, static_cast<bf16*>(act_a), rows, rpf, mod, shift_off, scale_off, 1, st);
+      else launch_ln<float>(c, resid, lw, lb, static_cast<float*>(act_a), rows, rpf, mod, shift_off, scale_off, 1, st);
+    };
+  };
+  // norm1 + modulation (shift_att = chunk 0, scale_att = chunk 1)
+  add_op(P, ln(bw.ln1_w, bw.ln1_b, bw.mod_off, bw.mod_off + c));
+  {  // conv1
+    GemmDesc d;
+    d.M = rows; d.N = 2 * c; d.K = c; d.A = act_a; d.lda = c; d.a_dtype = adt;
+    d.W = bw.w1; d.ldw = c; d.w_dtype = adt; d.bias = bw.b1; d.epi = EPI_BIAS;
+    d.out = act_h; d.ldo = 2 * c; d.out_dtype = adt;
+    add_gemm(h, P, d, rows_alloc);
+  }
+  {  // depthwise 3x3 + SimpleGate + pool
+    const float *dw_w = bw.dw_w, *dw_b = bw.dw_b;
+    add_op(P, [=](cudaStream_t st) {
+      dim3 grid(c / 64, B);
+      if (bf) dwconv_gate_pool_kernel<bf16><<<grid, 256, 0, st>>>(static_cast<const bf16*>(act_h), dw_w, dw_b,
+                                                                  static_cast<bf16*>(act_g), static_cast<bf16*>(pooled), sp, c);
+      else dwconv_gate_pool_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(act_h), dw_w, dw_b,
+                                                                static_cast<float*>(act_g), static_cast<float*>(pooled), sp, c);
+    });
+    P.flops_per_face += 2.0 * 9 * 2 * c * rpf;
+  }
+  {  // SCA 1x1 on the pooled vector
+    GemmDesc d;
+    d.M = B; d.N = c; d.K = c; d.A = pooled; d.lda = c; d.a_dtype = adt;
+    d.W = bw.wsca; d.ldw = c; d.w_dtype = adt; d.bias = bw.bsca; d.epi = EPI_BIAS;
+    d.out = sca_s; d.ldo = c; d.out_dtype = DT_F32;
+    add_gemm(h, P, d, h->Bcap);
+  }
+  add_op(P, [=](cudaStream_t st) {
+    const size_t total8 = static_cast<size_t>(rows) * c / 8;
+    if (bf) scale_rows_kernel<bf16><<<cdiv(total8, 256), 256, 0, st>>>(static_cast<bf16*>(act_g), sca_s, total8, c, rpf);
+    else scale_rows_kernel<float><<<cdiv(total8, 256), 256, 0, st>>>(static_cast<float*>(act_g), sca_s, total8, c, rpf);
+  });
+  {  // conv3 (+beta) + residual
+    GemmDesc d;
+    d.M = rows; d.N = c; d.K = c; d.A = act_g; d.lda = c; d.a_dtype = adt;
+    d.W = bw.w3; d.ldw = c; d.w_dtype = adt; d.bias = bw.b3; d.epi = EPI_RESID;
+    d.out = resid; d.ldo = c; d.out_dtype = DT_F32; d.resid = resid; d.ldr = c;
+    add_gemm(h, P, d, rows_alloc);
+  }
+  // norm2 + modulation (shift_ffn = chunk 2, scale_ffn = chunk 3)
+  add_op(P, ln(bw.ln2_w, bw.ln2_b, bw.mod_off + 2 * c, bw.mod_off + 3 * c));
+  {  // conv4 + SimpleGate
+    GemmDesc d;
+    d.M = rows; d.N = 2 * c; d.K = c; d.A = act_a; d.lda = c; d.a_dtype = adt;
+    d.W = bw.w4; d.ldw = c; d.w_dtype = adt; d.bias = bw.b4; d.epi = EPI_GATE;
+    d.out = act_g; d.ldo = c; d.out_dtype = adt;
+    add_gemm(h, P, d, rows_alloc);
+  }
+  {  // conv5 (+gamma) + residual
+    GemmDesc d;
+    d.M = rows; d.N = c; d.K = c; d.A = act_g; d.lda = c; d.a_dtype = adt;
+    d.W = bw.w5; d.ldw = c; d.w_dtype = adt; d.bias = bw.b5; d.epi = EPI_RESID;
+    d.out = resid; d.ldo = c; d.out_dtype = DT_F32; d.resid = resid; d.ldr = c;
+    TapInfo ti;
+    ti.ptr = resid; ti.dtype = DT_F32; ti.C = c; ti.HW = rpf; ti.ld = c;
+    add_gemm(h, P, d, rows_alloc, tapname, ti);
+  }
+}
+
+void add_hca(hd_handle* h, Plan& P, int j, int level) {
+  const HcaW& w = h->hca[j];
+  const int B = P.batch, d = w.d, sp = w.sp, rpf = sp * sp, rows = B * rpf;
+  const long long rows_alloc = static_cast<long long>(h->Bcap) * rpf;
+  const int adt = h->bf16 ? DT_BF16 : DT_F32;
+  const bool bf = h->bf16;
+  const float* fd = h->resid[level];
+  const float *wc = w.wc, *ws = w.ws;
+  const float* idc = j == 0 ? h->idc_add : nullptr;
+  void* act_a = h->act_a;
+  add_op(P, [=](cudaStream_t st) {
+    const size_t total8 = static_cast<size_t>(rows) * d / 8;
+    if (bf) hca_apply_kernel<bf16><<<cdiv(total8, 256), 256, 0, st>>>(fd, wc, ws, idc, static_cast<bf16*>(act_a), total8, d, rpf);
+    else hca_apply_kernel<float><<<cdiv(total8, 256), 256, 0, st>>>(fd, wc, ws, idc, static_cast<float*>(act_a), total8, d, rpf);
+  });
+  GemmDesc g;
+  g.M = rows; g.N = d; g.A = act_a; g.a_dtype = adt; g.w_dtype = adt; g.bias = w.bf; g.epi = EPI_RELU;
+  g.out = h->hca_out; g.ldo = d; g.out_dtype = adt; g.ldw = 9 * d;
+  if (sp == 1) {  // only the centre tap sees a pixel
+    g.a_mode = A_PLAIN; g.K = d; g.lda = d;
+    g.W = static_cast<const char*>(w.wf) + static_cast<size_t>(4) * d * esize(adt);
+  } else {
+    g.a_mode = A_CONV3; g.K = 9 * d; g.sp = sp; g.C = d; g.lda = d; g.W = w.wf;
+  }
+  TapInfo ti;
+  ti.ptr = h->hca_out; ti.dtype = adt; ti.C = d; ti.HW = rpf; ti.ld = d;
+  add_gemm(h, P, g, rows_alloc, "hcas." + std::to_string(j), ti);
+}
+
+Plan* get_plan(hd_handle* h, int B) {
+  auto it = h->plans.find(B);
+  if (it != h->plans.end()) return it->second.get();
+  std::unique_ptr<Plan> up(new Plan());
+  Plan& P = *up;
+  P.batch = B;
+  const int S = h->S;
+  const bool bf = h->bf16;
+  const int adt = bf ? DT_BF16 : DT_F32;
+
+  {  // intro
+    float* out = h->resid[0];
+    const float *w = h->intro_w, *b = h->intro_b;
+    TapInfo ti;
+    ti.ptr = out; ti.dtype = DT_F32; ti.C = kWidth; ti.HW = S * S; ti.ld = kWidth;
+    add_op(P, [=](cudaStream_t st) {
+      intro_conv_kernel<<<dim3(S, B), 128, 4 * 3 * (S + 2) * sizeof(float), st>>>(h->cur_x, w, b, out, S);
+    }, "intro", ti);
+    P.flops_per_face += 2.0 * 36 * 128 * S * S;
+  }
+  size_t bi = 0;
+  for (int l = 0; l < 4; ++l) {
+    for (int i = 0; i < kEncBlocks[l]; ++i, ++bi)
+      add_block(h, P, h->blocks[bi], "encoders." + std::to_string(l) + "." + std::to_string(i));
+    // down: 2x2 stride-2 conv as space-to-depth + GEMM
+    const int c = h->c[l], n = h->sp[l], rows_out = B * (n / 2) * (n / 2);
+    const float* src = h->resid[l];
+    void* act_a = h->act_a;
+    add_op(P, [=](cudaStream_t st) {
+      const size_t total8 = static_cast<size_t>(rows_out) * 4 * c / 8;
+      if (bf) s2d_kernel<bf16><<<cdiv(total8, 256), 256, 0, st>>>(src, static_cast<bf16*>(act_a), B, n, c);
+      else s2d_kernel<float><<<cdiv(total8, 256), 256, 0, st>>>(src, static_cast<float*>(act_a), B, n, c);
+    });
+    GemmDesc d;
+    d.M = rows_out; d.N = 2 * c; d.K = 4 * c; d.A = act_a; d.lda = 4 * c; d.a_dtype = adt;
+    d.W = h->down_w[l]; d.ldw = 4 * c; d.w_dtype = adt; d.bias = h->down_b[l]; d.epi = EPI_BIAS;
+    d.out = h->resid[l + 1]; d.ldo = 2 * c; d.out_dtype = DT_F32;
+    TapInfo ti;
+    ti.ptr = h->resid[l + 1]; ti.dtype = DT_F32; ti.C = 2 * c; ti.HW = (n / 2) * (n / 2); ti.ld = 2 * c;
+    add_gemm(h, P, d, static_cast<long long>(h->Bcap) * (n / 2) * (n / 2), "downs." + std::to_string(l), ti);
+  }
+  for (int i = 0; i < kMidBlocks; ++i, ++bi) add_block(h, P, h->blocks[bi], "middle_blks." + std::to_string(i));
+  if (h->fused) add_hca(h, P, 0, 4);
+  for (int L = 0; L < 4; ++L) {
+    const int lin = 4 - L, lout = 3 - L;
+    const int cin = h->c[lin], n = h->sp[lin], rows_in = B * n * n;
+    const void* a_ptr;
+    if (h->fused) {
+      a_ptr = h->hca_out;
+    } else {
+      const float* src = h->resid[lin];
+      void* act_a = h->act_a;
+      a_ptr = act_a;
+      add_op(P, [=](cudaStream_t st) {
+        const size_t total8 = static_cast<size_t>(rows_in) * cin / 8;
+        if (bf) cast_kernel<bf16><<<cdiv(total8, 256), 256, 0, st>>>(src, static_cast<bf16*>(act_a), total8);
+        else cast_kernel<float><<<cdiv(total8, 256), 256, 0, st>>>(src, static_cast<float*>(act_a), total8);
+      });
+    }
+    GemmDesc d;
+    d.M = rows_in; d.N = 2 * cin; d.K = cin; d.A = a_ptr; d.lda = cin; d.a_dtype = adt;
+    d.W = h->up_w[L]; d.ldw = cin; d.w_dtype = adt; d.bias = nullptr; d.epi = EPI_PIXSHUF; d.sp = n;
+    d.out = h->resid[lout]; d.ldo = cin / 2; d.out_dtype = DT_F32;
+    TapInfo ti;
+    ti.ptr = h->resid[lout]; ti.dtype = DT_F32; ti.C = cin / 2; ti.HW = 4 * n * n; ti.ld = cin / 2;
+    add_gemm(h, P, d, static_cast<long long>(h->Bcap) * n * n, "ups." + std::to_string(L), ti);
+    for (int i = 0; i < kDecBlocks[L]; ++i, ++bi)
+      add_block(h, P, h->blocks[bi], "decoders." + std::to_string(L) + "." + std::to_string(i));
+    if (h->fused) add_hca(h, P, L + 1, lout);
+  }
+  {  // ending
+    const float *w = h->end_w, *b = h->end_b;
+    const void* in = h->fused ? h->hca_out : static_cast<const void*>(h->resid[0]);
+    const bool in_bf = h->fused && bf;
+    add_op(P, [=](cudaStream_t st) {
+      const int grid = cdiv(static_cast<long long>(B) * S * S, 8);
+      if (in_bf) ending_conv_kernel<bf16><<<grid, 256, 0, st>>>(static_cast<const bf16*>(in), w, b, h->cur_eps, B, S);
+      else ending_conv_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(in), w, b, h->cur_eps, B, S);
+    });
+    P.flops_per_face += 2.0 * 9 * 128 * 4 * S * S;
+  }
+  Plan* raw = up.get();
+  h->plans[B] = std::move(up);
+  return raw;
+}
+
+// ------------------------------------------------------------------------------------------------
+// time-modulation table: rows r -> all 32 blocks' [shift_att, scale_att, shift_ffn, scale_ffn]
+// (model.py:22-29,46-51 ; conditional_naf.py:18-22,103-106) — fp32 FFMA, depends on t only
+// ------------------------------------------------------------------------------------------------
+void simt_f32(int M, int N, int K, const float* A, const float* W, const float* bias, float* out, int epi,
+              cudaStream_t st) {
+  GemmDesc d;
+  d.M = M; d.N = N; d.K = K; d.A = A; d.lda = K; d.W = W; d.ldw = K; d.bias = bias; d.epi = epi; d.out = out; d.ldo = N;
+  launch_simt(d, st);
+}
+
+void compute_time_rows(hd_handle* h, int R) {  // t_vals[0..R) already on device
+  cudaStream_t st = h->stream;
+  time_embed_kernel<<<cdiv(R * 64, 256), 256, 0, st>>>(h->t_vals, h->freqs, h->t_emb, R);
+  simt_f32(R, 2 * kTimeDim, kWidth, h->t_emb, h->tm1_w, h->tm1_b, h->t_h1, EPI_BIAS, st);
+  gate_split_kernel<<<cdiv(static_cast<long long>(R) * kTimeDim, 256), 256, 0, st>>>(h->t_h1, h->t_g1, R, kTimeDim);
+  simt_f32(R, kTimeDim, kTimeDim, h->t_g1, h->tm3_w, h->tm3_b, h->t_temb, EPI_BIAS, st);
+  gate_split_kernel<<<cdiv(static_cast<long long>(R) * 256, 256), 256, 0, st>>>(h->t_temb, h->t_g2, R, 256);
+  simt_f32(R, h->mod_stride, 256, h->t_g2, h->mlp_w, h->mlp_b, h->mod_table, EPI_BIAS, st);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void ensure_time_table(hd_handle* h, const std::vector<float>& ts) {
+  if (h->table_key == ts) return;
+  const int R = static_cast<int>(ts.size());
+  if (R > h->max_steps) HD_THROW(HD_ERR_INVALID, "%d timesteps exceed the table capacity %d", R, h->max_steps);
+  CUDA_CHECK(cudaMemcpyAsync(h->t_vals, ts.data(), R * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));  // ts may be a temporary
+  compute_time_rows(h, R);
+  h->table_key = ts;
+}
+
+void check_device_status(hd_handle* h) {
+  DeviceStatus s;
+  CUDA_CHECK(cudaMemcpy(&s, h->d_status, sizeof(s), cudaMemcpyDeviceToHost));
+  if (s.error != 0) {
+    DeviceStatus z{0, 0};
+    cudaMemcpy(h->d_status, &z, sizeof(z), cudaMemcpyHostToDevice);
+    HD_THROW(HD_ERR_KERNEL, "tcgen05 pipeline watchdog tripped (site 0x%x)", s.where);
+  }
+}
+
+void join_in(hd_handle* h, void* user_stream) {
+  cudaStream_t us = static_cast<cudaStream_t>(user_stream);
+  CUDA_CHECK(cudaEventRecord(h->ev_in, us));
+  CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_in, 0));
+}
+void join_out(hd_handle* h, void* user_stream) {
+  cudaStream_t us = static_cast<cudaStream_t>(user_stream);
+  CUDA_CHECK(cudaEventRecord(h->ev_out, h->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(us, h->ev_out, 0));
+}
+
+void run_plan(hd_handle* h, Plan* P, cudaStream_t st, const char* const* tap_names, float* const* tap_out, int n_taps,
+              int B) {
+  for (auto& op : P->ops) {
+    op.fn(st);
+    if (n_taps > 0 && !op.tap.empty()) {
+      for (int i = 0; i < n_taps; ++i) {
+        if (op.tap != tap_names[i]) continue;
+        const TapInfo& ti = op.info;
+        const size_t total = static_cast<size_t>(B) * ti.C * ti.HW;
+        float* dst = tap_out[i];
+        float* dev_dst = dst;
+        const bool host_dst = !is_device_ptr(dst);
+        if (host_dst) CUDA_CHECK(cudaMalloc(&dev_dst, total * 4));
+        if (ti.dtype == DT_BF16)
+          nhwc_to_nchw_kernel<bf16><<<cdiv(total, 256), 256, 0, st>>>(static_cast<const bf16*>(ti.ptr), dev_dst, B, ti.C, ti.HW, ti.ld);
+        else
+          nhwc_to_nchw_kernel<float><<<cdiv(total, 256), 256, 0, st>>>(static_cast<const float*>(ti.ptr), dev_dst, B, ti.C, ti.HW, ti.ld);
+        if (host_dst) {
+          CUDA_CHECK(cudaStreamSynchronize(st));
+          CUDA_CHECK(cudaMemcpy(dst, dev_dst, total * 4, cudaMemcpyDeviceToHost));
+          cudaFree(dev_dst);
+        }
+      }
+    }
+  }
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void denoise_impl(hd_handle* h, const float* x, const float* t, int t_len, float* eps_out, int B,
+                  const char* const* tap_names, float* const* tap_out, int n_taps, void* user_stream) {
+  if (!h->weights_loaded) HD_THROW(HD_ERR_STATE, "hd_load_weights has not been called");
+  if (h->fused && !h->condition_set) HD_THROW(HD_ERR_STATE, "hd_set_condition has not been called");
+  if (B < 1 || B > h->cfg.max_batch) HD_THROW(HD_ERR_INVALID, "batch %d outside [1, %d]", B, h->cfg.max_batch);
+  if (t_len != 1 && t_len != B) HD_THROW(HD_ERR_INVALID, "t_len must be 1 or batch");
+  if (t_len > h->max_steps) HD_THROW(HD_ERR_INVALID, "per-face timesteps (%d) exceed table rows (%d)", t_len, h->max_steps);
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  join_in(h, user_stream);
+  cudaStream_t st = h->stream;
+  const size_t xe = static_cast<size_t>(B) * 4 * h->S * h->S;
+  const bool x_dev = is_device_ptr(x), e_dev = is_device_ptr(eps_out);
+  if (!x_dev) CUDA_CHECK(cudaMemcpyAsync(h->x_stage, x, xe * 4, cudaMemcpyHostToDevice, st));
+  h->cur_x = x_dev ? x : h->x_stage;
+  h->cur_eps = e_dev ? eps_out : h->eps_buf;
+  // time rows: row r of the table <- t[r]
+  std::vector<float> ts(t_len);
+  CUDA_CHECK(cudaMemcpyAsync(ts.data(), t, t_len * sizeof(float), cudaMemcpyDefault, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  ensure_time_table(h, ts);
+  std::vector<int> rows(B);
+  for (int b = 0; b < B; ++b) rows[b] = t_len == 1 ? 0 : b;
+  CUDA_CHECK(cudaMemcpyAsync(h->row_idx, rows.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  Plan* P = get_plan(h, B);
+  run_plan(h, P, st, tap_names, tap_out, n_taps, B);
+  // "time_mlp" tap: (B,512) embedding
+  for (int i = 0; i < n_taps; ++i) {
+    if (std::string(tap_names[i]) != "time_mlp") continue;
+    for (int b = 0; b < B; ++b)
+      CUDA_CHECK(cudaMemcpyAsync(tap_out[i] + static_cast<size_t>(b) * kTimeDim,
+                                 h->t_temb + static_cast<size_t>(t_len == 1 ? 0 : b) * kTimeDim, kTimeDim * 4,
+                                 cudaMemcpyDefault, st));
+  }
+  if (!e_dev) {
+    CUDA_CHECK(cudaMemcpyAsync(eps_out, h->eps_buf, xe * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  join_out(h, user_stream);
+  if (!e_dev || n_taps > 0) check_device_status(h);
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+#define HD_API_BEGIN try {
+#define HD_API_END(h)                                      \
+  }                                                        \
+  catch (const HdError& e) {                               \
+    if (h) (h)->err = e.msg; else g_create_error = e.msg;  \
+    return e.code;                                         \
+  }                                                        \
+  catch (const std::exception& e) {                        \
+    if (h) (h)->err = e.what(); else g_create_error = e.what(); \
+    return HD_ERR_INVALID;                                 \
+  }                                                        \
+  return HD_OK;
+
+extern "C" {
+
+int32_t hd_abi_version(void) { return HD_ABI_VERSION; }
+
+const char* hd_last_error(const hd_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void hd_destroy(hd_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  for (auto& kv : h->plans)
+    if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph);
+  h->plans.clear();
+  h->arena.release();
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+  if (h->ev_out) cudaEventDestroy(h->ev_out);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int32_t hd_create(hd_handle** out, const hd_config* cfg) {
+  hd_handle* h = nullptr;
+  if (out) *out = nullptr;
+  hd_handle* null_handle = nullptr;
+  HD_API_BEGIN
+  if (!out || !cfg) HD_THROW(HD_ERR_INVALID, "null argument");
+  if (cfg->struct_size != (int32_t)sizeof(hd_config)) HD_THROW(HD_ERR_INVALID, "hd_config size mismatch");
+  if (cfg->latent_size != 16) HD_THROW(HD_ERR_UNSUPPORTED, "latent_size %d: only 16 (image_res 128) is supported", cfg->latent_size);
+  if (cfg->max_batch < 1) HD_THROW(HD_ERR_INVALID, "max_batch must be >= 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    HD_THROW(HD_ERR_UNSUPPORTED, "no CUDA device: hifidiff_b200 has no CPU path");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) HD_THROW(HD_ERR_INVALID, "device %d out of range", cfg->device);
+  CUDA_CHECK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) HD_THROW(HD_ERR_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+  h = new hd_handle();
+  struct Guard { hd_handle*& p; bool armed = true; ~Guard() { if (armed && p) { hd_destroy(p); p = nullptr; } } } guard{h};
+  h->cfg = *cfg;
+  h->fused = cfg->model == HD_MODEL_FUSED;
+  h->bf16 = cfg->precision == HD_PRECISION_BF16;
+  h->S = cfg->latent_size;
+  h->sm_count = prop.multiProcessorCount; h->sm_major = prop.major; h->sm_minor = prop.minor;
+  h->Bcap = ((cfg->max_batch + 127) / 128) * 128;
+  h->max_steps = std::max(std::max(cfg->max_steps, 1), cfg->max_batch);
+  for (int l = 0; l < kNumLevels; ++l) { h->c[l] = kWidth << l; h->sp[l] = h->S >> l; }
+  CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+  {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || fn == nullptr) HD_THROW(HD_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  // block table in execution order with table offsets
+  int off = 0;
+  auto push = [&](const std::string& prefix, int level) {
+    BlockW b;
+    b.prefix = prefix; b.level = level; b.c = h->c[level]; b.mod_off = off;
+    off += 4 * b.c;
+    h->blocks.push_back(b);
+  };
+  for (int l = 0; l < 4; ++l)
+    for (int i = 0; i < kEncBlocks[l]; ++i) push("encoders." + std::to_string(l) + "." + std::to_string(i) + ".", l);
+  for (int i = 0; i < kMidBlocks; ++i) push("middle_blks." + std::to_string(i) + ".", 4);
+  for (int L = 0; L < 4; ++L)
+    for (int i = 0; i < kDecBlocks[L]; ++i) push("decoders." + std::to_string(L) + "." + std::to_string(i) + ".", 3 - L);
+  h->mod_stride = off;
+  for (int j = 0; j < kNumLevels; ++j) { h->hca[j].d = h->c[4 - j]; h->hca[j].sp = h->sp[4 - j]; }
+
+  // workspace
+  Arena& A = h->arena;
+  const size_t before = A.total;
+  const size_t as = h->bf16 ? 2 : 4;
+  const size_t Bc = h->Bcap;
+  h->d_status = A.get<DeviceStatus>(1);
+  size_t max_pc = 0;
+  for (int l = 0; l < kNumLevels; ++l) {
+    const size_t pc = Bc * h->sp[l] * h->sp[l] * h->c[l];
+    h->resid[l] = A.get<float>(pc);
+    max_pc = std::max(max_pc, pc);
+  }
+  h->act_a = A.alloc(max_pc * as);
+  h->act_h = A.alloc(2 * max_pc * as);
+  h->act_g = A.alloc(max_pc * as);
+  h->hca_out = A.alloc(max_pc * as);
+  h->pooled = A.alloc(Bc * 2048 * as);
+  h->sca_s = A.get<float>(Bc * 2048);
+  if (!h->bf16) h->gate_tmp = A.get<float>(2 * max_pc);
+  const size_t xe = Bc * 4 * h->S * h->S;
+  h->x_state = A.get<float>(xe);
+  h->eps_buf = A.get<float>(xe);
+  h->x_stage = A.get<float>(xe);
+  const size_t R = h->max_steps;
+  h->t_vals = A.get<float>(R);
+  h->t_emb = A.get<float>(R * kWidth);
+  h->t_h1 = A.get<float>(R * 2 * kTimeDim);
+  h->t_g1 = A.get<float>(R * kTimeDim);
+  h->t_temb = A.get<float>(R * kTimeDim);
+  h->t_g2 = A.get<float>(R * 256);
+  h->mod_table = A.get<float>(R * h->mod_stride);
+  h->row_idx = A.get<int>(Bc);
+  h->coefs = A.get<StepCoef>(R);
+  h->state = A.get<StepState>(1);
+  h->freqs = A.get<float>(64);
+  {
+    // model.py:24-26: exp(arange(64) * -(ln(1e4) / 63)) evaluated in fp32
+    float f[64];
+    const float step = static_cast<float>(-(std::log(10000.0) / 63.0));
+    for (int i = 0; i < 64; ++i) f[i] = std::exp(static_cast<float>(i) * step);
+    CUDA_CHECK(cudaMemcpy(h->freqs, f, sizeof(f), cudaMemcpyHostToDevice));
+  }
+  if (h->fused) {
+    h->idc_add = A.get<float>(Bc * 2048);
+    h->cond_nhwc = A.get<float>(max_pc);
+    h->cond_stage = A.get<float>(max_pc);
+    h->cond_pool = A.get<float>(Bc * 2048);
+    h->cond_h = A.get<float>(Bc * 2048);
+    h->cond_hs = A.get<float>(max_pc / 2);
+    for (int j = 0; j < kNumLevels; ++j) {
+      h->hca[j].wc = A.get<float>(Bc * h->hca[j].d);
+      h->hca[j].ws = A.get<float>(Bc * h->hca[j].sp * h->hca[j].sp);
+    }
+  }
+  h->workspace_bytes = A.total - before;
+  guard.armed = false;
+  *out = h;
+  HD_API_END(null_handle)
+}
+
+int32_t hd_get_info(hd_handle* h, hd_info* info) {
+  HD_API_BEGIN
+  if (!h || !info) HD_THROW(HD_ERR_INVALID, "null argument");
+  memset(info, 0, sizeof(*info));
+  info->struct_size = sizeof(hd_info);
+  info->abi_version = HD_ABI_VERSION;
+  info->sm_major = h->sm_major; info->sm_minor = h->sm_minor; info->sm_count = h->sm_count;
+  info->workspace_bytes = static_cast<int64_t>(h->workspace_bytes);
+  info->weight_bytes = static_cast<int64_t>(h->arena.total - h->workspace_bytes);
+  info->weight_elems_per_step = h->weight_elems_step;
+  if (!h->plans.empty()) {
+    const Plan& P = *h->plans.rbegin()->second;
+    info->launches_per_step = static_cast<int32_t>(P.ops.size());
+    info->flops_per_face_step = P.flops_per_face;
+  }
+  HD_API_END(h)
+}
+
+int32_t hd_load_weights(hd_handle* h, const hd_tensor_desc* tensors, int32_t n, void* stream) {
+  HD_API_BEGIN
+  if (!h || !tensors || n <= 0) HD_THROW(HD_ERR_INVALID, "null argument");
+  if (h->weights_loaded) HD_THROW(HD_ERR_STATE, "weights already loaded; create a new handle to reload");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  (void)stream;
+  CUDA_CHECK(cudaDeviceSynchronize());
+  h->src.clear();
+  for (int i = 0; i < n; ++i) {
+    const hd_tensor_desc& t = tensors[i];
+    if (!t.name || !t.data) continue;
+    SrcTensor s;
+    s.data = t.data; s.dtype = t.dtype;
+    s.numel = 1;
+    for (int k = 0; k < t.ndim && k < 4; ++k) { s.shape.push_back(t.shape[k]); s.numel *= static_cast<size_t>(t.shape[k]); }
+    h->src[t.name] = s;
+  }
+  load_weights_impl(h);
+  HD_API_END(h)
+}
+
+int32_t hd_set_time_frequencies(hd_handle* h, const float* freqs64) {
+  HD_API_BEGIN
+  if (!h || !freqs64) HD_THROW(HD_ERR_INVALID, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  CUDA_CHECK(cudaMemcpy(h->freqs, freqs64, 64 * sizeof(float), cudaMemcpyDefault));
+  h->table_key.clear();
+  HD_API_END(h)
+}
+
+int32_t hd_set_condition(hd_handle* h, const float* const priors[5], const float* identity, int32_t B, void* stream) {
+  HD_API_BEGIN
+  if (!h || !priors || !identity) HD_THROW(HD_ERR_INVALID, "null argument");
+  if (!h->fused) HD_THROW(HD_ERR_STATE, "hd_set_condition needs HD_MODEL_FUSED");
+  if (!h->weights_loaded) HD_THROW(HD_ERR_STATE, "hd_load_weights has not been called");
+  if (B < 1 || B > h->cfg.max_batch) HD_THROW(HD_ERR_INVALID, "batch %d outside [1, %d]", B, h->cfg.max_batch);
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  join_in(h, stream);
+  cudaStream_t st = h->stream;
+  for (int j = 0; j < kNumLevels; ++j) {
+    HcaW& w = h->hca[j];
+    const int d = w.d, hw = w.sp * w.sp, rows = B * hw;
+    const size_t total = static_cast<size_t>(rows) * d;
+    const float* src = priors[j];
+    if (!src) HD_THROW(HD_ERR_INVALID, "priors[%d] is null", j);
+    if (!is_device_ptr(src)) {
+      CUDA_CHECK(cudaMemcpyAsync(h->cond_stage, src, total * 4, cudaMemcpyHostToDevice, st));
+      src = h->cond_stage;
+    }
+    nchw_to_nhwc_kernel<<<cdiv(total, 256), 256, 0, st>>>(src, h->cond_nhwc, B, d, hw);
+    // channel gate (hca.py:33-43)
+    pool_avgmax_kernel<<<cdiv(static_cast<long long>(B) * d, 256), 256, 0, st>>>(h->cond_nhwc, h->cond_pool, B, hw, d);
+    simt_f32(B, d, d, h->cond_pool, w.c0w, w.c0b, h->cond_h, EPI_RELU, st);
+    simt_f32(B, d, d, h->cond_h, w.c2w, w.c2b, w.wc, EPI_SIGMOID, st);
+    // spatial gate (hca.py:12-19,45-48), BN(eval) folded
+    simt_f32(rows, d / 2, d, h->cond_nhwc, w.s0w, w.s0b, h->cond_hs, EPI_RELU, st);
+    simt_f32(rows, 1, d / 2, h->cond_hs, w.s3w, w.s3b, w.ws, EPI_SIGMOID, st);
+  }
+  {  // idc_conv(identity) (model.py:245), identity is (B,2048,1,1) == (B,2048)
+    const float* src = identity;
+    if (!is_device_ptr(src)) {
+      CUDA_CHECK(cudaMemcpyAsync(h->cond_stage, src, static_cast<size_t>(B) * 2048 * 4, cudaMemcpyHostToDevice, st));
+      src = h->cond_stage;
+    }
+    simt_f32(B, 2048, 2048, src, h->idc_w, h->idc_b, h->idc_add, EPI_BIAS, st);
+  }
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(st));  // staging buffers are reused by the next call
+  h->condition_set = true;
+  join_out(h, stream);
+  HD_API_END(h)
+}
+
+int32_t hd_denoise_step(hd_handle* h, const float* x, const float* t, int32_t t_len, float* eps_out, int32_t batch,
+                        void* stream) {
+  HD_API_BEGIN
+  if (!h || !x || !t || !eps_out) HD_THROW(HD_ERR_INVALID, "null argument");
+  denoise_impl(h, x, t, t_len, eps_out, batch, nullptr, nullptr, 0, stream);
+  HD_API_END(h)
+}
+
+int32_t hd_denoise_step_taps(hd_handle* h, const float* x, const float* t, int32_t t_len, float* eps_out,
+                             int32_t batch, const char* const* tap_names, float* const* tap_out, int32_t n_taps,
+                             void* stream) {
+  HD_API_BEGIN
+  if (!h || !x || !t || !eps_out) HD_THROW(HD_ERR_INVALID, "null argument");
+  if (n_taps > 0 && (!tap_names || !tap_out)) HD_THROW(HD_ERR_INVALID, "null tap arrays");
+  denoise_impl(h, x, t, t_len, eps_out, batch, tap_names, tap_out, n_taps, stream);
+  HD_API_END(h)
+}
+
+int32_t hd_sampler_update(hd_handle* h, float* x_inout, const float* eps, const hd_step_coef* coef, int32_t step_index,
+                          uint64_t seed, int64_t first_face, int32_t B, const float* noise, void* stream) {
+  HD_API_BEGIN
+  if (!h || !x_inout || !eps || !coef) HD_THROW(HD_ERR_INVALID, "null argument");
+  if (B < 1 || B > h->cfg.max_batch) HD_THROW(HD_ERR_INVALID, "batch %d outside [1, %d]", B, h->cfg.max_batch);
+  if (step_index < 0 || step_index >= h->max_steps) HD_THROW(HD_ERR_INVALID, "step_index out of range");
+  if (!is_device_ptr(x_inout) || !is_device_ptr(eps) || (noise && !is_device_ptr(noise)))
+    HD_THROW(HD_ERR_INVALID, "hd_sampler_update takes device pointers");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  join_in(h, stream);
+  cudaStream_t st = h->stream;
+  static_assert(sizeof(hd_step_coef) == sizeof(StepCoef), "coef layout");
+  CUDA_CHECK(cudaMemcpyAsync(h->coefs + step_index, coef, sizeof(StepCoef), cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  const int epf = 4 * h->S * h->S;
+  const size_t threads = static_cast<size_t>(B) * epf / 4;
+  // explicit noise here is (B, epf) for this one step: offset the pointer so the kernel's
+  // step-major indexing lands on it
+  const float* nz = noise ? noise - static_cast<size_t>(step_index) * B * epf : nullptr;
+  sampler_update_kernel<<<cdiv(threads, 256), 256, 0, st>>>(x_inout, eps, h->coefs, nullptr, step_index, nz, seed,
+                                                           first_face, B, epf);
+  CUDA_CHECK(cudaGetLastError());
+  join_out(h, stream);
+  HD_API_END(h)
+}
+
+int32_t hd_sample(hd_handle* h, float* x_inout, const hd_step_coef* coef, int32_t n_steps, uint64_t seed,
+                  int64_t first_face, int32_t B, const float* noise, void* stream) {
+  HD_API_BEGIN
+  if (!h || !x_inout || !coef) HD_THROW(HD_ERR_INVALID, "null argument");
+  if (!h->weights_loaded) HD_THROW(HD_ERR_STATE, "hd_load_weights has not been called");
+  if (h->fused && !h->condition_set) HD_THROW(HD_ERR_STATE, "hd_set_condition has not been called");
+  if (B < 1 || B > h->cfg.max_batch) HD_THROW(HD_ERR_INVALID, "batch %d outside [1, %d]", B, h->cfg.max_batch);
+  if (n_steps < 1 || n_steps > h->max_steps) HD_THROW(HD_ERR_INVALID, "n_steps %d outside [1, %d]", n_steps, h->max_steps);
+  if (noise && !is_device_ptr(noise)) HD_THROW(HD_ERR_INVALID, "explicit noise must be a device pointer");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  join_in(h, stream);
+  cudaStream_t st = h->stream;
+  const int epf = 4 * h->S * h->S;
+  const size_t xe = static_cast<size_t>(B) * epf;
+  std::vector<float> ts(n_steps);
+  for (int i = 0; i < n_steps; ++i) ts[i] = coef[i].timestep;
+  ensure_time_table(h, ts);
+  CUDA_CHECK(cudaMemcpyAsync(h->coefs, coef, n_steps * sizeof(StepCoef), cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(h->x_state, x_inout, xe * 4, cudaMemcpyDefault, st));
+  CUDA_CHECK(cudaMemsetAsync(h->row_idx, 0, h->Bcap * sizeof(int), st));
+  set_step_kernel<<<1, 1, 0, st>>>(h->state, 0);
+  h->cur_x = h->x_state;
+  h->cur_eps = h->eps_buf;
+  Plan* P = get_plan(h, B);
+  const size_t threads = xe / 4;
+  float* xs = h->x_state;
+  float* eb = h->eps_buf;
+  StepCoef* cf = h->coefs;
+  StepState* ss = h->state;
+  int* ridx = h->row_idx;
+  const int Bcap = h->Bcap;
+  auto one_step = [&](cudaStream_t s) {
+    for (auto& op : P->ops) op.fn(s);
+    sampler_update_kernel<<<cdiv(threads, 256), 256, 0, s>>>(xs, eb, cf, ss, 0, noise, seed, first_face, B, epf);
+    advance_rows_kernel<<<1, 256, 0, s>>>(ss, ridx, Bcap);
+  };
+  // The graph bakes in seed / first_face / noise: re-capture when they change.
+  static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "seed width");
+  if (h->cfg.use_graph) {
+    const bool stale = P->graph_seed != seed || P->graph_first != first_face || P->graph_noise != noise;
+    if (P->graph == nullptr || stale) {
+      if (P->graph) { cudaGraphExecDestroy(P->graph); P->graph = nullptr; }
+      cudaGraph_t g = nullptr;
+      CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      one_step(st);
+      CUDA_CHECK(cudaStreamEndCapture(st, &g));
+      CUDA_CHECK(cudaGraphInstantiate(&P->graph, g, 0));
+      cudaGraphDestroy(g);
+      P->graph_seed = seed; P->graph_first = first_face; P->graph_noise = noise;
+    }
+    for (int i = 0; i < n_steps; ++i) CUDA_CHECK(cudaGraphLaunch(P->graph, st));
+  } else {
+    for (int i = 0; i < n_steps; ++i) one_step(st);
+  }
+  CUDA_CHECK(cudaGetLastError());
+  const bool x_dev = is_device_ptr(x_inout);
+  CUDA_CHECK(cudaMemcpyAsync(x_inout, h->x_state, xe * 4, cudaMemcpyDefault, st));
+  if (!x_dev) {
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    check_device_status(h);
+  }
+  join_out(h, stream);
+  HD_API_END(h)
+}
+
+int32_t hd_synchronize(hd_handle* h) {
+  HD_API_BEGIN
+  if (!h) HD_THROW(HD_ERR_INVALID, "null argument");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  CUDA_CHECK(cudaGetLastError());
+  check_device_status(h);
+  HD_API_END(h)
+}
+
+int32_t hd_debug_gemm(hd_handle* h, const float* a, const float* w, const float* bias, float* out, int32_t m,
+                      int32_t n, int32_t k, int32_t use_tc, void* stream) {
+  HD_API_BEGIN
+  if (!h || !a || !w || !out) HD_THROW(HD_ERR_INVALID, "null argument");
+  if (m < 1 || n < 1 || k < 1) HD_THROW(HD_ERR_INVALID, "bad shape");
+  if (use_tc && (k % 64 != 0 || n % 128 != 0)) HD_THROW(HD_ERR_INVALID, "tensor-core GEMM needs K %% 64 == 0 and N %% 128 == 0");
+  if (!is_device_ptr(a) || !is_device_ptr(w) || !is_device_ptr(out) || (bias && !is_device_ptr(bias)))
+    HD_THROW(HD_ERR_INVALID, "hd_debug_gemm takes device pointers");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  join_in(h, stream);
+  cudaStream_t st = h->stream;
+  const long long m_alloc = ((m + 127) / 128) * 128;
+  void *da = nullptr, *dw = nullptr;
+  float* zb = nullptr;
+  CUDA_CHECK(cudaMalloc(&zb, n * 4));
+  CUDA_CHECK(cudaMemsetAsync(zb, 0, n * 4, st));
+  GemmDesc d;
+  d.M = m; d.N = n; d.K = k; d.lda = k; d.ldw = k; d.bias = bias ? bias : zb; d.epi = EPI_BIAS;
+  d.out = out; d.ldo = n; d.out_dtype = DT_F32;
+  if (use_tc) {
+    CUDA_CHECK(cudaMalloc(&da, m_alloc * k * 2));
+    CUDA_CHECK(cudaMalloc(&dw, static_cast<size_t>(n) * k * 2));
+    CUDA_CHECK(cudaMemsetAsync(da, 0, m_alloc * k * 2, st));
+    const size_t ta = static_cast<size_t>(m) * k / 8, tw = static_cast<size_t>(n) * k / 8;
+    cast_kernel<bf16><<<cdiv(ta, 256), 256, 0, st>>>(a, static_cast<bf16*>(da), ta);
+    cast_kernel<bf16><<<cdiv(tw, 256), 256, 0, st>>>(w, static_cast<bf16*>(dw), tw);
+    d.A = da; d.W = dw; d.a_dtype = DT_BF16; d.w_dtype = DT_BF16;
+    const bool saved = h->bf16;
+    TcLaunch L = build_tc(h, d, m_alloc);
+    (void)saved;
+    launch_tc(L, st);
+  } else {
+    d.A = a; d.W = w;
+    launch_simt(d, st);
+  }
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  cudaFree(da); cudaFree(dw); cudaFree(zb);
+  check_device_status(h);
+  join_out(h, stream);
+  HD_API_END(h)
+}
+
+}  // extern "C"

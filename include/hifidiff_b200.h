@@ -1,0 +1,168 @@
+/*
+ * hifidiff_b200 — C ABI of the B200-native HifiDiff reverse-sampling hot path.
+ *
+ * The reference (js43o/HifiDiff) is pure PyTorch and has no FFI of its own; these entry points
+ * are what a binding for its hot path would call.  Each one names the reference interface it
+ * replaces (paths relative to the reference tree).  All functions return an hd_status
+ * (0 = ok); the message for the last failure is available from hd_last_error().  Nothing
+ * throws across this boundary, nothing here falls back to a CPU path: a device that is not
+ * sm_100 is a hard error at hd_create().
+ *
+ * Conventions
+ *   - Tensors crossing the boundary are dense fp32, NCHW, exactly as the reference's modules
+ *     take and return them (latents (B,4,S,S), priors (B,C,n,n), identity (B,2048,1,1)).
+ *   - Data pointers may be device pointers (on the handle's device) or host pointers; host
+ *     buffers are staged through the library's own pinned/device buffers on `stream`.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
+ *     enqueued on it; calls do not synchronise unless a host pointer has to be written.
+ *   - One handle per (process, device); a handle is not thread-safe.
+ *   - The caller owns every buffer it passes; the library owns only its packed-weight arena,
+ *     activation workspace and time-modulation tables.
+ */
+#ifndef HIFIDIFF_B200_H_
+#define HIFIDIFF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HD_ABI_VERSION 1
+
+typedef struct hd_handle hd_handle;
+
+typedef enum hd_status {
+  HD_OK = 0,
+  HD_ERR_INVALID = 1,      /* bad argument / shape / missing tensor */
+  HD_ERR_CUDA = 2,         /* a CUDA runtime / driver call failed */
+  HD_ERR_UNSUPPORTED = 3,  /* not an sm_100 device, unsupported size */
+  HD_ERR_STATE = 4,        /* call order (weights / condition / schedule not set) */
+  HD_ERR_KERNEL = 5        /* a device-side watchdog tripped (pipeline barrier timeout) */
+} hd_status;
+
+typedef enum hd_model_kind {
+  HD_MODEL_DENOISER = 0, /* models/denoiser/model.py:32-134  Denoiser(latent_size)      */
+  HD_MODEL_FUSED = 1     /* models/denoiser/model.py:137-266 FusedDenoiser(latent_size) */
+} hd_model_kind;
+
+typedef enum hd_precision {
+  HD_PRECISION_BF16 = 0, /* bf16 operands on tcgen05, fp32 accumulate, fp32 residual stream */
+  HD_PRECISION_FP32 = 1  /* fp32 FFMA everywhere (correctness mode, rel-L2 <= 1e-5)          */
+} hd_precision;
+
+typedef struct hd_config {
+  int32_t struct_size;  /* = sizeof(hd_config) */
+  int32_t model;        /* hd_model_kind */
+  int32_t precision;    /* hd_precision */
+  int32_t latent_size;  /* S: latents are (B,4,S,S); multiple of 16 (model.py:198-200), 16 supported */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t max_batch;    /* workspace is sized for this many faces per call */
+  int32_t max_steps;    /* rows of the time-modulation table (>= sampler steps) */
+  int32_t use_graph;    /* 1: replay the per-step launch sequence as a CUDA graph in hd_sample */
+} hd_config;
+
+/* One named parameter/buffer of the module's state_dict().  dtype: 0 = fp32,
+ * 1 = int64 (only BatchNorm num_batches_tracked, ignored). */
+typedef struct hd_tensor_desc {
+  const char* name;
+  const void* data;
+  int32_t dtype;
+  int32_t ndim;
+  int64_t shape[4];
+} hd_tensor_desc;
+
+/* Per-step coefficients of the x_{t-1} update, computed by the host scheduler exactly as
+ * diffusers 0.32.2 does (DDIMScheduler.step / DDPMScheduler.step; reference call sites
+ * train_refiner.py:120, pretrain_denoiser.py:110, test_refiner.py:91):
+ *     x0   = (x - sqrt_beta_prod * eps) / sqrt_alpha_prod ;  x0 = clamp(x0, -clip, clip) if clip > 0
+ *     x'   = k_x0 * x0 + k_eps * eps + k_x * x + k_noise * z
+ * DDIM(eta): k_x0 = sqrt(a_prev), k_eps = sqrt(1 - a_prev - std^2), k_x = 0, k_noise = std
+ * DDPM     : k_x0 = sqrt(a_prev) * beta_t / (1 - a_t), k_eps = 0,
+ *            k_x = sqrt(alpha_t) * (1 - a_prev) / (1 - a_t), k_noise = sqrt(var) (0 at t = 0) */
+typedef struct hd_step_coef {
+  float timestep;        /* value fed to the time embedding (model.py:22-29) */
+  float sqrt_beta_prod;  /* sqrt(1 - alphas_cumprod[t]) */
+  float sqrt_alpha_prod; /* sqrt(alphas_cumprod[t]) */
+  float clip;            /* <= 0: no clipping */
+  float k_x0, k_eps, k_x, k_noise;
+} hd_step_coef;
+
+typedef struct hd_info {
+  int32_t struct_size;
+  int32_t abi_version;
+  int32_t sm_major, sm_minor, sm_count;
+  int32_t launches_per_step; /* kernels launched by one denoise step at the current batch */
+  int64_t weight_bytes;      /* packed weight arena */
+  int64_t workspace_bytes;   /* activations + tables */
+  int64_t weight_elems_per_step; /* weight elements one denoise step streams */
+  double flops_per_face_step;    /* executed MAC*2 per face per step (incl. padding taps) */
+} hd_info;
+
+int32_t hd_abi_version(void);
+
+/* Create / destroy a handle.  Replaces module construction: Denoiser(latent_size) model.py:33,
+ * FusedDenoiser(latent_size) model.py:138. */
+int32_t hd_create(hd_handle** out, const hd_config* cfg);
+void hd_destroy(hd_handle* h);
+/* Message of the last error on this handle (h == NULL: last hd_create failure). */
+const char* hd_last_error(const hd_handle* h);
+int32_t hd_get_info(hd_handle* h, hd_info* info);
+
+/* Hand the module's state_dict to the library, which repacks it into its own arena (bf16,
+ * K-major, BatchNorm(eval) folded, beta/gamma folded into conv3/conv5, gate-interleaved conv4).
+ * Replaces nn.Module.load_state_dict as used at refiner.py:22-25 / test_refiner.py:162-164.
+ * Unknown names are ignored; a missing required tensor is HD_ERR_INVALID. */
+int32_t hd_load_weights(hd_handle* h, const hd_tensor_desc* tensors, int32_t n, void* stream);
+
+/* Optional: override the 64 sinusoidal frequencies (model.py:24-26) with host values. */
+int32_t hd_set_time_frequencies(hd_handle* h, const float* freqs64);
+
+/* Condition-only work, hoisted out of the timestep loop (it depends on neither x_t nor t):
+ * idc_conv(identity) (model.py:245-246) and the five HCA channel/spatial gates computed from
+ * the priors (hca.py:33-48).  priors[j]: (B, C_j, n_j, n_j) with C = 2048,1024,512,256,128 and
+ * n = S/16 * (1,2,4,8,16); identity: (B,2048,1,1).  HD_MODEL_FUSED only. */
+int32_t hd_set_condition(hd_handle* h, const float* const priors[5], const float* identity,
+                         int32_t batch, void* stream);
+
+/* One epsilon prediction.  Replaces Denoiser.forward (model.py:106-134) / FusedDenoiser.forward
+ * (model.py:217-266).  t has t_len == 1 (shared) or t_len == batch entries.  */
+int32_t hd_denoise_step(hd_handle* h, const float* x, const float* t, int32_t t_len,
+                        float* eps_out, int32_t batch, void* stream);
+
+/* Same, and additionally copies named intermediate activations (fp32 NCHW) for per-layer
+ * parity.  tap_names use the reference module paths ("intro", "encoders.0.1", "downs.2",
+ * "middle_blks.7", "ups.0", "decoders.3.1", "hcas.4", "time_mlp").  tap_out[i] must hold the
+ * layer's full output for `batch` faces. */
+int32_t hd_denoise_step_taps(hd_handle* h, const float* x, const float* t, int32_t t_len,
+                             float* eps_out, int32_t batch, const char* const* tap_names,
+                             float* const* tap_out, int32_t n_taps, void* stream);
+
+/* Whole reverse-sampling loop on a batch of faces: for each step i,
+ *   eps = model(x, coef[i].timestep) ; x = update(x, eps, coef[i], z_i)
+ * Replaces the loop body of ddim_sample (train_refiner.py:111-120, pretrain_denoiser.py:101-110,
+ * test_refiner.py:87-91).  z_i is Philox4x32-10 noise keyed by (seed, first_face + b, i, elem)
+ * unless `noise` (n_steps, batch, 4*S*S) is given.  x_inout: (batch,4,S,S), updated in place. */
+int32_t hd_sample(hd_handle* h, float* x_inout, const hd_step_coef* coef, int32_t n_steps,
+                  uint64_t seed, int64_t first_face, int32_t batch, const float* noise,
+                  void* stream);
+
+/* The x_{t-1} update alone (one vectorised elementwise kernel); eps and x are (batch,4,S,S).
+ * Replaces scheduler.step(noise_pred, t, latents, eta).prev_sample (train_refiner.py:120). */
+int32_t hd_sampler_update(hd_handle* h, float* x_inout, const float* eps, const hd_step_coef* coef,
+                          int32_t step_index, uint64_t seed, int64_t first_face, int32_t batch,
+                          const float* noise, void* stream);
+
+/* Waits for all work the handle has enqueued and reports a tripped device-side watchdog
+ * (HD_ERR_KERNEL) or a sticky CUDA error.  The asynchronous entry points above do not check. */
+int32_t hd_synchronize(hd_handle* h);
+
+/* Standalone C = A[M,K] * W[N,K]^T (+bias) on the tcgen05 path (bf16 operands given as fp32,
+ * converted internally); used by the parity tests to pin the tensor-core kernel alone. */
+int32_t hd_debug_gemm(hd_handle* h, const float* a, const float* w, const float* bias, float* out,
+                      int32_t m, int32_t n, int32_t k, int32_t use_tensor_cores, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIFIDIFF_B200_H_ */

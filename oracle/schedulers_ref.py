@@ -1,0 +1,138 @@
+"""Restatement of the diffusers==0.32.2 scheduler arithmetic the reference calls (TEST INFRA).
+
+PARITY UNPINNED: `diffusers` (requirements.txt:6, pinned 0.32.2) is neither vendored in
+/root/reference nor installed here, and the reference holds no test/golden vector at this
+boundary.  This file restates the published algorithm op by op in fp32 the
+way `DDIMScheduler` / `DDPMScheduler` execute it, and `tests/test_schedulers.py` checks its
+self-consistency.
+
+Reference call sites this mirrors:
+  ctor           train_refiner.py:337-348, pretrain_denoiser.py:261-272, test_refiner.py:166-171
+  set_timesteps  train_refiner.py:109, pretrain_denoiser.py:99, test_refiner.py:85
+  step           train_refiner.py:120, pretrain_denoiser.py:110, test_refiner.py:91
+  add_noise      train_refiner.py:168, pretrain_denoiser.py:163-167
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+
+Tensor = torch.Tensor
+
+
+class _Base:
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 1e-4,
+                 beta_end: float = 2e-2, beta_schedule: str = "scaled_linear",
+                 prediction_type: str = "epsilon", clip_sample: bool = True,
+                 clip_sample_range: float = 1.0):
+        if beta_schedule == "scaled_linear":
+            self.betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps,
+                                        dtype=torch.float32) ** 2
+        elif beta_schedule == "linear":
+            self.betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        else:
+            raise NotImplementedError(beta_schedule)
+        if prediction_type != "epsilon":
+            raise NotImplementedError(prediction_type)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.one = torch.tensor(1.0)
+        self.num_train_timesteps = num_train_timesteps
+        self.clip_sample = clip_sample
+        self.clip_sample_range = clip_sample_range
+        self.num_inference_steps: Optional[int] = None
+        self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64))
+
+    def set_timesteps(self, num_inference_steps: int, device=None) -> None:
+        """timestep_spacing='leading', steps_offset=0: (arange(n) * (T // n)).round()[::-1]."""
+        if num_inference_steps > self.num_train_timesteps:
+            raise ValueError("num_inference_steps > num_train_timesteps")
+        self.num_inference_steps = num_inference_steps
+        ratio = self.num_train_timesteps // num_inference_steps
+        ts = (np.arange(0, num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64)
+        self.timesteps = torch.from_numpy(ts)
+
+    def add_noise(self, original: Tensor, noise: Tensor, timesteps: Tensor) -> Tensor:
+        a = self.alphas_cumprod[timesteps] ** 0.5
+        s = (1 - self.alphas_cumprod[timesteps]) ** 0.5
+        while a.dim() < original.dim():
+            a, s = a.unsqueeze(-1), s.unsqueeze(-1)
+        return a * original + s * noise
+
+
+class DDIMSchedulerRef(_Base):
+    """DDIMScheduler(set_alpha_to_one=True): step() with prediction_type='epsilon',
+    use_clipped_model_output=False."""
+
+    def step(self, model_output: Tensor, timestep: int, sample: Tensor, eta: float = 0.0,
+             variance_noise: Optional[Tensor] = None) -> Tensor:
+        t = int(timestep)
+        prev_t = t - self.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[t]
+        a_p = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.one
+        beta_t = 1 - a_t
+        x0 = (sample - beta_t ** 0.5 * model_output) / a_t ** 0.5
+        if self.clip_sample:
+            x0 = x0.clamp(-self.clip_sample_range, self.clip_sample_range)
+        variance = ((1 - a_p) / (1 - a_t)) * (1 - a_t / a_p)
+        std = eta * variance ** 0.5
+        direction = (1 - a_p - std ** 2) ** 0.5 * model_output
+        prev = a_p ** 0.5 * x0 + direction
+        if eta > 0:
+            if variance_noise is None:
+                raise ValueError("eta > 0 needs explicit variance_noise in the oracle")
+            prev = prev + std * variance_noise
+        return prev
+
+
+class DDPMSchedulerRef(_Base):
+    """DDPMScheduler(variance_type='fixed_small'): ancestral step."""
+
+    def step(self, model_output: Tensor, timestep: int, sample: Tensor,
+             variance_noise: Optional[Tensor] = None) -> Tensor:
+        t = int(timestep)
+        n = self.num_inference_steps or self.num_train_timesteps
+        prev_t = t - self.num_train_timesteps // n
+        a_t = self.alphas_cumprod[t]
+        a_p = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.one
+        beta_prod_t = 1 - a_t
+        beta_prod_p = 1 - a_p
+        cur_alpha = a_t / a_p
+        cur_beta = 1 - cur_alpha
+        x0 = (sample - beta_prod_t ** 0.5 * model_output) / a_t ** 0.5
+        if self.clip_sample:
+            x0 = x0.clamp(-self.clip_sample_range, self.clip_sample_range)
+        c_x0 = (a_p ** 0.5 * cur_beta) / beta_prod_t
+        c_xt = cur_alpha ** 0.5 * beta_prod_p / beta_prod_t
+        prev = c_x0 * x0 + c_xt * sample
+        if t > 0:
+            if variance_noise is None:
+                raise ValueError("t > 0 needs explicit variance_noise in the oracle")
+            var = torch.clamp(beta_prod_p / beta_prod_t * cur_beta, min=1e-20)
+            prev = prev + (var ** 0.5) * variance_noise
+        return prev
+
+
+def sample_loop(eps_fn: Callable[[Tensor, int], Tensor], x_T: Tensor, scheduler: _Base,
+                num_inference_steps: int, noise_fn: Optional[Callable[[int, int], Tensor]] = None,
+                eta: float = 0.0, on_step: Optional[Callable[[int, int, Tensor, Tensor], None]] = None) -> Tensor:
+    """Latent-in / latent-out mirror of `ddim_sample` (train_refiner.py:86-125) without CR/VAE.
+
+    eps_fn(x, t)      -> epsilon prediction for integer timestep t (same t for the whole batch)
+    noise_fn(i, t)    -> z for step index i (DDPM, t > 0); unused for DDIM eta=0
+    """
+    scheduler.set_timesteps(num_inference_steps)
+    x = x_T
+    for i, t in enumerate(scheduler.timesteps.tolist()):
+        eps = eps_fn(x, t)
+        if isinstance(scheduler, DDPMSchedulerRef):
+            z = noise_fn(i, t) if (t > 0 and noise_fn is not None) else None
+            x_new = scheduler.step(eps, t, x, variance_noise=z)
+        else:
+            x_new = scheduler.step(eps, t, x, eta=eta)
+        if on_step is not None:
+            on_step(i, t, eps, x_new)
+        x = x_new
+    return x
