@@ -158,8 +158,10 @@ class FacialRefiner(nn.Module):
         if self._cond_src != key:
             was_training = self.training
             self.eval()  # BatchNorm must use running statistics on the sampling path
-            priors = self.fpg(cr_latent)
-            ident = self.idc(cr_face)
+            # full fp32 convolutions: the priors feed the fp32 correctness mode too, and this runs once per face
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                priors = self.fpg(cr_latent)
+                ident = self.idc(cr_face)
             self.train(was_training)
             self._cond = ([p.contiguous() for p in priors], ident.contiguous())
             self._cond_src = key

@@ -1,0 +1,122 @@
+"""GPU: Denoiser / FusedDenoiser single step through the module API (-> ctypes -> C ABI -> sm_100a)
+against the CPU oracle and the reference's stored outputs, per layer.
+
+Tolerances (BASELINE.json north_star): rel-L2 <= 1e-5 in the fp32 mode, <= 1e-2 in bf16.
+"""
+import numpy as np
+import pytest
+import torch
+
+import hifidiff_b200 as H
+from hifidiff_b200 import testing
+from oracle import denoiser_ref
+
+from gpu_util import build
+from util import golden, inputs, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-5, "bf16": 1e-2}
+DEN_TAPS = (["time_mlp", "intro"] + [f"encoders.{l}.{i}" for l, n in enumerate((2, 2, 4, 8)) for i in range(n)] +
+            [f"downs.{l}" for l in range(4)] + [f"middle_blks.{i}" for i in range(8)] +
+            [f"ups.{l}" for l in range(4)] + [f"decoders.{l}.{i}" for l in range(4) for i in range(2)])
+FUSED_TAPS = DEN_TAPS + [f"hcas.{j}" for j in range(5)]
+
+
+@pytest.fixture(scope="module", params=["fp32", "bf16"])
+def denoiser(request):
+    m, sd = build(H.Denoiser, seed=1, precision=request.param, max_batch=64)
+    yield m, sd, request.param
+    m.invalidate()
+
+
+@pytest.fixture(scope="module", params=["fp32", "bf16"])
+def fused(request):
+    m, sd = build(H.FusedDenoiser, seed=2, precision=request.param, max_batch=64)
+    yield m, sd, request.param
+    m.invalidate()
+
+
+def test_denoiser_step_per_layer(denoiser):
+    m, sd, prec = denoiser
+    g = golden("denoiser_step.npz")
+    x = inputs("latents", 2)
+    t = torch.from_numpy(g["t"])
+    out, taps = m.forward_with_taps(x.cuda(), t.cuda(), DEN_TAPS)
+    m.engine().synchronize()
+    ref_taps = {}
+    with torch.no_grad():
+        ref = denoiser_ref.denoiser_forward(sd, x, t, ref_taps)
+    assert rel_l2(ref, g["eps"]) < 2e-6                      # oracle == stored reference output
+    worst = max((rel_l2(taps[k], ref_taps[k]), k) for k in DEN_TAPS)
+    assert worst[0] <= TOL[prec], f"layer {worst[1]} rel-L2 {worst[0]:.3e}"
+    assert rel_l2(out.sample, g["eps"]) <= TOL[prec]
+    assert out.sample.dtype == torch.float32 and tuple(out.sample.shape) == (2, 4, 16, 16)
+
+
+def test_denoiser_timestep_forms(denoiser):
+    m, sd, prec = denoiser
+    g = golden("denoiser_step.npz")
+    x = inputs("latents", 2).cuda()
+    base = m(x, 500).sample
+    assert rel_l2(base, g["eps_t500"]) <= TOL[prec]
+    for tv in (500.0, torch.tensor(500), torch.tensor([500]), torch.tensor([500, 500]), torch.tensor([500.0, 500.0]).cuda()):
+        assert torch.equal(m(x, tv).sample, base)
+
+
+def test_fused_step_per_layer(fused):
+    m, sd, prec = fused
+    g = golden("fused_step.npz")
+    x = inputs("latents", 2, seed=1)
+    priors, ident = testing.synthetic_condition(2, 16, seed=0)
+    t = torch.from_numpy(g["t"])
+    out, taps = m.forward_with_taps(x.cuda(), t.cuda(), FUSED_TAPS, [p.cuda() for p in priors], ident.cuda())
+    m.engine().synchronize()
+    ref_taps = {}
+    with torch.no_grad():
+        ref = denoiser_ref.fused_denoiser_forward(sd, x, t, priors, ident, ref_taps)
+    assert rel_l2(ref, g["eps"]) < 2e-6
+    worst = max((rel_l2(taps[k], ref_taps[k]), k) for k in FUSED_TAPS)
+    assert worst[0] <= TOL[prec], f"layer {worst[1]} rel-L2 {worst[0]:.3e}"
+    assert rel_l2(out.sample, g["eps"]) <= TOL[prec]
+
+
+def test_fused_condition_cache_and_batch_one(fused):
+    m, sd, prec = fused
+    priors, ident = testing.synthetic_condition(3, 16, seed=5)
+    pc, ic = [p.cuda() for p in priors], ident.cuda()
+    x = inputs("latents", 3, seed=4)
+    a = m(x.cuda(), 77, pc, ic).sample
+    b = m(x.cuda(), torch.tensor([77]), pc, ic).sample       # cached condition, length-1 broadcast (model.py:228-229)
+    assert torch.equal(a, b)
+    with torch.no_grad():
+        ref = denoiser_ref.fused_denoiser_forward(sd, x, 77, priors, ident)
+    assert rel_l2(a, ref) <= TOL[prec]
+    # ragged batch: one face alone gives the same face-0 result (no cross-face reduction anywhere)
+    one = m(x[:1].cuda(), 77, [p[:1].contiguous() for p in pc], ic[:1].contiguous()).sample
+    assert rel_l2(one, ref[:1]) <= TOL[prec]
+
+
+def test_config2_batch64_bf16():
+    """BASELINE.json configs[1]: single-timestep forward, batch 64, bf16, per-layer vs the reference arithmetic."""
+    m, sd = build(H.FusedDenoiser, seed=2, precision="bf16", max_batch=64)
+    x = inputs("latents", 64, seed=9)
+    priors, ident = testing.synthetic_condition(64, 16, seed=9)
+    taps_wanted = ["intro", "encoders.0.1", "encoders.3.7", "middle_blks.7", "hcas.0", "decoders.1.1", "hcas.4"]
+    out, taps = m.forward_with_taps(x.cuda(), 500, taps_wanted, [p.cuda() for p in priors], ident.cuda())
+    m.engine().synchronize()
+    ref_taps = {}
+    with torch.no_grad():
+        ref = denoiser_ref.fused_denoiser_forward(sd, x, 500, priors, ident, ref_taps)
+    for k in taps_wanted:
+        assert rel_l2(taps[k], ref_taps[k]) <= 1e-2, k
+    assert rel_l2(out.sample, ref) <= 1e-2
+    m.invalidate()
+
+
+def test_errors_are_loud(denoiser):
+    m, _, _ = denoiser
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 4, 8, 8).cuda(), 1)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 4, 16, 16), 1)

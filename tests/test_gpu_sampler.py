@@ -1,0 +1,121 @@
+"""GPU: the x_{t-1} update kernel, Philox noise, and whole trajectories (hd_sample) against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import hifidiff_b200 as H
+from hifidiff_b200 import _lib, schedulers as S, testing
+from hifidiff_b200.sampler import _coef_array
+from oracle import denoiser_ref, philox, schedulers_ref as R
+
+from gpu_util import RawHandle, build
+from util import TRAJ_EPS_GAIN, gen, golden, inputs, psnr, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def raw():
+    h = RawHandle(max_batch=64, max_steps=1000)
+    yield h
+    h.close()
+
+
+def _update(raw, x, eps, coefs, idx, seed=0, first=0, noise=None):
+    xx = x.clone().cuda()
+    arr = _coef_array([coefs[idx]])
+    raw.check(raw.lib.hd_sampler_update(raw.h, xx.data_ptr(), eps.cuda().data_ptr(), arr, idx, C.c_uint64(seed),
+                                        C.c_int64(first), x.shape[0], noise.data_ptr() if noise is not None else None,
+                                        None), "hd_sampler_update")
+    torch.cuda.synchronize()
+    return xx.cpu()
+
+
+@pytest.mark.parametrize("clip", [False, True])
+def test_ddim_update_matches_oracle(raw, clip):
+    p = S.DDIMScheduler(beta_schedule="scaled_linear", clip_sample=clip, clip_sample_range=3.0)
+    o = R.DDIMSchedulerRef(clip_sample=clip, clip_sample_range=3.0)
+    p.set_timesteps(50)
+    o.set_timesteps(50)
+    coefs = p.step_coefficients()
+    x, eps = torch.randn(5, 4, 16, 16, generator=gen(1)) * 3, torch.randn(5, 4, 16, 16, generator=gen(2))
+    for idx in (0, 25, 49):
+        want = o.step(eps, int(o.timesteps[idx]), x)
+        got = _update(raw, x, eps, coefs, idx)
+        assert float((got - want).abs().max()) <= 4e-6 * float(want.abs().max())
+
+
+def test_ddpm_update_explicit_and_philox_noise(raw):
+    p = S.DDPMScheduler(beta_schedule="scaled_linear", clip_sample=False)
+    o = R.DDPMSchedulerRef(clip_sample=False)
+    p.set_timesteps(1000)
+    o.set_timesteps(1000)
+    coefs = p.step_coefficients()
+    x, eps = torch.randn(6, 4, 16, 16, generator=gen(3)), torch.randn(6, 4, 16, 16, generator=gen(4))
+    z = torch.randn(6, 4, 16, 16, generator=gen(5))
+    for idx in (0, 500, 998, 999):
+        t = int(o.timesteps[idx])
+        want = o.step(eps, t, x, variance_noise=z)
+        got = _update(raw, x, eps, coefs, idx, noise=z.cuda())
+        assert float((got - want).abs().max()) <= 4e-6 * float(want.abs().max()), idx
+    # Philox path: same integer stream as the numpy oracle, float transform within a few ulp
+    idx, seed, first = 123, 0xDEADBEEF12345, 40
+    zz = torch.from_numpy(philox.normal_noise(seed, first, 6, idx)).reshape(6, 4, 16, 16)
+    want = o.step(eps, int(o.timesteps[idx]), x, variance_noise=zz)
+    got = _update(raw, x, eps, coefs, idx, seed=seed, first=first)
+    assert float((got - want).abs().max()) <= 1e-5
+    # last step (t = 0) adds no noise
+    assert torch.equal(_update(raw, x, eps, coefs, 999, seed=1), _update(raw, x, eps, coefs, 999, seed=2))
+
+
+@pytest.mark.parametrize("prec,min_psnr", [("fp32", 80.0), ("bf16", 35.0)])
+def test_ddim50_trajectory_vs_reference(prec, min_psnr):
+    """Config 1 shape (B=1, 50 DDIM steps, eta 0): final latent against the reference's own trajectory."""
+    g = golden("denoiser_ddim50.npz")
+    m, sd = build(H.Denoiser, seed=1, precision=prec, eps_gain=TRAJ_EPS_GAIN, max_batch=4, max_steps=50)
+    sched = H.DDIMScheduler(num_train_timesteps=1000, beta_schedule="scaled_linear", prediction_type="epsilon",
+                            clip_sample=False)
+    xT = inputs("latents", 1, seed=7)
+    x0 = H.ddim_sample(m, xT.cuda(), sched, 50)
+    m.engine().synchronize()
+    q = psnr(x0, g["x0"])
+    print(f"DDIM-50 {prec}: PSNR vs reference x0 = {q:.2f} dB, rel-L2 {rel_l2(x0, g['x0']):.3e}")
+    assert q >= min_psnr
+    m.invalidate()
+
+
+def test_graph_and_plain_launch_agree_and_sharding_is_invariant():
+    m, sd = build(H.Denoiser, seed=1, precision="bf16", eps_gain=TRAJ_EPS_GAIN, max_batch=4, max_steps=20)
+    sched = H.DDPMScheduler(num_train_timesteps=1000, beta_schedule="scaled_linear", prediction_type="epsilon",
+                            clip_sample=False)
+    xT = inputs("latents", 4, seed=11).cuda()
+    full = H.ddpm_sample(m, xT, sched, 20, seed=7, first_face=100)
+    lo = H.ddpm_sample(m, xT[:2].contiguous(), sched, 20, seed=7, first_face=100)
+    hi = H.ddpm_sample(m, xT[2:].contiguous(), sched, 20, seed=7, first_face=102)
+    m.engine().synchronize()
+    assert torch.equal(full, torch.cat([lo, hi]))            # face trajectories do not depend on the sharding
+    assert not torch.equal(full, H.ddpm_sample(m, xT, sched, 20, seed=8, first_face=100))
+    m.configure(use_graph=False)
+    plain = H.ddpm_sample(m, xT, sched, 20, seed=7, first_face=100)
+    m.engine().synchronize()
+    assert torch.equal(full, plain)
+    m.invalidate()
+
+
+def test_ddpm_trajectory_matches_oracle_loop():
+    """20-step DDPM with explicit noise: CUDA loop vs oracle model + oracle scheduler."""
+    m, sd = build(H.Denoiser, seed=1, precision="fp32", eps_gain=TRAJ_EPS_GAIN, max_batch=2, max_steps=20)
+    sched = H.DDPMScheduler(num_train_timesteps=1000, beta_schedule="scaled_linear", prediction_type="epsilon",
+                            clip_sample=False)
+    o = R.DDPMSchedulerRef(clip_sample=False)
+    xT = inputs("latents", 2, seed=12)
+    z = torch.randn(20, 2, 1024, generator=gen(13))
+    got = H.ddpm_sample(m, xT.cuda(), sched, 20, noise=z.cuda())
+    m.engine().synchronize()
+    with torch.no_grad():
+        want = R.sample_loop(lambda xx, tt: denoiser_ref.denoiser_forward(sd, xx, torch.full((2,), tt, dtype=torch.long)),
+                             xT, o, 20, noise_fn=lambda i, t: z[i].reshape(2, 4, 16, 16))
+    assert psnr(got, want) >= 80.0
+    m.invalidate()
