@@ -28,72 +28,114 @@ struct ModRef {
 
 // ------------------------------------------------------------------------------------------------
 // intro: 3x3 conv 4 -> 128, NCHW fp32 latents -> NHWC fp32 residual stream (model.py:159-167,235)
-// grid (S, B), block 128 (one thread per output channel)
+// one block per face; thread = (pixel column, 8 output channels); weights [36][128] in smem
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) intro_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(256) intro_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, float* __restrict__ out,
                                                          int S) {
-  extern __shared__ float s_in[];  // [4][3][S+2]
-  const int h = blockIdx.x, b = blockIdx.y, o = threadIdx.x;
+  extern __shared__ float s_intro[];
+  float* s_w = s_intro;                 // [36][128]  (k = c*9 + ky*3 + kx major, channel minor)
+  float* s_in = s_intro + 36 * 128;     // [4][S+2][S+2] zero-padded face
+  const int b = blockIdx.x;
   const int W2 = S + 2;
-  for (int i = threadIdx.x; i < 4 * 3 * W2; i += blockDim.x) {
-    const int c = i / (3 * W2), r = (i / W2) % 3, col = i % W2;
-    const int hh = h + r - 1, ww = col - 1;
+  for (int i = threadIdx.x; i < 36 * 128; i += blockDim.x) {
+    const int k = i >> 7, o = i & 127;
+    s_w[i] = w[o * 36 + k];
+  }
+  for (int i = threadIdx.x; i < 4 * W2 * W2; i += blockDim.x) {
+    const int c = i / (W2 * W2), r = (i / W2) % W2, col = i % W2;
+    const int hh = r - 1, ww = col - 1;
     float v = 0.f;
     if (hh >= 0 && hh < S && ww >= 0 && ww < S) v = x[((static_cast<size_t>(b) * 4 + c) * S + hh) * S + ww];
     s_in[i] = v;
   }
-  float wr[36];
-#pragma unroll
-  for (int i = 0; i < 36; ++i) wr[i] = w[o * 36 + i];
-  const float bo = bias[o];
   __syncthreads();
-  for (int col = 0; col < S; ++col) {
-    float acc = bo;
+  const int cg = threadIdx.x & 15;        // 8 output channels each
+  const int pl = threadIdx.x >> 4;        // 16 pixel lanes
+  float bo[8];
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+  for (int i = 0; i < 8; ++i) bo[i] = bias[cg * 8 + i];
+  // register tile: 4 pixels x 8 channels per pass; the channel loop is kept rolled so the weight
+  // loads stay inside it (fully unrolled, the compiler hoists all 288 weights and spills)
+  for (int p0 = pl; p0 < S * S; p0 += 64) {
+    float acc[4][8];
+    int py[4], px[4];
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+    for (int j = 0; j < 4; ++j) {
+      const int p = min(p0 + 16 * j, S * S - 1);
+      py[j] = p / S;
+      px[j] = p - py[j] * S;
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) acc = fmaf(s_in[(c * 3 + r) * W2 + col + kx], wr[(c * 3 + r) * 3 + kx], acc);
-    out[((static_cast<size_t>(b) * S + h) * S + col) * 128 + o] = acc;
+      for (int i = 0; i < 8; ++i) acc[j][i] = bo[i];
+    }
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float* wp = s_w + (c * 9 + t) * 128 + cg * 8;
+        const float4 w0 = *reinterpret_cast<const float4*>(wp);
+        const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float v = s_in[(c * W2 + py[j] + t / 3) * W2 + px[j] + t % 3];
+          acc[j][0] = fmaf(v, w0.x, acc[j][0]); acc[j][1] = fmaf(v, w0.y, acc[j][1]);
+          acc[j][2] = fmaf(v, w0.z, acc[j][2]); acc[j][3] = fmaf(v, w0.w, acc[j][3]);
+          acc[j][4] = fmaf(v, w1.x, acc[j][4]); acc[j][5] = fmaf(v, w1.y, acc[j][5]);
+          acc[j][6] = fmaf(v, w1.z, acc[j][6]); acc[j][7] = fmaf(v, w1.w, acc[j][7]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int p = p0 + 16 * j;
+      if (p < S * S) store8(out + (static_cast<size_t>(b) * S * S + p) * 128 + cg * 8, acc[j]);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm2d + AdaLN modulation (utils.py:16-24, conditional_naf.py:114-115,126-127)
 //   y = (x - mu) / sqrt(var + eps) ; y = w*y + b ; out = y*(scale+1) + shift
-// one warp per pixel row; fp32 residual in, T out.  C in {128,...,2048}
+// LPR = min(32, C/16) lanes per pixel row (>= 4 independent float4 loads per lane), 32/LPR rows per
+// warp, 4 warps per block; fp32 residual in, T out.  C in {128,...,2048}
 // ------------------------------------------------------------------------------------------------
 template <int C, typename TOut>
-__global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x, const float* __restrict__ lw,
+__global__ void __launch_bounds__(128) ln_mod_kernel(const float* __restrict__ x, const float* __restrict__ lw,
                                                      const float* __restrict__ lb, TOut* __restrict__ out, int rows,
                                                      int rows_per_face, ModRef mod, int shift_off, int scale_off,
                                                      int has_mod) {
-  constexpr int PER = C / 32;  // elements per lane, in chunks of 4
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  constexpr int LPR = (C / 16) < 32 ? (C / 16) : 32;  // lanes per row
+  constexpr int RPW = 32 / LPR;                        // rows per warp
+  constexpr int NV = C / (4 * LPR);                    // float4 per lane
   const int lane = threadIdx.x & 31;
-  const float* xr = x + static_cast<size_t>(row) * C;
-  float v[PER];
+  const int sub = lane / LPR, sl = lane % LPR;
+  const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
+  const bool ok = row < rows;
+  const float* xr = x + static_cast<size_t>(ok ? row : 0) * C;
+  float v[NV * 4];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < PER / 4; ++i) {
-    const float4 q = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+  for (int i = 0; i < NV; ++i) {
+    const float4 q = *reinterpret_cast<const float4*>(xr + (i * LPR + sl) * 4);
     v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
     s += q.x + q.y + q.z + q.w;
   }
-  const float mu = warp_sum(s) * (1.f / C);
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mu = s * (1.f / C);
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < PER; ++i) { const float d = v[i] - mu; ss = fmaf(d, d, ss); }
-  const float var = warp_sum(ss) * (1.f / C);
+  for (int i = 0; i < NV * 4; ++i) { const float d = v[i] - mu; ss = fmaf(d, d, ss); }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (!ok) return;
+  const float var = ss * (1.f / C);
   const float denom = sqrtf(var + 1e-6f);
   const float* mrow = has_mod ? mod.row(row / rows_per_face) : nullptr;
   TOut* orow = out + static_cast<size_t>(row) * C;
 #pragma unroll
-  for (int i = 0; i < PER / 4; ++i) {
-    const int c0 = (i * 32 + lane) * 4;
+  for (int i = 0; i < NV; ++i) {
+    const int c0 = (i * LPR + sl) * 4;
     const float4 w4 = __ldg(reinterpret_cast<const float4*>(lw + c0));
     const float4 b4 = __ldg(reinterpret_cast<const float4*>(lb + c0));
     float y[4];
@@ -124,63 +166,97 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x
 // depthwise 3x3 (pad 1, bias) + SimpleGate + global average pool (conditional_naf.py:117-119, 54-65)
 //   in  h [B, sp, sp, 2c]   (x1 = channels [0,c), x2 = channels [c,2c))
 //   out g [B, sp, sp, c] = dw(x1) * dw(x2) ;  pooled[B, c] = mean_hw(g)
-// grid (c/64, B), block 256 = 8 channel-threads (8 channels each) x 32 pixel-threads
+// One block = 256 pixels (256/sp^2 whole faces) x 64 gate channels.  The 256 x 128 input tile is
+// staged in shared memory with independent 16-byte loads (high memory-level parallelism), the
+// 9-tap stencil runs out of shared memory, the gated tile goes back through shared memory (fp32)
+// for the per-face pooled means.   grid (c/64, ceil(B*sp^2/256)), block 256, dynamic smem 256*128*sizeof(T)
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) dwconv_gate_pool_kernel(const T* __restrict__ h, const float* __restrict__ w9,
                                                                const float* __restrict__ bias, T* __restrict__ g,
-                                                               T* __restrict__ pooled, int sp, int c) {
+                                                               T* __restrict__ pooled, int sp, int c, int total_px) {
+  extern __shared__ __align__(16) uint8_t s_dw_raw[];
+  T* tile = reinterpret_cast<T*>(s_dw_raw);             // [256 px][128 ch]: x1 chunk | x2 chunk
+  float* gout = reinterpret_cast<float*>(s_dw_raw);     // aliases the tile after the stencil: [256 px][64]
   __shared__ float s_w[9][2][64];
   __shared__ float s_b[2][64];
-  __shared__ float s_red[32][65];
   const int j0 = blockIdx.x * 64;
-  const int face = blockIdx.y;
-  const int ct = threadIdx.x & 7, pt = threadIdx.x >> 3;
+  const int px0 = blockIdx.y * 256;
   const int C2 = 2 * c;
+  const int npix = sp * sp;
   for (int i = threadIdx.x; i < 9 * 2 * 64; i += blockDim.x) {
     const int tap = i / 128, half = (i / 64) & 1, ch = i & 63;
     s_w[tap][half][ch] = w9[tap * C2 + half * c + j0 + ch];
   }
   if (threadIdx.x < 128) s_b[threadIdx.x >> 6][threadIdx.x & 63] = bias[(threadIdx.x >> 6) * c + j0 + (threadIdx.x & 63)];
+  // stage: 256 px x 16 chunks of 8 channels (chunks 0-7: x1, 8-15: x2)
+  {
+    const int chunk = threadIdx.x & 15;
+    const int half = chunk >> 3, cc = (chunk & 7) * 8;
+#pragma unroll 4
+    for (int r = threadIdx.x >> 4; r < 256; r += 16) {
+      const int p = px0 + r;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      uint4 v2 = make_uint4(0, 0, 0, 0);
+      if (p < total_px) {
+        const T* src = h + static_cast<size_t>(p) * C2 + half * c + j0 + cc;
+        v = *reinterpret_cast<const uint4*>(src);
+        if (sizeof(T) == 4) v2 = *reinterpret_cast<const uint4*>(src + 4);
+      }
+      T* dst = tile + r * 128 + chunk * 8;
+      *reinterpret_cast<uint4*>(dst) = v;
+      if (sizeof(T) == 4) *reinterpret_cast<uint4*>(dst + 4) = v2;
+    }
+  }
   __syncthreads();
 
-  float psum[8];
+  const int ct = threadIdx.x & 7, pt = threadIdx.x >> 3;
+  float o[8][8];  // [pixel i][channel]
 #pragma unroll
-  for (int i = 0; i < 8; ++i) psum[i] = 0.f;
-  const T* hf = h + static_cast<size_t>(face) * sp * sp * C2;
-  const int npix = sp * sp;
-  for (int p = pt; p < npix; p += 32) {
-    const int py = p / sp, px = p - py * sp;
+  for (int i = 0; i < 8; ++i) {
+    const int r = pt + 32 * i;               // pixel within the tile
+    const int pf = r % npix;                 // pixel within its face (tiles hold whole faces)
+    const int py = pf / sp, pxx = pf - py * sp;
     float a1[8], a2[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { a1[i] = s_b[0][ct * 8 + i]; a2[i] = s_b[1][ct * 8 + i]; }
+    for (int k = 0; k < 8; ++k) { a1[k] = s_b[0][ct * 8 + k]; a2[k] = s_b[1][ct * 8 + k]; }
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
-      const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+      const int yy = py + dy, xx = pxx + dx;
       if (yy < 0 || yy >= sp || xx < 0 || xx >= sp) continue;
-      const T* src = hf + static_cast<size_t>(yy * sp + xx) * C2 + j0 + ct * 8;
+      const T* src = tile + (r + dy * sp + dx) * 128 + ct * 8;
       float v1[8], v2[8];
       load8(src, v1);
-      load8(src + c, v2);
+      load8(src + 64, v2);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        a1[i] = fmaf(v1[i], s_w[tap][0][ct * 8 + i], a1[i]);
-        a2[i] = fmaf(v2[i], s_w[tap][1][ct * 8 + i], a2[i]);
+      for (int k = 0; k < 8; ++k) {
+        a1[k] = fmaf(v1[k], s_w[tap][0][ct * 8 + k], a1[k]);
+        a2[k] = fmaf(v2[k], s_w[tap][1][ct * 8 + k], a2[k]);
       }
     }
-    float o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { o[i] = a1[i] * a2[i]; psum[i] += o[i]; }
-    store8(g + (static_cast<size_t>(face) * npix + p) * c + j0 + ct * 8, o);
+    for (int k = 0; k < 8; ++k) o[i][k] = a1[k] * a2[k];
+    const int p = px0 + r;
+    if (p < total_px) store8(g + static_cast<size_t>(p) * c + j0 + ct * 8, o[i]);
   }
+  __syncthreads();  // everyone is done reading the input tile
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s_red[pt][ct * 8 + i] = psum[i];
+  for (int i = 0; i < 8; ++i) {
+    float* dst = gout + (pt + 32 * i) * 64 + ct * 8;
+    *reinterpret_cast<float4*>(dst) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(o[i][4], o[i][5], o[i][6], o[i][7]);
+  }
   __syncthreads();
-  if (threadIdx.x < 64) {
-    float s = 0.f;
-#pragma unroll 8
-    for (int r = 0; r < 32; ++r) s += s_red[r][threadIdx.x];
-    pooled[static_cast<size_t>(face) * c + j0 + threadIdx.x] = from_f32<T>(s / static_cast<float>(npix));
+  // per-face means: (256 / npix) faces x 64 channels
+  const int faces_in_tile = 256 / npix;
+  for (int i = threadIdx.x; i < faces_in_tile * 64; i += blockDim.x) {
+    const int f = i >> 6, ch = i & 63;
+    const int face = px0 / npix + f;
+    if (face * npix >= total_px) continue;
+    float sum = 0.f;
+    for (int q = 0; q < npix; ++q) sum += gout[(f * npix + q) * 64 + ch];
+    pooled[static_cast<size_t>(face) * c + j0 + ch] = from_f32<T>(sum / static_cast<float>(npix));
   }
 }
 
@@ -282,43 +358,61 @@ __global__ void __launch_bounds__(256) hca_apply_kernel(const float* __restrict_
 
 // ------------------------------------------------------------------------------------------------
 // ending: 3x3 conv 128 -> 4 (model.py:168-176,261-262), NHWC in, NCHW fp32 epsilon out.
-// one warp per pixel; weights [4][9][128] in shared memory
+// one block per face: the S*S x 128 input tile is staged in shared memory (16-byte chunks XOR-
+// swizzled by row so that pixel-per-thread reads are conflict-free), thread = pixel.
+// dynamic smem: S*S*128*sizeof(TIn) + 4*9*128*4
 // ------------------------------------------------------------------------------------------------
 template <typename TIn>
 __global__ void __launch_bounds__(256) ending_conv_kernel(const TIn* __restrict__ x, const float* __restrict__ w,
                                                           const float* __restrict__ bias, float* __restrict__ eps,
                                                           int B, int S) {
-  __shared__ float s_w[4 * 9 * 128];
+  extern __shared__ __align__(16) uint8_t s_end_raw[];
+  constexpr int EPC = 16 / sizeof(TIn);          // elements per 16-byte chunk
+  constexpr int CPR = 128 / EPC;                 // chunks per pixel row
+  const int npix = S * S;
+  TIn* tile = reinterpret_cast<TIn*>(s_end_raw);
+  float* s_w = reinterpret_cast<float*>(s_end_raw + static_cast<size_t>(npix) * 128 * sizeof(TIn));
+  const int face = blockIdx.x;
   for (int i = threadIdx.x; i < 4 * 9 * 128; i += blockDim.x) s_w[i] = w[i];
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const size_t pix = static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const size_t npix = static_cast<size_t>(B) * S * S;
-  if (pix >= npix) return;
-  const int face = static_cast<int>(pix / (S * S));
-  const int rem = static_cast<int>(pix - static_cast<size_t>(face) * S * S);
-  const int py = rem / S, px = rem - py * S;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
-    if (yy < 0 || yy >= S || xx < 0 || xx >= S) continue;
-    const TIn* src = x + ((static_cast<size_t>(face) * S + yy) * S + xx) * 128 + lane * 4;
-    float v[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = to_f32(src[i]);
-#pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      const float* wr = s_w + (o * 9 + tap) * 128 + lane * 4;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) acc[o] = fmaf(v[i], wr[i], acc[o]);
-    }
+  const TIn* xf = x + static_cast<size_t>(face) * npix * 128;
+  for (int i = threadIdx.x; i < npix * CPR; i += blockDim.x) {
+    const int r = i / CPR, ck = i % CPR;
+    const uint4 v = *reinterpret_cast<const uint4*>(xf + static_cast<size_t>(r) * 128 + ck * EPC);
+    *reinterpret_cast<uint4*>(tile + r * 128 + ((ck ^ (r % CPR)) * EPC)) = v;
   }
+  __syncthreads();
+  for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+    const int py = p / S, px = p - py * S;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int o = 0; o < 4; ++o) acc[o] = warp_sum(acc[o]);
-  if (lane < 4) {
-    const float r = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
-    eps[((static_cast<size_t>(face) * 4 + lane) * S + py) * S + px] = r + bias[lane];
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+      if (yy < 0 || yy >= S || xx < 0 || xx >= S) continue;
+      const int r = yy * S + xx;
+      const TIn* row = tile + r * 128;
+      const float* wt = s_w + tap * 128;
+#pragma unroll 4
+      for (int ck = 0; ck < CPR; ++ck) {
+        float v[EPC];
+        if (sizeof(TIn) == 2) {
+          float t8[8];
+          load8(reinterpret_cast<const bf16*>(row) + ((ck ^ (r % CPR)) * EPC), t8);
+#pragma unroll
+          for (int k = 0; k < EPC; ++k) v[k] = t8[k];
+        } else {
+          const float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(row) + ((ck ^ (r % CPR)) * EPC));
+          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const float* wr = wt + o * 9 * 128 + ck * EPC;
+#pragma unroll
+          for (int k = 0; k < EPC; ++k) acc[o] = fmaf(v[k], wr[k], acc[o]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) eps[((static_cast<size_t>(face) * 4 + o) * S + py) * S + px] = acc[o] + bias[o];
   }
 }
 

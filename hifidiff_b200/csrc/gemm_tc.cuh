@@ -35,14 +35,20 @@ struct TcArgs {
   DeviceStatus* status;
 };
 
-template <int BN> struct TileCfg {
-  static constexpr int STAGES = (BN >= 256) ? 4 : 6;
+template <int BN, int STAGES> struct TileCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_BYTES = BM * BN * 4;  // fp32 accumulator tile, aliases the ring after the mainloop
+  static_assert(RING_BYTES >= STAGING_BYTES, "epilogue staging must fit in the operand ring");
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;                         // power of two >= 32
+  static constexpr int SMEM_BYTES = RING_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;               // power of two >= 32
+  // co-resident CTAs per SM (228 KB shared memory, 512 TMEM columns): short-K GEMMs are dominated by
+  // prologue/epilogue, so several small CTAs per SM overlap one tile's epilogue with another's mainloop
+  static constexpr int MIN_BLOCKS = SMEM_BYTES <= 74 * 1024 ? 3 : (SMEM_BYTES <= 113 * 1024 ? 2 : 1);
+  static_assert(MIN_BLOCKS * TMEM_COLS <= 512, "TMEM over-subscribed");
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -170,44 +176,61 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// epilogue helpers: `v` holds 32 consecutive accumulator columns of one output row
+// Epilogue.  Phase A: each epilogue warp drains its 32 TMEM lanes (= 32 output rows) into an fp32
+// staging tile in shared memory (16-byte chunks XOR-swizzled by row: conflict-free both ways).
+// Phase B: the same warp walks its rows with lanes along the columns, so every global access
+// (bias, residual read, output write) is a contiguous, fully coalesced row segment.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void add_bias32(float (&v)[32], const float* __restrict__ bias) {
-#pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    float4 b = __ldg(reinterpret_cast<const float4*>(bias + j));
-    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-  }
+__device__ __forceinline__ uint32_t cluster_nctaid_z() {
+  uint32_t v;
+  asm volatile("mov.u32 %0, %%cluster_nctaid.z;" : "=r"(v));
+  return v;
 }
-__device__ __forceinline__ void store_row32(float* dst, const float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void store_row32(bf16* dst, const float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    uint4 p;
-    p.x = pack_bf16x2(v[j], v[j + 1]);
-    p.y = pack_bf16x2(v[j + 2], v[j + 3]);
-    p.z = pack_bf16x2(v[j + 4], v[j + 5]);
-    p.w = pack_bf16x2(v[j + 6], v[j + 7]);
-    *reinterpret_cast<uint4*>(dst + j) = p;
-  }
+// 16-byte load from the shared memory of CTA `rank` of this cluster (DSMEM); rank == own rank is local
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(remote)
+               : "memory");
+  return v;
+}
+template <typename TOut> __device__ __forceinline__ void store4(TOut* dst, float4 v);
+template <> __device__ __forceinline__ void store4<float>(float* dst, float4 v) {
+  *reinterpret_cast<float4*>(dst) = v;
+}
+template <> __device__ __forceinline__ void store4<bf16>(bf16* dst, float4 v) {
+  uint2 p;
+  p.x = pack_bf16x2(v.x, v.y);
+  p.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(dst) = p;
 }
 
-template <int BN, int EPI, int AMODE, typename TOut>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// Split-K: gridDim.z CTAs forming one thread-block cluster (1,1,S) share an output tile; CTA z
+// accumulates k-blocks [z*num_kb/S, (z+1)*num_kb/S) in its own TMEM, stages the partial tile in its
+// own shared memory, and after a cluster barrier reduces rows [z*128/S, (z+1)*128/S) of all S
+// partial tiles over distributed shared memory in fixed order (deterministic), applying the real
+// epilogue once.  This turns the small-M, weight-streaming GEMMs of the 2x2 / 1x1 levels into
+// >= 120 CTAs with deep TMA rings without atomics or a global workspace.
+template <int BN, int STAGES, int EPI, int AMODE, typename TOut>
+__global__ void __launch_bounds__(NUM_THREADS, (TileCfg<BN, STAGES>::MIN_BLOCKS))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs args) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, STAGES>;
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
   static_assert(EPI != EPI_GATE || BN == 128, "gate epilogue needs 128-column packed groups");
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B operand tiles need 1024-byte alignment
+  // SWIZZLE_128B operand tiles need 1024-byte alignment (same offset in every CTA of the cluster)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* bar_base = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint8_t* bar_base = smem + Cfg::RING_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
-  uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -215,12 +238,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int m_tile = blockIdx.x;
   const int n0 = blockIdx.y * BN;
   const int m0 = m_tile * BM;
-  const int num_kb = args.num_kb;
+  const int nsplit = static_cast<int>(cluster_nctaid_z());
+  const int zrank = blockIdx.z;  // == rank in the (1,1,S) cluster
+  const int kb_count = args.num_kb / nsplit;
+  const int kb_begin = zrank * kb_count;
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&mapA);
     prefetch_tensormap(&mapB);
-    for (int s = 0; s < Cfg::STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
@@ -236,6 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  float* stage = reinterpret_cast<float*>(smem);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -250,9 +277,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           conv_h0 = (m_tile % tiles_per_face) * args.conv_bh;
         }
       }
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % Cfg::STAGES;
-        const uint32_t ph = (kb / Cfg::STAGES) & 1;
+      for (int i = 0; i < kb_count; ++i) {
+        const int kb = kb_begin + i;
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u, args.status, 0x100u);
         const uint32_t fb = smem_u32(&full_bar[s]);
         const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
@@ -273,9 +301,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = make_idesc(BM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % Cfg::STAGES;
-        const uint32_t ph = (kb / Cfg::STAGES) & 1;
+      for (int i = 0; i < kb_count; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(smem_u32(&full_bar[s]), ph, args.status, 0x200u);
         tc_fence_after_sync();
         const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
@@ -284,99 +312,147 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           // advance 16 bf16 = 32 bytes inside the 128B swizzle row: +2 in the (addr >> 4) field
-          umma_bf16(da + 2 * k, db + 2 * k, tmem_base, (kb | k) != 0 ? 1u : 0u, idesc);
+          umma_bf16(da + 2 * k, db + 2 * k, tmem_base, (i | k) != 0 ? 1u : 0u, idesc);
         }
         umma_commit(smem_u32(&empty_bar[s]));
       }
       umma_commit(smem_u32(tmem_full_bar));
     }
   } else {
-    // ---------------- epilogue (warps 2..5) ----------------
+    // ---------------- epilogue phase A (warps 2..5): TMEM -> swizzled fp32 staging tile ----------------
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-    const int row_in_tile = quad * 32 + lane;
-    const int m = m0 + row_in_tile;
     mbar_wait(smem_u32(tmem_full_bar), 0u, args.status, 0x300u);
     tc_fence_after_sync();
+    // All MMAs have completed: every TMA load has landed and been consumed, the ring is free.
+    const int r = quad * 32 + lane;
     const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const bool row_ok = m < args.M;
-
-    if (EPI == EPI_GATE) {
-      // packed 128-column groups: columns [0,64) are x1 channels, [64,128) the matching x2 channels
-      TOut* orow = reinterpret_cast<TOut*>(args.out) + static_cast<size_t>(m) * args.ldo + (n0 >> 1);
+    float* srow = stage + r * BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t r1[32], r2[32];
-        tmem_ld32(taddr_row + c0, r1);
-        tmem_ld32(taddr_row + 64 + c0, r2);
-        tmem_wait_ld();
-        float v1[32], v2[32];
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(taddr_row + c0, v);
+      tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { v1[j] = __uint_as_float(r1[j]); v2[j] = __uint_as_float(r2[j]); }
-        add_bias32(v1, args.bias + n0 + c0);
-        add_bias32(v2, args.bias + n0 + 64 + c0);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v1[j] *= v2[j];
-        if (row_ok) store_row32(orow + c0, v1);
-      }
-    } else {
-      size_t out_row = static_cast<size_t>(m);
-      int out_col0 = n0;
-      if (EPI == EPI_PIXSHUF) {
-        const int quarter = args.N >> 2;
-        const int q = n0 / quarter;  // q = 2*i + j of PixelShuffle(2)
-        out_col0 = n0 - q * quarter;
-        const int sp = args.sp;
-        const int face = m / (sp * sp);
-        const int rem = m - face * sp * sp;
-        const int h = rem / sp, w = rem - h * sp;
-        out_row = (static_cast<size_t>(face) * (2 * sp) + (2 * h + (q >> 1))) * (2 * sp) + (2 * w + (q & 1));
-      }
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr_row + c0, r);
-        tmem_wait_ld();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (EPI != EPI_PIXSHUF) add_bias32(v, args.bias + n0 + c0);
-        if (EPI == EPI_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (EPI == EPI_SIGMOID) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
-        }
-        if (row_ok) {
-          if (EPI == EPI_RESID) {
-            const float* rrow = args.resid + static_cast<size_t>(m) * args.ldr + n0 + c0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 x = *reinterpret_cast<const float4*>(rrow + j);
-              v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
-            }
-          }
-          if (EPI == EPI_PIXSHUF) {
-            float* orow = reinterpret_cast<float*>(args.out) + out_row * args.ldo + out_col0 + c0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 x = *reinterpret_cast<const float4*>(orow + j);
-              v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
-            }
-            store_row32(orow, v);
-          } else {
-            TOut* orow = reinterpret_cast<TOut*>(args.out) + out_row * args.ldo + out_col0 + c0;
-            store_row32(orow, v);
-          }
-        }
+      for (int j = 0; j < 8; ++j) {
+        const int ck = (c0 >> 2) + j;
+        *reinterpret_cast<uint4*>(srow + ((ck ^ (r & 7)) << 2)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
     }
   }
 
   __syncwarp();
   tc_fence_before_sync();
-  __syncthreads();
+  if (nsplit > 1) cluster_sync_all(); else __syncthreads();
+
+  if (warp >= 2) {
+    // ---------------- epilogue phase B: lanes along columns, coalesced global traffic ----------------
+    constexpr int CH = (EPI == EPI_GATE) ? BN / 8 : BN / 4;  // output 4-column chunks per row
+    constexpr int LPR = CH < 32 ? CH : 32;                  // lanes per row
+    constexpr int RPI = 32 / LPR;                           // rows per warp pass
+    constexpr int CPL = CH / LPR;                           // chunks per lane
+    constexpr int U = 4;                                    // passes batched for memory-level parallelism
+    const int ew = warp - 2;
+    const int sub = lane / LPR, sl = lane % LPR;
+    const int rows_here = BM / nsplit;                      // rows of the tile this CTA finishes
+    const int row_base = zrank * rows_here;
+    const uint32_t stage_u32 = smem_u32(stage);
+
+    int out_col0 = n0;
+    int q = 0;
+    if (EPI == EPI_PIXSHUF) {
+      const int quarter = args.N >> 2;
+      q = n0 / quarter;  // q = 2*i + j of PixelShuffle(2)
+      out_col0 = n0 - q * quarter;
+    }
+    if (EPI == EPI_GATE) out_col0 = n0 >> 1;
+
+    float4 bias_r[CPL], bias2_r[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      const int ck = i * LPR + sl;
+      bias_r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      bias2_r[i] = bias_r[i];
+      if (EPI != EPI_PIXSHUF) bias_r[i] = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + ck * 4));
+      if (EPI == EPI_GATE) bias2_r[i] = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + 64 + ck * 4));
+    }
+
+    const int passes = (rows_here + 4 * RPI - 1) / (4 * RPI);
+#pragma unroll 1
+    for (int it0 = 0; it0 < passes; it0 += U) {
+      float4 acc[U][CPL], acc2[U][CPL], ext[U][CPL];
+      bool ok[U];
+      TOut* dst[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int rl = ((it0 + u) * 4 + ew) * RPI + sub;    // row within this CTA's slice
+        const int r = row_base + rl;
+        const int m = m0 + r;
+        ok[u] = (it0 + u) < passes && rl < rows_here && m < args.M;
+        const int rc = ok[u] ? r : row_base;                // clamp: loads stay in bounds
+        const int mc = ok[u] ? m : m0 + row_base;
+        size_t out_row = static_cast<size_t>(mc);
+        if (EPI == EPI_PIXSHUF) {
+          const int sp = args.sp;
+          const int face = mc / (sp * sp);
+          const int rem = mc - face * sp * sp;
+          const int hh = rem / sp, ww = rem - hh * sp;
+          out_row = (static_cast<size_t>(face) * (2 * sp) + (2 * hh + (q >> 1))) * (2 * sp) + (2 * ww + (q & 1));
+        }
+        dst[u] = reinterpret_cast<TOut*>(args.out) + out_row * args.ldo + out_col0 + sl * 4;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          const int ck = i * LPR + sl;
+          const uint32_t a1 = stage_u32 + static_cast<uint32_t>((rc * BN + ((ck ^ (rc & 7)) << 2)) * 4);
+          const uint32_t a2 = stage_u32 + static_cast<uint32_t>((rc * BN + (((ck + 16) ^ (rc & 7)) << 2)) * 4);
+          acc[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          acc2[u][i] = acc[u][i];
+          ext[u][i] = acc[u][i];
+          if (nsplit == 1) {
+            acc[u][i] = *reinterpret_cast<const float4*>(stage + rc * BN + ((ck ^ (rc & 7)) << 2));
+            if (EPI == EPI_GATE) acc2[u][i] = *reinterpret_cast<const float4*>(stage + rc * BN + (((ck + 16) ^ (rc & 7)) << 2));
+          } else {
+            for (int sidx = 0; sidx < nsplit; ++sidx) {       // fixed order: deterministic
+              const float4 t = ld_dsmem_f4(a1, static_cast<uint32_t>(sidx));
+              acc[u][i].x += t.x; acc[u][i].y += t.y; acc[u][i].z += t.z; acc[u][i].w += t.w;
+              if (EPI == EPI_GATE) {
+                const float4 t2 = ld_dsmem_f4(a2, static_cast<uint32_t>(sidx));
+                acc2[u][i].x += t2.x; acc2[u][i].y += t2.y; acc2[u][i].z += t2.z; acc2[u][i].w += t2.w;
+              }
+            }
+          }
+          if (EPI == EPI_RESID)
+            ext[u][i] = *reinterpret_cast<const float4*>(args.resid + static_cast<size_t>(mc) * args.ldr + n0 + ck * 4);
+          if (EPI == EPI_PIXSHUF) ext[u][i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dst[u]) + i * LPR * 4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          float4 v = acc[u][i];
+          v.x += bias_r[i].x; v.y += bias_r[i].y; v.z += bias_r[i].z; v.w += bias_r[i].w;
+          if (EPI == EPI_GATE) {
+            const float4 g = acc2[u][i];
+            v.x *= g.x + bias2_r[i].x; v.y *= g.y + bias2_r[i].y; v.z *= g.z + bias2_r[i].z; v.w *= g.w + bias2_r[i].w;
+          }
+          if (EPI == EPI_RELU) {
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+          }
+          if (EPI == EPI_SIGMOID) {
+            v.x = 1.f / (1.f + __expf(-v.x)); v.y = 1.f / (1.f + __expf(-v.y));
+            v.z = 1.f / (1.f + __expf(-v.z)); v.w = 1.f / (1.f + __expf(-v.w));
+          }
+          if (EPI == EPI_RESID || EPI == EPI_PIXSHUF) {
+            v.x += ext[u][i].x; v.y += ext[u][i].y; v.z += ext[u][i].z; v.w += ext[u][i].w;
+          }
+          if (ok[u]) store4<TOut>(dst[u] + i * LPR * 4, v);
+        }
+      }
+    }
+  }
+
+  // no CTA may exit (or free TMEM) while a peer can still read its staging tile
+  if (nsplit > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);

@@ -116,7 +116,10 @@ struct Op {
   std::function<void(cudaStream_t)> fn;
   std::string tap;
   TapInfo info;
+  std::string label;  // kernel kind + shape, for hd_profile_step
 };
+
+thread_local std::string g_label;  // label picked up by the next add_op
 
 struct Plan {
   int batch = 0;
@@ -225,18 +228,41 @@ struct TcLaunch {
   CUtensorMap mapA, mapB;
   tc::TcArgs args;
   dim3 grid;
-  int epi, a_mode, out_dtype;
+  int epi, a_mode, out_dtype, stages;
 };
 
-template <int EPI, int AMODE, typename TOut>
-void launch_tc_inst(const TcLaunch& L, cudaStream_t st) {
-  auto kern = tc::gemm_tc_kernel<128, EPI, AMODE, TOut>;
+template <int STAGES, int EPI, int AMODE, typename TOut>
+void launch_tc_inst2(const TcLaunch& L, cudaStream_t st) {
+  auto kern = tc::gemm_tc_kernel<128, STAGES, EPI, AMODE, TOut>;
+  using Cfg = tc::TileCfg<128, STAGES>;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TileCfg<128>::SMEM_BYTES);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     configured = true;
   }
-  kern<<<L.grid, tc::NUM_THREADS, tc::TileCfg<128>::SMEM_BYTES, st>>>(L.mapA, L.mapB, L.args);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = L.grid;
+  cfg.blockDim = dim3(tc::NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = L.grid.z;  // split-K CTAs of one tile form a cluster
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, L.mapA, L.mapB, L.args);
+}
+
+// ring depth: <= 2 k-blocks per CTA needs two stages (3 CTAs/SM); a grid that fits in one wave gets the
+// deep 6-stage ring (weight streaming); everything else 3 stages (2 CTAs/SM)
+template <int EPI, int AMODE, typename TOut>
+void launch_tc_inst(const TcLaunch& L, cudaStream_t st) {
+  if (L.stages == 2) launch_tc_inst2<2, EPI, AMODE, TOut>(L, st);
+  else if (L.stages == 6) launch_tc_inst2<6, EPI, AMODE, TOut>(L, st);
+  else launch_tc_inst2<3, EPI, AMODE, TOut>(L, st);
 }
 
 void launch_tc(const TcLaunch& L, cudaStream_t st) {
@@ -300,7 +326,13 @@ TcLaunch build_tc(hd_handle* h, const GemmDesc& d, long long a_rows_alloc) {
     cuuint32_t box[2] = {64, 128};
     encode_map(h, &L.mapB, d.W, 2, dims, strides, box);
   }
-  L.grid = dim3(cdiv(d.M, 128), d.N / 128);
+  // split-K over a (1,1,S) cluster until the grid can cover the chip (>= 120 CTAs)
+  const int tiles = cdiv(d.M, 128) * (d.N / 128);
+  int split = 1;
+  while (tiles * split < 120 && split < 8 && a.num_kb % (2 * split) == 0 && a.num_kb / (2 * split) >= 2) split *= 2;
+  L.grid = dim3(cdiv(d.M, 128), d.N / 128, split);
+  const int local_kb = a.num_kb / split;
+  L.stages = local_kb <= 2 ? 2 : (tiles * split <= 160 ? 6 : 3);
   return L;
 }
 
@@ -542,6 +574,7 @@ void add_op(Plan& P, std::function<void(cudaStream_t)> fn, const std::string& ta
   op.fn = std::move(fn);
   op.tap = tap;
   op.info = info;
+  op.label = g_label;
   P.ops.push_back(std::move(op));
 }
 
@@ -550,8 +583,12 @@ void add_gemm(hd_handle* h, Plan& P, GemmDesc d, long long a_rows_alloc, const s
   const long long taps_exec = d.a_mode == A_CONV3 ? 1 : 1;
   (void)taps_exec;
   P.flops_per_face += 2.0 * d.M * static_cast<double>(d.N) * d.K / P.batch;
+  static const char* epi_names[] = {"bias", "relu", "sigmoid", "resid", "gate", "pixshuf"};
+  const std::string what = g_label;
   if (tc_eligible(h, d)) {
     TcLaunch L = build_tc(h, d, a_rows_alloc);
+    g_label = fmt("%s gemm_tc %s%s M=%d N=%d K=%d grid=(%d,%d,%d) stages=%d", what.c_str(), epi_names[d.epi],
+                  d.a_mode == A_CONV3 ? "+conv3" : "", d.M, d.N, d.K, L.grid.x, L.grid.y, L.grid.z, L.stages);
     add_op(P, [L](cudaStream_t st) { launch_tc(L, st); }, tap, info);
     return;
   }
@@ -567,7 +604,9 @@ void add_gemm(hd_handle* h, Plan& P, GemmDesc d, long long a_rows_alloc, const s
     const int odt = d.out_dtype;
     const size_t rows = d.M;
     float* tmp = h->gate_tmp;
+    g_label = fmt("%s gemm_ffma bias M=%d N=%d K=%d", what.c_str(), d.M, d.N, d.K);
     add_op(P, [g](cudaStream_t st) { launch_simt(g, st); });
+    g_label = what + " gate_packed";
     add_op(P, [=](cudaStream_t st) {
       const int blocks = cdiv(rows * c, 256);
       if (odt == DT_BF16) gate_packed_kernel<bf16><<<blocks, 256, 0, st>>>(tmp, static_cast<bf16*>(out), rows, c);
@@ -577,19 +616,21 @@ void add_gemm(hd_handle* h, Plan& P, GemmDesc d, long long a_rows_alloc, const s
   }
   const bool abf = d.a_dtype == DT_BF16, wbf = d.w_dtype == DT_BF16;
   if (abf != wbf) HD_THROW(HD_ERR_INVALID, "mixed-precision operands reached the FFMA GEMM");
+  g_label = fmt("%s gemm_ffma %s M=%d N=%d K=%d", what.c_str(), epi_names[d.epi], d.M, d.N, d.K);
   add_op(P, [d](cudaStream_t st) { launch_simt(d, st); }, tap, info);
 }
 
 template <typename T>
 void launch_ln(int c, const float* x, const float* lw, const float* lb, T* out, int rows, int rpf, ModRef mod,
                int shift_off, int scale_off, int has_mod, cudaStream_t st) {
-  const int grid = cdiv(rows, 8);
+  const int lpr = std::min(32, c / 16);
+  const int grid = cdiv(rows, 4 * (32 / lpr));  // 4 warps per block, 32/lpr rows per warp
   switch (c) {
-    case 128: ln_mod_kernel<128, T><<<grid, 256, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
-    case 256: ln_mod_kernel<256, T><<<grid, 256, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
-    case 512: ln_mod_kernel<512, T><<<grid, 256, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
-    case 1024: ln_mod_kernel<1024, T><<<grid, 256, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
-    case 2048: ln_mod_kernel<2048, T><<<grid, 256, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
+    case 128: ln_mod_kernel<128, T><<<grid, 128, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
+    case 256: ln_mod_kernel<256, T><<<grid, 128, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
+    case 512: ln_mod_kernel<512, T><<<grid, 128, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
+    case 1024: ln_mod_kernel<1024, T><<<grid, 128, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
+    case 2048: ln_mod_kernel<2048, T><<<grid, 128, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
     default: break;
   }
 }
@@ -611,8 +652,11 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
       else launch_ln<float>(c, resid, lw, lb, static_cast<float*>(act_a), rows, rpf, mod, shift_off, scale_off, 1, st);
     };
   };
+  const std::string L0 = fmt("L%d c=%d ", l, c);
   // norm1 + modulation (shift_att = chunk 0, scale_att = chunk 1)
+  g_label = L0 + "ln1";
   add_op(P, ln(bw.ln1_w, bw.ln1_b, bw.mod_off, bw.mod_off + c));
+  g_label = L0 + "conv1";
   {  // conv1
     GemmDesc d;
     d.M = rows; d.N = 2 * c; d.K = c; d.A = act_a; d.lda = c; d.a_dtype = adt;
@@ -620,17 +664,19 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
     d.out = act_h; d.ldo = 2 * c; d.out_dtype = adt;
     add_gemm(h, P, d, rows_alloc);
   }
+  g_label = L0 + "dwconv_gate_pool";
   {  // depthwise 3x3 + SimpleGate + pool
     const float *dw_w = bw.dw_w, *dw_b = bw.dw_b;
     add_op(P, [=](cudaStream_t st) {
-      dim3 grid(c / 64, B);
-      if (bf) dwconv_gate_pool_kernel<bf16><<<grid, 256, 0, st>>>(static_cast<const bf16*>(act_h), dw_w, dw_b,
-                                                                  static_cast<bf16*>(act_g), static_cast<bf16*>(pooled), sp, c);
-      else dwconv_gate_pool_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(act_h), dw_w, dw_b,
-                                                                static_cast<float*>(act_g), static_cast<float*>(pooled), sp, c);
+      dim3 grid(c / 64, cdiv(rows, 256));
+      if (bf) dwconv_gate_pool_kernel<bf16><<<grid, 256, 256 * 128 * 2, st>>>(static_cast<const bf16*>(act_h), dw_w, dw_b,
+                                                                  static_cast<bf16*>(act_g), static_cast<bf16*>(pooled), sp, c, rows);
+      else dwconv_gate_pool_kernel<float><<<grid, 256, 256 * 128 * 4, st>>>(static_cast<const float*>(act_h), dw_w, dw_b,
+                                                                static_cast<float*>(act_g), static_cast<float*>(pooled), sp, c, rows);
     });
     P.flops_per_face += 2.0 * 9 * 2 * c * rpf;
   }
+  g_label = L0 + "sca";
   {  // SCA 1x1 on the pooled vector
     GemmDesc d;
     d.M = B; d.N = c; d.K = c; d.A = pooled; d.lda = c; d.a_dtype = adt;
@@ -638,11 +684,13 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
     d.out = sca_s; d.ldo = c; d.out_dtype = DT_F32;
     add_gemm(h, P, d, h->Bcap);
   }
+  g_label = L0 + "scale_rows";
   add_op(P, [=](cudaStream_t st) {
     const size_t total8 = static_cast<size_t>(rows) * c / 8;
     if (bf) scale_rows_kernel<bf16><<<cdiv(total8, 256), 256, 0, st>>>(static_cast<bf16*>(act_g), sca_s, total8, c, rpf);
     else scale_rows_kernel<float><<<cdiv(total8, 256), 256, 0, st>>>(static_cast<float*>(act_g), sca_s, total8, c, rpf);
   });
+  g_label = L0 + "conv3";
   {  // conv3 (+beta) + residual
     GemmDesc d;
     d.M = rows; d.N = c; d.K = c; d.A = act_g; d.lda = c; d.a_dtype = adt;
@@ -651,7 +699,9 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
     add_gemm(h, P, d, rows_alloc);
   }
   // norm2 + modulation (shift_ffn = chunk 2, scale_ffn = chunk 3)
+  g_label = L0 + "ln2";
   add_op(P, ln(bw.ln2_w, bw.ln2_b, bw.mod_off + 2 * c, bw.mod_off + 3 * c));
+  g_label = L0 + "conv4";
   {  // conv4 + SimpleGate
     GemmDesc d;
     d.M = rows; d.N = 2 * c; d.K = c; d.A = act_a; d.lda = c; d.a_dtype = adt;
@@ -659,6 +709,7 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
     d.out = act_g; d.ldo = c; d.out_dtype = adt;
     add_gemm(h, P, d, rows_alloc);
   }
+  g_label = L0 + "conv5";
   {  // conv5 (+gamma) + residual
     GemmDesc d;
     d.M = rows; d.N = c; d.K = c; d.A = act_g; d.lda = c; d.a_dtype = adt;
@@ -680,6 +731,7 @@ void add_hca(hd_handle* h, Plan& P, int j, int level) {
   const float *wc = w.wc, *ws = w.ws;
   const float* idc = j == 0 ? h->idc_add : nullptr;
   void* act_a = h->act_a;
+  g_label = fmt("hca%d apply", j);
   add_op(P, [=](cudaStream_t st) {
     const size_t total8 = static_cast<size_t>(rows) * d / 8;
     if (bf) hca_apply_kernel<bf16><<<cdiv(total8, 256), 256, 0, st>>>(fd, wc, ws, idc, static_cast<bf16*>(act_a), total8, d, rpf);
@@ -696,6 +748,7 @@ void add_hca(hd_handle* h, Plan& P, int j, int level) {
   }
   TapInfo ti;
   ti.ptr = h->hca_out; ti.dtype = adt; ti.C = d; ti.HW = rpf; ti.ld = d;
+  g_label = fmt("hca%d conv3x3", j);
   add_gemm(h, P, g, rows_alloc, "hcas." + std::to_string(j), ti);
 }
 
@@ -714,8 +767,9 @@ Plan* get_plan(hd_handle* h, int B) {
     const float *w = h->intro_w, *b = h->intro_b;
     TapInfo ti;
     ti.ptr = out; ti.dtype = DT_F32; ti.C = kWidth; ti.HW = S * S; ti.ld = kWidth;
+    g_label = "intro conv3x3";
     add_op(P, [=](cudaStream_t st) {
-      intro_conv_kernel<<<dim3(S, B), 128, 4 * 3 * (S + 2) * sizeof(float), st>>>(h->cur_x, w, b, out, S);
+      intro_conv_kernel<<<B, 256, (36 * 128 + 4 * (S + 2) * (S + 2)) * sizeof(float), st>>>(h->cur_x, w, b, out, S);
     }, "intro", ti);
     P.flops_per_face += 2.0 * 36 * 128 * S * S;
   }
@@ -727,6 +781,7 @@ Plan* get_plan(hd_handle* h, int B) {
     const int c = h->c[l], n = h->sp[l], rows_out = B * (n / 2) * (n / 2);
     const float* src = h->resid[l];
     void* act_a = h->act_a;
+    g_label = fmt("down%d s2d", l);
     add_op(P, [=](cudaStream_t st) {
       const size_t total8 = static_cast<size_t>(rows_out) * 4 * c / 8;
       if (bf) s2d_kernel<bf16><<<cdiv(total8, 256), 256, 0, st>>>(src, static_cast<bf16*>(act_a), B, n, c);
@@ -738,6 +793,7 @@ Plan* get_plan(hd_handle* h, int B) {
     d.out = h->resid[l + 1]; d.ldo = 2 * c; d.out_dtype = DT_F32;
     TapInfo ti;
     ti.ptr = h->resid[l + 1]; ti.dtype = DT_F32; ti.C = 2 * c; ti.HW = (n / 2) * (n / 2); ti.ld = 2 * c;
+    g_label = fmt("down%d", l);
     add_gemm(h, P, d, static_cast<long long>(h->Bcap) * (n / 2) * (n / 2), "downs." + std::to_string(l), ti);
   }
   for (int i = 0; i < kMidBlocks; ++i, ++bi) add_block(h, P, h->blocks[bi], "middle_blks." + std::to_string(i));
@@ -752,6 +808,7 @@ Plan* get_plan(hd_handle* h, int B) {
       const float* src = h->resid[lin];
       void* act_a = h->act_a;
       a_ptr = act_a;
+      g_label = fmt("up%d cast", L);
       add_op(P, [=](cudaStream_t st) {
         const size_t total8 = static_cast<size_t>(rows_in) * cin / 8;
         if (bf) cast_kernel<bf16><<<cdiv(total8, 256), 256, 0, st>>>(src, static_cast<bf16*>(act_a), total8);
@@ -764,6 +821,7 @@ Plan* get_plan(hd_handle* h, int B) {
     d.out = h->resid[lout]; d.ldo = cin / 2; d.out_dtype = DT_F32;
     TapInfo ti;
     ti.ptr = h->resid[lout]; ti.dtype = DT_F32; ti.C = cin / 2; ti.HW = 4 * n * n; ti.ld = cin / 2;
+    g_label = fmt("up%d", L);
     add_gemm(h, P, d, static_cast<long long>(h->Bcap) * n * n, "ups." + std::to_string(L), ti);
     for (int i = 0; i < kDecBlocks[L]; ++i, ++bi)
       add_block(h, P, h->blocks[bi], "decoders." + std::to_string(L) + "." + std::to_string(i));
@@ -773,10 +831,11 @@ Plan* get_plan(hd_handle* h, int B) {
     const float *w = h->end_w, *b = h->end_b;
     const void* in = h->fused ? h->hca_out : static_cast<const void*>(h->resid[0]);
     const bool in_bf = h->fused && bf;
+    g_label = "ending conv3x3";
     add_op(P, [=](cudaStream_t st) {
-      const int grid = cdiv(static_cast<long long>(B) * S * S, 8);
-      if (in_bf) ending_conv_kernel<bf16><<<grid, 256, 0, st>>>(static_cast<const bf16*>(in), w, b, h->cur_eps, B, S);
-      else ending_conv_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(in), w, b, h->cur_eps, B, S);
+      const size_t wbytes = 4 * 9 * 128 * sizeof(float);
+      if (in_bf) ending_conv_kernel<bf16><<<B, 256, S * S * 128 * 2 + wbytes, st>>>(static_cast<const bf16*>(in), w, b, h->cur_eps, B, S);
+      else ending_conv_kernel<float><<<B, 256, S * S * 128 * 4 + wbytes, st>>>(static_cast<const float*>(in), w, b, h->cur_eps, B, S);
     });
     P.flops_per_face += 2.0 * 9 * 128 * 4 * S * S;
   }
@@ -985,6 +1044,10 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
     if (qres != cudaDriverEntryPointSuccess || fn == nullptr) HD_THROW(HD_ERR_CUDA, "cuTensorMapEncodeTiled not available");
     h->encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
+  CUDA_CHECK(cudaFuncSetAttribute(dwconv_gate_pool_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 128 * 2));
+  CUDA_CHECK(cudaFuncSetAttribute(dwconv_gate_pool_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 128 * 4));
+  CUDA_CHECK(cudaFuncSetAttribute(ending_conv_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 128 * 2 + 4 * 9 * 128 * 4));
+  CUDA_CHECK(cudaFuncSetAttribute(ending_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 128 * 4 + 4 * 9 * 128 * 4));
   // block table in execution order with table offsets
   int off = 0;
   auto push = [&](const std::string& prefix, int level) {
@@ -1258,6 +1321,47 @@ int32_t hd_sample(hd_handle* h, float* x_inout, const hd_step_coef* coef, int32_
     check_device_status(h);
   }
   join_out(h, stream);
+  HD_API_END(h)
+}
+
+int32_t hd_profile_step(hd_handle* h, int32_t batch, int32_t reps, float* ms_out, char* labels_out, int32_t label_stride,
+                        int32_t cap, int32_t* n_ops) {
+  HD_API_BEGIN
+  if (!h || !ms_out || !n_ops) HD_THROW(HD_ERR_INVALID, "null argument");
+  if (!h->weights_loaded) HD_THROW(HD_ERR_STATE, "hd_load_weights has not been called");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  Plan* P = get_plan(h, batch);
+  const int n = static_cast<int>(P->ops.size());
+  *n_ops = n;
+  if (n > cap) HD_THROW(HD_ERR_INVALID, "need room for %d ops", n);
+  if (h->cur_x == nullptr) { h->cur_x = h->x_state; h->cur_eps = h->eps_buf; }
+  cudaStream_t st = h->stream;
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
+  std::vector<double> acc(n, 0.0);
+  for (int rep = 0; rep < reps + 1; ++rep) {
+    CUDA_CHECK(cudaEventRecord(ev[0], st));
+    for (int i = 0; i < n; ++i) {
+      P->ops[i].fn(st);
+      CUDA_CHECK(cudaEventRecord(ev[i + 1], st));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (rep == 0) continue;  // warm-up
+    for (int i = 0; i < n; ++i) {
+      float ms = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      acc[i] += ms;
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    ms_out[i] = static_cast<float>(acc[i] / std::max(reps, 1));
+    if (labels_out && label_stride > 0) {
+      strncpy(labels_out + static_cast<size_t>(i) * label_stride, P->ops[i].label.c_str(), label_stride - 1);
+      labels_out[static_cast<size_t>(i) * label_stride + label_stride - 1] = 0;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  check_device_status(h);
   HD_API_END(h)
 }
 

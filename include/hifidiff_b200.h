@@ -157,6 +157,11 @@ int32_t hd_sampler_update(hd_handle* h, float* x_inout, const float* eps, const 
  * (HD_ERR_KERNEL) or a sticky CUDA error.  The asynchronous entry points above do not check. */
 int32_t hd_synchronize(hd_handle* h);
 
+/* Times every kernel of one denoise step (plain launches, CUDA events between launches, warm L2),
+ * averaged over `reps` repetitions.  ms_out[i] / labels_out[i*label_stride] describe launch i. */
+int32_t hd_profile_step(hd_handle* h, int32_t batch, int32_t reps, float* ms_out, char* labels_out,
+                        int32_t label_stride, int32_t cap, int32_t* n_ops);
+
 /* Standalone C = A[M,K] * W[N,K]^T (+bias) on the tcgen05 path (bf16 operands given as fp32,
  * converted internally); used by the parity tests to pin the tensor-core kernel alone. */
 int32_t hd_debug_gemm(hd_handle* h, const float* a, const float* w, const float* bias, float* out,
