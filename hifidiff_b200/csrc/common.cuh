@@ -104,6 +104,13 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = a;
 }
 
+// Programmatic dependent launch: every per-step kernel lets its successor start launching right away
+// (pdl_trigger) and touches activation memory only after its predecessor has fully completed
+// (pdl_wait).  Constants (weights, biases) may be fetched before the wait.  Both are no-ops when the
+// kernel was launched without the programmatic-stream-serialization attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -38,10 +38,12 @@ __global__ void __launch_bounds__(256) intro_conv_kernel(const float* __restrict
   float* s_in = s_intro + 36 * 128;     // [4][S+2][S+2] zero-padded face
   const int b = blockIdx.x;
   const int W2 = S + 2;
+  pdl_trigger();
   for (int i = threadIdx.x; i < 36 * 128; i += blockDim.x) {
     const int k = i >> 7, o = i & 127;
     s_w[i] = w[o * 36 + k];
   }
+  pdl_wait();
   for (int i = threadIdx.x; i < 4 * W2 * W2; i += blockDim.x) {
     const int c = i / (W2 * W2), r = (i / W2) % W2, col = i % W2;
     const int hh = r - 1, ww = col - 1;
@@ -112,6 +114,8 @@ __global__ void __launch_bounds__(128) ln_mod_kernel(const float* __restrict__ x
   const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
   const bool ok = row < rows;
   const float* xr = x + static_cast<size_t>(ok ? row : 0) * C;
+  pdl_trigger();
+  pdl_wait();
   float v[NV * 4];
   float s = 0.f;
 #pragma unroll
@@ -184,11 +188,13 @@ __global__ void __launch_bounds__(256) dwconv_gate_pool_kernel(const T* __restri
   const int px0 = blockIdx.y * 256;
   const int C2 = 2 * c;
   const int npix = sp * sp;
+  pdl_trigger();
   for (int i = threadIdx.x; i < 9 * 2 * 64; i += blockDim.x) {
     const int tap = i / 128, half = (i / 64) & 1, ch = i & 63;
     s_w[tap][half][ch] = w9[tap * C2 + half * c + j0 + ch];
   }
   if (threadIdx.x < 128) s_b[threadIdx.x >> 6][threadIdx.x & 63] = bias[(threadIdx.x >> 6) * c + j0 + (threadIdx.x & 63)];
+  pdl_wait();
   // stage: 256 px x 16 chunks of 8 channels (chunks 0-7: x1, 8-15: x2)
   {
     const int chunk = threadIdx.x & 15;
@@ -264,6 +270,8 @@ __global__ void __launch_bounds__(256) dwconv_gate_pool_kernel(const T* __restri
 template <typename T>
 __global__ void __launch_bounds__(256) scale_rows_kernel(T* __restrict__ g, const float* __restrict__ s, size_t total8,
                                                          int c, int rows_per_face) {
+  pdl_trigger();
+  pdl_wait();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total8) return;
   const size_t e = i * 8;
@@ -290,6 +298,8 @@ __global__ void gate_split_kernel(const float* __restrict__ in, float* __restric
 // SimpleGate on the gate-packed conv4 output (fp32 mode): 128-column groups [x1(64) | x2(64)]
 template <typename TOut>
 __global__ void gate_packed_kernel(const float* __restrict__ in, TOut* __restrict__ out, size_t rows, int c) {
+  pdl_trigger();
+  pdl_wait();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= rows * c) return;
   const size_t r = i / c;
@@ -302,6 +312,8 @@ __global__ void gate_packed_kernel(const float* __restrict__ in, TOut* __restric
 // space-to-depth for the 2x2 stride-2 down conv (model.py:86): [B,n,n,c] fp32 -> [B,(n/2)^2, (i,j,c)] T
 template <typename T>
 __global__ void __launch_bounds__(256) s2d_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int n, int c) {
+  pdl_trigger();
+  pdl_wait();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int n2 = n >> 1;
   const size_t total8 = static_cast<size_t>(B) * n2 * n2 * 4 * c / 8;
@@ -322,6 +334,8 @@ __global__ void __launch_bounds__(256) s2d_kernel(const float* __restrict__ x, T
 
 template <typename T>
 __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ x, T* __restrict__ out, size_t total8) {
+  pdl_trigger();
+  pdl_wait();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total8) return;
   float v[8];
@@ -335,6 +349,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) hca_apply_kernel(const float* __restrict__ fd, const float* __restrict__ wc,
                                                         const float* __restrict__ ws, const float* __restrict__ idc,
                                                         T* __restrict__ out, size_t total8, int c, int rows_per_face) {
+  pdl_trigger();
+  pdl_wait();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total8) return;
   const size_t e = i * 8;
@@ -373,7 +389,9 @@ __global__ void __launch_bounds__(256) ending_conv_kernel(const TIn* __restrict_
   TIn* tile = reinterpret_cast<TIn*>(s_end_raw);
   float* s_w = reinterpret_cast<float*>(s_end_raw + static_cast<size_t>(npix) * 128 * sizeof(TIn));
   const int face = blockIdx.x;
+  pdl_trigger();
   for (int i = threadIdx.x; i < 4 * 9 * 128; i += blockDim.x) s_w[i] = w[i];
+  pdl_wait();
   const TIn* xf = x + static_cast<size_t>(face) * npix * 128;
   for (int i = threadIdx.x; i < npix * CPR; i += blockDim.x) {
     const int r = i / CPR, ck = i % CPR;
@@ -442,6 +460,8 @@ __global__ void __launch_bounds__(256) sampler_update_kernel(float* __restrict__
                                                              long long first_face, int batch, int elems_per_face) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int groups = elems_per_face >> 2;
+  pdl_trigger();
+  pdl_wait();
   if (i >= static_cast<size_t>(batch) * groups) return;
   const int step = state != nullptr ? state->step : fixed_step;
   const StepCoef cf = coefs[step];
@@ -483,6 +503,8 @@ __global__ void __launch_bounds__(256) sampler_update_kernel(float* __restrict__
 
 // end of a sampler step: step += 1 and point every face at the next table row (single block)
 __global__ void advance_rows_kernel(StepState* st, int* __restrict__ row_idx, int n) {
+  pdl_trigger();
+  pdl_wait();
   const int next = st->step + 1;
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) row_idx[i] = next;

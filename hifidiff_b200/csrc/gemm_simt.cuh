@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs g) {
   __shared__ float Ws[TK][TN + 4];
   const int t = threadIdx.x;
   const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+  pdl_trigger();
+  pdl_wait();
   const int lr = t >> 2, lk = (t & 3) * 4;  // loader: row/col within tile, k quad
   const int ty = t >> 4, tx = t & 15;
   float acc[4][4];

@@ -33,6 +33,7 @@ struct TcArgs {
   int kb_per_tap;             // A_CONV3: C / 64
   int conv_bh, conv_bb;       // A_CONV3: box rows in h and in batch (conv_bh * sp * conv_bb == 128)
   DeviceStatus* status;
+  long long* trace;           // optional per-CTA timeline (16 slots per CTA), nullptr in production
 };
 
 template <int BN, int STAGES> struct TileCfg {
@@ -74,22 +75,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ uint64_t global_timer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// Bounded wait: a broken pipeline trips a watchdog (2 s) instead of hanging the GPU; once any CTA
-// has tripped, every other wait gives up immediately.  The host reports HD_ERR_KERNEL.
+// Bounded wait.  The fast path is a tight spin on mbarrier.try_wait (which itself suspends the thread in
+// hardware for a bounded time); only every 4096 failed polls does the thread look at the SM clock and
+// at the handle's error word.  A broken pipeline therefore trips a watchdog (~2 s) instead of hanging
+// the GPU, and once any CTA has tripped every other wait gives up quickly.  The host reports
+// HD_ERR_KERNEL.  (Polling %globaltimer / global memory on every spin costs ~1 us per poll and
+// serialises the TMA->MMA pipeline: measured 3x slower GEMMs.)
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, DeviceStatus* st, uint32_t site) {
   if (mbar_try_wait(bar, parity)) return true;
-  const uint64_t t0 = global_timer_ns();
-  while (true) {
+  const long long t0 = clock64();
+  for (uint32_t it = 1;; ++it) {
     if (mbar_try_wait(bar, parity)) return true;
-    if (*reinterpret_cast<volatile unsigned int*>(&st->error) != 0u) return false;
-    if (global_timer_ns() - t0 > 2000000000ull) {
-      if (atomicCAS(&st->error, 0u, 1u) == 0u) st->where = site;
-      return false;
+    if ((it & 0xFFFu) == 0u) {
+      if (*reinterpret_cast<volatile unsigned int*>(&st->error) != 0u) return false;
+      if (clock64() - t0 > 4000000000ll) {
+        if (atomicCAS(&st->error, 0u, 1u) == 0u) st->where = site;
+        return false;
+      }
     }
   }
 }
@@ -238,6 +240,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int m_tile = blockIdx.x;
   const int n0 = blockIdx.y * BN;
   const int m0 = m_tile * BM;
+  long long* trace = args.trace;
+  if (trace != nullptr) {
+    trace += 16 * ((static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+    if (threadIdx.x == 0) {
+      unsigned long long gt;
+      unsigned int smid;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      trace[0] = clock64(); trace[9] = static_cast<long long>(gt); trace[10] = smid;
+    }
+  }
+  pdl_trigger();
   const int nsplit = static_cast<int>(cluster_nctaid_z());
   const int zrank = blockIdx.z;  // == rank in the (1,1,S) cluster
   const int kb_count = args.num_kb / nsplit;
@@ -263,6 +277,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tc_fence_after_sync();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   float* stage = reinterpret_cast<float*>(smem);
+  if (trace != nullptr && threadIdx.x == 0) trace[1] = clock64();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -277,15 +292,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           conv_h0 = (m_tile % tiles_per_face) * args.conv_bh;
         }
       }
+      // Weights do not depend on the preceding kernel: fill the ring's W halves before the
+      // programmatic-dependency wait, so the weight stream overlaps the predecessor's tail.
+      const int pre = kb_count < STAGES ? kb_count : STAGES;
+      for (int i = 0; i < pre; ++i) {
+        const uint32_t fb = smem_u32(&full_bar[i]);
+        mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+        tma_load_2d(smem_u32(smem + i * Cfg::STAGE_BYTES) + Cfg::A_BYTES, &mapB, (kb_begin + i) * BK, n0, fb);
+      }
+      pdl_wait();
       for (int i = 0; i < kb_count; ++i) {
         const int kb = kb_begin + i;
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u, args.status, 0x100u);
         const uint32_t fb = smem_u32(&full_bar[s]);
         const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
         const uint32_t sb = sa + Cfg::A_BYTES;
-        mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+        if (i >= pre) {
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u, args.status, 0x100u);
+          mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+        }
         if (AMODE == A_CONV3) {
           const int tap = kb / args.kb_per_tap;
           const int c0 = (kb - tap * args.kb_per_tap) * BK;
@@ -294,7 +320,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         } else {
           tma_load_2d(sa, &mapA, kb * BK, m0, fb);
         }
-        tma_load_2d(sb, &mapB, kb * BK, n0, fb);
+        if (i >= pre) tma_load_2d(sb, &mapB, kb * BK, n0, fb);
       }
     }
   } else if (warp == 1) {
@@ -306,6 +332,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(smem_u32(&full_bar[s]), ph, args.status, 0x200u);
         tc_fence_after_sync();
+        if (trace != nullptr && i == 0) trace[2] = clock64();
         const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
         const uint64_t da = make_smem_desc(sa);
         const uint64_t db = make_smem_desc(sa + Cfg::A_BYTES);
@@ -317,12 +344,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         umma_commit(smem_u32(&empty_bar[s]));
       }
       umma_commit(smem_u32(tmem_full_bar));
+      if (trace != nullptr) trace[3] = clock64();
     }
   } else {
     // ---------------- epilogue phase A (warps 2..5): TMEM -> swizzled fp32 staging tile ----------------
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    pdl_wait();                 // phase B reads the residual / overwrites buffers the predecessor may still use
     mbar_wait(smem_u32(tmem_full_bar), 0u, args.status, 0x300u);
     tc_fence_after_sync();
+    if (trace != nullptr && threadIdx.x == 64) trace[4] = clock64();
     // All MMAs have completed: every TMA load has landed and been consumed, the ring is free.
     const int r = quad * 32 + lane;
     const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
@@ -341,8 +371,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 
   __syncwarp();
+  if (trace != nullptr && threadIdx.x == 64) trace[5] = clock64();
   tc_fence_before_sync();
   if (nsplit > 1) cluster_sync_all(); else __syncthreads();
+  if (trace != nullptr && threadIdx.x == 64) trace[6] = clock64();
 
   if (warp >= 2) {
     // ---------------- epilogue phase B: lanes along columns, coalesced global traffic ----------------
@@ -377,82 +409,117 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
 
     const int passes = (rows_here + 4 * RPI - 1) / (4 * RPI);
+
+    // one row-chunk: bias / activation / residual, then the store
+    auto finish = [&](float4 v, float4 g, float4 e, int i, TOut* d, bool okay) {
+      v.x += bias_r[i].x; v.y += bias_r[i].y; v.z += bias_r[i].z; v.w += bias_r[i].w;
+      if (EPI == EPI_GATE) {
+        v.x *= g.x + bias2_r[i].x; v.y *= g.y + bias2_r[i].y; v.z *= g.z + bias2_r[i].z; v.w *= g.w + bias2_r[i].w;
+      }
+      if (EPI == EPI_RELU) {
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+      }
+      if (EPI == EPI_SIGMOID) {
+        v.x = 1.f / (1.f + __expf(-v.x)); v.y = 1.f / (1.f + __expf(-v.y));
+        v.z = 1.f / (1.f + __expf(-v.z)); v.w = 1.f / (1.f + __expf(-v.w));
+      }
+      if (EPI == EPI_RESID || EPI == EPI_PIXSHUF) { v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w; }
+      if (okay) store4<TOut>(d + i * LPR * 4, v);
+    };
+    // row bookkeeping shared by both paths
+    auto locate = [&](int pass, bool& okay, int& rc, int& mc, TOut*& d) {
+      const int rl = (pass * 4 + ew) * RPI + sub;          // row within this CTA's slice
+      const int r = row_base + rl;
+      const int m = m0 + r;
+      okay = pass < passes && rl < rows_here && m < args.M;
+      rc = okay ? r : row_base;                            // clamp: loads stay in bounds
+      mc = okay ? m : m0 + row_base;
+      size_t out_row = static_cast<size_t>(mc);
+      if (EPI == EPI_PIXSHUF) {
+        const int sp = args.sp;
+        const int face = mc / (sp * sp);
+        const int rem = mc - face * sp * sp;
+        const int hh = rem / sp, ww = rem - hh * sp;
+        out_row = (static_cast<size_t>(face) * (2 * sp) + (2 * hh + (q >> 1))) * (2 * sp) + (2 * ww + (q & 1));
+      }
+      d = reinterpret_cast<TOut*>(args.out) + out_row * args.ldo + out_col0 + sl * 4;
+    };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    if (nsplit == 1) {
+      constexpr int U = 4;                                  // passes batched for memory-level parallelism
 #pragma unroll 1
-    for (int it0 = 0; it0 < passes; it0 += U) {
-      float4 acc[U][CPL], acc2[U][CPL], ext[U][CPL];
-      bool ok[U];
-      TOut* dst[U];
+      for (int it0 = 0; it0 < passes; it0 += U) {
+        float4 acc[U][CPL], acc2[U][CPL], ext[U][CPL];
+        bool ok[U];
+        TOut* dst[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int rl = ((it0 + u) * 4 + ew) * RPI + sub;    // row within this CTA's slice
-        const int r = row_base + rl;
-        const int m = m0 + r;
-        ok[u] = (it0 + u) < passes && rl < rows_here && m < args.M;
-        const int rc = ok[u] ? r : row_base;                // clamp: loads stay in bounds
-        const int mc = ok[u] ? m : m0 + row_base;
-        size_t out_row = static_cast<size_t>(mc);
-        if (EPI == EPI_PIXSHUF) {
-          const int sp = args.sp;
-          const int face = mc / (sp * sp);
-          const int rem = mc - face * sp * sp;
-          const int hh = rem / sp, ww = rem - hh * sp;
-          out_row = (static_cast<size_t>(face) * (2 * sp) + (2 * hh + (q >> 1))) * (2 * sp) + (2 * ww + (q & 1));
+        for (int u = 0; u < U; ++u) {
+          int rc, mc;
+          locate(it0 + u, ok[u], rc, mc, dst[u]);
+#pragma unroll
+          for (int i = 0; i < CPL; ++i) {
+            const int ck = i * LPR + sl;
+            acc[u][i] = *reinterpret_cast<const float4*>(stage + rc * BN + ((ck ^ (rc & 7)) << 2));
+            acc2[u][i] = zero4;
+            ext[u][i] = zero4;
+            if (EPI == EPI_GATE) acc2[u][i] = *reinterpret_cast<const float4*>(stage + rc * BN + (((ck + 16) ^ (rc & 7)) << 2));
+            if (EPI == EPI_RESID)
+              ext[u][i] = *reinterpret_cast<const float4*>(args.resid + static_cast<size_t>(mc) * args.ldr + n0 + ck * 4);
+            if (EPI == EPI_PIXSHUF) ext[u][i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dst[u]) + i * LPR * 4);
+          }
         }
-        dst[u] = reinterpret_cast<TOut*>(args.out) + out_row * args.ldo + out_col0 + sl * 4;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int i = 0; i < CPL; ++i) finish(acc[u][i], acc2[u][i], ext[u][i], i, dst[u], ok[u]);
+      }
+    } else {
+      // split-K: all DSMEM loads of a pass are issued before the first add (they are ~200+ cycles each
+      // and would otherwise serialise), then summed in fixed split order -> deterministic
+      constexpr int MAXS = 8;
+      constexpr int NP = (EPI == EPI_GATE) ? 2 : 1;
+#pragma unroll 1
+      for (int pass = 0; pass < passes; ++pass) {
+        bool okay;
+        int rc, mc;
+        TOut* d;
+        locate(pass, okay, rc, mc, d);
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
           const int ck = i * LPR + sl;
-          const uint32_t a1 = stage_u32 + static_cast<uint32_t>((rc * BN + ((ck ^ (rc & 7)) << 2)) * 4);
-          const uint32_t a2 = stage_u32 + static_cast<uint32_t>((rc * BN + (((ck + 16) ^ (rc & 7)) << 2)) * 4);
-          acc[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          acc2[u][i] = acc[u][i];
-          ext[u][i] = acc[u][i];
-          if (nsplit == 1) {
-            acc[u][i] = *reinterpret_cast<const float4*>(stage + rc * BN + ((ck ^ (rc & 7)) << 2));
-            if (EPI == EPI_GATE) acc2[u][i] = *reinterpret_cast<const float4*>(stage + rc * BN + (((ck + 16) ^ (rc & 7)) << 2));
-          } else {
-            for (int sidx = 0; sidx < nsplit; ++sidx) {       // fixed order: deterministic
-              const float4 t = ld_dsmem_f4(a1, static_cast<uint32_t>(sidx));
-              acc[u][i].x += t.x; acc[u][i].y += t.y; acc[u][i].z += t.z; acc[u][i].w += t.w;
+          float4 part[NP][MAXS];
+          float4 e = zero4;
+#pragma unroll
+          for (int pi = 0; pi < NP; ++pi) {
+            const uint32_t a = stage_u32 + static_cast<uint32_t>((rc * BN + (((ck + 16 * pi) ^ (rc & 7)) << 2)) * 4);
+#pragma unroll
+            for (int sidx = 0; sidx < MAXS; ++sidx)
+              if (sidx < nsplit) part[pi][sidx] = ld_dsmem_f4(a, static_cast<uint32_t>(sidx));
+          }
+          if (EPI == EPI_RESID)
+            e = *reinterpret_cast<const float4*>(args.resid + static_cast<size_t>(mc) * args.ldr + n0 + ck * 4);
+          if (EPI == EPI_PIXSHUF) e = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d) + i * LPR * 4);
+          float4 v = zero4, g = zero4;
+#pragma unroll
+          for (int sidx = 0; sidx < MAXS; ++sidx) {
+            if (sidx < nsplit) {
+              v.x += part[0][sidx].x; v.y += part[0][sidx].y; v.z += part[0][sidx].z; v.w += part[0][sidx].w;
               if (EPI == EPI_GATE) {
-                const float4 t2 = ld_dsmem_f4(a2, static_cast<uint32_t>(sidx));
-                acc2[u][i].x += t2.x; acc2[u][i].y += t2.y; acc2[u][i].z += t2.z; acc2[u][i].w += t2.w;
+                g.x += part[NP - 1][sidx].x; g.y += part[NP - 1][sidx].y; g.z += part[NP - 1][sidx].z; g.w += part[NP - 1][sidx].w;
               }
             }
           }
-          if (EPI == EPI_RESID)
-            ext[u][i] = *reinterpret_cast<const float4*>(args.resid + static_cast<size_t>(mc) * args.ldr + n0 + ck * 4);
-          if (EPI == EPI_PIXSHUF) ext[u][i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dst[u]) + i * LPR * 4);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) {
-          float4 v = acc[u][i];
-          v.x += bias_r[i].x; v.y += bias_r[i].y; v.z += bias_r[i].z; v.w += bias_r[i].w;
-          if (EPI == EPI_GATE) {
-            const float4 g = acc2[u][i];
-            v.x *= g.x + bias2_r[i].x; v.y *= g.y + bias2_r[i].y; v.z *= g.z + bias2_r[i].z; v.w *= g.w + bias2_r[i].w;
-          }
-          if (EPI == EPI_RELU) {
-            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-          }
-          if (EPI == EPI_SIGMOID) {
-            v.x = 1.f / (1.f + __expf(-v.x)); v.y = 1.f / (1.f + __expf(-v.y));
-            v.z = 1.f / (1.f + __expf(-v.z)); v.w = 1.f / (1.f + __expf(-v.w));
-          }
-          if (EPI == EPI_RESID || EPI == EPI_PIXSHUF) {
-            v.x += ext[u][i].x; v.y += ext[u][i].y; v.z += ext[u][i].z; v.w += ext[u][i].w;
-          }
-          if (ok[u]) store4<TOut>(dst[u] + i * LPR * 4, v);
+          finish(v, g, e, i, d, okay);
         }
       }
     }
   }
 
+  if (trace != nullptr && threadIdx.x == 64) trace[7] = clock64();
   // no CTA may exit (or free TMEM) while a peer can still read its staging tile
   if (nsplit > 1) cluster_sync_all(); else __syncthreads();
+  if (trace != nullptr && threadIdx.x == 0) trace[8] = clock64();
   if (warp == 1) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);

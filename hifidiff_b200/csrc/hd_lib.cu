@@ -54,6 +54,26 @@ constexpr float kBnEps = 1e-5f;
 
 inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
+bool g_use_pdl = true;  // HD_PDL=0 disables programmatic dependent launch
+
+// Per-step kernel launch: programmatic stream serialization lets kernel N+1 be scheduled (and run its
+// prologue / weight prefetch) while kernel N drains; every such kernel executes pdl_wait() first.
+template <typename... KArgs, typename... Args>
+void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------------
 // chunked bump allocator for everything the library owns on the device
 // ------------------------------------------------------------------------------------------------
@@ -206,11 +226,11 @@ void launch_simt_typed(const GemmDesc& d, cudaStream_t st) {
   g.out = d.out; g.ldo = d.ldo; g.resid = d.resid; g.ldr = d.ldr;
   dim3 grid(cdiv(d.M, simt::TM), cdiv(d.N, simt::TN));
   switch (d.epi) {
-    case EPI_BIAS: simt::gemm_simt_kernel<TA, TW, TOut, EPI_BIAS><<<grid, 256, 0, st>>>(g); break;
-    case EPI_RELU: simt::gemm_simt_kernel<TA, TW, TOut, EPI_RELU><<<grid, 256, 0, st>>>(g); break;
-    case EPI_SIGMOID: simt::gemm_simt_kernel<TA, TW, TOut, EPI_SIGMOID><<<grid, 256, 0, st>>>(g); break;
-    case EPI_RESID: simt::gemm_simt_kernel<TA, TW, TOut, EPI_RESID><<<grid, 256, 0, st>>>(g); break;
-    case EPI_PIXSHUF: simt::gemm_simt_kernel<TA, TW, TOut, EPI_PIXSHUF><<<grid, 256, 0, st>>>(g); break;
+    case EPI_BIAS: launch_k(simt::gemm_simt_kernel<TA, TW, TOut, EPI_BIAS>, grid, 256, 0, st, g); break;
+    case EPI_RELU: launch_k(simt::gemm_simt_kernel<TA, TW, TOut, EPI_RELU>, grid, 256, 0, st, g); break;
+    case EPI_SIGMOID: launch_k(simt::gemm_simt_kernel<TA, TW, TOut, EPI_SIGMOID>, grid, 256, 0, st, g); break;
+    case EPI_RESID: launch_k(simt::gemm_simt_kernel<TA, TW, TOut, EPI_RESID>, grid, 256, 0, st, g); break;
+    case EPI_PIXSHUF: launch_k(simt::gemm_simt_kernel<TA, TW, TOut, EPI_PIXSHUF>, grid, 256, 0, st, g); break;
     default: break;
   }
 }
@@ -246,13 +266,15 @@ void launch_tc_inst2(const TcLaunch& L, cudaStream_t st) {
   cfg.blockDim = dim3(tc::NUM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = L.grid.z;  // split-K CTAs of one tile form a cluster
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_use_pdl ? 2 : 1;
   cudaLaunchKernelEx(&cfg, kern, L.mapA, L.mapB, L.args);
 }
 
@@ -303,6 +325,7 @@ TcLaunch build_tc(hd_handle* h, const GemmDesc& d, long long a_rows_alloc) {
   a.bias = d.bias; a.out = d.out; a.ldo = d.ldo; a.resid = d.resid; a.ldr = d.ldr;
   a.sp = d.sp; a.kb_per_tap = 1; a.conv_bh = 1; a.conv_bb = 1;
   a.status = h->d_status;
+  a.trace = nullptr;
   if (d.a_mode == A_CONV3) {
     const int n = d.sp, C = d.C;
     if (128 % n != 0 || (n * n < 128 && 128 % (n * n) != 0)) HD_THROW(HD_ERR_UNSUPPORTED, "conv tile: spatial %d", n);
@@ -609,8 +632,8 @@ void add_gemm(hd_handle* h, Plan& P, GemmDesc d, long long a_rows_alloc, const s
     g_label = what + " gate_packed";
     add_op(P, [=](cudaStream_t st) {
       const int blocks = cdiv(rows * c, 256);
-      if (odt == DT_BF16) gate_packed_kernel<bf16><<<blocks, 256, 0, st>>>(tmp, static_cast<bf16*>(out), rows, c);
-      else gate_packed_kernel<float><<<blocks, 256, 0, st>>>(tmp, static_cast<float*>(out), rows, c);
+      if (odt == DT_BF16) launch_k(gate_packed_kernel<bf16>, dim3(blocks), dim3(256), 0, st, tmp, static_cast<bf16*>(out), rows, c);
+      else launch_k(gate_packed_kernel<float>, dim3(blocks), dim3(256), 0, st, tmp, static_cast<float*>(out), rows, c);
     }, tap, info);
     return;
   }
@@ -626,11 +649,11 @@ void launch_ln(int c, const float* x, const float* lw, const float* lb, T* out, 
   const int lpr = std::min(32, c / 16);
   const int grid = cdiv(rows, 4 * (32 / lpr));  // 4 warps per block, 32/lpr rows per warp
   switch (c) {
-    case 128: ln_mod_kernel<128, T><<<grid, 128, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
-    case 256: ln_mod_kernel<256, T><<<grid, 128, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
-    case 512: ln_mod_kernel<512, T><<<grid, 128, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
-    case 1024: ln_mod_kernel<1024, T><<<grid, 128, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
-    case 2048: ln_mod_kernel<2048, T><<<grid, 128, 0, st>>>(x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
+    case 128: launch_k(ln_mod_kernel<128, T>, dim3(grid), dim3(128), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
+    case 256: launch_k(ln_mod_kernel<256, T>, dim3(grid), dim3(128), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
+    case 512: launch_k(ln_mod_kernel<512, T>, dim3(grid), dim3(128), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
+    case 1024: launch_k(ln_mod_kernel<1024, T>, dim3(grid), dim3(128), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
+    case 2048: launch_k(ln_mod_kernel<2048, T>, dim3(grid), dim3(128), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
     default: break;
   }
 }
@@ -669,9 +692,9 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
     const float *dw_w = bw.dw_w, *dw_b = bw.dw_b;
     add_op(P, [=](cudaStream_t st) {
       dim3 grid(c / 64, cdiv(rows, 256));
-      if (bf) dwconv_gate_pool_kernel<bf16><<<grid, 256, 256 * 128 * 2, st>>>(static_cast<const bf16*>(act_h), dw_w, dw_b,
+      if (bf) launch_k(dwconv_gate_pool_kernel<bf16>, dim3(grid), dim3(256), 256 * 128 * 2, st, static_cast<const bf16*>(act_h), dw_w, dw_b,
                                                                   static_cast<bf16*>(act_g), static_cast<bf16*>(pooled), sp, c, rows);
-      else dwconv_gate_pool_kernel<float><<<grid, 256, 256 * 128 * 4, st>>>(static_cast<const float*>(act_h), dw_w, dw_b,
+      else launch_k(dwconv_gate_pool_kernel<float>, dim3(grid), dim3(256), 256 * 128 * 4, st, static_cast<const float*>(act_h), dw_w, dw_b,
                                                                 static_cast<float*>(act_g), static_cast<float*>(pooled), sp, c, rows);
     });
     P.flops_per_face += 2.0 * 9 * 2 * c * rpf;
@@ -687,8 +710,8 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
   g_label = L0 + "scale_rows";
   add_op(P, [=](cudaStream_t st) {
     const size_t total8 = static_cast<size_t>(rows) * c / 8;
-    if (bf) scale_rows_kernel<bf16><<<cdiv(total8, 256), 256, 0, st>>>(static_cast<bf16*>(act_g), sca_s, total8, c, rpf);
-    else scale_rows_kernel<float><<<cdiv(total8, 256), 256, 0, st>>>(static_cast<float*>(act_g), sca_s, total8, c, rpf);
+    if (bf) launch_k(scale_rows_kernel<bf16>, dim3(cdiv(total8, 256)), dim3(256), 0, st, static_cast<bf16*>(act_g), sca_s, total8, c, rpf);
+    else launch_k(scale_rows_kernel<float>, dim3(cdiv(total8, 256)), dim3(256), 0, st, static_cast<float*>(act_g), sca_s, total8, c, rpf);
   });
   g_label = L0 + "conv3";
   {  // conv3 (+beta) + residual
@@ -734,8 +757,8 @@ void add_hca(hd_handle* h, Plan& P, int j, int level) {
   g_label = fmt("hca%d apply", j);
   add_op(P, [=](cudaStream_t st) {
     const size_t total8 = static_cast<size_t>(rows) * d / 8;
-    if (bf) hca_apply_kernel<bf16><<<cdiv(total8, 256), 256, 0, st>>>(fd, wc, ws, idc, static_cast<bf16*>(act_a), total8, d, rpf);
-    else hca_apply_kernel<float><<<cdiv(total8, 256), 256, 0, st>>>(fd, wc, ws, idc, static_cast<float*>(act_a), total8, d, rpf);
+    if (bf) launch_k(hca_apply_kernel<bf16>, dim3(cdiv(total8, 256)), dim3(256), 0, st, fd, wc, ws, idc, static_cast<bf16*>(act_a), total8, d, rpf);
+    else launch_k(hca_apply_kernel<float>, dim3(cdiv(total8, 256)), dim3(256), 0, st, fd, wc, ws, idc, static_cast<float*>(act_a), total8, d, rpf);
   });
   GemmDesc g;
   g.M = rows; g.N = d; g.A = act_a; g.a_dtype = adt; g.w_dtype = adt; g.bias = w.bf; g.epi = EPI_RELU;
@@ -769,7 +792,7 @@ Plan* get_plan(hd_handle* h, int B) {
     ti.ptr = out; ti.dtype = DT_F32; ti.C = kWidth; ti.HW = S * S; ti.ld = kWidth;
     g_label = "intro conv3x3";
     add_op(P, [=](cudaStream_t st) {
-      intro_conv_kernel<<<B, 256, (36 * 128 + 4 * (S + 2) * (S + 2)) * sizeof(float), st>>>(h->cur_x, w, b, out, S);
+      launch_k(intro_conv_kernel, dim3(B), dim3(256), (36 * 128 + 4 * (S + 2) * (S + 2)) * sizeof(float), st, h->cur_x, w, b, out, S);
     }, "intro", ti);
     P.flops_per_face += 2.0 * 36 * 128 * S * S;
   }
@@ -784,8 +807,8 @@ Plan* get_plan(hd_handle* h, int B) {
     g_label = fmt("down%d s2d", l);
     add_op(P, [=](cudaStream_t st) {
       const size_t total8 = static_cast<size_t>(rows_out) * 4 * c / 8;
-      if (bf) s2d_kernel<bf16><<<cdiv(total8, 256), 256, 0, st>>>(src, static_cast<bf16*>(act_a), B, n, c);
-      else s2d_kernel<float><<<cdiv(total8, 256), 256, 0, st>>>(src, static_cast<float*>(act_a), B, n, c);
+      if (bf) launch_k(s2d_kernel<bf16>, dim3(cdiv(total8, 256)), dim3(256), 0, st, src, static_cast<bf16*>(act_a), B, n, c);
+      else launch_k(s2d_kernel<float>, dim3(cdiv(total8, 256)), dim3(256), 0, st, src, static_cast<float*>(act_a), B, n, c);
     });
     GemmDesc d;
     d.M = rows_out; d.N = 2 * c; d.K = 4 * c; d.A = act_a; d.lda = 4 * c; d.a_dtype = adt;
@@ -811,8 +834,8 @@ Plan* get_plan(hd_handle* h, int B) {
       g_label = fmt("up%d cast", L);
       add_op(P, [=](cudaStream_t st) {
         const size_t total8 = static_cast<size_t>(rows_in) * cin / 8;
-        if (bf) cast_kernel<bf16><<<cdiv(total8, 256), 256, 0, st>>>(src, static_cast<bf16*>(act_a), total8);
-        else cast_kernel<float><<<cdiv(total8, 256), 256, 0, st>>>(src, static_cast<float*>(act_a), total8);
+        if (bf) launch_k(cast_kernel<bf16>, dim3(cdiv(total8, 256)), dim3(256), 0, st, src, static_cast<bf16*>(act_a), total8);
+        else launch_k(cast_kernel<float>, dim3(cdiv(total8, 256)), dim3(256), 0, st, src, static_cast<float*>(act_a), total8);
       });
     }
     GemmDesc d;
@@ -834,8 +857,8 @@ Plan* get_plan(hd_handle* h, int B) {
     g_label = "ending conv3x3";
     add_op(P, [=](cudaStream_t st) {
       const size_t wbytes = 4 * 9 * 128 * sizeof(float);
-      if (in_bf) ending_conv_kernel<bf16><<<B, 256, S * S * 128 * 2 + wbytes, st>>>(static_cast<const bf16*>(in), w, b, h->cur_eps, B, S);
-      else ending_conv_kernel<float><<<B, 256, S * S * 128 * 4 + wbytes, st>>>(static_cast<const float*>(in), w, b, h->cur_eps, B, S);
+      if (in_bf) launch_k(ending_conv_kernel<bf16>, dim3(B), dim3(256), S * S * 128 * 2 + wbytes, st, static_cast<const bf16*>(in), w, b, h->cur_eps, B, S);
+      else launch_k(ending_conv_kernel<float>, dim3(B), dim3(256), S * S * 128 * 4 + wbytes, st, static_cast<const float*>(in), w, b, h->cur_eps, B, S);
     });
     P.flops_per_face += 2.0 * 9 * 128 * 4 * S * S;
   }
@@ -1024,6 +1047,7 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   cudaDeviceProp prop;
   CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10) HD_THROW(HD_ERR_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+  if (const char* e = getenv("HD_PDL")) g_use_pdl = atoi(e) != 0;
   h = new hd_handle();
   struct Guard { hd_handle*& p; bool armed = true; ~Guard() { if (armed && p) { hd_destroy(p); p = nullptr; } } } guard{h};
   h->cfg = *cfg;
@@ -1292,8 +1316,8 @@ int32_t hd_sample(hd_handle* h, float* x_inout, const hd_step_coef* coef, int32_
   const int Bcap = h->Bcap;
   auto one_step = [&](cudaStream_t s) {
     for (auto& op : P->ops) op.fn(s);
-    sampler_update_kernel<<<cdiv(threads, 256), 256, 0, s>>>(xs, eb, cf, ss, 0, noise, seed, first_face, B, epf);
-    advance_rows_kernel<<<1, 256, 0, s>>>(ss, ridx, Bcap);
+    launch_k(sampler_update_kernel, dim3(cdiv(threads, 256)), dim3(256), 0, s, xs, eb, cf, ss, 0, noise, seed, first_face, B, epf);
+    launch_k(advance_rows_kernel, dim3(1), dim3(256), 0, s, ss, ridx, Bcap);
   };
   // The graph bakes in seed / first_face / noise: re-capture when they change.
   static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "seed width");
@@ -1339,10 +1363,14 @@ int32_t hd_profile_step(hd_handle* h, int32_t batch, int32_t reps, float* ms_out
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
   std::vector<double> acc(n, 0.0);
-  for (int rep = 0; rep < reps + 1; ++rep) {
+  const int outer = reps < 0 ? -reps : reps;
+  for (int rep = 0; rep < outer + 1; ++rep) {
     CUDA_CHECK(cudaEventRecord(ev[0], st));
     for (int i = 0; i < n; ++i) {
-      P->ops[i].fn(st);
+      // reps < 0: run each launch 16x back to back so event and launch latency amortise
+      // (the step's numerics are meaningless in that mode)
+      const int inner = reps < 0 ? 16 : 1;
+      for (int k = 0; k < inner; ++k) P->ops[i].fn(st);
       CUDA_CHECK(cudaEventRecord(ev[i + 1], st));
     }
     CUDA_CHECK(cudaStreamSynchronize(st));
@@ -1354,7 +1382,7 @@ int32_t hd_profile_step(hd_handle* h, int32_t batch, int32_t reps, float* ms_out
     }
   }
   for (int i = 0; i < n; ++i) {
-    ms_out[i] = static_cast<float>(acc[i] / std::max(reps, 1));
+    ms_out[i] = static_cast<float>(acc[i] / std::max(outer, 1) / (reps < 0 ? 16 : 1));
     if (labels_out && label_stride > 0) {
       strncpy(labels_out + static_cast<size_t>(i) * label_stride, P->ops[i].label.c_str(), label_stride - 1);
       labels_out[static_cast<size_t>(i) * label_stride + label_stride - 1] = 0;
@@ -1373,6 +1401,32 @@ int32_t hd_synchronize(hd_handle* h) {
   CUDA_CHECK(cudaGetLastError());
   check_device_status(h);
   HD_API_END(h)
+}
+
+static long long* g_trace_dev = nullptr;  // set by hd_debug_gemm_trace around one hd_debug_gemm call
+static int g_trace_ctas = 0;
+
+int32_t hd_debug_gemm_trace(hd_handle* h, const float* a, const float* w, float* out, int32_t m, int32_t n, int32_t k,
+                            long long* trace_host, int32_t cap_ctas, int32_t* n_ctas, int32_t* grid_xyz) {
+  int32_t rc;
+  {
+    HD_API_BEGIN
+    if (!h || !trace_host || !n_ctas) HD_THROW(HD_ERR_INVALID, "null argument");
+    CUDA_CHECK(cudaSetDevice(h->cfg.device));
+    CUDA_CHECK(cudaMalloc(&g_trace_dev, static_cast<size_t>(cap_ctas) * 16 * sizeof(long long)));
+    CUDA_CHECK(cudaMemset(g_trace_dev, 0, static_cast<size_t>(cap_ctas) * 16 * sizeof(long long)));
+    g_trace_ctas = cap_ctas;
+    } catch (const HdError& e) { h->err = e.msg; return e.code; }
+  }
+  rc = hd_debug_gemm(h, a, w, nullptr, out, m, n, k, 1, nullptr);
+  if (rc == HD_OK) {
+    cudaMemcpy(trace_host, g_trace_dev, static_cast<size_t>(cap_ctas) * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+    *n_ctas = g_trace_ctas;
+    if (grid_xyz) { grid_xyz[0] = g_trace_ctas; }
+  }
+  cudaFree(g_trace_dev);
+  g_trace_dev = nullptr;
+  return rc;
 }
 
 int32_t hd_debug_gemm(hd_handle* h, const float* a, const float* w, const float* bias, float* out, int32_t m,
@@ -1399,13 +1453,23 @@ int32_t hd_debug_gemm(hd_handle* h, const float* a, const float* w, const float*
     CUDA_CHECK(cudaMalloc(&dw, static_cast<size_t>(n) * k * 2));
     CUDA_CHECK(cudaMemsetAsync(da, 0, m_alloc * k * 2, st));
     const size_t ta = static_cast<size_t>(m) * k / 8, tw = static_cast<size_t>(n) * k / 8;
-    cast_kernel<bf16><<<cdiv(ta, 256), 256, 0, st>>>(a, static_cast<bf16*>(da), ta);
-    cast_kernel<bf16><<<cdiv(tw, 256), 256, 0, st>>>(w, static_cast<bf16*>(dw), tw);
+    launch_k(cast_kernel<bf16>, dim3(cdiv(ta, 256)), dim3(256), 0, st, a, static_cast<bf16*>(da), ta);
+    launch_k(cast_kernel<bf16>, dim3(cdiv(tw, 256)), dim3(256), 0, st, w, static_cast<bf16*>(dw), tw);
     d.A = da; d.W = dw; d.a_dtype = DT_BF16; d.w_dtype = DT_BF16;
     const bool saved = h->bf16;
     TcLaunch L = build_tc(h, d, m_alloc);
     (void)saved;
+    launch_tc(L, st);  // warm-up (also warms L2 with the operands)
     launch_tc(L, st);
+    if (g_trace_dev != nullptr) {
+      const int ctas = static_cast<int>(L.grid.x * L.grid.y * L.grid.z);
+      if (ctas <= g_trace_ctas) {
+        L.args.trace = g_trace_dev;
+        g_trace_ctas = ctas;
+        launch_tc(L, st);
+        L.args.trace = nullptr;
+      }
+    }
   } else {
     d.A = a; d.W = w;
     launch_simt(d, st);

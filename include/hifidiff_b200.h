@@ -167,6 +167,13 @@ int32_t hd_profile_step(hd_handle* h, int32_t batch, int32_t reps, float* ms_out
 int32_t hd_debug_gemm(hd_handle* h, const float* a, const float* w, const float* bias, float* out,
                       int32_t m, int32_t n, int32_t k, int32_t use_tensor_cores, void* stream);
 
+/* hd_debug_gemm on the tensor-core path with a per-CTA clock64 timeline (16 slots per CTA:
+ * 0 entry, 1 setup done, 2 first operands landed, 3 last MMA issued, 4 accumulator ready,
+ * 5 staged, 6 after tile barrier, 7 stored, 8 exit, 9 globaltimer at entry, 10 SM id). */
+int32_t hd_debug_gemm_trace(hd_handle* h, const float* a, const float* w, float* out, int32_t m, int32_t n,
+                            int32_t k, long long* trace_host, int32_t cap_ctas, int32_t* n_ctas,
+                            int32_t* grid_xyz);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@ import hifidiff_b200 as H  # noqa: E402
 from hifidiff_b200 import testing  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+REPS = int(sys.argv[2]) if len(sys.argv) > 2 else 10  # negative: each launch 16x back to back
 with torch.device("meta"):
     m = H.FusedDenoiser(16)
 sd0 = m.state_dict()
@@ -32,7 +33,7 @@ cap, stride = 1024, 160
 ms = (C.c_float * cap)()
 labels = C.create_string_buffer(cap * stride)
 n = C.c_int32()
-eng.check(eng.lib.hd_profile_step(eng.handle, B, 10, ms, labels, stride, cap, C.byref(n)), "hd_profile_step")
+eng.check(eng.lib.hd_profile_step(eng.handle, B, REPS, ms, labels, stride, cap, C.byref(n)), "hd_profile_step")
 rows = [(labels.raw[i * stride:(i + 1) * stride].split(b"\0")[0].decode(), ms[i] * 1e3) for i in range(n.value)]
 tot = sum(v for _, v in rows)
 print(f"# B={B}: {n.value} launches, {tot:.1f} us per step (event-to-event, warm)")
