@@ -170,37 +170,54 @@ __global__ void __launch_bounds__(128) ln_mod_kernel(const float* __restrict__ x
 // depthwise 3x3 (pad 1, bias) + SimpleGate + global average pool (conditional_naf.py:117-119, 54-65)
 //   in  h [B, sp, sp, 2c]   (x1 = channels [0,c), x2 = channels [c,2c))
 //   out g [B, sp, sp, c] = dw(x1) * dw(x2) ;  pooled[B, c] = mean_hw(g)
-// One block = 256 pixels (256/sp^2 whole faces) x 64 gate channels.  The 256 x 128 input tile is
-// staged in shared memory with independent 16-byte loads (high memory-level parallelism), the
-// 9-tap stencil runs out of shared memory, the gated tile goes back through shared memory (fp32)
-// for the per-face pooled means.   grid (c/64, ceil(B*sp^2/256)), block 256, dynamic smem 256*128*sizeof(T)
+// One block = 256 pixels (256/sp^2 whole faces) x 64 gate channels, staged in shared memory with
+// independent 16-byte loads.  A thread owns 2 gate channels (2 x1 + 2 x2 inputs) with all 36 filter
+// taps in registers and walks image columns top to bottom with a 3x3 register window, so each new
+// output pixel costs 3 shared-memory loads per half instead of 9 (the kernel is instruction-bound,
+// not bandwidth-bound).  Column sums go through shared memory and are added per face in fixed
+// order (deterministic).  tile_px = 256 at 16x16 (one face), 64 below (more blocks).
+// grid (c/64, ceil(B*sp^2/tile_px)), block 256, dynamic smem tile_px*128*sizeof(T)
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ld_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 ld_pair(const bf16* p) { return unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p)); }
+__device__ __forceinline__ void st_pair(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void st_pair(bf16* p, float a, float b) { *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(a, b); }
+
 template <typename T>
-__global__ void __launch_bounds__(256) dwconv_gate_pool_kernel(const T* __restrict__ h, const float* __restrict__ w9,
-                                                               const float* __restrict__ bias, T* __restrict__ g,
-                                                               T* __restrict__ pooled, int sp, int c, int total_px) {
+__global__ void __launch_bounds__(256, 2) dwconv_gate_pool_kernel(const T* __restrict__ h, const float* __restrict__ w9,
+                                                                  const float* __restrict__ bias, T* __restrict__ g,
+                                                                  T* __restrict__ pooled, int sp, int c, int total_px,
+                                                                  int tile_px) {
   extern __shared__ __align__(16) uint8_t s_dw_raw[];
-  T* tile = reinterpret_cast<T*>(s_dw_raw);             // [256 px][128 ch]: x1 chunk | x2 chunk
-  float* gout = reinterpret_cast<float*>(s_dw_raw);     // aliases the tile after the stencil: [256 px][64]
-  __shared__ float s_w[9][2][64];
-  __shared__ float s_b[2][64];
+  T* tile = reinterpret_cast<T*>(s_dw_raw);             // [tile_px][128 ch]: 64 x1 | 64 x2
+  float* colsum = reinterpret_cast<float*>(s_dw_raw);   // aliases the tile after the stencil: [tile_px/sp columns][64]
   const int j0 = blockIdx.x * 64;
-  const int px0 = blockIdx.y * 256;
+  const int px0 = blockIdx.y * tile_px;
   const int C2 = 2 * c;
   const int npix = sp * sp;
+  const int cl = threadIdx.x & 31;   // channel lane: gate channels j0 + 2*cl, +1
+  const int pl = threadIdx.x >> 5;   // column lane (8)
   pdl_trigger();
-  for (int i = threadIdx.x; i < 9 * 2 * 64; i += blockDim.x) {
-    const int tap = i / 128, half = (i / 64) & 1, ch = i & 63;
-    s_w[tap][half][ch] = w9[tap * C2 + half * c + j0 + ch];
+  // filter taps and biases of this thread's 2+2 channels (constants: before the dependency wait)
+  float w1[9][2], w2[9][2], b1[2], b2[2];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float2 a = *reinterpret_cast<const float2*>(w9 + t * C2 + j0 + 2 * cl);
+    const float2 b = *reinterpret_cast<const float2*>(w9 + t * C2 + c + j0 + 2 * cl);
+    w1[t][0] = a.x; w1[t][1] = a.y; w2[t][0] = b.x; w2[t][1] = b.y;
   }
-  if (threadIdx.x < 128) s_b[threadIdx.x >> 6][threadIdx.x & 63] = bias[(threadIdx.x >> 6) * c + j0 + (threadIdx.x & 63)];
+  {
+    const float2 a = *reinterpret_cast<const float2*>(bias + j0 + 2 * cl);
+    const float2 b = *reinterpret_cast<const float2*>(bias + c + j0 + 2 * cl);
+    b1[0] = a.x; b1[1] = a.y; b2[0] = b.x; b2[1] = b.y;
+  }
   pdl_wait();
-  // stage: 256 px x 16 chunks of 8 channels (chunks 0-7: x1, 8-15: x2)
+  // stage: 256 px x 16 chunks of 16 bytes (bf16: 8 ch; fp32: two 16-byte halves of 8 ch)
   {
     const int chunk = threadIdx.x & 15;
     const int half = chunk >> 3, cc = (chunk & 7) * 8;
 #pragma unroll 4
-    for (int r = threadIdx.x >> 4; r < 256; r += 16) {
+    for (int r = threadIdx.x >> 4; r < tile_px; r += 16) {
       const int p = px0 + r;
       uint4 v = make_uint4(0, 0, 0, 0);
       uint4 v2 = make_uint4(0, 0, 0, 0);
@@ -216,52 +233,86 @@ __global__ void __launch_bounds__(256) dwconv_gate_pool_kernel(const T* __restri
   }
   __syncthreads();
 
-  const int ct = threadIdx.x & 7, pt = threadIdx.x >> 3;
-  float o[8][8];  // [pixel i][channel]
+  const int ncols = tile_px / sp;  // image columns in the tile (all faces), each sp pixels tall
+  const T* t1 = tile + 2 * cl;
+  const T* t2 = tile + 64 + 2 * cl;
+  float csum[32][2];           // per-column sums of this thread (at most 256/sp/8 = 32 columns for sp = 1)
+  int ncol_mine = 0;
+  for (int col = pl; col < ncols; col += 8, ++ncol_mine) {
+    const int f = col / sp, x = col - f * sp;        // face within the tile, image column
+    const int base = f * npix + x;                   // pixel (y = 0, x) of that face, tile-relative
+    const bool has_l = x > 0, has_r = x + 1 < sp;
+    // window rows: top (y-1), mid (y), bot (y+1); each 3 pixels x (2 x1 + 2 x2)
+    float top1[3][2], top2[3][2], mid1[3][2], mid2[3][2], bot1[3][2], bot2[3][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = pt + 32 * i;               // pixel within the tile
-    const int pf = r % npix;                 // pixel within its face (tiles hold whole faces)
-    const int py = pf / sp, pxx = pf - py * sp;
-    float a1[8], a2[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { a1[k] = s_b[0][ct * 8 + k]; a2[k] = s_b[1][ct * 8 + k]; }
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-      const int yy = py + dy, xx = pxx + dx;
-      if (yy < 0 || yy >= sp || xx < 0 || xx >= sp) continue;
-      const T* src = tile + (r + dy * sp + dx) * 128 + ct * 8;
-      float v1[8], v2[8];
-      load8(src, v1);
-      load8(src + 64, v2);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        a1[k] = fmaf(v1[k], s_w[tap][0][ct * 8 + k], a1[k]);
-        a2[k] = fmaf(v2[k], s_w[tap][1][ct * 8 + k], a2[k]);
-      }
+    for (int k = 0; k < 3; ++k) {
+      top1[k][0] = top1[k][1] = top2[k][0] = top2[k][1] = 0.f;
+      mid1[k][0] = mid1[k][1] = mid2[k][0] = mid2[k][1] = 0.f;
     }
+    auto load_row = [&](int y, float (&r1)[3][2], float (&r2)[3][2]) {
+      const int p = base + y * sp;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[i][k] = a1[k] * a2[k];
-    const int p = px0 + r;
-    if (p < total_px) store8(g + static_cast<size_t>(p) * c + j0 + ct * 8, o[i]);
+      for (int k = 0; k < 3; ++k) {
+        const bool ok = (k == 1) || (k == 0 ? has_l : has_r);
+        float2 a = make_float2(0.f, 0.f), b = a;
+        if (ok) {
+          a = ld_pair(t1 + (p + k - 1) * 128);
+          b = ld_pair(t2 + (p + k - 1) * 128);
+        }
+        r1[k][0] = a.x; r1[k][1] = a.y; r2[k][0] = b.x; r2[k][1] = b.y;
+      }
+    };
+    load_row(0, mid1, mid2);
+    float s0 = 0.f, s1 = 0.f;
+    for (int y = 0; y < sp; ++y) {
+      if (y + 1 < sp) {
+        load_row(y + 1, bot1, bot2);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bot1[k][0] = bot1[k][1] = bot2[k][0] = bot2[k][1] = 0.f;
+      }
+      float a1[2] = {b1[0], b1[1]}, a2[2] = {b2[0], b2[1]};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          a1[e] = fmaf(top1[k][e], w1[k][e], a1[e]);
+          a1[e] = fmaf(mid1[k][e], w1[3 + k][e], a1[e]);
+          a1[e] = fmaf(bot1[k][e], w1[6 + k][e], a1[e]);
+          a2[e] = fmaf(top2[k][e], w2[k][e], a2[e]);
+          a2[e] = fmaf(mid2[k][e], w2[3 + k][e], a2[e]);
+          a2[e] = fmaf(bot2[k][e], w2[6 + k][e], a2[e]);
+        }
+      }
+      const float o0 = a1[0] * a2[0], o1 = a1[1] * a2[1];
+      s0 += o0; s1 += o1;
+      const int p = px0 + base + y * sp;
+      if (p < total_px) st_pair(g + static_cast<size_t>(p) * c + j0 + 2 * cl, o0, o1);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          top1[k][e] = mid1[k][e]; top2[k][e] = mid2[k][e];
+          mid1[k][e] = bot1[k][e]; mid2[k][e] = bot2[k][e];
+        }
+    }
+    csum[ncol_mine][0] = s0;
+    csum[ncol_mine][1] = s1;
   }
   __syncthreads();  // everyone is done reading the input tile
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float* dst = gout + (pt + 32 * i) * 64 + ct * 8;
-    *reinterpret_cast<float4*>(dst) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
-    *reinterpret_cast<float4*>(dst + 4) = make_float4(o[i][4], o[i][5], o[i][6], o[i][7]);
+  {
+    int i = 0;
+    for (int col = pl; col < ncols; col += 8, ++i) st_pair(colsum + col * 64 + 2 * cl, csum[i][0], csum[i][1]);
   }
   __syncthreads();
-  // per-face means: (256 / npix) faces x 64 channels
-  const int faces_in_tile = 256 / npix;
+  // per-face means: (256 / npix) faces x 64 channels, columns added in fixed order
+  const int faces_in_tile = tile_px / npix;
   for (int i = threadIdx.x; i < faces_in_tile * 64; i += blockDim.x) {
     const int f = i >> 6, ch = i & 63;
     const int face = px0 / npix + f;
     if (face * npix >= total_px) continue;
     float sum = 0.f;
-    for (int q = 0; q < npix; ++q) sum += gout[(f * npix + q) * 64 + ch];
+    for (int q = 0; q < sp; ++q) sum += colsum[(f * sp + q) * 64 + ch];
     pooled[static_cast<size_t>(face) * c + j0 + ch] = from_f32<T>(sum / static_cast<float>(npix));
   }
 }

@@ -5,8 +5,10 @@
 //               multi-stage shared-memory ring, 128B-swizzled, completion on an mbarrier.
 //   warp 1      allocates TMEM, issues tcgen05.mma (M=128, N=BN, K=16, kind::f16) from one thread,
 //               frees ring slots with tcgen05.commit.
-//   warps 2-5   epilogue: tcgen05.ld the fp32 accumulator (one TMEM lane = one output row) and
-//               apply bias / ReLU / residual add / SimpleGate / PixelShuffle scatter.
+//   warps 2-9   epilogue: tcgen05.ld the fp32 accumulator (one TMEM lane = one output row; two warps per
+//               lane quadrant, half the columns each) into a staging tile, then apply bias / ReLU /
+//               residual add / SimpleGate / PixelShuffle scatter row-coalesced.  Eight warps because the
+//               epilogue is issue-latency-bound: rows are independent, more warps = more rows in flight.
 // The A operand is either a dense [M,K] matrix (1x1 convs, linears, packed 2x2-s2 convs) or an
 // implicit 3x3/pad-1 im2col over an NHWC tensor fetched with a 4-D tensor map whose out-of-bounds
 // zero fill supplies the padding (the HCA fused 3x3, reference models/fpg/hca.py:21-23).
@@ -20,7 +22,8 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 64;       // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;                      // two per TMEM lane quadrant
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 
 struct TcArgs {
   int M, N, num_kb;           // rows, packed weight rows, K / 64
@@ -48,7 +51,8 @@ template <int BN, int STAGES> struct TileCfg {
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;               // power of two >= 32
   // co-resident CTAs per SM (228 KB shared memory, 512 TMEM columns): short-K GEMMs are dominated by
   // prologue/epilogue, so several small CTAs per SM overlap one tile's epilogue with another's mainloop
-  static constexpr int MIN_BLOCKS = SMEM_BYTES <= 74 * 1024 ? 3 : (SMEM_BYTES <= 113 * 1024 ? 2 : 1);
+  // (320 threads per CTA: two CTAs keep the register budget at ~100 per thread)
+  static constexpr int MIN_BLOCKS = SMEM_BYTES <= 113 * 1024 ? 2 : 1;
   static_assert(MIN_BLOCKS * TMEM_COLS <= 512, "TMEM over-subscribed");
 };
 
@@ -267,6 +271,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     mbar_init(smem_u32(tmem_full_bar), 1);
     fence_barrier_init();
     fence_proxy_async_smem();
+    // Weights do not depend on the preceding kernel: fill the ring's W halves right away — before the
+    // CTA-wide setup barrier (TMEM allocation) and before the programmatic-dependency wait — so the
+    // weight stream overlaps both this CTA's setup and the predecessor's tail.
+    const int pre0 = kb_count < STAGES ? kb_count : STAGES;
+    for (int i = 0; i < pre0; ++i) {
+      const uint32_t fb = smem_u32(&full_bar[i]);
+      mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+      tma_load_2d(smem_u32(smem + i * Cfg::STAGE_BYTES) + Cfg::A_BYTES, &mapB, (kb_begin + i) * BK, n0, fb);
+    }
   }
   if (warp == 1) {
     tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
@@ -292,14 +305,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           conv_h0 = (m_tile % tiles_per_face) * args.conv_bh;
         }
       }
-      // Weights do not depend on the preceding kernel: fill the ring's W halves before the
-      // programmatic-dependency wait, so the weight stream overlaps the predecessor's tail.
-      const int pre = kb_count < STAGES ? kb_count : STAGES;
-      for (int i = 0; i < pre; ++i) {
-        const uint32_t fb = smem_u32(&full_bar[i]);
-        mbar_expect_tx(fb, Cfg::STAGE_BYTES);
-        tma_load_2d(smem_u32(smem + i * Cfg::STAGE_BYTES) + Cfg::A_BYTES, &mapB, (kb_begin + i) * BK, n0, fb);
-      }
+      const int pre = kb_count < STAGES ? kb_count : STAGES;  // W halves already in flight (setup)
       pdl_wait();
       for (int i = 0; i < kb_count; ++i) {
         const int kb = kb_begin + i;
@@ -357,8 +363,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int r = quad * 32 + lane;
     const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     float* srow = stage + r * BN;
+    constexpr int COLS_PER_WARP = BN / (NUM_EPI_WARPS / 4);
+    const int cbeg = ((warp - 2) >> 2) * COLS_PER_WARP;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = cbeg; c0 < cbeg + COLS_PER_WARP; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(taddr_row + c0, v);
       tmem_wait_ld();
@@ -408,7 +416,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (EPI == EPI_GATE) bias2_r[i] = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + 64 + ck * 4));
     }
 
-    const int passes = (rows_here + 4 * RPI - 1) / (4 * RPI);
+    const int passes = (rows_here + NUM_EPI_WARPS * RPI - 1) / (NUM_EPI_WARPS * RPI);
 
     // one row-chunk: bias / activation / residual, then the store
     auto finish = [&](float4 v, float4 g, float4 e, int i, TOut* d, bool okay) {
@@ -428,7 +436,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     };
     // row bookkeeping shared by both paths
     auto locate = [&](int pass, bool& okay, int& rc, int& mc, TOut*& d) {
-      const int rl = (pass * 4 + ew) * RPI + sub;          // row within this CTA's slice
+      const int rl = (pass * NUM_EPI_WARPS + ew) * RPI + sub;  // row within this CTA's slice
       const int r = row_base + rl;
       const int m = m0 + r;
       okay = pass < passes && rl < rows_here && m < args.M;

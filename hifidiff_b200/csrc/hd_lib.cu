@@ -116,6 +116,7 @@ struct BlockW {
   void *w1 = nullptr, *wsca = nullptr, *w3 = nullptr, *w4 = nullptr, *w5 = nullptr;
   float *b1 = nullptr, *bsca = nullptr, *b3 = nullptr, *b4 = nullptr, *b5 = nullptr;
   float *dw_w = nullptr, *dw_b = nullptr;
+  bool dw_folded = false;  // 1x1 level: depthwise 3x3 == per-channel scale, folded into conv1 (gate-packed)
 };
 
 struct HcaW {
@@ -459,8 +460,29 @@ void load_block(hd_handle* h, BlockW& bw, int wdt) {
   auto beta = host_vec(h, need(h, p + "beta", {c}));
   auto gamma = host_vec(h, need(h, p + "gamma", {c}));
 
-  bw.w1 = pack_matrix(h, need(h, p + "conv1.weight", {2 * c, c}), 2 * c, c, 1, nullptr, nullptr, wdt);
-  bw.b1 = upload_f32(h, host_vec(h, need(h, p + "conv1.bias", {2 * c})));
+  if (h->sp[bw.level] == 1) {
+    // At 1x1 spatial only the centre tap of the depthwise 3x3 sees a pixel (zero padding), so
+    // conv2(conv1(x)) = dwc * (W1 x + b1) + bdw per channel: fold it into conv1 and let the
+    // SimpleGate run in conv1's epilogue (same 128-row [64 x1 | 64 x2] packing as conv4).
+    auto dw = host_vec(h, need(h, p + "conv2.weight", {2 * c, 9}));
+    auto dwb = host_vec(h, need(h, p + "conv2.bias", {2 * c}));
+    auto b1 = host_vec(h, need(h, p + "conv1.bias", {2 * c}));
+    std::vector<int> perm(2 * c);
+    std::vector<float> rs(2 * c), bp(2 * c);
+    for (int n = 0; n < 2 * c; ++n) {
+      const int g = n / 128, r = n % 128;
+      const int ch = r < 64 ? g * 64 + r : c + g * 64 + (r - 64);
+      perm[n] = ch;
+      rs[n] = dw[static_cast<size_t>(ch) * 9 + 4];
+      bp[n] = rs[n] * b1[ch] + dwb[ch];
+    }
+    bw.w1 = pack_matrix(h, need(h, p + "conv1.weight", {2 * c, c}), 2 * c, c, 1, &perm, &rs, wdt);
+    bw.b1 = upload_f32(h, bp);
+    bw.dw_folded = true;
+  } else {
+    bw.w1 = pack_matrix(h, need(h, p + "conv1.weight", {2 * c, c}), 2 * c, c, 1, nullptr, nullptr, wdt);
+    bw.b1 = upload_f32(h, host_vec(h, need(h, p + "conv1.bias", {2 * c})));
+  }
 
   {  // depthwise 3x3: [2c,1,3,3] -> [9][2c]
     auto w = host_vec(h, need(h, p + "conv2.weight", {2 * c, 9}));
@@ -680,7 +702,13 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
   g_label = L0 + "ln1";
   add_op(P, ln(bw.ln1_w, bw.ln1_b, bw.mod_off, bw.mod_off + c));
   g_label = L0 + "conv1";
-  {  // conv1
+  if (bw.dw_folded) {  // conv1 + (folded) depthwise + SimpleGate; the pooled mean over 1 pixel is g itself
+    GemmDesc d;
+    d.M = rows; d.N = 2 * c; d.K = c; d.A = act_a; d.lda = c; d.a_dtype = adt;
+    d.W = bw.w1; d.ldw = c; d.w_dtype = adt; d.bias = bw.b1; d.epi = EPI_GATE;
+    d.out = act_g; d.ldo = c; d.out_dtype = adt;
+    add_gemm(h, P, d, rows_alloc);
+  } else {  // conv1
     GemmDesc d;
     d.M = rows; d.N = 2 * c; d.K = c; d.A = act_a; d.lda = c; d.a_dtype = adt;
     d.W = bw.w1; d.ldw = c; d.w_dtype = adt; d.bias = bw.b1; d.epi = EPI_BIAS;
@@ -688,21 +716,22 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
     add_gemm(h, P, d, rows_alloc);
   }
   g_label = L0 + "dwconv_gate_pool";
-  {  // depthwise 3x3 + SimpleGate + pool
+  if (!bw.dw_folded) {  // depthwise 3x3 + SimpleGate + pool
     const float *dw_w = bw.dw_w, *dw_b = bw.dw_b;
     add_op(P, [=](cudaStream_t st) {
-      dim3 grid(c / 64, cdiv(rows, 256));
-      if (bf) launch_k(dwconv_gate_pool_kernel<bf16>, dim3(grid), dim3(256), 256 * 128 * 2, st, static_cast<const bf16*>(act_h), dw_w, dw_b,
-                                                                  static_cast<bf16*>(act_g), static_cast<bf16*>(pooled), sp, c, rows);
-      else launch_k(dwconv_gate_pool_kernel<float>, dim3(grid), dim3(256), 256 * 128 * 4, st, static_cast<const float*>(act_h), dw_w, dw_b,
-                                                                static_cast<float*>(act_g), static_cast<float*>(pooled), sp, c, rows);
+      const int tile_px = sp >= 16 ? sp * sp : 64;   // whole faces per tile; small tiles below 16x16 for parallelism
+      dim3 grid(c / 64, cdiv(rows, tile_px));
+      if (bf) launch_k(dwconv_gate_pool_kernel<bf16>, dim3(grid), dim3(256), tile_px * 128 * 2, st, static_cast<const bf16*>(act_h), dw_w, dw_b,
+                                                                  static_cast<bf16*>(act_g), static_cast<bf16*>(pooled), sp, c, rows, tile_px);
+      else launch_k(dwconv_gate_pool_kernel<float>, dim3(grid), dim3(256), tile_px * 128 * 4, st, static_cast<const float*>(act_h), dw_w, dw_b,
+                                                                static_cast<float*>(act_g), static_cast<float*>(pooled), sp, c, rows, tile_px);
     });
     P.flops_per_face += 2.0 * 9 * 2 * c * rpf;
   }
   g_label = L0 + "sca";
   {  // SCA 1x1 on the pooled vector
     GemmDesc d;
-    d.M = B; d.N = c; d.K = c; d.A = pooled; d.lda = c; d.a_dtype = adt;
+    d.M = B; d.N = c; d.K = c; d.A = bw.dw_folded ? act_g : pooled; d.lda = c; d.a_dtype = adt;
     d.W = bw.wsca; d.ldw = c; d.w_dtype = adt; d.bias = bw.bsca; d.epi = EPI_BIAS;
     d.out = sca_s; d.ldo = c; d.out_dtype = DT_F32;
     add_gemm(h, P, d, h->Bcap);
@@ -1364,25 +1393,50 @@ int32_t hd_profile_step(hd_handle* h, int32_t batch, int32_t reps, float* ms_out
   for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
   std::vector<double> acc(n, 0.0);
   const int outer = reps < 0 ? -reps : reps;
-  for (int rep = 0; rep < outer + 1; ++rep) {
-    CUDA_CHECK(cudaEventRecord(ev[0], st));
+  if (reps < 0) {
+    // device-side cost: each launch captured 16x back to back into its own CUDA graph (no host launch
+    // latency in the measurement; the step's numerics are meaningless in this mode)
+    const int inner = 16;
     for (int i = 0; i < n; ++i) {
-      // reps < 0: run each launch 16x back to back so event and launch latency amortise
-      // (the step's numerics are meaningless in that mode)
-      const int inner = reps < 0 ? 16 : 1;
+      cudaGraph_t g = nullptr;
+      cudaGraphExec_t ge = nullptr;
+      CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       for (int k = 0; k < inner; ++k) P->ops[i].fn(st);
-      CUDA_CHECK(cudaEventRecord(ev[i + 1], st));
+      CUDA_CHECK(cudaStreamEndCapture(st, &g));
+      CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
+      CUDA_CHECK(cudaGraphLaunch(ge, st));  // warm-up
+      double best = 1e30;
+      for (int rep = 0; rep < outer; ++rep) {
+        CUDA_CHECK(cudaEventRecord(ev[0], st));
+        CUDA_CHECK(cudaGraphLaunch(ge, st));
+        CUDA_CHECK(cudaEventRecord(ev[1], st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+        best = std::min(best, static_cast<double>(ms));
+      }
+      acc[i] = best / inner * outer;
+      cudaGraphExecDestroy(ge);
+      cudaGraphDestroy(g);
     }
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    if (rep == 0) continue;  // warm-up
-    for (int i = 0; i < n; ++i) {
-      float ms = 0.f;
-      CUDA_CHECK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
-      acc[i] += ms;
+  } else {
+    for (int rep = 0; rep < outer + 1; ++rep) {
+      CUDA_CHECK(cudaEventRecord(ev[0], st));
+      for (int i = 0; i < n; ++i) {
+        P->ops[i].fn(st);
+        CUDA_CHECK(cudaEventRecord(ev[i + 1], st));
+      }
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      if (rep == 0) continue;  // warm-up
+      for (int i = 0; i < n; ++i) {
+        float ms = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+        acc[i] += ms;
+      }
     }
   }
   for (int i = 0; i < n; ++i) {
-    ms_out[i] = static_cast<float>(acc[i] / std::max(outer, 1) / (reps < 0 ? 16 : 1));
+    ms_out[i] = static_cast<float>(acc[i] / std::max(outer, 1));
     if (labels_out && label_stride > 0) {
       strncpy(labels_out + static_cast<size_t>(i) * label_stride, P->ops[i].label.c_str(), label_stride - 1);
       labels_out[static_cast<size_t>(i) * label_stride + label_stride - 1] = 0;

@@ -36,7 +36,7 @@ n = C.c_int32()
 eng.check(eng.lib.hd_profile_step(eng.handle, B, REPS, ms, labels, stride, cap, C.byref(n)), "hd_profile_step")
 rows = [(labels.raw[i * stride:(i + 1) * stride].split(b"\0")[0].decode(), ms[i] * 1e3) for i in range(n.value)]
 tot = sum(v for _, v in rows)
-print(f"# B={B}: {n.value} launches, {tot:.1f} us per step (event-to-event, warm)")
+print(f"# B={B}: {n.value} launches, {tot:.1f} us per step ({'each launch 16x in its own CUDA graph, best of ' + str(-REPS) if REPS < 0 else 'event-to-event plain launches'}, warm)")
 agg = collections.defaultdict(lambda: [0, 0.0])
 for lab, v in rows:
     key = re.sub(r" M=.*", "", lab)
