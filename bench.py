@@ -31,6 +31,7 @@ if ROOT not in sys.path:
 
 # algorithmic work per face per denoise step (non-padding MACs x 2, hoistable
 # t-only / condition-only work excluded) and weight elements streamed per step.
+CPU_FACES = 8  # batch of the CPU baseline sample
 GFLOP_PER_FACE_STEP = 2.0765
 WEIGHT_ELEMS_PER_STEP = 394.7e6
 
@@ -48,6 +49,16 @@ def parse():
     p.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     return p.parse_args()
+
+
+def load_traffic():
+    """DRAM bytes per denoise step from the committed ncu pass (profiles/r1_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)["per_step_bytes"]
+    except Exception:
+        return None
 
 
 def load_peaks():
@@ -105,8 +116,9 @@ class ClockSampler:
 
 def cpu_baseline(args, n_threads=None):
     """The CPU oracle (kind 'port': functional PyTorch restatement of the reference's modules, which
-    is itself device-agnostic PyTorch) on a bounded sample: 1 face, the first n DDPM steps of the
-    same schedule, FusedDenoiser with hoisted priors.  faces/s = 1 / (sampler_steps * s_per_step)."""
+    is itself device-agnostic PyTorch) on a bounded sample: CPU_FACES faces (the reference's own default
+    eval batch, train_refiner.py:26), the first n steps of the same schedule, FusedDenoiser with hoisted
+    priors.  faces/s = CPU_FACES / (sampler_steps * s_per_step)."""
     import torch
     from oracle import denoiser_ref, schedulers_ref
     from hifidiff_b200 import testing
@@ -118,13 +130,14 @@ def cpu_baseline(args, n_threads=None):
     sd0 = m.state_dict()
     sd = testing.random_state({k: v.shape for k, v in sd0.items()}, {k: v.dtype for k, v in sd0.items()}, seed=2,
                               eps_gain=0.15)
-    priors, ident = testing.synthetic_condition(1, 16, seed=0)
-    x = torch.randn((1, 4, 16, 16), generator=torch.Generator().manual_seed(0))
+    nf = CPU_FACES
+    priors, ident = testing.synthetic_condition(nf, 16, seed=0)
+    x = torch.randn((nf, 4, 16, 16), generator=torch.Generator().manual_seed(0))
     sched = schedulers_ref.DDPMSchedulerRef(clip_sample=False) if args.sampler == "ddpm" else \
         schedulers_ref.DDIMSchedulerRef(clip_sample=False)
     sched.set_timesteps(args.sampler_steps)
     ts = sched.timesteps.tolist()
-    z = torch.randn((1, 4, 16, 16), generator=torch.Generator().manual_seed(1))
+    z = torch.randn((nf, 4, 16, 16), generator=torch.Generator().manual_seed(1))
 
     def one(x, t):
         eps = denoiser_ref.fused_denoiser_forward(sd, x, t, priors, ident)
@@ -141,9 +154,9 @@ def cpu_baseline(args, n_threads=None):
             n += 1
         dt = time.perf_counter() - t0
     s_per_step = dt / max(n, 1)
-    return {"value": 1.0 / (args.sampler_steps * s_per_step), "unit": "faces/s", "cores": torch.get_num_threads(),
-            "kind": "port", "ms_per_denoise_step": 1e3 * s_per_step,
-            "sample": f"1 face, first {n} of {args.sampler_steps} {args.sampler.upper()} steps (FusedDenoiser, priors hoisted), "
+    return {"value": nf / (args.sampler_steps * s_per_step), "unit": "faces/s", "cores": torch.get_num_threads(),
+            "kind": "port", "ms_per_denoise_step": 1e3 * s_per_step, "faces": nf,
+            "sample": f"{nf} faces, first {n} of {args.sampler_steps} {args.sampler.upper()} steps (FusedDenoiser, priors hoisted), "
                       f"fp32 PyTorch CPU oracle, extrapolated to the full trajectory"}
 
 
@@ -317,7 +330,8 @@ def main():
             "launches_per_denoise_step": info.launches_per_step + 2,
             "roofline": {
                 "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["bf16_tflops_sustained"], "traffic": None,
+                "frac": achieved_tf / peaks["bf16_tflops_sustained"], "traffic": load_traffic() if B == 256 else None,
+                "traffic_note": "ncu cold-cache sum over the step's launches (upper bound), see profiles/r1_traffic.json",
                 "kernel": "one denoise step = one CUDA-graph launch (tcgen05 GEMM family dominates)",
                 "algorithmic": f"{GFLOP_PER_FACE_STEP} GFLOP/face/step x {B} faces",
                 "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)",

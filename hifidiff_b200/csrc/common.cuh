@@ -23,6 +23,7 @@ enum Epi : int {
   EPI_RESID = 3,    // out[m,n] = resid[m,n] + acc + bias[n]         (fp32 residual stream)
   EPI_GATE = 4,     // packed 128-column groups: out[m, g*64+i] = (acc[m,g*128+i]+b) * (acc[m,g*128+64+i]+b)
   EPI_PIXSHUF = 5,  // 1x1 up-conv + PixelShuffle(2) + skip add, in place on the fp32 skip buffer
+  EPI_RESID_LN = 6, // EPI_RESID, and the following LayerNorm2d + AdaLN modulation of the same rows (N == 128)
 };
 
 enum AMode : int {
@@ -50,6 +51,14 @@ struct GemmDesc {
   int out_dtype = DT_F32;
   const float* resid = nullptr;
   int ldr = 0;
+  // EPI_RESID_LN: the consumer's LayerNorm affine, where its modulation vectors sit in the table row,
+  // and the bf16 output that replaces a separate ln_mod_kernel launch
+  const float* ln_w = nullptr;
+  const float* ln_b = nullptr;
+  const float* mod_table = nullptr;
+  const int* mod_row_idx = nullptr;
+  int mod_stride = 0, ln_shift_off = 0, ln_scale_off = 0, rows_per_face = 1;
+  void* ln_out = nullptr;
 };
 
 // Device-side error word shared by all kernels of a handle (pipeline watchdog).

@@ -113,48 +113,140 @@ __global__ void __launch_bounds__(128) ln_mod_kernel(const float* __restrict__ x
   const int sub = lane / LPR, sl = lane % LPR;
   const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
   const bool ok = row < rows;
-  const float* xr = x + static_cast<size_t>(ok ? row : 0) * C;
+  const int rowc = ok ? row : 0;
   pdl_trigger();
+  // every load is issued before the reductions: one memory latency deep
+  float4 w4[NV], b4[NV], sc[NV], sh[NV], xv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c0 = (i * LPR + sl) * 4;
+    w4[i] = __ldg(reinterpret_cast<const float4*>(lw + c0));
+    b4[i] = __ldg(reinterpret_cast<const float4*>(lb + c0));
+  }
   pdl_wait();
-  float v[NV * 4];
+  const float* mrow = has_mod ? mod.row(rowc / rows_per_face) : nullptr;
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const float4 q = *reinterpret_cast<const float4*>(xr + (i * LPR + sl) * 4);
-    v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
-    s += q.x + q.y + q.z + q.w;
+    const int c0 = (i * LPR + sl) * 4;
+    xv[i] = *reinterpret_cast<const float4*>(x + static_cast<size_t>(rowc) * C + c0);
+    sc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sh[i] = sc[i];
+    if (has_mod) {
+      sc[i] = __ldg(reinterpret_cast<const float4*>(mrow + scale_off + c0));
+      sh[i] = __ldg(reinterpret_cast<const float4*>(mrow + shift_off + c0));
+    }
+    s += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
   }
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mu = s * (1.f / C);
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < NV * 4; ++i) { const float d = v[i] - mu; ss = fmaf(d, d, ss); }
+  for (int i = 0; i < NV; ++i) {
+    const float d0 = xv[i].x - mu, d1 = xv[i].y - mu, d2 = xv[i].z - mu, d3 = xv[i].w - mu;
+    ss = fmaf(d0, d0, ss); ss = fmaf(d1, d1, ss); ss = fmaf(d2, d2, ss); ss = fmaf(d3, d3, ss);
+  }
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   if (!ok) return;
-  const float var = ss * (1.f / C);
-  const float denom = sqrtf(var + 1e-6f);
-  const float* mrow = has_mod ? mod.row(row / rows_per_face) : nullptr;
+  const float denom = sqrtf(ss * (1.f / C) + 1e-6f);
   TOut* orow = out + static_cast<size_t>(row) * C;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c0 = (i * LPR + sl) * 4;
-    const float4 w4 = __ldg(reinterpret_cast<const float4*>(lw + c0));
-    const float4 b4 = __ldg(reinterpret_cast<const float4*>(lb + c0));
     float y[4];
-    y[0] = w4.x * ((v[4 * i] - mu) / denom) + b4.x;
-    y[1] = w4.y * ((v[4 * i + 1] - mu) / denom) + b4.y;
-    y[2] = w4.z * ((v[4 * i + 2] - mu) / denom) + b4.z;
-    y[3] = w4.w * ((v[4 * i + 3] - mu) / denom) + b4.w;
+    y[0] = w4[i].x * ((xv[i].x - mu) / denom) + b4[i].x;
+    y[1] = w4[i].y * ((xv[i].y - mu) / denom) + b4[i].y;
+    y[2] = w4[i].z * ((xv[i].z - mu) / denom) + b4[i].z;
+    y[3] = w4[i].w * ((xv[i].w - mu) / denom) + b4[i].w;
     if (has_mod) {
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(mrow + scale_off + c0));
-      const float4 sh = __ldg(reinterpret_cast<const float4*>(mrow + shift_off + c0));
-      y[0] = y[0] * (sc.x + 1.f) + sh.x;
-      y[1] = y[1] * (sc.y + 1.f) + sh.y;
-      y[2] = y[2] * (sc.z + 1.f) + sh.z;
-      y[3] = y[3] * (sc.w + 1.f) + sh.w;
+      y[0] = y[0] * (sc[i].x + 1.f) + sh[i].x;
+      y[1] = y[1] * (sc[i].y + 1.f) + sh[i].y;
+      y[2] = y[2] * (sc[i].z + 1.f) + sh[i].z;
+      y[3] = y[3] * (sc[i].w + 1.f) + sh[i].w;
     }
+    if (sizeof(TOut) == 4) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(orow) + c0) = make_float4(y[0], y[1], y[2], y[3]);
+    } else {
+      uint2 p;
+      p.x = pack_bf16x2(y[0], y[1]);
+      p.y = pack_bf16x2(y[2], y[3]);
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(orow) + c0) = p;
+    }
+  }
+}
+
+// Wide rows, few of them (1024 / 2048 channels at the 2x2 / 1x1 levels): one 256-thread block per pixel
+// row, every load (x, LayerNorm affine, modulation) issued before the block reduction so the kernel
+// is one memory latency deep instead of three.
+template <int C, typename TOut>
+__global__ void __launch_bounds__(256) ln_mod_wide_kernel(const float* __restrict__ x, const float* __restrict__ lw,
+                                                          const float* __restrict__ lb, TOut* __restrict__ out, int rows,
+                                                          int rows_per_face, ModRef mod, int shift_off, int scale_off,
+                                                          int has_mod) {
+  constexpr int NV = C / 1024;  // float4 per thread
+  __shared__ float s_red[2][8];
+  const int row = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, wp = t >> 5;
+  pdl_trigger();
+  float4 w4[NV], b4[NV], sc[NV], sh[NV], xv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {  // constants first (independent of the predecessor)
+    const int c0 = (i * 256 + t) * 4;
+    w4[i] = __ldg(reinterpret_cast<const float4*>(lw + c0));
+    b4[i] = __ldg(reinterpret_cast<const float4*>(lb + c0));
+  }
+  pdl_wait();
+  const float* mrow = has_mod ? mod.row(row / rows_per_face) : nullptr;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c0 = (i * 256 + t) * 4;
+    xv[i] = *reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * C + c0);
+    sc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sh[i] = sc[i];
+    if (has_mod) {
+      sc[i] = __ldg(reinterpret_cast<const float4*>(mrow + scale_off + c0));
+      sh[i] = __ldg(reinterpret_cast<const float4*>(mrow + shift_off + c0));
+    }
+    s += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
+  }
+  s = warp_sum(s);
+  if (lane == 0) s_red[0][wp] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += s_red[0][i];
+  const float mu = tot * (1.f / C);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float d0 = xv[i].x - mu, d1 = xv[i].y - mu, d2 = xv[i].z - mu, d3 = xv[i].w - mu;
+    ss = fmaf(d0, d0, ss); ss = fmaf(d1, d1, ss); ss = fmaf(d2, d2, ss); ss = fmaf(d3, d3, ss);
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) s_red[1][wp] = ss;
+  __syncthreads();
+  float vt = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) vt += s_red[1][i];
+  const float denom = sqrtf(vt * (1.f / C) + 1e-6f);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c0 = (i * 256 + t) * 4;
+    float y[4];
+    y[0] = w4[i].x * ((xv[i].x - mu) / denom) + b4[i].x;
+    y[1] = w4[i].y * ((xv[i].y - mu) / denom) + b4[i].y;
+    y[2] = w4[i].z * ((xv[i].z - mu) / denom) + b4[i].z;
+    y[3] = w4[i].w * ((xv[i].w - mu) / denom) + b4[i].w;
+    if (has_mod) {
+      y[0] = y[0] * (sc[i].x + 1.f) + sh[i].x;
+      y[1] = y[1] * (sc[i].y + 1.f) + sh[i].y;
+      y[2] = y[2] * (sc[i].z + 1.f) + sh[i].z;
+      y[3] = y[3] * (sc[i].w + 1.f) + sh[i].w;
+    }
+    TOut* orow = out + static_cast<size_t>(row) * C;
     if (sizeof(TOut) == 4) {
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(orow) + c0) = make_float4(y[0], y[1], y[2], y[3]);
     } else {

@@ -22,8 +22,9 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 64;       // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;                      // two per TMEM lane quadrant
-constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
+// warp 0 TMA, warp 1 MMA, warps 2.. epilogue: EW = 8 (two per TMEM lane quadrant) for multi-wave grids,
+// EW = 16 for grids that fit one wave (one CTA per SM anyway: spend the idle issue slots on the epilogue)
+constexpr int num_threads(int ew) { return 64 + 32 * ew; }
 
 struct TcArgs {
   int M, N, num_kb;           // rows, packed weight rows, K / 64
@@ -36,10 +37,17 @@ struct TcArgs {
   int kb_per_tap;             // A_CONV3: C / 64
   int conv_bh, conv_bb;       // A_CONV3: box rows in h and in batch (conv_bh * sp * conv_bb == 128)
   DeviceStatus* status;
+  // EPI_RESID_LN
+  const float* ln_w;
+  const float* ln_b;
+  const float* mod_table;
+  const int* mod_row_idx;
+  int mod_stride, ln_shift_off, ln_scale_off, rows_per_face;
+  bf16* ln_out;
   long long* trace;           // optional per-CTA timeline (16 slots per CTA), nullptr in production
 };
 
-template <int BN, int STAGES> struct TileCfg {
+template <int BN, int STAGES, int EW = 8> struct TileCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -51,8 +59,8 @@ template <int BN, int STAGES> struct TileCfg {
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;               // power of two >= 32
   // co-resident CTAs per SM (228 KB shared memory, 512 TMEM columns): short-K GEMMs are dominated by
   // prologue/epilogue, so several small CTAs per SM overlap one tile's epilogue with another's mainloop
-  // (320 threads per CTA: two CTAs keep the register budget at ~100 per thread)
-  static constexpr int MIN_BLOCKS = SMEM_BYTES <= 113 * 1024 ? 2 : 1;
+  // (320 threads per CTA: two CTAs keep the register budget at ~100 per thread; 576 threads: one CTA)
+  static constexpr int MIN_BLOCKS = (EW > 8) ? 1 : (SMEM_BYTES <= 113 * 1024 ? 2 : 1);
   static_assert(MIN_BLOCKS * TMEM_COLS <= 512, "TMEM over-subscribed");
 };
 
@@ -224,12 +232,16 @@ template <> __device__ __forceinline__ void store4<bf16>(bf16* dst, float4 v) {
 // partial tiles over distributed shared memory in fixed order (deterministic), applying the real
 // epilogue once.  This turns the small-M, weight-streaming GEMMs of the 2x2 / 1x1 levels into
 // >= 120 CTAs with deep TMA rings without atomics or a global workspace.
-template <int BN, int STAGES, int EPI, int AMODE, typename TOut>
-__global__ void __launch_bounds__(NUM_THREADS, (TileCfg<BN, STAGES>::MIN_BLOCKS))
+template <int BN, int STAGES, int EPI, int AMODE, typename TOut, int EW>
+__global__ void __launch_bounds__(num_threads(EW), (TileCfg<BN, STAGES, EW>::MIN_BLOCKS))
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs args) {
-  using Cfg = TileCfg<BN, STAGES>;
+  using Cfg = TileCfg<BN, STAGES, EW>;
+  constexpr int NUM_EPI_WARPS = EW;
+  static_assert(EW == 8 || EW == 16, "epilogue warps: 2 or 4 per TMEM lane quadrant");
+  static_assert(BN / (EW / 4) >= 32, "each epilogue warp drains at least one 32-column TMEM chunk");
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
   static_assert(EPI != EPI_GATE || BN == 128, "gate epilogue needs 128-column packed groups");
+  static_assert(EPI != EPI_RESID_LN || BN == 128, "fused LayerNorm needs the whole 128-channel row in one tile");
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment (same offset in every CTA of the cluster)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -419,7 +431,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int passes = (rows_here + NUM_EPI_WARPS * RPI - 1) / (NUM_EPI_WARPS * RPI);
 
     // one row-chunk: bias / activation / residual, then the store
-    auto finish = [&](float4 v, float4 g, float4 e, int i, TOut* d, bool okay) {
+    auto finish = [&](float4 v, float4 g, float4 e, int i, TOut* d, bool okay) -> float4 {
       v.x += bias_r[i].x; v.y += bias_r[i].y; v.z += bias_r[i].z; v.w += bias_r[i].w;
       if (EPI == EPI_GATE) {
         v.x *= g.x + bias2_r[i].x; v.y *= g.y + bias2_r[i].y; v.z *= g.z + bias2_r[i].z; v.w *= g.w + bias2_r[i].w;
@@ -431,8 +443,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         v.x = 1.f / (1.f + __expf(-v.x)); v.y = 1.f / (1.f + __expf(-v.y));
         v.z = 1.f / (1.f + __expf(-v.z)); v.w = 1.f / (1.f + __expf(-v.w));
       }
-      if (EPI == EPI_RESID || EPI == EPI_PIXSHUF) { v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w; }
+      if (EPI == EPI_RESID || EPI == EPI_RESID_LN || EPI == EPI_PIXSHUF) { v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w; }
       if (okay) store4<TOut>(d + i * LPR * 4, v);
+      return v;
+    };
+    // EPI_RESID_LN: the warp holds the whole 128-channel row (4 values per lane): LayerNorm2d statistics
+    // by warp shuffles (two-pass, as utils.py:16-24), affine, AdaLN modulation, bf16 store
+    auto layer_norm_row = [&](float4 v, int mc, bool okay) {
+      const float mu = warp_sum(v.x + v.y + v.z + v.w) * (1.f / 128.f);
+      const float d0 = v.x - mu, d1 = v.y - mu, d2 = v.z - mu, d3 = v.w - mu;
+      const float var = warp_sum(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3) * (1.f / 128.f);
+      const float denom = sqrtf(var + 1e-6f);
+      const int c0 = sl * 4;
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(args.ln_w + c0));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.ln_b + c0));
+      const float* mrow = args.mod_table + static_cast<size_t>(args.mod_row_idx[mc / args.rows_per_face]) * args.mod_stride;
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(mrow + args.ln_scale_off + c0));
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(mrow + args.ln_shift_off + c0));
+      float4 y;
+      y.x = (w4.x * (d0 / denom) + b4.x) * (sc.x + 1.f) + sh.x;
+      y.y = (w4.y * (d1 / denom) + b4.y) * (sc.y + 1.f) + sh.y;
+      y.z = (w4.z * (d2 / denom) + b4.z) * (sc.z + 1.f) + sh.z;
+      y.w = (w4.w * (d3 / denom) + b4.w) * (sc.w + 1.f) + sh.w;
+      if (okay) store4<bf16>(args.ln_out + static_cast<size_t>(mc) * 128 + c0, y);
     };
     // row bookkeeping shared by both paths
     auto locate = [&](int pass, bool& okay, int& rc, int& mc, TOut*& d) {
@@ -461,6 +494,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         float4 acc[U][CPL], acc2[U][CPL], ext[U][CPL];
         bool ok[U];
         TOut* dst[U];
+        int mrow_idx[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           int rc, mc;
@@ -472,15 +506,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             acc2[u][i] = zero4;
             ext[u][i] = zero4;
             if (EPI == EPI_GATE) acc2[u][i] = *reinterpret_cast<const float4*>(stage + rc * BN + (((ck + 16) ^ (rc & 7)) << 2));
-            if (EPI == EPI_RESID)
+            if (EPI == EPI_RESID || EPI == EPI_RESID_LN)
               ext[u][i] = *reinterpret_cast<const float4*>(args.resid + static_cast<size_t>(mc) * args.ldr + n0 + ck * 4);
             if (EPI == EPI_PIXSHUF) ext[u][i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dst[u]) + i * LPR * 4);
           }
+          mrow_idx[u] = mc;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
-          for (int i = 0; i < CPL; ++i) finish(acc[u][i], acc2[u][i], ext[u][i], i, dst[u], ok[u]);
+          for (int i = 0; i < CPL; ++i) {
+            const float4 r = finish(acc[u][i], acc2[u][i], ext[u][i], i, dst[u], ok[u]);
+            if (EPI == EPI_RESID_LN) layer_norm_row(r, mrow_idx[u], ok[u]);
+          }
       }
     } else {
       // split-K: all DSMEM loads of a pass are issued before the first add (they are ~200+ cycles each

@@ -252,10 +252,10 @@ struct TcLaunch {
   int epi, a_mode, out_dtype, stages;
 };
 
-template <int STAGES, int EPI, int AMODE, typename TOut>
+template <int STAGES, int EW, int EPI, int AMODE, typename TOut>
 void launch_tc_inst2(const TcLaunch& L, cudaStream_t st) {
-  auto kern = tc::gemm_tc_kernel<128, STAGES, EPI, AMODE, TOut>;
-  using Cfg = tc::TileCfg<128, STAGES>;
+  auto kern = tc::gemm_tc_kernel<128, STAGES, EPI, AMODE, TOut, EW>;
+  using Cfg = tc::TileCfg<128, STAGES, EW>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -264,7 +264,7 @@ void launch_tc_inst2(const TcLaunch& L, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = L.grid;
-  cfg.blockDim = dim3(tc::NUM_THREADS);
+  cfg.blockDim = dim3(tc::num_threads(EW));
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -279,13 +279,13 @@ void launch_tc_inst2(const TcLaunch& L, cudaStream_t st) {
   cudaLaunchKernelEx(&cfg, kern, L.mapA, L.mapB, L.args);
 }
 
-// ring depth: <= 2 k-blocks per CTA needs two stages (3 CTAs/SM); a grid that fits in one wave gets the
-// deep 6-stage ring (weight streaming); everything else 3 stages (2 CTAs/SM)
+// ring depth: <= 2 k-blocks per CTA needs two stages; a grid that fits in one wave gets the deep 6-stage
+// ring (weight streaming, one CTA per SM) and 16 epilogue warps; everything else 3 stages (2 CTAs/SM)
 template <int EPI, int AMODE, typename TOut>
 void launch_tc_inst(const TcLaunch& L, cudaStream_t st) {
-  if (L.stages == 2) launch_tc_inst2<2, EPI, AMODE, TOut>(L, st);
-  else if (L.stages == 6) launch_tc_inst2<6, EPI, AMODE, TOut>(L, st);
-  else launch_tc_inst2<3, EPI, AMODE, TOut>(L, st);
+  if (L.stages == 2) launch_tc_inst2<2, 8, EPI, AMODE, TOut>(L, st);
+  else if (L.stages == 6) launch_tc_inst2<6, 16, EPI, AMODE, TOut>(L, st);
+  else launch_tc_inst2<3, 8, EPI, AMODE, TOut>(L, st);
 }
 
 void launch_tc(const TcLaunch& L, cudaStream_t st) {
@@ -301,6 +301,7 @@ void launch_tc(const TcLaunch& L, cudaStream_t st) {
       break;
     case EPI_RELU: launch_tc_inst<EPI_RELU, A_PLAIN, bf16>(L, st); break;
     case EPI_RESID: launch_tc_inst<EPI_RESID, A_PLAIN, float>(L, st); break;
+    case EPI_RESID_LN: launch_tc_inst<EPI_RESID_LN, A_PLAIN, float>(L, st); break;
     case EPI_GATE: launch_tc_inst<EPI_GATE, A_PLAIN, bf16>(L, st); break;
     case EPI_PIXSHUF: launch_tc_inst<EPI_PIXSHUF, A_PLAIN, float>(L, st); break;
     default: break;
@@ -326,6 +327,9 @@ TcLaunch build_tc(hd_handle* h, const GemmDesc& d, long long a_rows_alloc) {
   a.bias = d.bias; a.out = d.out; a.ldo = d.ldo; a.resid = d.resid; a.ldr = d.ldr;
   a.sp = d.sp; a.kb_per_tap = 1; a.conv_bh = 1; a.conv_bb = 1;
   a.status = h->d_status;
+  a.ln_w = d.ln_w; a.ln_b = d.ln_b; a.mod_table = d.mod_table; a.mod_row_idx = d.mod_row_idx;
+  a.mod_stride = d.mod_stride; a.ln_shift_off = d.ln_shift_off; a.ln_scale_off = d.ln_scale_off;
+  a.rows_per_face = d.rows_per_face; a.ln_out = static_cast<bf16*>(d.ln_out);
   a.trace = nullptr;
   if (d.a_mode == A_CONV3) {
     const int n = d.sp, C = d.C;
@@ -354,6 +358,7 @@ TcLaunch build_tc(hd_handle* h, const GemmDesc& d, long long a_rows_alloc) {
   const int tiles = cdiv(d.M, 128) * (d.N / 128);
   int split = 1;
   while (tiles * split < 120 && split < 8 && a.num_kb % (2 * split) == 0 && a.num_kb / (2 * split) >= 2) split *= 2;
+  if (d.epi == EPI_RESID_LN) split = 1;  // the fused LayerNorm needs the finished row in one CTA
   L.grid = dim3(cdiv(d.M, 128), d.N / 128, split);
   const int local_kb = a.num_kb / split;
   L.stages = local_kb <= 2 ? 2 : (tiles * split <= 160 ? 6 : 3);
@@ -628,7 +633,7 @@ void add_gemm(hd_handle* h, Plan& P, GemmDesc d, long long a_rows_alloc, const s
   const long long taps_exec = d.a_mode == A_CONV3 ? 1 : 1;
   (void)taps_exec;
   P.flops_per_face += 2.0 * d.M * static_cast<double>(d.N) * d.K / P.batch;
-  static const char* epi_names[] = {"bias", "relu", "sigmoid", "resid", "gate", "pixshuf"};
+  static const char* epi_names[] = {"bias", "relu", "sigmoid", "resid", "gate", "pixshuf", "resid+ln"};
   const std::string what = g_label;
   if (tc_eligible(h, d)) {
     TcLaunch L = build_tc(h, d, a_rows_alloc);
@@ -674,13 +679,16 @@ void launch_ln(int c, const float* x, const float* lw, const float* lb, T* out, 
     case 128: launch_k(ln_mod_kernel<128, T>, dim3(grid), dim3(128), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
     case 256: launch_k(ln_mod_kernel<256, T>, dim3(grid), dim3(128), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
     case 512: launch_k(ln_mod_kernel<512, T>, dim3(grid), dim3(128), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
-    case 1024: launch_k(ln_mod_kernel<1024, T>, dim3(grid), dim3(128), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
-    case 2048: launch_k(ln_mod_kernel<2048, T>, dim3(grid), dim3(128), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
+    case 1024: launch_k(ln_mod_wide_kernel<1024, T>, dim3(rows), dim3(256), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
+    case 2048: launch_k(ln_mod_wide_kernel<2048, T>, dim3(rows), dim3(256), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
     default: break;
   }
 }
 
-void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapname) {
+// next_ln1: the block that follows at the same level (its norm1 can be fused into this block's conv5
+// epilogue); skip_ln1: this block's norm1 output was already produced by its predecessor.
+void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapname, const BlockW* next_ln1 = nullptr,
+               bool skip_ln1 = false) {
   const int B = P.batch, l = bw.level, c = bw.c, sp = h->sp[l];
   const int rows = B * sp * sp, rpf = sp * sp;
   const long long rows_alloc = static_cast<long long>(h->Bcap) * rpf;
@@ -699,8 +707,17 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
   };
   const std::string L0 = fmt("L%d c=%d ", l, c);
   // norm1 + modulation (shift_att = chunk 0, scale_att = chunk 1)
-  g_label = L0 + "ln1";
-  add_op(P, ln(bw.ln1_w, bw.ln1_b, bw.mod_off, bw.mod_off + c));
+  // c == 128: one GEMM tile holds the whole channel row, so LayerNorm + modulation ride in the residual epilogue
+  const bool fuse_ln = bf && c == 128;
+  auto fused_ln = [&](GemmDesc& d, const float* lw, const float* lb, int shift_off, int scale_off) {
+    d.epi = EPI_RESID_LN;
+    d.ln_w = lw; d.ln_b = lb; d.mod_table = h->mod_table; d.mod_row_idx = h->row_idx; d.mod_stride = h->mod_stride;
+    d.ln_shift_off = shift_off; d.ln_scale_off = scale_off; d.rows_per_face = rpf; d.ln_out = act_a;
+  };
+  if (!(fuse_ln && skip_ln1)) {
+    g_label = L0 + "ln1";
+    add_op(P, ln(bw.ln1_w, bw.ln1_b, bw.mod_off, bw.mod_off + c));
+  }
   g_label = L0 + "conv1";
   if (bw.dw_folded) {  // conv1 + (folded) depthwise + SimpleGate; the pooled mean over 1 pixel is g itself
     GemmDesc d;
@@ -748,11 +765,14 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
     d.M = rows; d.N = c; d.K = c; d.A = act_g; d.lda = c; d.a_dtype = adt;
     d.W = bw.w3; d.ldw = c; d.w_dtype = adt; d.bias = bw.b3; d.epi = EPI_RESID;
     d.out = resid; d.ldo = c; d.out_dtype = DT_F32; d.resid = resid; d.ldr = c;
+    if (fuse_ln) fused_ln(d, bw.ln2_w, bw.ln2_b, bw.mod_off + 2 * c, bw.mod_off + 3 * c);
     add_gemm(h, P, d, rows_alloc);
   }
   // norm2 + modulation (shift_ffn = chunk 2, scale_ffn = chunk 3)
-  g_label = L0 + "ln2";
-  add_op(P, ln(bw.ln2_w, bw.ln2_b, bw.mod_off + 2 * c, bw.mod_off + 3 * c));
+  if (!fuse_ln) {
+    g_label = L0 + "ln2";
+    add_op(P, ln(bw.ln2_w, bw.ln2_b, bw.mod_off + 2 * c, bw.mod_off + 3 * c));
+  }
   g_label = L0 + "conv4";
   {  // conv4 + SimpleGate
     GemmDesc d;
@@ -767,6 +787,8 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
     d.M = rows; d.N = c; d.K = c; d.A = act_g; d.lda = c; d.a_dtype = adt;
     d.W = bw.w5; d.ldw = c; d.w_dtype = adt; d.bias = bw.b5; d.epi = EPI_RESID;
     d.out = resid; d.ldo = c; d.out_dtype = DT_F32; d.resid = resid; d.ldr = c;
+    if (fuse_ln && next_ln1 != nullptr)
+      fused_ln(d, next_ln1->ln1_w, next_ln1->ln1_b, next_ln1->mod_off, next_ln1->mod_off + c);
     TapInfo ti;
     ti.ptr = resid; ti.dtype = DT_F32; ti.C = c; ti.HW = rpf; ti.ld = c;
     add_gemm(h, P, d, rows_alloc, tapname, ti);
@@ -828,7 +850,8 @@ Plan* get_plan(hd_handle* h, int B) {
   size_t bi = 0;
   for (int l = 0; l < 4; ++l) {
     for (int i = 0; i < kEncBlocks[l]; ++i, ++bi)
-      add_block(h, P, h->blocks[bi], "encoders." + std::to_string(l) + "." + std::to_string(i));
+      add_block(h, P, h->blocks[bi], "encoders." + std::to_string(l) + "." + std::to_string(i),
+                i + 1 < kEncBlocks[l] ? &h->blocks[bi + 1] : nullptr, i > 0);
     // down: 2x2 stride-2 conv as space-to-depth + GEMM
     const int c = h->c[l], n = h->sp[l], rows_out = B * (n / 2) * (n / 2);
     const float* src = h->resid[l];
@@ -848,7 +871,9 @@ Plan* get_plan(hd_handle* h, int B) {
     g_label = fmt("down%d", l);
     add_gemm(h, P, d, static_cast<long long>(h->Bcap) * (n / 2) * (n / 2), "downs." + std::to_string(l), ti);
   }
-  for (int i = 0; i < kMidBlocks; ++i, ++bi) add_block(h, P, h->blocks[bi], "middle_blks." + std::to_string(i));
+  for (int i = 0; i < kMidBlocks; ++i, ++bi)
+    add_block(h, P, h->blocks[bi], "middle_blks." + std::to_string(i), i + 1 < kMidBlocks ? &h->blocks[bi + 1] : nullptr,
+              i > 0);
   if (h->fused) add_hca(h, P, 0, 4);
   for (int L = 0; L < 4; ++L) {
     const int lin = 4 - L, lout = 3 - L;
@@ -876,7 +901,8 @@ Plan* get_plan(hd_handle* h, int B) {
     g_label = fmt("up%d", L);
     add_gemm(h, P, d, static_cast<long long>(h->Bcap) * n * n, "ups." + std::to_string(L), ti);
     for (int i = 0; i < kDecBlocks[L]; ++i, ++bi)
-      add_block(h, P, h->blocks[bi], "decoders." + std::to_string(L) + "." + std::to_string(i));
+      add_block(h, P, h->blocks[bi], "decoders." + std::to_string(L) + "." + std::to_string(i),
+                i + 1 < kDecBlocks[L] ? &h->blocks[bi + 1] : nullptr, i > 0);
     if (h->fused) add_hca(h, P, L + 1, lout);
   }
   {  // ending
