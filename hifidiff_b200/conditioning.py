@@ -150,6 +150,12 @@ class FacialRefiner(nn.Module):
                     param.requires_grad = False
         self._cond_src = None
         self._cond: Optional[tuple] = None
+        self.native_fpg = True   # run FPG on the sm_100a kernels (False: PyTorch eager)
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._drop_condition())
+
+    def _drop_condition(self) -> None:
+        self._cond_src = None
+        self._cond = None
 
     @torch.no_grad()
     def condition(self, cr_face: torch.Tensor, cr_latent: torch.Tensor):
@@ -158,9 +164,15 @@ class FacialRefiner(nn.Module):
         if self._cond_src != key:
             was_training = self.training
             self.eval()  # BatchNorm must use running statistics on the sampling path
-            # full fp32 convolutions: the priors feed the fp32 correctness mode too, and this runs once per face
+            # full fp32 convolutions: the identity feeds the fp32 correctness mode too, and this runs once per face
             with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-                priors = self.fpg(cr_latent)
+                if self.native_fpg and cr_latent.device.type == "cuda":
+                    eng = self.denoiser.engine(cr_latent.shape[0])
+                    if not eng.fpg_loaded:
+                        eng.load_fpg_state(self.fpg.state_dict())
+                    priors = eng.fpg_forward(cr_latent, self.denoiser.config.sample_size, self.denoiser.width)
+                else:
+                    priors = self.fpg(cr_latent)
                 ident = self.idc(cr_face)
             self.train(was_training)
             self._cond = ([p.contiguous() for p in priors], ident.contiguous())

@@ -117,6 +117,19 @@ struct BlockW {
   float *b1 = nullptr, *bsca = nullptr, *b3 = nullptr, *b4 = nullptr, *b5 = nullptr;
   float *dw_w = nullptr, *dw_b = nullptr;
   bool dw_folded = false;  // 1x1 level: depthwise 3x3 == per-channel scale, folded into conv1 (gate-packed)
+  bool has_mod = true;     // false: unconditional NAFBlock of the FPG encoder (models/fpg/naf.py:105-126)
+};
+
+// FacialPriorGuidance (models/fpg/model.py:7-64): NAFNet encoder over the CR latent, run once per face batch
+struct FpgW {
+  bool loaded = false;
+  std::vector<BlockW> blocks;
+  void* down_w[4] = {};
+  float* down_b[4] = {};
+  float *intro_w = nullptr, *intro_b = nullptr;
+  void* convs_w[5] = {};     // convs[0]: plain 1x1; convs[1..4]: 1x1 + PixelShuffle(2), rows grouped by quadrant
+  float* zero_bias = nullptr;
+  float* p0 = nullptr;       // prior 0 (B, 2048) fp32
 };
 
 struct HcaW {
@@ -204,6 +217,9 @@ struct hd_handle {
   const float* cur_x = nullptr;
   float* cur_eps = nullptr;
   std::map<int, std::unique_ptr<Plan>> plans;
+  FpgW fpg;
+  std::map<int, std::unique_ptr<Plan>> fpg_plans;
+  const float* fpg_in = nullptr;
   size_t workspace_bytes = 0;
 
   // transient during load
@@ -524,14 +540,14 @@ void load_block(hd_handle* h, BlockW& bw, int wdt) {
     bw.w5 = pack_matrix(h, need(h, p + "conv5.weight", {c, c}), c, c, 1, nullptr, &gamma, wdt);
     bw.b5 = upload_f32(h, b5);
   }
-  // per-block time MLP rows go into the concatenated [mod_stride, 256] matrix
-  pack_matrix(h, need(h, p + "mlp.1.weight", {4 * c, 256}), 4 * c, 256, 1, nullptr, nullptr, DT_F32,
-              h->mlp_w + static_cast<size_t>(bw.mod_off) * 256);
-  {
+  if (bw.has_mod) {
+    // per-block time MLP rows go into the concatenated [mod_stride, 256] matrix
+    pack_matrix(h, need(h, p + "mlp.1.weight", {4 * c, 256}), 4 * c, 256, 1, nullptr, nullptr, DT_F32,
+                h->mlp_w + static_cast<size_t>(bw.mod_off) * 256);
     const SrcTensor& t = need(h, p + "mlp.1.bias", {4 * c});
     CUDA_CHECK(cudaMemcpy(h->mlp_b + bw.mod_off, t.data, static_cast<size_t>(4) * c * 4, cudaMemcpyDefault));
+    h->weight_elems_step += static_cast<int64_t>(c) * c * 7 + 18 * c;
   }
-  h->weight_elems_step += static_cast<int64_t>(c) * c * 7 + 18 * c;
 }
 
 void load_weights_impl(hd_handle* h) {
@@ -699,16 +715,17 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
   void *act_a = h->act_a, *act_h = h->act_h, *act_g = h->act_g, *pooled = h->pooled;
   float* sca_s = h->sca_s;
 
+  const int has_mod = bw.has_mod ? 1 : 0;
   auto ln = [=](const float* lw, const float* lb, int shift_off, int scale_off) {
     return [=](cudaStream_t st) {
-      if (bf) launch_ln<bf16>(c, resid, lw, lb, static_cast<bf16*>(act_a), rows, rpf, mod, shift_off, scale_off, 1, st);
-      else launch_ln<float>(c, resid, lw, lb, static_cast<float*>(act_a), rows, rpf, mod, shift_off, scale_off, 1, st);
+      if (bf) launch_ln<bf16>(c, resid, lw, lb, static_cast<bf16*>(act_a), rows, rpf, mod, shift_off, scale_off, has_mod, st);
+      else launch_ln<float>(c, resid, lw, lb, static_cast<float*>(act_a), rows, rpf, mod, shift_off, scale_off, has_mod, st);
     };
   };
   const std::string L0 = fmt("L%d c=%d ", l, c);
   // norm1 + modulation (shift_att = chunk 0, scale_att = chunk 1)
   // c == 128: one GEMM tile holds the whole channel row, so LayerNorm + modulation ride in the residual epilogue
-  const bool fuse_ln = bf && c == 128;
+  const bool fuse_ln = bf && c == 128 && bw.has_mod;
   auto fused_ln = [&](GemmDesc& d, const float* lw, const float* lb, int shift_off, int scale_off) {
     d.epi = EPI_RESID_LN;
     d.ln_w = lw; d.ln_b = lb; d.mod_table = h->mod_table; d.mod_row_idx = h->row_idx; d.mod_stride = h->mod_stride;
@@ -919,6 +936,121 @@ Plan* get_plan(hd_handle* h, int B) {
   }
   Plan* raw = up.get();
   h->plans[B] = std::move(up);
+  return raw;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FacialPriorGuidance: the same NAF-block kernels without modulation
+// ------------------------------------------------------------------------------------------------
+void load_fpg_impl(hd_handle* h) {
+  const int wdt = h->bf16 ? DT_BF16 : DT_F32;
+  FpgW& F = h->fpg;
+  F.blocks.clear();
+  for (int l = 0; l < 4; ++l)
+    for (int i = 0; i < kEncBlocks[l]; ++i) {
+      BlockW b;
+      b.prefix = "encoders." + std::to_string(l) + "." + std::to_string(i) + ".";
+      b.level = l; b.c = h->c[l]; b.mod_off = 0; b.has_mod = false;
+      F.blocks.push_back(b);
+    }
+  const int64_t keep = h->weight_elems_step;
+  for (auto& b : F.blocks) load_block(h, b, wdt);
+  F.intro_w = upload_f32(h, host_vec(h, need(h, "intro.weight", {kWidth, 36})));
+  F.intro_b = upload_f32(h, host_vec(h, need(h, "intro.bias", {kWidth})));
+  for (int l = 0; l < 4; ++l) {
+    const int c = h->c[l];
+    const std::string p = "downs." + std::to_string(l) + ".";
+    F.down_w[l] = pack_matrix(h, need(h, p + "weight", {2 * c, c, 4}), 2 * c, 4 * c, 4, nullptr, nullptr, wdt);
+    F.down_b[l] = upload_f32(h, host_vec(h, need(h, p + "bias", {2 * c})));
+  }
+  F.convs_w[0] = pack_matrix(h, need(h, "convs.0.0.weight", {2048, 2048}), 2048, 2048, 1, nullptr, nullptr, wdt);
+  for (int j = 1; j < 5; ++j) {
+    const int cin = h->c[5 - j];  // 2048, 1024, 512, 256
+    const int N = 2 * cin, quarter = N / 4;
+    std::vector<int> perm(N);
+    for (int n = 0; n < N; ++n) perm[n] = 4 * (n % quarter) + n / quarter;
+    F.convs_w[j] = pack_matrix(h, need(h, "convs." + std::to_string(j) + ".0.weight", {N, cin}), N, cin, 1, &perm, nullptr, wdt);
+  }
+  F.zero_bias = h->arena.get<float>(4096);  // arena memory is zero-initialised
+  F.p0 = h->arena.get<float>(static_cast<size_t>(h->Bcap) * 2048);
+  h->weight_elems_step = keep;
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  for (void* p : h->temp_dev) cudaFree(p);
+  h->temp_dev.clear();
+  h->src.clear();
+  F.loaded = true;
+  h->fpg_plans.clear();
+}
+
+Plan* get_fpg_plan(hd_handle* h, int B) {
+  auto it = h->fpg_plans.find(B);
+  if (it != h->fpg_plans.end()) return it->second.get();
+  std::unique_ptr<Plan> up(new Plan());
+  Plan& P = *up;
+  P.batch = B;
+  const int S = h->S;
+  const bool bf = h->bf16;
+  const int adt = bf ? DT_BF16 : DT_F32;
+  const FpgW& F = h->fpg;
+  {
+    float* out = h->resid[0];
+    const float *w = F.intro_w, *b = F.intro_b;
+    g_label = "fpg intro conv3x3";
+    add_op(P, [=](cudaStream_t st) {
+      launch_k(intro_conv_kernel, dim3(B), dim3(256), (36 * 128 + 4 * (S + 2) * (S + 2)) * sizeof(float), st, h->fpg_in, w, b, out, S);
+    });
+  }
+  size_t bi = 0;
+  for (int l = 0; l < 4; ++l) {
+    for (int i = 0; i < kEncBlocks[l]; ++i, ++bi) add_block(h, P, F.blocks[bi], std::string());
+    const int c = h->c[l], n = h->sp[l], rows_out = B * (n / 2) * (n / 2);
+    const float* src = h->resid[l];
+    void* act_a = h->act_a;
+    g_label = fmt("fpg down%d s2d", l);
+    add_op(P, [=](cudaStream_t st) {
+      const size_t total8 = static_cast<size_t>(rows_out) * 4 * c / 8;
+      if (bf) launch_k(s2d_kernel<bf16>, dim3(cdiv(total8, 256)), dim3(256), 0, st, src, static_cast<bf16*>(act_a), B, n, c);
+      else launch_k(s2d_kernel<float>, dim3(cdiv(total8, 256)), dim3(256), 0, st, src, static_cast<float*>(act_a), B, n, c);
+    });
+    GemmDesc d;
+    d.M = rows_out; d.N = 2 * c; d.K = 4 * c; d.A = act_a; d.lda = 4 * c; d.a_dtype = adt;
+    d.W = F.down_w[l]; d.ldw = 4 * c; d.w_dtype = adt; d.bias = F.down_b[l]; d.epi = EPI_BIAS;
+    d.out = h->resid[l + 1]; d.ldo = 2 * c; d.out_dtype = DT_F32;
+    g_label = fmt("fpg down%d", l);
+    add_gemm(h, P, d, static_cast<long long>(h->Bcap) * (n / 2) * (n / 2));
+  }
+  auto cast_to_act = [&](const float* src, size_t elems) {
+    void* act_a = h->act_a;
+    g_label = "fpg cast";
+    add_op(P, [=](cudaStream_t st) {
+      const size_t total8 = elems / 8;
+      if (bf) launch_k(cast_kernel<bf16>, dim3(cdiv(total8, 256)), dim3(256), 0, st, src, static_cast<bf16*>(act_a), total8);
+      else launch_k(cast_kernel<float>, dim3(cdiv(total8, 256)), dim3(256), 0, st, src, static_cast<float*>(act_a), total8);
+    });
+  };
+  {  // convs[0]: 1x1 2048 -> 2048, no bias, PixelShuffle(1) == identity  (fpg/model.py:34-36,56-57)
+    const int n = h->sp[4], rows = B * n * n;
+    cast_to_act(h->resid[4], static_cast<size_t>(rows) * 2048);
+    GemmDesc d;
+    d.M = rows; d.N = 2048; d.K = 2048; d.A = h->act_a; d.lda = 2048; d.a_dtype = adt;
+    d.W = F.convs_w[0]; d.ldw = 2048; d.w_dtype = adt; d.bias = F.zero_bias; d.epi = EPI_BIAS;
+    d.out = F.p0; d.ldo = 2048; d.out_dtype = DT_F32;
+    g_label = "fpg convs0";
+    add_gemm(h, P, d, static_cast<long long>(h->Bcap) * n * n);
+  }
+  for (int j = 1; j < 5; ++j) {  // x = PixelShuffle(conv(x)) + skip, accumulated in place on the skip buffer
+    const int lin = 5 - j, lout = 4 - j;
+    const int cin = h->c[lin], n = h->sp[lin], rows_in = B * n * n;
+    cast_to_act(j == 1 ? F.p0 : h->resid[lin], static_cast<size_t>(rows_in) * cin);
+    GemmDesc d;
+    d.M = rows_in; d.N = 2 * cin; d.K = cin; d.A = h->act_a; d.lda = cin; d.a_dtype = adt;
+    d.W = F.convs_w[j]; d.ldw = cin; d.w_dtype = adt; d.bias = nullptr; d.epi = EPI_PIXSHUF; d.sp = n;
+    d.out = h->resid[lout]; d.ldo = cin / 2; d.out_dtype = DT_F32;
+    g_label = fmt("fpg convs%d", j);
+    add_gemm(h, P, d, static_cast<long long>(h->Bcap) * n * n);
+  }
+  Plan* raw = up.get();
+  h->fpg_plans[B] = std::move(up);
   return raw;
 }
 
@@ -1399,6 +1531,59 @@ int32_t hd_sample(hd_handle* h, float* x_inout, const hd_step_coef* coef, int32_
     CUDA_CHECK(cudaStreamSynchronize(st));
     check_device_status(h);
   }
+  join_out(h, stream);
+  HD_API_END(h)
+}
+
+int32_t hd_load_fpg_weights(hd_handle* h, const hd_tensor_desc* tensors, int32_t n, void* stream) {
+  HD_API_BEGIN
+  if (!h || !tensors || n <= 0) HD_THROW(HD_ERR_INVALID, "null argument");
+  if (h->fpg.loaded) HD_THROW(HD_ERR_STATE, "FPG weights already loaded; create a new handle to reload");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  (void)stream;
+  CUDA_CHECK(cudaDeviceSynchronize());
+  h->src.clear();
+  for (int i = 0; i < n; ++i) {
+    const hd_tensor_desc& t = tensors[i];
+    if (!t.name || !t.data) continue;
+    SrcTensor s;
+    s.data = t.data; s.dtype = t.dtype;
+    s.numel = 1;
+    for (int k = 0; k < t.ndim && k < 4; ++k) { s.shape.push_back(t.shape[k]); s.numel *= static_cast<size_t>(t.shape[k]); }
+    h->src[t.name] = s;
+  }
+  load_fpg_impl(h);
+  HD_API_END(h)
+}
+
+int32_t hd_fpg_forward(hd_handle* h, const float* cr_latent, float* const priors_out[5], int32_t B, void* stream) {
+  HD_API_BEGIN
+  if (!h || !cr_latent || !priors_out) HD_THROW(HD_ERR_INVALID, "null argument");
+  if (!h->fpg.loaded) HD_THROW(HD_ERR_STATE, "hd_load_fpg_weights has not been called");
+  if (B < 1 || B > h->cfg.max_batch) HD_THROW(HD_ERR_INVALID, "batch %d outside [1, %d]", B, h->cfg.max_batch);
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  join_in(h, stream);
+  cudaStream_t st = h->stream;
+  const size_t xe = static_cast<size_t>(B) * 4 * h->S * h->S;
+  if (!is_device_ptr(cr_latent)) {
+    CUDA_CHECK(cudaMemcpyAsync(h->x_stage, cr_latent, xe * 4, cudaMemcpyHostToDevice, st));
+    h->fpg_in = h->x_stage;
+  } else {
+    h->fpg_in = cr_latent;
+  }
+  Plan* P = get_fpg_plan(h, B);
+  for (auto& op : P->ops) op.fn(st);
+  // priors: p0 and the four skip buffers (now skip + upsampled), NHWC fp32 -> NCHW fp32 (model.py:46-64 order)
+  for (int j = 0; j < 5; ++j) {
+    const int lvl = 4 - j, C = h->c[lvl], hw = h->sp[lvl] * h->sp[lvl];
+    const float* src = j == 0 ? h->fpg.p0 : h->resid[lvl];
+    float* dst = priors_out[j];
+    if (!dst) HD_THROW(HD_ERR_INVALID, "priors_out[%d] is null", j);
+    if (!is_device_ptr(dst)) HD_THROW(HD_ERR_INVALID, "hd_fpg_forward writes device buffers");
+    const size_t total = static_cast<size_t>(B) * C * hw;
+    nhwc_to_nchw_kernel<float><<<cdiv(total, 256), 256, 0, st>>>(src, dst, B, C, hw, C);
+  }
+  CUDA_CHECK(cudaGetLastError());
   join_out(h, stream);
   HD_API_END(h)
 }

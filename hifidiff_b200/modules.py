@@ -98,6 +98,7 @@ class _Engine:
         lib = _lib.load()
         self.lib = lib
         self.handle = C.c_void_p()
+        self.fpg_loaded = False
         self.max_batch = max_batch
         self.max_steps = max_steps
         cfg = _lib.HdConfig(C.sizeof(_lib.HdConfig), model_kind, precision, latent_size,
@@ -122,7 +123,8 @@ class _Engine:
     def check(self, status: int, what: str) -> None:
         _lib.check(self.handle, status, what)
 
-    def load_state(self, state: dict) -> None:
+    @staticmethod
+    def _descs(state: dict):
         keep = []
         descs = (_lib.HdTensorDesc * len(state))()
         n = 0
@@ -146,8 +148,29 @@ class _Engine:
                 d.ndim = 1
                 d.shape[0] = 1
             n += 1
+        return descs, n, keep
+
+    def load_state(self, state: dict) -> None:
+        descs, n, keep = self._descs(state)
         self.check(self.lib.hd_load_weights(self.handle, descs, n, None), "hd_load_weights")
         del keep
+
+    def load_fpg_state(self, state: dict) -> None:
+        descs, n, keep = self._descs(state)
+        self.check(self.lib.hd_load_fpg_weights(self.handle, descs, n, None), "hd_load_fpg_weights")
+        self.fpg_loaded = True
+        del keep
+
+    def fpg_forward(self, cr_latent: torch.Tensor, latent_size: int = 16, width: int = 128):
+        """FacialPriorGuidance.forward on the sm_100a kernels -> list of 5 fp32 NCHW priors."""
+        x = cr_latent.to(torch.float32).contiguous()
+        b = x.shape[0]
+        outs = [torch.empty((b, width << (4 - j), latent_size >> (4 - j), latent_size >> (4 - j)),
+                            dtype=torch.float32, device=x.device) for j in range(5)]
+        ptrs = (C.c_void_p * 5)(*[o.data_ptr() for o in outs])
+        with torch.cuda.device(x.device):
+            self.check(self.lib.hd_fpg_forward(self.handle, x.data_ptr(), ptrs, b, _stream_ptr(x.device)), "hd_fpg_forward")
+        return outs
 
     def info(self) -> "_lib.HdInfo":
         info = _lib.HdInfo()
@@ -191,6 +214,8 @@ class _DenoiserBase(nn.Module):
         self.max_batch = 64
         self.max_steps = 1000
         self.use_graph = True
+        # a parent's load_state_dict reaches sub-modules through hooks, not through our override
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
 
     # ---- engine management -------------------------------------------------------------------
     def configure(self, precision: Optional[str] = None, max_batch: Optional[int] = None,

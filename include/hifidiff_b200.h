@@ -118,6 +118,14 @@ int32_t hd_load_weights(hd_handle* h, const hd_tensor_desc* tensors, int32_t n, 
 /* Optional: override the 64 sinusoidal frequencies (model.py:24-26) with host values. */
 int32_t hd_set_time_frequencies(hd_handle* h, const float* freqs64);
 
+/* FacialPriorGuidance on the same kernels (SURVEY.md §8f "next" row 1).  hd_load_fpg_weights takes the
+ * FPG module's state_dict (intro.*, encoders.L.i.*, downs.L.*, convs.j.0.weight; replaces
+ * fpg.load_state_dict, refiner.py:25); hd_fpg_forward replaces FacialPriorGuidance.forward
+ * (models/fpg/model.py:46-64): cr_latent (B,4,S,S) -> priors_out[j] (B, C_j, n_j, n_j) fp32 device buffers. */
+int32_t hd_load_fpg_weights(hd_handle* h, const hd_tensor_desc* tensors, int32_t n, void* stream);
+int32_t hd_fpg_forward(hd_handle* h, const float* cr_latent, float* const priors_out[5], int32_t batch,
+                       void* stream);
+
 /* Condition-only work, hoisted out of the timestep loop (it depends on neither x_t nor t):
  * idc_conv(identity) (model.py:245-246) and the five HCA channel/spatial gates computed from
  * the priors (hca.py:33-48).  priors[j]: (B, C_j, n_j, n_j) with C = 2048,1024,512,256,128 and
