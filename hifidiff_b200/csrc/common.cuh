@@ -24,6 +24,8 @@ enum Epi : int {
   EPI_GATE = 4,     // packed 128-column groups: out[m, g*64+i] = (acc[m,g*128+i]+b) * (acc[m,g*128+64+i]+b)
   EPI_PIXSHUF = 5,  // 1x1 up-conv + PixelShuffle(2) + skip add, in place on the fp32 skip buffer
   EPI_RESID_LN = 6, // EPI_RESID, and the following LayerNorm2d + AdaLN modulation of the same rows (N == 128)
+  EPI_DWGATE = 7,   // conv1 + bias, then depthwise 3x3 + SimpleGate + per-face mean over the staged tile
+                    // (gate-packed 128-column groups; tile = whole faces, spatial 2/4/8)
 };
 
 enum AMode : int {
@@ -59,6 +61,10 @@ struct GemmDesc {
   const int* mod_row_idx = nullptr;
   int mod_stride = 0, ln_shift_off = 0, ln_scale_off = 0, rows_per_face = 1;
   void* ln_out = nullptr;
+  // EPI_DWGATE: depthwise taps [9][N] and bias [N] in the packed column order, pooled means out (bf16 [faces, N/2])
+  const float* dw_w = nullptr;
+  const float* dw_b = nullptr;
+  void* pooled = nullptr;
 };
 
 // Device-side error word shared by all kernels of a handle (pipeline watchdog).

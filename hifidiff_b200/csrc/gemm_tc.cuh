@@ -44,6 +44,10 @@ struct TcArgs {
   const int* mod_row_idx;
   int mod_stride, ln_shift_off, ln_scale_off, rows_per_face;
   bf16* ln_out;
+  // EPI_DWGATE
+  const float* dw_w;
+  const float* dw_b;
+  bf16* pooled;
   long long* trace;           // optional per-CTA timeline (16 slots per CTA), nullptr in production
 };
 
@@ -54,7 +58,8 @@ template <int BN, int STAGES, int EW = 8> struct TileCfg {
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr int STAGING_BYTES = BM * BN * 4;  // fp32 accumulator tile, aliases the ring after the mainloop
   static_assert(RING_BYTES >= STAGING_BYTES, "epilogue staging must fit in the operand ring");
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int SEG_BYTES = 32 * 64 * 4;        // EPI_DWGATE: per-segment channel sums for the pooled mean
+  static constexpr int BAR_BYTES = 256 + SEG_BYTES;
   static constexpr int SMEM_BYTES = RING_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;               // power of two >= 32
   // co-resident CTAs per SM (228 KB shared memory, 512 TMEM columns): short-K GEMMs are dominated by
@@ -242,6 +247,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
   static_assert(EPI != EPI_GATE || BN == 128, "gate epilogue needs 128-column packed groups");
   static_assert(EPI != EPI_RESID_LN || BN == 128, "fused LayerNorm needs the whole 128-channel row in one tile");
+  static_assert(EPI != EPI_DWGATE || BN == 128, "depthwise+gate epilogue needs 128-column packed groups");
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment (same offset in every CTA of the cluster)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -396,6 +402,79 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (nsplit > 1) cluster_sync_all(); else __syncthreads();
   if (trace != nullptr && threadIdx.x == 64) trace[6] = clock64();
 
+  if (EPI == EPI_DWGATE) {
+    // ---------------- epilogue phase B': depthwise 3x3 + SimpleGate + pooled mean over the staged tile ----------------
+    // The tile holds whole faces (128 % sp^2 == 0).  A lane owns 2 gate channels (2 x1 + 2 x2 columns) with
+    // its 36 taps in registers; a warp walks 128/EW consecutive pixel rows.  conv1's output never leaves
+    // the SM and is never rounded (reference: conditional_naf.py:116-119).
+    float* s_seg = reinterpret_cast<float*>(bar_base + 256);  // [<=32 segments][64 channels]
+    if (warp >= 2) {
+      const int ew = warp - 2;
+      const int sp = args.sp, npix = sp * sp;
+      constexpr int RPW = BM / NUM_EPI_WARPS;                  // rows per warp
+      const int seg_len = npix < RPW ? npix : RPW;             // rows whose sums a warp keeps in registers
+      const int col1 = 2 * lane, col2 = 64 + 2 * lane;         // packed columns: x1 | x2
+      float w1[9][2], w2[9][2], bd1[2], bd2[2], bc1[2], bc2[2];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float2 a = __ldg(reinterpret_cast<const float2*>(args.dw_w + static_cast<size_t>(t) * args.N + n0 + col1));
+        const float2 b = __ldg(reinterpret_cast<const float2*>(args.dw_w + static_cast<size_t>(t) * args.N + n0 + col2));
+        w1[t][0] = a.x; w1[t][1] = a.y; w2[t][0] = b.x; w2[t][1] = b.y;
+      }
+      {
+        const float2 a = __ldg(reinterpret_cast<const float2*>(args.dw_b + n0 + col1));
+        const float2 b = __ldg(reinterpret_cast<const float2*>(args.dw_b + n0 + col2));
+        const float2 c = __ldg(reinterpret_cast<const float2*>(args.bias + n0 + col1));
+        const float2 d = __ldg(reinterpret_cast<const float2*>(args.bias + n0 + col2));
+        bd1[0] = a.x; bd1[1] = a.y; bd2[0] = b.x; bd2[1] = b.y;
+        bc1[0] = c.x; bc1[1] = c.y; bc2[0] = d.x; bc2[1] = d.y;
+      }
+      const int ck1 = lane >> 1, ck2 = 16 + (lane >> 1), sub2 = (lane & 1) * 2;
+      bf16* gout = reinterpret_cast<bf16*>(args.out);
+      float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll 1
+      for (int rr = 0; rr < RPW; ++rr) {
+        const int r = ew * RPW + rr;
+        const int pf = r % npix;
+        const int py = pf / sp, px = pf - py * sp;
+        float a1[2] = {bd1[0], bd1[1]}, a2[2] = {bd2[0], bd2[1]};
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int dy = t / 3 - 1, dx = t % 3 - 1;
+          const int yy = py + dy, xx = px + dx;
+          if (yy < 0 || yy >= sp || xx < 0 || xx >= sp) continue;
+          const int r2 = r + dy * sp + dx;
+          const float* row2 = stage + r2 * BN;
+          const float2 x1 = *reinterpret_cast<const float2*>(row2 + ((ck1 ^ (r2 & 7)) << 2) + sub2);
+          const float2 x2 = *reinterpret_cast<const float2*>(row2 + ((ck2 ^ (r2 & 7)) << 2) + sub2);
+          a1[0] = fmaf(x1.x + bc1[0], w1[t][0], a1[0]);
+          a1[1] = fmaf(x1.y + bc1[1], w1[t][1], a1[1]);
+          a2[0] = fmaf(x2.x + bc2[0], w2[t][0], a2[0]);
+          a2[1] = fmaf(x2.y + bc2[1], w2[t][1], a2[1]);
+        }
+        const float o0 = a1[0] * a2[0], o1 = a1[1] * a2[1];
+        ps0 += o0; ps1 += o1;
+        const int m = m0 + r;
+        if (m < args.M)
+          *reinterpret_cast<uint32_t*>(gout + static_cast<size_t>(m) * args.ldo + (n0 >> 1) + 2 * lane) = pack_bf16x2(o0, o1);
+        if ((rr + 1) % seg_len == 0) {
+          *reinterpret_cast<float2*>(s_seg + (r / seg_len) * 64 + 2 * lane) = make_float2(ps0, ps1);
+          ps0 = 0.f; ps1 = 0.f;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+      // per-face means, segments added in fixed order (deterministic)
+      const int faces_in_tile = BM / npix, segs_per_face = npix / seg_len;
+      for (int i = threadIdx.x - 64; i < faces_in_tile * 64; i += 32 * NUM_EPI_WARPS) {
+        const int f = i >> 6, ch = i & 63;
+        const int face = m0 / npix + f;
+        if (face * npix >= args.M) continue;
+        float sum = 0.f;
+        for (int q = 0; q < segs_per_face; ++q) sum += s_seg[(f * segs_per_face + q) * 64 + ch];
+        args.pooled[static_cast<size_t>(face) * args.ldo + (n0 >> 1) + ch] = __float2bfloat16_rn(sum / static_cast<float>(npix));
+      }
+    }
+  } else
   if (warp >= 2) {
     // ---------------- epilogue phase B: lanes along columns, coalesced global traffic ----------------
     constexpr int CH = (EPI == EPI_GATE) ? BN / 8 : BN / 4;  // output 4-column chunks per row

@@ -55,6 +55,10 @@ constexpr float kBnEps = 1e-5f;
 inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
 bool g_use_pdl = true;  // HD_PDL=0 disables programmatic dependent launch
+// HD_FUSE_DW=1 runs depthwise 3x3 + gate + pool in conv1's epilogue at the 2x2..8x8 levels (EPI_DWGATE).
+// Measured on B200 at B=256: parity-equal but slower (2.75 vs 2.62 ms/step: the 9-tap stencil is
+// latency-bound on the 8 epilogue warps), so the standalone sliding-window kernel stays the default.
+bool g_fuse_dw = false;
 
 // Per-step kernel launch: programmatic stream serialization lets kernel N+1 be scheduled (and run its
 // prologue / weight prefetch) while kernel N drains; every such kernel executes pdl_wait() first.
@@ -118,6 +122,7 @@ struct BlockW {
   float *dw_w = nullptr, *dw_b = nullptr;
   bool dw_folded = false;  // 1x1 level: depthwise 3x3 == per-channel scale, folded into conv1 (gate-packed)
   bool has_mod = true;     // false: unconditional NAFBlock of the FPG encoder (models/fpg/naf.py:105-126)
+  bool dw_fused = false;   // 2x2..8x8 levels, bf16: depthwise 3x3 + gate + pool run in conv1's epilogue (gate-packed)
 };
 
 // FacialPriorGuidance (models/fpg/model.py:7-64): NAFNet encoder over the CR latent, run once per face batch
@@ -319,6 +324,7 @@ void launch_tc(const TcLaunch& L, cudaStream_t st) {
     case EPI_RESID: launch_tc_inst<EPI_RESID, A_PLAIN, float>(L, st); break;
     case EPI_RESID_LN: launch_tc_inst<EPI_RESID_LN, A_PLAIN, float>(L, st); break;
     case EPI_GATE: launch_tc_inst<EPI_GATE, A_PLAIN, bf16>(L, st); break;
+    case EPI_DWGATE: launch_tc_inst<EPI_DWGATE, A_PLAIN, bf16>(L, st); break;
     case EPI_PIXSHUF: launch_tc_inst<EPI_PIXSHUF, A_PLAIN, float>(L, st); break;
     default: break;
   }
@@ -346,6 +352,7 @@ TcLaunch build_tc(hd_handle* h, const GemmDesc& d, long long a_rows_alloc) {
   a.ln_w = d.ln_w; a.ln_b = d.ln_b; a.mod_table = d.mod_table; a.mod_row_idx = d.mod_row_idx;
   a.mod_stride = d.mod_stride; a.ln_shift_off = d.ln_shift_off; a.ln_scale_off = d.ln_scale_off;
   a.rows_per_face = d.rows_per_face; a.ln_out = static_cast<bf16*>(d.ln_out);
+  a.dw_w = d.dw_w; a.dw_b = d.dw_b; a.pooled = static_cast<bf16*>(d.pooled);
   a.trace = nullptr;
   if (d.a_mode == A_CONV3) {
     const int n = d.sp, C = d.C;
@@ -374,7 +381,7 @@ TcLaunch build_tc(hd_handle* h, const GemmDesc& d, long long a_rows_alloc) {
   const int tiles = cdiv(d.M, 128) * (d.N / 128);
   int split = 1;
   while (tiles * split < 120 && split < 8 && a.num_kb % (2 * split) == 0 && a.num_kb / (2 * split) >= 2) split *= 2;
-  if (d.epi == EPI_RESID_LN) split = 1;  // the fused LayerNorm needs the finished row in one CTA
+  if (d.epi == EPI_RESID_LN || d.epi == EPI_DWGATE) split = 1;  // these epilogues need the finished tile in one CTA
   L.grid = dim3(cdiv(d.M, 128), d.N / 128, split);
   const int local_kb = a.num_kb / split;
   L.stages = local_kb <= 2 ? 2 : (tiles * split <= 160 ? 6 : 3);
@@ -500,12 +507,33 @@ void load_block(hd_handle* h, BlockW& bw, int wdt) {
     bw.w1 = pack_matrix(h, need(h, p + "conv1.weight", {2 * c, c}), 2 * c, c, 1, &perm, &rs, wdt);
     bw.b1 = upload_f32(h, bp);
     bw.dw_folded = true;
+  } else if (g_fuse_dw && wdt == DT_BF16 && h->sp[bw.level] <= 8) {
+    // conv1 rows (and its bias, the depthwise taps and bias) in the gate-packed column order, so that the
+    // depthwise 3x3 + SimpleGate + pool can run over conv1's staged accumulator tile (EPI_DWGATE)
+    auto dw = host_vec(h, need(h, p + "conv2.weight", {2 * c, 9}));
+    auto dwb = host_vec(h, need(h, p + "conv2.bias", {2 * c}));
+    auto b1 = host_vec(h, need(h, p + "conv1.bias", {2 * c}));
+    std::vector<int> perm(2 * c);
+    std::vector<float> b1p(2 * c), dwbp(2 * c), dwp(static_cast<size_t>(18) * c);
+    for (int n = 0; n < 2 * c; ++n) {
+      const int g = n / 128, r = n % 128;
+      const int ch = r < 64 ? g * 64 + r : c + g * 64 + (r - 64);
+      perm[n] = ch;
+      b1p[n] = b1[ch];
+      dwbp[n] = dwb[ch];
+      for (int t = 0; t < 9; ++t) dwp[static_cast<size_t>(t) * 2 * c + n] = dw[static_cast<size_t>(ch) * 9 + t];
+    }
+    bw.w1 = pack_matrix(h, need(h, p + "conv1.weight", {2 * c, c}), 2 * c, c, 1, &perm, nullptr, wdt);
+    bw.b1 = upload_f32(h, b1p);
+    bw.dw_w = upload_f32(h, dwp);
+    bw.dw_b = upload_f32(h, dwbp);
+    bw.dw_fused = true;
   } else {
     bw.w1 = pack_matrix(h, need(h, p + "conv1.weight", {2 * c, c}), 2 * c, c, 1, nullptr, nullptr, wdt);
     bw.b1 = upload_f32(h, host_vec(h, need(h, p + "conv1.bias", {2 * c})));
   }
 
-  {  // depthwise 3x3: [2c,1,3,3] -> [9][2c]
+  if (!bw.dw_fused) {  // depthwise 3x3: [2c,1,3,3] -> [9][2c]
     auto w = host_vec(h, need(h, p + "conv2.weight", {2 * c, 9}));
     std::vector<float> t(static_cast<size_t>(18) * c);
     for (int ch = 0; ch < 2 * c; ++ch)
@@ -649,7 +677,7 @@ void add_gemm(hd_handle* h, Plan& P, GemmDesc d, long long a_rows_alloc, const s
   const long long taps_exec = d.a_mode == A_CONV3 ? 1 : 1;
   (void)taps_exec;
   P.flops_per_face += 2.0 * d.M * static_cast<double>(d.N) * d.K / P.batch;
-  static const char* epi_names[] = {"bias", "relu", "sigmoid", "resid", "gate", "pixshuf", "resid+ln"};
+  static const char* epi_names[] = {"bias", "relu", "sigmoid", "resid", "gate", "pixshuf", "resid+ln", "dw3x3+gate+pool"};
   const std::string what = g_label;
   if (tc_eligible(h, d)) {
     TcLaunch L = build_tc(h, d, a_rows_alloc);
@@ -736,7 +764,14 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
     add_op(P, ln(bw.ln1_w, bw.ln1_b, bw.mod_off, bw.mod_off + c));
   }
   g_label = L0 + "conv1";
-  if (bw.dw_folded) {  // conv1 + (folded) depthwise + SimpleGate; the pooled mean over 1 pixel is g itself
+  if (bw.dw_fused) {  // conv1 with depthwise 3x3 + SimpleGate + per-face mean in the epilogue
+    GemmDesc d;
+    d.M = rows; d.N = 2 * c; d.K = c; d.A = act_a; d.lda = c; d.a_dtype = adt;
+    d.W = bw.w1; d.ldw = c; d.w_dtype = adt; d.bias = bw.b1; d.epi = EPI_DWGATE; d.sp = sp;
+    d.out = act_g; d.ldo = c; d.out_dtype = adt; d.dw_w = bw.dw_w; d.dw_b = bw.dw_b; d.pooled = pooled;
+    add_gemm(h, P, d, rows_alloc);
+    P.flops_per_face += 2.0 * 9 * 2 * c * rpf;
+  } else if (bw.dw_folded) {  // conv1 + (folded) depthwise + SimpleGate; the pooled mean over 1 pixel is g itself
     GemmDesc d;
     d.M = rows; d.N = 2 * c; d.K = c; d.A = act_a; d.lda = c; d.a_dtype = adt;
     d.W = bw.w1; d.ldw = c; d.w_dtype = adt; d.bias = bw.b1; d.epi = EPI_GATE;
@@ -750,7 +785,7 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
     add_gemm(h, P, d, rows_alloc);
   }
   g_label = L0 + "dwconv_gate_pool";
-  if (!bw.dw_folded) {  // depthwise 3x3 + SimpleGate + pool
+  if (!bw.dw_folded && !bw.dw_fused) {  // depthwise 3x3 + SimpleGate + pool
     const float *dw_w = bw.dw_w, *dw_b = bw.dw_b;
     add_op(P, [=](cudaStream_t st) {
       const int tile_px = sp >= 16 ? sp * sp : 64;   // whole faces per tile; small tiles below 16x16 for parallelism
@@ -1235,6 +1270,7 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10) HD_THROW(HD_ERR_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
   if (const char* e = getenv("HD_PDL")) g_use_pdl = atoi(e) != 0;
+  if (const char* e = getenv("HD_FUSE_DW")) g_fuse_dw = atoi(e) != 0;
   h = new hd_handle();
   struct Guard { hd_handle*& p; bool armed = true; ~Guard() { if (armed && p) { hd_destroy(p); p = nullptr; } } } guard{h};
   h->cfg = *cfg;
