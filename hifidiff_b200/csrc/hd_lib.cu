@@ -55,6 +55,7 @@ constexpr float kBnEps = 1e-5f;
 inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
 bool g_use_pdl = true;  // HD_PDL=0 disables programmatic dependent launch
+bool g_bn256 = true;    // HD_BN256=0: 128x128 tiles for the dense 3x3 convs too
 // HD_FUSE_DW=1 runs depthwise 3x3 + gate + pool in conv1's epilogue at the 2x2..8x8 levels (EPI_DWGATE).
 // Measured on B200 at B=256: parity-equal but slower (2.75 vs 2.62 ms/step: the 9-tap stencil is
 // latency-bound on the 8 epilogue warps), so the standalone sliding-window kernel stays the default.
@@ -270,13 +271,13 @@ struct TcLaunch {
   CUtensorMap mapA, mapB;
   tc::TcArgs args;
   dim3 grid;
-  int epi, a_mode, out_dtype, stages;
+  int epi, a_mode, out_dtype, stages, bn;
 };
 
-template <int STAGES, int EW, int EPI, int AMODE, typename TOut>
+template <int STAGES, int EW, int EPI, int AMODE, typename TOut, int BN = 128>
 void launch_tc_inst2(const TcLaunch& L, cudaStream_t st) {
-  auto kern = tc::gemm_tc_kernel<128, STAGES, EPI, AMODE, TOut, EW>;
-  using Cfg = tc::TileCfg<128, STAGES, EW>;
+  auto kern = tc::gemm_tc_kernel<BN, STAGES, EPI, AMODE, TOut, EW>;
+  using Cfg = tc::TileCfg<BN, STAGES, EW>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -312,7 +313,11 @@ void launch_tc_inst(const TcLaunch& L, cudaStream_t st) {
 void launch_tc(const TcLaunch& L, cudaStream_t st) {
   const bool obf = L.out_dtype == DT_BF16;
   if (L.a_mode == A_CONV3) {
-    if (L.epi == EPI_RELU && obf) launch_tc_inst<EPI_RELU, A_CONV3, bf16>(L, st);
+    if (L.epi == EPI_RELU && obf) {
+      // dense 3x3 (K = 9C, operand-fill-bound): 128x256 tiles halve the A fill per flop
+      if (L.bn == 256) launch_tc_inst2<3, 8, EPI_RELU, A_CONV3, bf16, 256>(L, st);
+      else launch_tc_inst<EPI_RELU, A_CONV3, bf16>(L, st);
+    }
     return;
   }
   switch (L.epi) {
@@ -371,18 +376,20 @@ TcLaunch build_tc(hd_handle* h, const GemmDesc& d, long long a_rows_alloc) {
     cuuint32_t box[2] = {64, 128};
     encode_map(h, &L.mapA, d.A, 2, dims, strides, box);
   }
+  const int bn = (g_bn256 && d.a_mode == A_CONV3 && d.epi == EPI_RELU && d.out_dtype == DT_BF16 && d.N % 256 == 0) ? 256 : 128;
+  L.bn = bn;
   {
     cuuint64_t dims[2] = {(cuuint64_t)d.K, (cuuint64_t)d.N};
     cuuint64_t strides[1] = {(cuuint64_t)d.ldw * 2};
-    cuuint32_t box[2] = {64, 128};
+    cuuint32_t box[2] = {64, (cuuint32_t)bn};
     encode_map(h, &L.mapB, d.W, 2, dims, strides, box);
   }
   // split-K over a (1,1,S) cluster until the grid can cover the chip (>= 120 CTAs)
-  const int tiles = cdiv(d.M, 128) * (d.N / 128);
+  const int tiles = cdiv(d.M, 128) * (d.N / bn);
   int split = 1;
   while (tiles * split < 120 && split < 8 && a.num_kb % (2 * split) == 0 && a.num_kb / (2 * split) >= 2) split *= 2;
   if (d.epi == EPI_RESID_LN || d.epi == EPI_DWGATE) split = 1;  // these epilogues need the finished tile in one CTA
-  L.grid = dim3(cdiv(d.M, 128), d.N / 128, split);
+  L.grid = dim3(cdiv(d.M, 128), d.N / bn, split);
   const int local_kb = a.num_kb / split;
   L.stages = local_kb <= 2 ? 2 : (tiles * split <= 160 ? 6 : 3);
   return L;
@@ -682,7 +689,7 @@ void add_gemm(hd_handle* h, Plan& P, GemmDesc d, long long a_rows_alloc, const s
   if (tc_eligible(h, d)) {
     TcLaunch L = build_tc(h, d, a_rows_alloc);
     g_label = fmt("%s gemm_tc %s%s M=%d N=%d K=%d grid=(%d,%d,%d) stages=%d", what.c_str(), epi_names[d.epi],
-                  d.a_mode == A_CONV3 ? "+conv3" : "", d.M, d.N, d.K, L.grid.x, L.grid.y, L.grid.z, L.stages);
+                  d.a_mode == A_CONV3 ? (L.bn == 256 ? "+conv3 BN=256" : "+conv3") : "", d.M, d.N, d.K, L.grid.x, L.grid.y, L.grid.z, L.stages);
     add_op(P, [L](cudaStream_t st) { launch_tc(L, st); }, tap, info);
     return;
   }
@@ -1271,6 +1278,7 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   if (prop.major != 10) HD_THROW(HD_ERR_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
   if (const char* e = getenv("HD_PDL")) g_use_pdl = atoi(e) != 0;
   if (const char* e = getenv("HD_FUSE_DW")) g_fuse_dw = atoi(e) != 0;
+  if (const char* e = getenv("HD_BN256")) g_bn256 = atoi(e) != 0;
   h = new hd_handle();
   struct Guard { hd_handle*& p; bool armed = true; ~Guard() { if (armed && p) { hd_destroy(p); p = nullptr; } } } guard{h};
   h->cfg = *cfg;
