@@ -1,0 +1,88 @@
+"""GPU: ragged and edge-case inputs through the module API (row tails across 128-row tiles, partial
+face groups in the dwconv / split-K paths, batch growth, empty batches, state reuse)."""
+import pytest
+import torch
+
+import hifidiff_b200 as H
+from hifidiff_b200 import testing
+from oracle import denoiser_ref
+
+from gpu_util import build
+from util import inputs, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fused32():
+    m, sd = build(H.FusedDenoiser, seed=2, precision="fp32", max_batch=4)
+    yield m, sd
+    m.invalidate()
+
+
+@pytest.fixture(scope="module")
+def fused16():
+    m, sd = build(H.FusedDenoiser, seed=2, precision="bf16", max_batch=4)
+    yield m, sd
+    m.invalidate()
+
+
+@pytest.mark.parametrize("batch", [1, 3, 130])
+def test_ragged_batch_fp32(fused32, batch):
+    """130 faces = one full 128-face tile + 2 at the 1x1 level, 65 tiles at 8x8, ... every tail path."""
+    m, sd = fused32
+    x = inputs("latents", batch, seed=20 + batch)
+    priors, ident = testing.synthetic_condition(batch, 16, seed=batch)
+    t = torch.arange(batch) * 7 % 1000                    # per-face timesteps
+    out = m(x.cuda(), t.cuda(), [p.cuda() for p in priors], ident.cuda()).sample
+    m.engine().synchronize()
+    assert m.max_batch >= batch                            # the engine grew its workspace on demand
+    with torch.no_grad():
+        ref = denoiser_ref.fused_denoiser_forward(sd, x, t, priors, ident)
+    assert rel_l2(out, ref) <= 1e-5
+    # faces are independent: face 0 alone gives the same answer
+    one = m(x[:1].cuda(), t[:1].cuda(), [p[:1].contiguous().cuda() for p in priors], ident[:1].contiguous().cuda()).sample
+    assert rel_l2(one, ref[:1]) <= 1e-5
+
+
+@pytest.mark.parametrize("batch", [1, 5, 130])
+def test_ragged_batch_bf16(fused16, batch):
+    m, sd = fused16
+    x = inputs("latents", batch, seed=40 + batch)
+    priors, ident = testing.synthetic_condition(batch, 16, seed=100 + batch)
+    out = m(x.cuda(), 321, [p.cuda() for p in priors], ident.cuda()).sample
+    m.engine().synchronize()
+    with torch.no_grad():
+        ref = denoiser_ref.fused_denoiser_forward(sd, x, 321, priors, ident)
+    assert rel_l2(out, ref) <= 1e-2
+    assert torch.isfinite(out).all()
+
+
+def test_empty_and_malformed_inputs_raise(fused16):
+    m, _ = fused16
+    priors, ident = testing.synthetic_condition(2, 16, seed=0)
+    pc, ic = [p.cuda() for p in priors], ident.cuda()
+    with pytest.raises((RuntimeError, ValueError)):
+        m(torch.zeros(0, 4, 16, 16).cuda(), 5, [p[:0] for p in pc], ic[:0])
+    with pytest.raises(ValueError):
+        m(torch.zeros(2, 4, 16, 16).cuda(), torch.tensor([1, 2, 3]), pc, ic)          # 3 timesteps for 2 faces
+    with pytest.raises(ValueError):
+        m(torch.zeros(2, 4, 16, 16).cuda(), 5, pc[:4], ic)                             # 4 priors
+    with pytest.raises(ValueError):
+        m(torch.zeros(2, 4, 16, 16).cuda(), 5, [pc[1]] + pc[1:], ic)                   # wrong prior shape
+
+
+def test_sampler_ragged_and_repeatable(fused16):
+    m, sd = fused16
+    sched = H.DDIMScheduler(num_train_timesteps=1000, beta_schedule="scaled_linear", prediction_type="epsilon",
+                            clip_sample=True, clip_sample_range=3.0)              # test_refiner.py:166-171 variant
+    x = inputs("latents", 3, seed=77).cuda()
+    priors, ident = testing.synthetic_condition(3, 16, seed=77)
+    pc, ic = [p.cuda() for p in priors], ident.cuda()
+    a = H.ddim_sample(m, x, sched, 7, facial_priors=pc, identity_embedding=ic)
+    b = H.ddim_sample(m, x, sched, 7, facial_priors=pc, identity_embedding=ic)
+    m.engine().synchronize()
+    assert torch.equal(a, b) and torch.isfinite(a).all()
+    assert not torch.equal(a, x)                                                    # input untouched, output new
+    c = H.ddim_sample(m, x, sched, 8, facial_priors=pc, identity_embedding=ic)      # different schedule -> new table
+    assert not torch.equal(a, c)
