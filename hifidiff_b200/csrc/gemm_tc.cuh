@@ -566,7 +566,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     };
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    if (nsplit == 1) {
+    if (nsplit == 1 && EPI != EPI_PIXSHUF) {
+      // Fast path: the CTA finishes all 128 rows; a lane group's rows advance by STEP (a multiple of 8, so
+      // the staging swizzle phase is pass-invariant) and every address is base + compile-time offset.
+      constexpr int STEP = NUM_EPI_WARPS * RPI;
+      constexpr int PASSES = BM / STEP;
+      constexpr int U = PASSES < 4 ? PASSES : 4;            // passes batched for memory-level parallelism
+      static_assert(STEP % 8 == 0 && PASSES % U == 0, "row walk");
+      const int r0 = ew * RPI + sub;
+      const int swz = r0 & 7;
+      const float* sbase = stage + r0 * BN;
+      TOut* dbase = reinterpret_cast<TOut*>(args.out) + static_cast<size_t>(m0 + r0) * args.ldo + out_col0 + sl * 4;
+      const float* rbase = (EPI == EPI_RESID || EPI == EPI_RESID_LN)
+                               ? args.resid + static_cast<size_t>(m0 + r0) * args.ldr + n0 + sl * 4 : nullptr;
+      const size_t dstep = static_cast<size_t>(STEP) * args.ldo, rstep = static_cast<size_t>(STEP) * args.ldr;
+      int soff[CPL], soff2[CPL];
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        soff[i] = ((i * LPR + sl) ^ swz) << 2;
+        soff2[i] = ((i * LPR + sl + 16) ^ swz) << 2;
+      }
+#pragma unroll 1
+      for (int it0 = 0; it0 < PASSES; it0 += U) {
+        float4 acc[U][CPL], acc2[U][CPL], ext[U][CPL];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int p = it0 + u;
+          ok[u] = m0 + r0 + p * STEP < args.M;
+#pragma unroll
+          for (int i = 0; i < CPL; ++i) {
+            acc[u][i] = *reinterpret_cast<const float4*>(sbase + p * (STEP * BN) + soff[i]);
+            acc2[u][i] = zero4;
+            ext[u][i] = zero4;
+            if (EPI == EPI_GATE) acc2[u][i] = *reinterpret_cast<const float4*>(sbase + p * (STEP * BN) + soff2[i]);
+            if ((EPI == EPI_RESID || EPI == EPI_RESID_LN) && ok[u])
+              ext[u][i] = *reinterpret_cast<const float4*>(rbase + p * rstep + i * LPR * 4);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int i = 0; i < CPL; ++i) {
+            const float4 r = finish(acc[u][i], acc2[u][i], ext[u][i], i, dbase + (it0 + u) * dstep, ok[u]);
+            if (EPI == EPI_RESID_LN) layer_norm_row(r, m0 + r0 + (it0 + u) * STEP, ok[u]);
+          }
+      }
+    } else if (nsplit == 1) {
       constexpr int U = 4;                                  // passes batched for memory-level parallelism
 #pragma unroll 1
       for (int it0 = 0; it0 < passes; it0 += U) {
