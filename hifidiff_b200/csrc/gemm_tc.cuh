@@ -697,5 +697,266 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 }
 
+
+// ================================================================================================
+// 2-CTA variant (tcgen05 cta_group::2): a thread-block cluster (2,1,1) of two SMs computes one 256 x 256
+// output tile.  Each CTA TMA-loads its own 128 A rows and its half (128 rows) of the W tile; the leader
+// CTA issues M=256, N=256, K=16 MMAs that read A and W from both CTAs' shared memory and write each CTA's
+// 128 accumulator rows into that CTA's TMEM.  Operand fill per CTA and k-block stays 32 KB for twice the
+// flops of the 128x128 tile — the fill (~60 B/clk/SM) is what bounds the 1-CTA mainloop.
+//   - TMA loads of both CTAs complete on the LEADER's full barrier (peer bit of the barrier address
+//     cleared); the leader's producer arms it with the bytes of both CTAs.
+//   - tcgen05.commit.cta_group::2 multicasts slot-free / accumulator-ready arrivals to both CTAs.
+//   - TMEM is allocated with cta_group::2 by the same warp in both CTAs.
+// No split-K; epilogues: bias, ReLU, SimpleGate, +residual (rows walked coalesced, as in the 1-CTA kernel).
+// ================================================================================================
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t v;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(v));
+  return v;
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(leader_bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                             uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(leader_bar)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint64_t desc_a, uint64_t desc_b, uint32_t tmem_d, uint32_t accumulate,
+                                           uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {  // arrive on the same barrier in both CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+
+struct Tile2Cfg {
+  static constexpr int BN = 256;                 // pair tile: 256 rows x 256 columns
+  static constexpr int STAGES = 4;
+  static constexpr int A_BYTES = BM * BK * 2;    // this CTA's 128 A rows
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the W tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;   // 128 KB == fp32 staging of 128 x 256
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = RING_BYTES + BAR_BYTES + 1024;
+  static constexpr int EW = 8;
+};
+
+template <int EPI, int AMODE, typename TOut>
+__global__ void __launch_bounds__(num_threads(Tile2Cfg::EW), 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcArgs args) {
+  using Cfg = Tile2Cfg;
+  constexpr int BN = Cfg::BN, STAGES = Cfg::STAGES, NUM_EPI_WARPS = Cfg::EW;
+  static_assert(EPI == EPI_BIAS || EPI == EPI_RELU || EPI == EPI_GATE || EPI == EPI_RESID, "2-CTA epilogues");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bar_base = smem + Cfg::RING_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();       // 0 = leader
+  const int m_tile = blockIdx.x;                 // 128-row tile of this CTA (pair = blockIdx.x / 2)
+  const int m0 = m_tile * BM;
+  const int n0 = blockIdx.y * BN;
+  const int num_kb = args.num_kb;
+  pdl_trigger();
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&mapA);
+    prefetch_tensormap(&mapB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);   // leader: its producer's arrive.expect_tx (bytes of both CTAs)
+      mbar_init(smem_u32(&empty_bar[s]), 1);  // one multicast tcgen05.commit per use
+    }
+    mbar_init(smem_u32(tmem_full_bar), 1);
+    fence_barrier_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) {
+    tmem_alloc2(smem_u32(tmem_slot), 256);
+    tmem_relinquish2();
+  }
+  tc_fence_before_sync();
+  cluster_sync_all();  // barriers of both CTAs are initialised before anyone signals them
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  float* stage = reinterpret_cast<float*>(smem);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer (both CTAs) ----------------
+      int conv_b0 = 0, conv_h0 = 0;
+      if (AMODE == A_CONV3) {
+        if (args.conv_bb > 1) {
+          conv_b0 = m_tile * args.conv_bb;
+        } else {
+          const int tiles_per_face = args.sp / args.conv_bh;
+          conv_b0 = m_tile / tiles_per_face;
+          conv_h0 = (m_tile % tiles_per_face) * args.conv_bh;
+        }
+      }
+      pdl_wait();
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u, args.status, 0x500u);
+        const uint32_t fb_local = smem_u32(&full_bar[s]);
+        const uint32_t fb_leader = fb_local & kPeerBitMask;
+        const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t sb = sa + Cfg::A_BYTES;
+        if (rank == 0) mbar_expect_tx(fb_local, 2 * Cfg::STAGE_BYTES);
+        if (AMODE == A_CONV3) {
+          const int tap = i / args.kb_per_tap;
+          const int c0 = (i - tap * args.kb_per_tap) * BK;
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          tma2_load_4d(sa, &mapA, c0, dx, conv_h0 + dy, conv_b0, fb_leader);
+        } else {
+          tma2_load_2d(sa, &mapA, i * BK, m0, fb_leader);
+        }
+        tma2_load_2d(sb, &mapB, i * BK, n0 + static_cast<int>(rank) * (BN / 2), fb_leader);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ---------------- MMA issuer (leader CTA only) ----------------
+      constexpr uint32_t idesc = make_idesc(2 * BM, BN);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(smem_u32(&full_bar[s]), ph, args.status, 0x600u);
+        tc_fence_after_sync();
+        const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint64_t da = make_smem_desc(sa);
+        const uint64_t db = make_smem_desc(sa + Cfg::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) umma2_bf16(da + 2 * k, db + 2 * k, tmem_base, (i | k) != 0 ? 1u : 0u, idesc);
+        umma2_commit_mc(smem_u32(&empty_bar[s]));
+      }
+      umma2_commit_mc(smem_u32(tmem_full_bar));
+    }
+  } else {
+    // ---------------- epilogue phase A: this CTA's 128 accumulator rows -> staging ----------------
+    const int quad = warp & 3;
+    pdl_wait();
+    mbar_wait(smem_u32(tmem_full_bar), 0u, args.status, 0x700u);
+    tc_fence_after_sync();
+    const int r = quad * 32 + lane;
+    const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    float* srow = stage + r * BN;
+    constexpr int COLS_PER_WARP = BN / (NUM_EPI_WARPS / 4);
+    const int cbeg = ((warp - 2) >> 2) * COLS_PER_WARP;
+#pragma unroll 1
+    for (int c0 = cbeg; c0 < cbeg + COLS_PER_WARP; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(taddr_row + c0, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ck = (c0 >> 2) + j;
+        *reinterpret_cast<uint4*>(srow + ((ck ^ (r & 7)) << 2)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before_sync();
+  __syncthreads();
+
+  if (warp >= 2) {
+    // ---------------- epilogue phase B ----------------
+    // gate: the 256 packed columns are two 128-column groups [64 x1 | 64 x2]; output chunk j (of 32) takes
+    // staged chunks (j/16)*32 + j%16 and +16
+    constexpr int CH = (EPI == EPI_GATE) ? BN / 8 : BN / 4;
+    constexpr int LPR = 32, RPI = 1, CPL = CH / LPR;
+    constexpr int STEP = NUM_EPI_WARPS * RPI, PASSES = BM / STEP, U = 4;
+    const int ew = warp - 2, sl = lane;
+    const int out_col0 = (EPI == EPI_GATE) ? (n0 >> 1) : n0;
+    const int r0 = ew;
+    const int swz = r0 & 7;
+    const float* sbase = stage + r0 * BN;
+    TOut* dbase = reinterpret_cast<TOut*>(args.out) + static_cast<size_t>(m0 + r0) * args.ldo + out_col0 + sl * 4;
+    const float* rbase = (EPI == EPI_RESID) ? args.resid + static_cast<size_t>(m0 + r0) * args.ldr + n0 + sl * 4 : nullptr;
+    const size_t dstep = static_cast<size_t>(STEP) * args.ldo, rstep = static_cast<size_t>(STEP) * args.ldr;
+    float4 bias_r[CPL], bias2_r[CPL];
+    int soff[CPL], soff2[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      const int j = i * LPR + sl;                                   // output chunk
+      const int ck = (EPI == EPI_GATE) ? ((j >> 4) * 32 + (j & 15)) : j;  // staged chunk
+      soff[i] = (ck ^ swz) << 2;
+      soff2[i] = ((ck + 16) ^ swz) << 2;
+      bias_r[i] = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + ck * 4));
+      bias2_r[i] = bias_r[i];
+      if (EPI == EPI_GATE) bias2_r[i] = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + (ck + 16) * 4));
+    }
+#pragma unroll 1
+    for (int it0 = 0; it0 < PASSES; it0 += U) {
+      float4 acc[U][CPL], acc2[U][CPL], ext[U][CPL];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int p = it0 + u;
+        ok[u] = m0 + r0 + p * STEP < args.M;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          acc[u][i] = *reinterpret_cast<const float4*>(sbase + p * (STEP * BN) + soff[i]);
+          acc2[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          ext[u][i] = acc2[u][i];
+          if (EPI == EPI_GATE) acc2[u][i] = *reinterpret_cast<const float4*>(sbase + p * (STEP * BN) + soff2[i]);
+          if (EPI == EPI_RESID && ok[u]) ext[u][i] = *reinterpret_cast<const float4*>(rbase + p * rstep + i * LPR * 4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          float4 v = acc[u][i];
+          v.x += bias_r[i].x; v.y += bias_r[i].y; v.z += bias_r[i].z; v.w += bias_r[i].w;
+          if (EPI == EPI_GATE) {
+            const float4 g = acc2[u][i];
+            v.x *= g.x + bias2_r[i].x; v.y *= g.y + bias2_r[i].y; v.z *= g.z + bias2_r[i].z; v.w *= g.w + bias2_r[i].w;
+          }
+          if (EPI == EPI_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          if (EPI == EPI_RESID) { v.x += ext[u][i].x; v.y += ext[u][i].y; v.z += ext[u][i].z; v.w += ext[u][i].w; }
+          if (ok[u]) store4<TOut>(dbase + (it0 + u) * dstep + i * LPR * 4, v);
+        }
+    }
+  }
+  // neither CTA may exit (its shared memory is an MMA operand of the pair) or free TMEM before both are done
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc2(tmem_base, 256);
+  }
+}
+
 }  // namespace tc
 }  // namespace hd

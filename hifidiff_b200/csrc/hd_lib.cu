@@ -56,6 +56,7 @@ inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) 
 
 bool g_use_pdl = true;  // HD_PDL=0 disables programmatic dependent launch
 bool g_bn256 = true;    // HD_BN256=0: 128x128 tiles for the dense 3x3 convs too
+int g_two_cta = 1;      // HD_TWO_CTA=0: never use cta_group::2 pairs; 2: wherever the shape allows (tests)
 int g_max_stages = 6;   // HD_MAX_STAGES=3: no 6-stage / 16-epilogue-warp variant (one CTA per SM)
 // HD_FUSE_LN=1 computes LayerNorm + modulation in the residual GEMM's epilogue where the tile holds the whole
 // row (c = 128).  Measured on B200 at B=256: the fused epilogue costs 31.6 us against 14.2 us (GEMM) + 10.2 us
@@ -277,6 +278,7 @@ struct TcLaunch {
   tc::TcArgs args;
   dim3 grid;
   int epi, a_mode, out_dtype, stages, bn;
+  bool two_cta;  // cta_group::2: CTA pairs on 256x256 tiles
 };
 
 template <int STAGES, int EW, int EPI, int AMODE, typename TOut, int BN = 128>
@@ -315,7 +317,52 @@ void launch_tc_inst(const TcLaunch& L, cudaStream_t st) {
   else launch_tc_inst2<3, 8, EPI, AMODE, TOut>(L, st);
 }
 
+template <int EPI, int AMODE, typename TOut>
+void launch_tc2_inst(const TcLaunch& L, cudaStream_t st) {
+  auto kern = tc::gemm_tc2_kernel<EPI, AMODE, TOut>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Tile2Cfg::SMEM_BYTES);
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = L.grid;
+  cfg.blockDim = dim3(tc::num_threads(tc::Tile2Cfg::EW));
+  cfg.dynamicSmemBytes = tc::Tile2Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;  // the CTA pair
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, kern, L.mapA, L.mapB, L.args);
+}
+
+void launch_tc2(const TcLaunch& L, cudaStream_t st) {
+  const bool obf = L.out_dtype == DT_BF16;
+  if (L.a_mode == A_CONV3) {
+    launch_tc2_inst<EPI_RELU, A_CONV3, bf16>(L, st);
+    return;
+  }
+  switch (L.epi) {
+    case EPI_BIAS:
+      if (obf) launch_tc2_inst<EPI_BIAS, A_PLAIN, bf16>(L, st);
+      else launch_tc2_inst<EPI_BIAS, A_PLAIN, float>(L, st);
+      break;
+    case EPI_RELU: launch_tc2_inst<EPI_RELU, A_PLAIN, bf16>(L, st); break;
+    case EPI_GATE: launch_tc2_inst<EPI_GATE, A_PLAIN, bf16>(L, st); break;
+    case EPI_RESID: launch_tc2_inst<EPI_RESID, A_PLAIN, float>(L, st); break;
+    default: break;
+  }
+}
+
 void launch_tc(const TcLaunch& L, cudaStream_t st) {
+  if (L.two_cta) { launch_tc2(L, st); return; }
   const bool obf = L.out_dtype == DT_BF16;
   if (L.a_mode == A_CONV3) {
     if (L.epi == EPI_RELU && obf) {
@@ -380,6 +427,26 @@ TcLaunch build_tc(hd_handle* h, const GemmDesc& d, long long a_rows_alloc) {
     cuuint64_t strides[1] = {(cuuint64_t)d.lda * 2};
     cuuint32_t box[2] = {64, 128};
     encode_map(h, &L.mapA, d.A, 2, dims, strides, box);
+  }
+  // cta_group::2 pairs on 256x256 tiles: only where the mainloop dominates (K >= 1152: +5..15 % measured, -8..-25 %
+  // on short-K shapes where one CTA per SM loses the inter-CTA overlap), the pair grid still covers the chip, and
+  // the epilogue kind is supported
+  const int m_tiles = cdiv(d.M, 128);
+  const bool epi2 = d.epi == EPI_BIAS || d.epi == EPI_GATE || d.epi == EPI_RESID ||
+                    (d.epi == EPI_RELU && d.out_dtype == DT_BF16);
+  const bool conv_ok = d.a_mode != A_CONV3 || (d.epi == EPI_RELU && d.out_dtype == DT_BF16);
+  const long long pair_ctas = static_cast<long long>((m_tiles + 1) / 2) * 2 * (d.N / 256);
+  L.two_cta = g_two_cta != 0 && epi2 && conv_ok && d.N % 256 == 0 && a_rows_alloc % 256 == 0 &&
+              (g_two_cta == 2 || (a.num_kb >= 18 && pair_ctas >= 128));  // measured: wins from K >= 1152 (tools/gemm_bench.py)
+  if (L.two_cta) {
+    L.bn = 256;
+    cuuint64_t dims[2] = {(cuuint64_t)d.K, (cuuint64_t)d.N};
+    cuuint64_t strides[1] = {(cuuint64_t)d.ldw * 2};
+    cuuint32_t box[2] = {64, 128};  // each CTA of the pair loads its half of the 256-row W tile
+    encode_map(h, &L.mapB, d.W, 2, dims, strides, box);
+    L.grid = dim3(((m_tiles + 1) / 2) * 2, d.N / 256, 1);
+    L.stages = 4;
+    return L;
   }
   const int bn = (g_bn256 && d.a_mode == A_CONV3 && d.epi == EPI_RELU && d.out_dtype == DT_BF16 && d.N % 256 == 0) ? 256 : 128;
   L.bn = bn;
@@ -695,7 +762,8 @@ void add_gemm(hd_handle* h, Plan& P, GemmDesc d, long long a_rows_alloc, const s
   if (tc_eligible(h, d)) {
     TcLaunch L = build_tc(h, d, a_rows_alloc);
     g_label = fmt("%s gemm_tc %s%s M=%d N=%d K=%d grid=(%d,%d,%d) stages=%d", what.c_str(), epi_names[d.epi],
-                  d.a_mode == A_CONV3 ? (L.bn == 256 ? "+conv3 BN=256" : "+conv3") : "", d.M, d.N, d.K, L.grid.x, L.grid.y, L.grid.z, L.stages);
+                  L.two_cta ? (d.a_mode == A_CONV3 ? "+conv3 2CTA" : " 2CTA") : d.a_mode == A_CONV3 ? (L.bn == 256 ? "+conv3 BN=256" : "+conv3") : "",
+                  d.M, d.N, d.K, L.grid.x, L.grid.y, L.grid.z, L.stages);
     add_op(P, [L](cudaStream_t st) { launch_tc(L, st); }, tap, info);
     return;
   }
@@ -1285,6 +1353,7 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   if (const char* e = getenv("HD_PDL")) g_use_pdl = atoi(e) != 0;
   if (const char* e = getenv("HD_FUSE_DW")) g_fuse_dw = atoi(e) != 0;
   if (const char* e = getenv("HD_BN256")) g_bn256 = atoi(e) != 0;
+  if (const char* e = getenv("HD_TWO_CTA")) g_two_cta = atoi(e);
   if (const char* e = getenv("HD_MAX_STAGES")) g_max_stages = atoi(e);
   if (const char* e = getenv("HD_FUSE_LN")) g_fuse_ln = atoi(e) != 0;
   h = new hd_handle();
@@ -1720,8 +1789,21 @@ int32_t hd_synchronize(hd_handle* h) {
   HD_API_END(h)
 }
 
+static int g_time_reps = 0;       // set by hd_debug_gemm_time around one hd_debug_gemm call
+static float g_time_ms = 0.f;
 static long long* g_trace_dev = nullptr;  // set by hd_debug_gemm_trace around one hd_debug_gemm call
 static int g_trace_ctas = 0;
+
+int32_t hd_debug_gemm_time(hd_handle* h, const float* a, const float* w, float* out, int32_t m, int32_t n, int32_t k,
+                           int32_t mode, int32_t reps, float* ms_per_launch) {
+  if (!ms_per_launch || reps < 1) return HD_ERR_INVALID;
+  g_time_reps = reps;
+  g_time_ms = 0.f;
+  const int32_t rc = hd_debug_gemm(h, a, w, nullptr, out, m, n, k, mode, nullptr);
+  g_time_reps = 0;
+  *ms_per_launch = g_time_ms;
+  return rc;
+}
 
 int32_t hd_debug_gemm_trace(hd_handle* h, const float* a, const float* w, float* out, int32_t m, int32_t n, int32_t k,
                             long long* trace_host, int32_t cap_ctas, int32_t* n_ctas, int32_t* grid_xyz) {
@@ -1757,7 +1839,7 @@ int32_t hd_debug_gemm(hd_handle* h, const float* a, const float* w, const float*
   CUDA_CHECK(cudaSetDevice(h->cfg.device));
   join_in(h, stream);
   cudaStream_t st = h->stream;
-  const long long m_alloc = ((m + 127) / 128) * 128;
+  const long long m_alloc = ((m + 255) / 256) * 256;
   void *da = nullptr, *dw = nullptr;
   float* zb = nullptr;
   CUDA_CHECK(cudaMalloc(&zb, n * 4));
@@ -1773,11 +1855,26 @@ int32_t hd_debug_gemm(hd_handle* h, const float* a, const float* w, const float*
     launch_k(cast_kernel<bf16>, dim3(cdiv(ta, 256)), dim3(256), 0, st, a, static_cast<bf16*>(da), ta);
     launch_k(cast_kernel<bf16>, dim3(cdiv(tw, 256)), dim3(256), 0, st, w, static_cast<bf16*>(dw), tw);
     d.A = da; d.W = dw; d.a_dtype = DT_BF16; d.w_dtype = DT_BF16;
-    const bool saved = h->bf16;
+    const int saved = g_two_cta;
+    g_two_cta = use_tc == 2 ? 2 : (use_tc == 3 ? 0 : saved);  // 2: force cta_group::2 pairs, 3: force single-CTA tiles
     TcLaunch L = build_tc(h, d, m_alloc);
-    (void)saved;
+    g_two_cta = saved;
+    if (use_tc == 2 && !L.two_cta) HD_THROW(HD_ERR_INVALID, "shape not eligible for the 2-CTA kernel (N %% 256)");
     launch_tc(L, st);  // warm-up (also warms L2 with the operands)
     launch_tc(L, st);
+    if (g_time_reps > 0) {
+      cudaEvent_t e0, e1;
+      CUDA_CHECK(cudaEventCreate(&e0));
+      CUDA_CHECK(cudaEventCreate(&e1));
+      CUDA_CHECK(cudaEventRecord(e0, st));
+      for (int i = 0; i < g_time_reps; ++i) launch_tc(L, st);
+      CUDA_CHECK(cudaEventRecord(e1, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      CUDA_CHECK(cudaEventElapsedTime(&g_time_ms, e0, e1));
+      g_time_ms /= g_time_reps;
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
     if (g_trace_dev != nullptr) {
       const int ctas = static_cast<int>(L.grid.x * L.grid.y * L.grid.z);
       if (ctas <= g_trace_ctas) {

@@ -171,9 +171,16 @@ int32_t hd_profile_step(hd_handle* h, int32_t batch, int32_t reps, float* ms_out
                         int32_t label_stride, int32_t cap, int32_t* n_ops);
 
 /* Standalone C = A[M,K] * W[N,K]^T (+bias) on the tcgen05 path (bf16 operands given as fp32,
- * converted internally); used by the parity tests to pin the tensor-core kernel alone. */
+ * converted internally); used by the parity tests to pin the tensor-core kernel alone.
+ * use_tensor_cores: 0 = fp32 FFMA, 1 = library heuristics, 2 = force cta_group::2 pairs (N % 256 == 0),
+ * 3 = force single-CTA tiles. */
 int32_t hd_debug_gemm(hd_handle* h, const float* a, const float* w, const float* bias, float* out,
                       int32_t m, int32_t n, int32_t k, int32_t use_tensor_cores, void* stream);
+
+/* hd_debug_gemm (mode = its use_tensor_cores) followed by `reps` back-to-back launches of the same GEMM timed
+ * with CUDA events on the library stream: milliseconds per launch, operands L2-warm. */
+int32_t hd_debug_gemm_time(hd_handle* h, const float* a, const float* w, float* out, int32_t m, int32_t n,
+                           int32_t k, int32_t mode, int32_t reps, float* ms_per_launch);
 
 /* hd_debug_gemm on the tensor-core path with a per-CTA clock64 timeline (16 slots per CTA:
  * 0 entry, 1 setup done, 2 first operands landed, 3 last MMA issued, 4 accumulator ready,

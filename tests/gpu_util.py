@@ -45,6 +45,6 @@ class RawHandle:
         n = w.shape[0]
         out = torch.empty((m, n), dtype=torch.float32, device="cuda")
         self.check(self.lib.hd_debug_gemm(self.h, a.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None,
-                                          out.data_ptr(), m, n, k, 1 if use_tc else 0, None), "hd_debug_gemm")
+                                          out.data_ptr(), m, n, k, int(use_tc), None), "hd_debug_gemm")
         torch.cuda.synchronize()
         return out

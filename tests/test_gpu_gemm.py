@@ -33,6 +33,22 @@ def test_tc_gemm_matches_fp32_reference(raw, m, n, k):
     assert rel_l2(out, ref_fp) < 1e-2
 
 
+TWO_CTA_SHAPES = [(256, 256, 64), (256, 256, 512), (1000, 512, 1024), (4096, 1024, 512), (130, 256, 2048), (16384, 256, 128)]
+
+
+@pytest.mark.parametrize("m,n,k", TWO_CTA_SHAPES)
+def test_two_cta_gemm_matches_fp32_reference(raw, m, n, k):
+    """cta_group::2: a CTA pair per 256x256 tile (ragged M: the odd 128-row tile and row tails are masked)."""
+    a = torch.randn((m, k), generator=gen(m + n + 1)).cuda()
+    w = (torch.randn((n, k), generator=gen(k + 2)) / k ** 0.5).cuda()
+    b = torch.randn((n,), generator=gen(4)).cuda()
+    out = raw.gemm(a, w, b, use_tc=2)
+    ref_bf = a.bfloat16().double() @ w.bfloat16().double().t() + b.double()
+    assert rel_l2(out, ref_bf) < 2e-5
+    one = raw.gemm(a, w, b, use_tc=3)                     # single-CTA tiles (may split K: different fp32 summation order)
+    assert rel_l2(out, one) < 1e-5
+
+
 @pytest.mark.parametrize("m,n,k", [(1, 1, 64), (70, 130, 36 * 4), (257, 64, 128), (64, 124928 // 64, 256)])
 def test_ffma_gemm_matches_fp32_reference(raw, m, n, k):
     a = torch.randn((m, k), generator=gen(m)).cuda()
