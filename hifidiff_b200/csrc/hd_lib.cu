@@ -15,6 +15,7 @@
 #include "elem_kernels.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "chain.cuh"
 
 using namespace hd;
 
@@ -57,6 +58,7 @@ inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) 
 bool g_use_pdl = true;  // HD_PDL=0 disables programmatic dependent launch
 bool g_bn256 = true;    // HD_BN256=0: 128x128 tiles for the dense 3x3 convs too
 int g_two_cta = 1;      // HD_TWO_CTA=0: never use cta_group::2 pairs; 2: wherever the shape allows (tests)
+bool g_chain = false;   // HD_CHAIN=1: run the 1x1-level blocks as one persistent cooperative kernel (measured slower)
 int g_max_stages = 6;   // HD_MAX_STAGES=3: no 6-stage / 16-epilogue-warp variant (one CTA per SM)
 // HD_FUSE_LN=1 computes LayerNorm + modulation in the residual GEMM's epilogue where the tile holds the whole
 // row (c = 128).  Measured on B200 at B=256: the fused epilogue costs 31.6 us against 14.2 us (GEMM) + 10.2 us
@@ -228,7 +230,8 @@ struct hd_handle {
   std::vector<float> table_key;  // timesteps currently held by mod_table rows
   const float* cur_x = nullptr;
   float* cur_eps = nullptr;
-  std::map<int, std::unique_ptr<Plan>> plans;
+  std::map<int, std::unique_ptr<Plan>> plans;      // fast plans (persistent chain kernel where enabled)
+  std::map<int, std::unique_ptr<Plan>> plans_dbg;  // one kernel per op: per-layer taps
   FpgW fpg;
   std::map<int, std::unique_ptr<Plan>> fpg_plans;
   const float* fpg_in = nullptr;
@@ -959,9 +962,145 @@ void add_hca(hd_handle* h, Plan& P, int j, int level) {
   add_gemm(h, P, g, rows_alloc, "hcas." + std::to_string(j), ti);
 }
 
-Plan* get_plan(hd_handle* h, int B) {
-  auto it = h->plans.find(B);
-  if (it != h->plans.end()) return it->second.get();
+// Persistent chain over the blocks [first, first + count) of one 1x1-spatial level (see chain.cuh).
+// Expects blocks[first]'s norm1 output in act_a; leaves the level's residual stream finished in resid[level].
+void add_chain_1x1(hd_handle* h, Plan& P, size_t first, int count) {
+  const int B = P.batch;
+  const BlockW& b0 = h->blocks[first];
+  const int c = b0.c, level = b0.level;
+  const int m_tiles = cdiv(B, 128);
+  const long long rows_alloc = h->Bcap;
+  const int grid_target = std::min(h->sm_count, 128);
+  std::vector<chain::Phase> phases;
+  std::vector<CUtensorMap> maps;
+  auto add_map = [&](const void* base, int K, long long rows, int ld) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, 128};
+    encode_map(h, &m, base, 2, dims, strides, box);
+    maps.push_back(m);
+    return static_cast<int>(maps.size()) - 1;
+  };
+  const int map_a = add_map(h->act_a, c, rows_alloc, c);
+  const int map_g = add_map(h->act_g, c, rows_alloc, c);
+  int max_units = 0;
+  auto gemm = [&](int mapA, const void* W, int N, int K) {
+    chain::Phase ph;
+    memset(&ph, 0, sizeof(ph));
+    ph.kind = chain::PH_GEMM;
+    ph.map_a = mapA;
+    ph.map_w = add_map(W, K, N, K);
+    ph.n_tiles = N / 128;
+    ph.num_kb = K / 64;
+    int split = 1;
+    while (m_tiles * ph.n_tiles * split * 2 <= grid_target && split < 8 && ph.num_kb % (2 * split) == 0 &&
+           ph.num_kb / (2 * split) >= 2)
+      split *= 2;
+    ph.split = split;
+    max_units = std::max(max_units, m_tiles * ph.n_tiles * split);
+    phases.push_back(ph);
+    P.flops_per_face += 2.0 * B * static_cast<double>(N) * K / P.batch;
+    return ph;
+  };
+  auto fix = [&](int kind, const chain::Phase& g, int N, const float* bias) {
+    chain::Phase ph;
+    memset(&ph, 0, sizeof(ph));
+    ph.kind = kind;
+    ph.N = N;
+    ph.src_n_tiles = g.n_tiles;
+    ph.src_split = g.split;
+    ph.bias = bias;
+    return ph;
+  };
+  bf16* act_a = static_cast<bf16*>(h->act_a);
+  bf16* act_g = static_cast<bf16*>(h->act_g);
+  float* x = h->resid[level];
+  for (int i = 0; i < count; ++i) {
+    const BlockW& bw = h->blocks[first + i];
+    const BlockW* nx = i + 1 < count ? &h->blocks[first + i + 1] : nullptr;
+    {  // conv1 (+ folded depthwise) -> SimpleGate -> g
+      auto g = gemm(map_a, bw.w1, 2 * c, c);
+      auto f = fix(chain::PH_FIX_GATE, g, 2 * c, bw.b1);
+      f.out = act_g;
+      phases.push_back(f);
+    }
+    {  // SCA: g *= Wsca g + b   (mean over one pixel is g itself)
+      auto g = gemm(map_g, bw.wsca, c, c);
+      auto f = fix(chain::PH_FIX_SCALE, g, c, bw.bsca);
+      f.in = act_g; f.out = act_g;
+      phases.push_back(f);
+    }
+    {  // conv3 (+beta) + residual, then norm2 + modulation
+      auto g = gemm(map_g, bw.w3, c, c);
+      auto f = fix(chain::PH_FIX_RESID, g, c, bw.b3);
+      f.x = x; f.out = act_a; f.ln_w = bw.ln2_w; f.ln_b = bw.ln2_b;
+      f.shift_off = bw.mod_off + 2 * c; f.scale_off = bw.mod_off + 3 * c;
+      phases.push_back(f);
+    }
+    {  // conv4 -> SimpleGate
+      auto g = gemm(map_a, bw.w4, 2 * c, c);
+      auto f = fix(chain::PH_FIX_GATE, g, 2 * c, bw.b4);
+      f.out = act_g;
+      phases.push_back(f);
+    }
+    {  // conv5 (+gamma) + residual, then the next block's norm1 + modulation
+      auto g = gemm(map_g, bw.w5, c, c);
+      auto f = fix(chain::PH_FIX_RESID, g, c, bw.b5);
+      f.x = x; f.out = act_a;
+      if (nx != nullptr) {
+        f.ln_w = nx->ln1_w; f.ln_b = nx->ln1_b; f.shift_off = nx->mod_off; f.scale_off = nx->mod_off + c;
+      }
+      phases.push_back(f);
+    }
+  }
+  // device copies
+  chain::Phase* d_ph = static_cast<chain::Phase*>(h->arena.alloc(phases.size() * sizeof(chain::Phase)));
+  CUtensorMap* d_maps = static_cast<CUtensorMap*>(h->arena.alloc(maps.size() * sizeof(CUtensorMap)));
+  CUDA_CHECK(cudaMemcpy(d_ph, phases.data(), phases.size() * sizeof(chain::Phase), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  chain::ChainArgs ca;
+  memset(&ca, 0, sizeof(ca));
+  ca.phases = d_ph;
+  ca.n_phases = static_cast<int>(phases.size());
+  ca.maps = d_maps;
+  ca.partial = h->arena.get<float>(static_cast<size_t>(max_units) * 128 * 128);
+  ca.barrier = h->arena.get<unsigned int>(64);
+  ca.rows = B;
+  ca.m_tiles = m_tiles;
+  ca.mod_table = h->mod_table;
+  ca.mod_row_idx = h->row_idx;
+  ca.mod_stride = h->mod_stride;
+  ca.rows_per_face = 1;
+  ca.status = h->d_status;
+  const int grid = std::min(h->sm_count, max_units);
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(chain::chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES));
+    configured = true;
+  }
+  g_label = fmt("L%d c=%d chain of %d blocks: %zu phases, grid %d", level, c, count, phases.size(), grid);
+  add_op(P, [=](cudaStream_t st) {
+    cudaMemsetAsync(ca.barrier, 0, sizeof(unsigned int), st);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(chain::THREADS);
+    cfg.dynamicSmemBytes = chain::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the grid barrier cannot deadlock
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, chain::chain_kernel, ca);
+  });
+}
+
+Plan* get_plan(hd_handle* h, int B, bool debug = false) {
+  auto& cache = debug ? h->plans_dbg : h->plans;
+  auto it = cache.find(B);
+  if (it != cache.end()) return it->second.get();
   std::unique_ptr<Plan> up(new Plan());
   Plan& P = *up;
   P.batch = B;
@@ -1004,9 +1143,24 @@ Plan* get_plan(hd_handle* h, int B) {
     g_label = fmt("down%d", l);
     add_gemm(h, P, d, static_cast<long long>(h->Bcap) * (n / 2) * (n / 2), "downs." + std::to_string(l), ti);
   }
-  for (int i = 0; i < kMidBlocks; ++i, ++bi)
-    add_block(h, P, h->blocks[bi], "middle_blks." + std::to_string(i), i + 1 < kMidBlocks ? &h->blocks[bi + 1] : nullptr,
-              i > 0);
+  if (g_chain && !debug && bf && h->sp[4] == 1 && h->blocks[bi].dw_folded) {
+    // the 8 bottleneck blocks as one persistent cooperative kernel (chain.cuh); norm1 of the first block first
+    const BlockW& b0 = h->blocks[bi];
+    const int c = b0.c, rows = B;
+    const float* resid = h->resid[4];
+    void* act_a = h->act_a;
+    ModRef mod{h->mod_table, h->row_idx, h->mod_stride};
+    const float *lw = b0.ln1_w, *lb = b0.ln1_b;
+    const int so = b0.mod_off, co = b0.mod_off + c;
+    g_label = "L4 chain ln1";
+    add_op(P, [=](cudaStream_t st) { launch_ln<bf16>(c, resid, lw, lb, static_cast<bf16*>(act_a), rows, 1, mod, so, co, 1, st); });
+    add_chain_1x1(h, P, bi, kMidBlocks);
+    bi += kMidBlocks;
+  } else {
+    for (int i = 0; i < kMidBlocks; ++i, ++bi)
+      add_block(h, P, h->blocks[bi], "middle_blks." + std::to_string(i), i + 1 < kMidBlocks ? &h->blocks[bi + 1] : nullptr,
+                i > 0);
+  }
   if (h->fused) add_hca(h, P, 0, 4);
   for (int L = 0; L < 4; ++L) {
     const int lin = 4 - L, lout = 3 - L;
@@ -1051,7 +1205,7 @@ Plan* get_plan(hd_handle* h, int B) {
     P.flops_per_face += 2.0 * 9 * 128 * 4 * S * S;
   }
   Plan* raw = up.get();
-  h->plans[B] = std::move(up);
+  cache[B] = std::move(up);
   return raw;
 }
 
@@ -1275,7 +1429,7 @@ void denoise_impl(hd_handle* h, const float* x, const float* t, int t_len, float
   for (int b = 0; b < B; ++b) rows[b] = t_len == 1 ? 0 : b;
   CUDA_CHECK(cudaMemcpyAsync(h->row_idx, rows.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
-  Plan* P = get_plan(h, B);
+  Plan* P = get_plan(h, B, /*debug=*/n_taps > 0);
   run_plan(h, P, st, tap_names, tap_out, n_taps, B);
   // "time_mlp" tap: (B,512) embedding
   for (int i = 0; i < n_taps; ++i) {
@@ -1324,6 +1478,7 @@ void hd_destroy(hd_handle* h) {
   for (auto& kv : h->plans)
     if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph);
   h->plans.clear();
+  h->plans_dbg.clear();
   h->arena.release();
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
@@ -1354,6 +1509,7 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   if (const char* e = getenv("HD_FUSE_DW")) g_fuse_dw = atoi(e) != 0;
   if (const char* e = getenv("HD_BN256")) g_bn256 = atoi(e) != 0;
   if (const char* e = getenv("HD_TWO_CTA")) g_two_cta = atoi(e);
+  if (const char* e = getenv("HD_CHAIN")) g_chain = atoi(e) != 0;
   if (const char* e = getenv("HD_MAX_STAGES")) g_max_stages = atoi(e);
   if (const char* e = getenv("HD_FUSE_LN")) g_fuse_ln = atoi(e) != 0;
   h = new hd_handle();
