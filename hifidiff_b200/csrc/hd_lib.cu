@@ -16,6 +16,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "chain.cuh"
+#include "face_block.cuh"
 
 using namespace hd;
 
@@ -58,6 +59,7 @@ inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) 
 bool g_use_pdl = true;  // HD_PDL=0 disables programmatic dependent launch
 bool g_bn256 = true;    // HD_BN256=0: 128x128 tiles for the dense 3x3 convs too
 int g_two_cta = 1;      // HD_TWO_CTA=0: never use cta_group::2 pairs; 2: wherever the shape allows (tests)
+bool g_face = true;     // HD_FACE=0: per-op kernels at the 16x16 level instead of the fused per-face block kernel
 bool g_chain = false;   // HD_CHAIN=1: run the 1x1-level blocks as one persistent cooperative kernel (measured slower)
 int g_max_stages = 6;   // HD_MAX_STAGES=3: no 6-stage / 16-epilogue-warp variant (one CTA per SM)
 // HD_FUSE_LN=1 computes LayerNorm + modulation in the residual GEMM's epilogue where the tile holds the whole
@@ -129,6 +131,7 @@ struct BlockW {
   void *w1 = nullptr, *wsca = nullptr, *w3 = nullptr, *w4 = nullptr, *w5 = nullptr;
   float *b1 = nullptr, *bsca = nullptr, *b3 = nullptr, *b4 = nullptr, *b5 = nullptr;
   float *dw_w = nullptr, *dw_b = nullptr;
+  float* wsca_t = nullptr;  // 16x16 level: SCA weight transposed [k][n] fp32 for the fused face kernel's GEMV
   bool dw_folded = false;  // 1x1 level: depthwise 3x3 == per-channel scale, folded into conv1 (gate-packed)
   bool has_mod = true;     // false: unconditional NAFBlock of the FPG encoder (models/fpg/naf.py:105-126)
   bool dw_fused = false;   // 2x2..8x8 levels, bf16: depthwise 3x3 + gate + pool run in conv1's epilogue (gate-packed)
@@ -626,6 +629,13 @@ void load_block(hd_handle* h, BlockW& bw, int wdt) {
   }
   bw.wsca = pack_matrix(h, need(h, p + "sca.1.weight", {c, c}), c, c, 1, nullptr, nullptr, wdt);
   bw.bsca = upload_f32(h, host_vec(h, need(h, p + "sca.1.bias", {c})));
+  if (c == fb::C && h->sp[bw.level] == fb::SP) {
+    auto w = host_vec(h, need(h, p + "sca.1.weight", {c, c}));
+    std::vector<float> t(w.size());
+    for (int n = 0; n < c; ++n)
+      for (int k = 0; k < c; ++k) t[static_cast<size_t>(k) * c + n] = w[static_cast<size_t>(n) * c + k];
+    bw.wsca_t = upload_f32(h, t);
+  }
 
   {  // conv3 with beta folded: y = inp + beta * (W3 x + b3)
     auto b3 = host_vec(h, need(h, p + "conv3.bias", {c}));
@@ -962,6 +972,72 @@ void add_hca(hd_handle* h, Plan& P, int j, int level) {
   add_gemm(h, P, g, rows_alloc, "hcas." + std::to_string(j), ti);
 }
 
+// Fused per-face kernel (face_block.cuh) over the blocks [first, first + count) of the 16x16 level:
+// reads and writes the level's fp32 residual stream in place.
+bool face_blocks_ok(hd_handle* h, size_t first, int count, bool debug) {
+  if (!g_face || debug || !h->bf16 || count > fb::MAX_BLOCKS) return false;
+  for (int i = 0; i < count; ++i) {
+    const BlockW& bw = h->blocks[first + i];
+    if (bw.c != fb::C || h->sp[bw.level] != fb::SP || !bw.has_mod || bw.dw_fused || bw.dw_folded || bw.wsca_t == nullptr) return false;
+  }
+  return true;
+}
+
+void add_face_blocks(hd_handle* h, Plan& P, size_t first, int count) {
+  const int B = P.batch;
+  const int c = fb::C, rpf = fb::PX;
+  std::vector<CUtensorMap> maps;
+  std::vector<fb::BlockParams> bps;
+  auto add_map = [&](const void* base, int N) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)c, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)c * 2};
+    cuuint32_t box[2] = {64, 128};
+    encode_map(h, &m, base, 2, dims, strides, box);
+    maps.push_back(m);
+  };
+  for (int i = 0; i < count; ++i) {
+    const BlockW& bw = h->blocks[first + i];
+    add_map(bw.w1, 2 * c);
+    add_map(bw.w3, c);
+    add_map(bw.w4, 2 * c);
+    add_map(bw.w5, c);
+    fb::BlockParams bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.ln1_w = bw.ln1_w; bp.ln1_b = bw.ln1_b; bp.ln2_w = bw.ln2_w; bp.ln2_b = bw.ln2_b;
+    bp.b1 = bw.b1; bp.dw_w = bw.dw_w; bp.dw_b = bw.dw_b; bp.wsca_t = bw.wsca_t; bp.bsca = bw.bsca;
+    bp.b3 = bw.b3; bp.b4 = bw.b4; bp.b5 = bw.b5; bp.mod_off = bw.mod_off;
+    bps.push_back(bp);
+    P.flops_per_face += 2.0 * rpf * 6.0 * c * c + 2.0 * c * c + 2.0 * 9 * 2 * c * rpf;
+  }
+  fb::Args a;
+  memset(&a, 0, sizeof(a));
+  CUtensorMap* d_maps = static_cast<CUtensorMap*>(h->arena.alloc(maps.size() * sizeof(CUtensorMap)));
+  fb::BlockParams* d_bps = static_cast<fb::BlockParams*>(h->arena.alloc(bps.size() * sizeof(fb::BlockParams)));
+  CUDA_CHECK(cudaMemcpy(d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(d_bps, bps.data(), bps.size() * sizeof(fb::BlockParams), cudaMemcpyHostToDevice));
+  a.maps = d_maps;
+  a.blocks = d_bps;
+  a.n_blocks = count;
+  a.x = h->resid[h->blocks[first].level];
+  a.mod_table = h->mod_table;
+  a.mod_row_idx = h->row_idx;
+  a.mod_stride = h->mod_stride;
+  a.status = h->d_status;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(fb::face_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fb::SMEM_BYTES));
+    configured = true;
+  }
+  g_label = fmt("L%d c=%d face_block x%d (%s)", h->blocks[first].level, c, count, h->blocks[first].prefix.c_str());
+  // the run's last block output is still observable (per-layer parity of the fused kernel itself)
+  TapInfo ti;
+  ti.ptr = a.x; ti.dtype = DT_F32; ti.C = c; ti.HW = rpf; ti.ld = c;
+  std::string tap = h->blocks[first + count - 1].prefix;
+  if (!tap.empty() && tap.back() == '.') tap.pop_back();
+  add_op(P, [=](cudaStream_t st) { launch_k(fb::face_block_kernel, dim3(B), dim3(fb::THREADS), fb::SMEM_BYTES, st, a); }, tap, ti);
+}
+
 // Persistent chain over the blocks [first, first + count) of one 1x1-spatial level (see chain.cuh).
 // Expects blocks[first]'s norm1 output in act_a; leaves the level's residual stream finished in resid[level].
 void add_chain_1x1(hd_handle* h, Plan& P, size_t first, int count) {
@@ -1121,9 +1197,14 @@ Plan* get_plan(hd_handle* h, int B, bool debug = false) {
   }
   size_t bi = 0;
   for (int l = 0; l < 4; ++l) {
-    for (int i = 0; i < kEncBlocks[l]; ++i, ++bi)
-      add_block(h, P, h->blocks[bi], "encoders." + std::to_string(l) + "." + std::to_string(i),
-                i + 1 < kEncBlocks[l] ? &h->blocks[bi + 1] : nullptr, i > 0);
+    if (face_blocks_ok(h, bi, kEncBlocks[l], debug)) {
+      add_face_blocks(h, P, bi, kEncBlocks[l]);
+      bi += kEncBlocks[l];
+    } else {
+      for (int i = 0; i < kEncBlocks[l]; ++i, ++bi)
+        add_block(h, P, h->blocks[bi], "encoders." + std::to_string(l) + "." + std::to_string(i),
+                  i + 1 < kEncBlocks[l] ? &h->blocks[bi + 1] : nullptr, i > 0);
+    }
     // down: 2x2 stride-2 conv as space-to-depth + GEMM
     const int c = h->c[l], n = h->sp[l], rows_out = B * (n / 2) * (n / 2);
     const float* src = h->resid[l];
@@ -1187,9 +1268,14 @@ Plan* get_plan(hd_handle* h, int B, bool debug = false) {
     ti.ptr = h->resid[lout]; ti.dtype = DT_F32; ti.C = cin / 2; ti.HW = 4 * n * n; ti.ld = cin / 2;
     g_label = fmt("up%d", L);
     add_gemm(h, P, d, static_cast<long long>(h->Bcap) * n * n, "ups." + std::to_string(L), ti);
-    for (int i = 0; i < kDecBlocks[L]; ++i, ++bi)
-      add_block(h, P, h->blocks[bi], "decoders." + std::to_string(L) + "." + std::to_string(i),
-                i + 1 < kDecBlocks[L] ? &h->blocks[bi + 1] : nullptr, i > 0);
+    if (face_blocks_ok(h, bi, kDecBlocks[L], debug)) {
+      add_face_blocks(h, P, bi, kDecBlocks[L]);
+      bi += kDecBlocks[L];
+    } else {
+      for (int i = 0; i < kDecBlocks[L]; ++i, ++bi)
+        add_block(h, P, h->blocks[bi], "decoders." + std::to_string(L) + "." + std::to_string(i),
+                  i + 1 < kDecBlocks[L] ? &h->blocks[bi + 1] : nullptr, i > 0);
+    }
     if (h->fused) add_hca(h, P, L + 1, lout);
   }
   {  // ending
@@ -1429,7 +1515,13 @@ void denoise_impl(hd_handle* h, const float* x, const float* t, int t_len, float
   for (int b = 0; b < B; ++b) rows[b] = t_len == 1 ? 0 : b;
   CUDA_CHECK(cudaMemcpyAsync(h->row_idx, rows.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
-  Plan* P = get_plan(h, B, /*debug=*/n_taps > 0);
+  // taps come from the production plan when it exposes every requested one, else from the per-op plan
+  Plan* P = get_plan(h, B, false);
+  for (int i = 0; i < n_taps; ++i) {
+    bool found = false;
+    for (auto& op : P->ops) found = found || op.tap == tap_names[i];
+    if (!found) { P = get_plan(h, B, true); break; }
+  }
   run_plan(h, P, st, tap_names, tap_out, n_taps, B);
   // "time_mlp" tap: (B,512) embedding
   for (int i = 0; i < n_taps; ++i) {
@@ -1510,6 +1602,7 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   if (const char* e = getenv("HD_BN256")) g_bn256 = atoi(e) != 0;
   if (const char* e = getenv("HD_TWO_CTA")) g_two_cta = atoi(e);
   if (const char* e = getenv("HD_CHAIN")) g_chain = atoi(e) != 0;
+  if (const char* e = getenv("HD_FACE")) g_face = atoi(e) != 0;
   if (const char* e = getenv("HD_MAX_STAGES")) g_max_stages = atoi(e);
   if (const char* e = getenv("HD_FUSE_LN")) g_fuse_ln = atoi(e) != 0;
   h = new hd_handle();

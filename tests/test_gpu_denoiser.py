@@ -114,6 +114,33 @@ def test_config2_batch64_bf16():
     m.invalidate()
 
 
+def test_fused_face_kernel_taps_and_plans_agree():
+    """The production plan (fused per-face block kernel at 16x16) against the oracle at the taps it exposes,
+    and against the one-kernel-per-op plan that serves all other taps."""
+    m, sd = build(H.FusedDenoiser, seed=2, precision="bf16", max_batch=64)
+    for batch in (3, 40):
+        x = inputs("latents", batch, seed=11)
+        priors, ident = testing.synthetic_condition(batch, 16, seed=11)
+        cond = ([p.cuda() for p in priors], ident.cuda())
+        t = torch.arange(batch) * 7 + 3 if batch == 3 else 321
+        t_dev = t.cuda() if torch.is_tensor(t) else t
+        fast_names = ["encoders.0.1", "decoders.3.1"]
+        out_fast, taps_fast = m.forward_with_taps(x.cuda(), t_dev, fast_names, *cond)
+        out_dbg, taps_dbg = m.forward_with_taps(x.cuda(), t_dev, fast_names + ["intro"], *cond)
+        plain = m(x.cuda(), t_dev, *cond).sample
+        m.engine().synchronize()
+        ref_taps = {}
+        with torch.no_grad():
+            ref = denoiser_ref.fused_denoiser_forward(sd, x, t, priors, ident, ref_taps)
+        assert torch.equal(plain, out_fast.sample)               # the tapped run used the production plan
+        for k in fast_names:
+            assert rel_l2(taps_fast[k], ref_taps[k]) <= 1e-2, (batch, k)
+            assert rel_l2(taps_fast[k], taps_dbg[k]) <= 6e-3, (batch, k)
+        assert rel_l2(out_fast.sample, ref) <= 1e-2
+        assert rel_l2(out_fast.sample, out_dbg.sample) <= 8e-3
+    m.invalidate()
+
+
 def test_errors_are_loud(denoiser):
     m, _, _ = denoiser
     with pytest.raises(ValueError):
