@@ -15,7 +15,7 @@
 //
 // Shared memory (232000 B):  A 64 KB | T 128 KB (two planes; also parking space for W1 / W4) | W3/W5 32 KB | misc
 // Tensor memory (512 cols):  x m-tile 0 | x m-tile 1 | accumulator m-tile 0 | accumulator m-tile 1
-// Threads: 8 worker warps (thread <-> pixel row <-> TMEM lane) + 1 controller warp (TMA + MMA issue).
+// Threads: 8 worker warps (thread <-> pixel row <-> TMEM lane); thread 0 also issues the TMA loads and MMAs.
 #pragma once
 
 #include "common.cuh"
@@ -28,7 +28,7 @@ constexpr int C = 128;
 constexpr int SP = 16;
 constexpr int PX = SP * SP;
 constexpr int WORKERS = 256;
-constexpr int THREADS = WORKERS + 32;
+constexpr int THREADS = WORKERS;          // thread 0 doubles as the controller (TMA + MMA issue): 8 warps keep 255 regs/thread
 constexpr int TILE = 16384;               // one 128-row x 64-col bf16 operand tile
 constexpr int A_OFF = 0;                  // [m-tile 2][k-block 2] tiles
 constexpr int T_OFF = 4 * TILE;           // plane 0 | plane 1, each [256 px][128 ch] bf16
@@ -58,6 +58,7 @@ struct Args {
   const int* mod_row_idx;
   int mod_stride;
   DeviceStatus* status;
+  long long* trace;                // optional: clock64 stamps of CTA 0's phase boundaries (diagnostics)
 };
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -81,6 +82,33 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) {
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+// packed pairs of fp32 for the 2-wide FMA pipe (fma.rn.f32x2)
+__device__ __forceinline__ uint64_t pack_f2(float2 v) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f2(uint64_t r) {
+  float2 v;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(r));
+  return v;
+}
+__device__ __forceinline__ uint64_t bf2_to_f2(uint32_t u) {  // (bf16 lo, bf16 hi) -> (f32, f32)
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(u << 16), "r"(u & 0xffff0000u));
+  return r;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
 }
 
 // the controller lane / sub-warp branches rejoin their warps before the CTA barrier
@@ -148,13 +176,18 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
   float* s_sca = reinterpret_cast<float*>(smem + S_OFF);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool worker = warp < 8;
-  const bool ctrl = warp == 8 && lane == 0;
+  const bool ctrl = tid == 0;
   const int face = blockIdx.x;
   const uint32_t wbar0 = smem_u32(&bars[0]), mma_bar = smem_u32(&bars[4]);
   const int nb = args.n_blocks;
+  int n_stamp = 0;
+  auto stamp = [&]() {
+    if (args.trace != nullptr && blockIdx.x == 0 && tid == 0) args.trace[n_stamp] = clock64();
+    ++n_stamp;
+  };
 
   pdl_trigger();
+  stamp();
   if (tid == 0) {
     if ((sbase & 1023u) != 0u) {
       if (atomicCAS(&args.status->error, 0u, 3u) == 0u) args.status->where = 0xA00u;
@@ -163,7 +196,8 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
     fence_barrier_init();
     fence_proxy_async_smem();
   }
-  if (warp == 8) {
+  if (warp == 0) {
+    __syncwarp();
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
   }
@@ -201,6 +235,7 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
     load_w(1, sW3, 1, 1);
   }
   pdl_wait();
+  stamp();
 
   // worker geometry
   const int R = tid;                                  // pixel row (workers)
@@ -211,19 +246,33 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
   const float* mrow = args.mod_table + static_cast<size_t>(__ldg(args.mod_row_idx + face)) * args.mod_stride;
   // depthwise geometry: warp -> (channel block, 4-row strip), lane -> channel pair
   const int cb = warp & 1, strip = (warp >> 1) & 3, j = cb * 64 + lane * 2;
+  // fp32 row staging for the coalesced load / store of x: rows 0..127 in the A region, 128..255 in T plane 0;
+  // 16-byte chunks XOR-swizzled by row so that both the row-per-warp and the row-per-thread side are conflict-free
+  auto stage_row = [&](int r) { return (r < 128 ? sA : sT - 128 * 512) + static_cast<uint32_t>(r) * 512u; };
 
   uint32_t mph = 0;  // parity of the MMA-done barrier
-  float v[C];        // this thread's pixel row of the residual stream (workers)
+  float v[C];        // this thread's pixel row of the residual stream
 
   {
     const BlockParams bp = args.blocks[0];
     if (tid < C) make_ln_params(eff, bp.ln1_w, bp.ln1_b, mrow, bp.mod_off, bp.mod_off + C, tid);
-    if (worker) {
-      const float* xr = args.x + (static_cast<size_t>(face) * PX + R) * C;
+    {
+      const float* xw = args.x + (static_cast<size_t>(face) * PX + warp * 32) * C + lane * 4;
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(xw + static_cast<size_t>(i) * C);
+        const int r = warp * 32 + i;
+        sts128(stage_row(r) + ((lane ^ (r & 7)) << 4), __float_as_uint(t.x), __float_as_uint(t.y), __float_as_uint(t.z),
+               __float_as_uint(t.w));
+      }
+    }
+    block_sync();
+    {
+      const uint32_t srow = stage_row(R);
 #pragma unroll
-      for (int i = 0; i < C / 4; ++i) {
-        const float4 t = *reinterpret_cast<const float4*>(xr + 4 * i);
-        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+      for (int q = 0; q < 32; ++q) {
+        const float4 t = lds128(srow + ((q ^ (R & 7)) << 4));
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
       }
 #pragma unroll
       for (int c0 = 0; c0 < C; c0 += 32) {
@@ -233,14 +282,13 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
         tmem_st32(t_x + c0, r);
       }
     }
-    block_sync();
-    if (worker) {
-      ln_row_to_a(v, eff, eff + C, sA, R);
-      tmem_wait_st();
-    }
+    block_sync();  // every row has left the staging area before the A operand is written over it
+    ln_row_to_a(v, eff, eff + C, sA, R);
+    tmem_wait_st();
   }
 
   for (int b = 0; b < nb; ++b) {
+    stamp();  // A ready (norm1)
     const BlockParams bp = args.blocks[b];
     const bool last = b + 1 == nb;
     const uint32_t wpar = static_cast<uint32_t>(b & 1);
@@ -248,111 +296,106 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
     // ---------------- conv1: two 128-column halves through the accumulator, drained to the T planes ----------------
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
-      if (worker) {
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
       block_sync();
       if (ctrl) {
         tc_fence_after_sync();
         if (h == 0) mbar_wait(wbar0, wpar, args.status, 0xA10u);
         issue(sT + PLANE + h * 2 * TILE, ACC_COL, 0u);
       }
-      if (worker) {
-        mbar_wait(mma_bar, mph, args.status, 0xA11u);
-        tc_fence_after_sync();
-        const uint32_t plane = sT + h * PLANE;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(t_acc + c0, r);
-          tmem_wait_ld();
-          const float* bias = bp.b1 + h * 128 + c0;
+      mbar_wait(mma_bar, mph, args.status, 0xA11u);
+      tc_fence_after_sync();
+      {
+        const uint32_t prow = sT + h * PLANE + static_cast<uint32_t>(R) * 256u;
+        uint32_t r[4][32];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint32_t p[4];
+        for (int c = 0; c < 4; ++c) tmem_ld32(t_acc + c * 32, r[c]);
+        tmem_wait_ld();
+        const float4* bias = reinterpret_cast<const float4*>(bp.b1 + h * 128);
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              p[e] = pack_bf16x2(__uint_as_float(r[q * 8 + 2 * e]) + __ldg(bias + q * 8 + 2 * e),
-                                 __uint_as_float(r[q * 8 + 2 * e + 1]) + __ldg(bias + q * 8 + 2 * e + 1));
-            sts128(plane + t_chunk_off(R, (c0 >> 3) + q), p[0], p[1], p[2], p[3]);
-          }
+        for (int q = 0; q < 16; ++q) {
+          const float4 b0 = __ldg(bias + 2 * q), b1 = __ldg(bias + 2 * q + 1);
+          const uint32_t* rr = &r[q >> 2][(q & 3) * 8];
+          sts128(prow + ((q ^ (R & 7)) << 4), pack_bf16x2(__uint_as_float(rr[0]) + b0.x, __uint_as_float(rr[1]) + b0.y),
+                 pack_bf16x2(__uint_as_float(rr[2]) + b0.z, __uint_as_float(rr[3]) + b0.w),
+                 pack_bf16x2(__uint_as_float(rr[4]) + b1.x, __uint_as_float(rr[5]) + b1.y),
+                 pack_bf16x2(__uint_as_float(rr[6]) + b1.z, __uint_as_float(rr[7]) + b1.w));
         }
       }
       mph ^= 1u;
     }
     block_sync();  // T complete
+    stamp();
 
     // ---------------- depthwise 3x3 + bias + SimpleGate -> A operand, pool partials ----------------
-    if (worker) {
-      float wk[9][4], bz[4];
+    {
+      uint64_t wk1[9], wk2[9];  // taps of this lane's (x1a, x1b) and (x2a, x2b) channel pairs, packed for FFMA2
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        const float2 a = __ldg(reinterpret_cast<const float2*>(bp.dw_w + t * 256 + j));
-        const float2 c2 = __ldg(reinterpret_cast<const float2*>(bp.dw_w + t * 256 + 128 + j));
-        wk[t][0] = a.x; wk[t][1] = a.y; wk[t][2] = c2.x; wk[t][3] = c2.y;
+        wk1[t] = pack_f2(__ldg(reinterpret_cast<const float2*>(bp.dw_w + t * 256 + j)));
+        wk2[t] = pack_f2(__ldg(reinterpret_cast<const float2*>(bp.dw_w + t * 256 + 128 + j)));
       }
-      {
-        const float2 a = __ldg(reinterpret_cast<const float2*>(bp.dw_b + j));
-        const float2 c2 = __ldg(reinterpret_cast<const float2*>(bp.dw_b + 128 + j));
-        bz[0] = a.x; bz[1] = a.y; bz[2] = c2.x; bz[3] = c2.y;
+      const uint64_t bz1 = pack_f2(__ldg(reinterpret_cast<const float2*>(bp.dw_b + j)));
+      const uint64_t bz2 = pack_f2(__ldg(reinterpret_cast<const float2*>(bp.dw_b + 128 + j)));
+      uint32_t lx[8], ax[8];    // swizzle terms by (x & 7): load side (T planes) and store side (A operand)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        lx[k] = static_cast<uint32_t>((((j >> 3) ^ k) << 4) + (j & 7) * 2);
+        ax[k] = static_cast<uint32_t>((((lane >> 2) ^ k) << 4) + (lane & 3) * 4);
       }
       float ps0 = 0.f, ps1 = 0.f;
-      const int jq = j >> 3, jin = (j & 7) * 2;
 #pragma unroll 1
       for (int y = strip * 4; y < strip * 4 + 4; ++y) {
-        float win[3][3][4];  // [column slot][dy][x1a, x1b, x2a, x2b]
-        auto load_col = [&](int x, float (&col)[3][4]) {
-#pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
-            const int yy = y + dy - 1;
-            if (yy >= 0 && yy < SP) {
-              const int px = yy * SP + x;
-              const uint32_t off = t_chunk_off(px, jq) + jin;
-              const float2 a = unpack_bf16x2(lds32(sT + off));
-              const float2 c2 = unpack_bf16x2(lds32(sT + PLANE + off));
-              col[dy][0] = a.x; col[dy][1] = a.y; col[dy][2] = c2.x; col[dy][3] = c2.y;
-            } else {
-              col[dy][0] = col[dy][1] = col[dy][2] = col[dy][3] = 0.f;
-            }
-          }
+        const bool up = y > 0, dn = y < SP - 1;
+        const uint32_t trow = sT + static_cast<uint32_t>(y * SP) * 256u;                       // pixel (y, 0) in plane 0
+        const uint32_t arow = sA + static_cast<uint32_t>(((y >> 3) * 2 + cb) * TILE + (y & 7) * SP * 128);
+        uint64_t w1v[3][3], w2v[3][3];  // [column slot][dy]
+        auto load_col = [&](int x, uint64_t (&c1)[3], uint64_t (&c2)[3]) {
+          const uint32_t a = trow + lx[x & 7] + x * 256;
+          c1[0] = up ? bf2_to_f2(lds32(a - SP * 256)) : 0ull;
+          c2[0] = up ? bf2_to_f2(lds32(a - SP * 256 + PLANE)) : 0ull;
+          c1[1] = bf2_to_f2(lds32(a));
+          c2[1] = bf2_to_f2(lds32(a + PLANE));
+          c1[2] = dn ? bf2_to_f2(lds32(a + SP * 256)) : 0ull;
+          c2[2] = dn ? bf2_to_f2(lds32(a + SP * 256 + PLANE)) : 0ull;
         };
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) win[0][dy][e] = 0.f;
-        load_col(0, win[1]);
+        for (int dy = 0; dy < 3; ++dy) w1v[0][dy] = w2v[0][dy] = 0ull;
+        load_col(0, w1v[1], w2v[1]);
 #pragma unroll
         for (int x = 0; x < SP; ++x) {
-          float (&cl)[3][4] = win[x % 3];
-          float (&cm)[3][4] = win[(x + 1) % 3];
-          float (&cr)[3][4] = win[(x + 2) % 3];
+          uint64_t (&l1)[3] = w1v[x % 3], (&l2)[3] = w2v[x % 3];
+          uint64_t (&m1)[3] = w1v[(x + 1) % 3], (&m2)[3] = w2v[(x + 1) % 3];
+          uint64_t (&r1)[3] = w1v[(x + 2) % 3], (&r2)[3] = w2v[(x + 2) % 3];
           if (x + 1 < SP) {
-            load_col(x + 1, cr);
+            load_col(x + 1, r1, r2);
           } else {
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-              for (int e = 0; e < 4; ++e) cr[dy][e] = 0.f;
+            for (int dy = 0; dy < 3; ++dy) r1[dy] = r2[dy] = 0ull;
           }
-          float acc[4] = {bz[0], bz[1], bz[2], bz[3]};
+          uint64_t a1 = bz1, a2 = bz2;
 #pragma unroll
-          for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              acc[e] = fmaf(wk[dy * 3 + 0][e], cl[dy][e], acc[e]);
-              acc[e] = fmaf(wk[dy * 3 + 1][e], cm[dy][e], acc[e]);
-              acc[e] = fmaf(wk[dy * 3 + 2][e], cr[dy][e], acc[e]);
-            }
-          const float g0 = acc[0] * acc[2], g1 = acc[1] * acc[3];
+          for (int dy = 0; dy < 3; ++dy) {
+            a1 = ffma2(wk1[dy * 3 + 0], l1[dy], a1); a2 = ffma2(wk2[dy * 3 + 0], l2[dy], a2);
+            a1 = ffma2(wk1[dy * 3 + 1], m1[dy], a1); a2 = ffma2(wk2[dy * 3 + 1], m2[dy], a2);
+            a1 = ffma2(wk1[dy * 3 + 2], r1[dy], a1); a2 = ffma2(wk2[dy * 3 + 2], r2[dy], a2);
+          }
+          const float2 f1 = unpack_f2(a1), f2 = unpack_f2(a2);
+          const float g0 = f1.x * f2.x, g1 = f1.y * f2.y;
           ps0 += g0; ps1 += g1;
-          const int Rp = y * SP + x;
-          sts32(sA + a_chunk_off(Rp, cb * 8 + (lane >> 2)) + (lane & 3) * 4, pack_bf16x2(g0, g1));
+          sts32(arow + ax[x & 7] + x * 128, pack_bf16x2(g0, g1));
         }
       }
       *reinterpret_cast<float2*>(scr + strip * C + j) = make_float2(ps0, ps1);
     }
+    // SCA weights for this thread's half of the GEMV: fetched before the barrier, consumed after it
+    const int sn = tid & (C - 1), skh = tid >> 7;
+    float wv[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) wv[i] = __ldg(bp.wsca_t + (skh * 64 + i) * C + sn);
     block_sync();  // T free; partials visible
+    stamp();
     if (ctrl) {
       load_w(b * 4 + 2, sT, 2, 2);                           // W4 -> plane 0
       if (!last) load_w((b + 1) * 4 + 0, sT + PLANE, 2, 0);  // next block's W1 -> plane 1
@@ -360,26 +403,25 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
     // ---------------- SCA: s = Wsca mean + b ----------------
     if (tid < C) scr[tid] = (scr[tid] + scr[C + tid] + scr[2 * C + tid] + scr[3 * C + tid]) * (1.f / PX);
     block_sync();
-    if (tid < C) {
-      float a0 = __ldg(bp.bsca + tid), a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-      for (int k = 0; k < C; k += 4) {
-        a0 = fmaf(__ldg(bp.wsca_t + (k + 0) * C + tid), scr[k + 0], a0);
-        a1 = fmaf(__ldg(bp.wsca_t + (k + 1) * C + tid), scr[k + 1], a1);
-        a2 = fmaf(__ldg(bp.wsca_t + (k + 2) * C + tid), scr[k + 2], a2);
-        a3 = fmaf(__ldg(bp.wsca_t + (k + 3) * C + tid), scr[k + 3], a3);
+    {
+      float a0 = skh == 0 ? __ldg(bp.bsca + sn) : 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+        const float4 m = *reinterpret_cast<const float4*>(scr + skh * 64 + i);
+        a0 = fmaf(wv[i], m.x, a0); a1 = fmaf(wv[i + 1], m.y, a1); a2 = fmaf(wv[i + 2], m.z, a2); a3 = fmaf(wv[i + 3], m.w, a3);
       }
-      s_sca[tid] = (a0 + a1) + (a2 + a3);
-    } else if (tid < 2 * C) {
-      make_ln_params(eff, bp.ln2_w, bp.ln2_b, mrow, bp.mod_off + 2 * C, bp.mod_off + 3 * C, tid - C);
+      // halves: k < 64 -> s_sca, k >= 64 -> scr[128..255] (strip-1 partials, dead since the mean was taken)
+      (skh == 0 ? s_sca : scr + C)[sn] = (a0 + a1) + (a2 + a3);
+      if (tid >= C) make_ln_params(eff, bp.ln2_w, bp.ln2_b, mrow, bp.mod_off + 2 * C, bp.mod_off + 3 * C, tid - C);
     }
     block_sync();
-    if (worker) {  // rescale this thread's own gated values
-      const float s0 = s_sca[j], s1 = s_sca[j + 1];
-#pragma unroll 4
+    {  // rescale this thread's own gated values
+      const float s0 = s_sca[j] + scr[C + j], s1 = s_sca[j + 1] + scr[C + j + 1];
+      const uint32_t abase = sA + static_cast<uint32_t>(((strip >> 1) * 2 + cb) * TILE + (strip & 1) * 64 * 128) +
+                             static_cast<uint32_t>((lane & 3) * 4);
+#pragma unroll 8
       for (int i = 0; i < 64; ++i) {
-        const int Rp = strip * 64 + i;
-        const uint32_t a = sA + a_chunk_off(Rp, cb * 8 + (lane >> 2)) + (lane & 3) * 4;
+        const uint32_t a = abase + i * 128 + (((lane >> 2) ^ (i & 7)) << 4);
         const float2 g = unpack_bf16x2(lds32(a));
         sts32(a, pack_bf16x2(g.x * s0, g.y * s1));
       }
@@ -387,6 +429,7 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
       tc_fence_before_sync();
     }
     block_sync();
+    stamp();
 
     // ---------------- conv3 (+beta) accumulated onto x; then x += b3, norm2 + modulation -> A ----------------
     if (ctrl) {
@@ -396,20 +439,24 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
       mbar_wait(mma_bar, mph, args.status, 0xA21u);
       load_w(b * 4 + 3, sW3, 1, 3);  // W5 takes W3's place
     }
-    if (worker) {
-      mbar_wait(mma_bar, mph, args.status, 0xA22u);
-      tc_fence_after_sync();
+    mbar_wait(mma_bar, mph, args.status, 0xA22u);
+    tc_fence_after_sync();
+    {
+      uint32_t r[4][32];
 #pragma unroll
-      for (int c0 = 0; c0 < C; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(t_x + c0, r);
-        tmem_wait_ld();
+      for (int c = 0; c < 4; ++c) tmem_ld32(t_x + c * 32, r[c]);
+      tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          v[c0 + i] = __uint_as_float(r[i]) + __ldg(bp.b3 + c0 + i);
-          r[i] = __float_as_uint(v[c0 + i]);
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(bp.b3 + c * 32 + i));
+          v[c * 32 + i] = __uint_as_float(r[c][i]) + bb.x; v[c * 32 + i + 1] = __uint_as_float(r[c][i + 1]) + bb.y;
+          v[c * 32 + i + 2] = __uint_as_float(r[c][i + 2]) + bb.z; v[c * 32 + i + 3] = __uint_as_float(r[c][i + 3]) + bb.w;
         }
-        tmem_st32(t_x + c0, r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[c][i] = __float_as_uint(v[c * 32 + i]);
+        tmem_st32(t_x + c * 32, r[c]);
       }
       ln_row_to_a(v, eff, eff + C, sA, R);
       tmem_wait_st();
@@ -418,6 +465,7 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
     }
     mph ^= 1u;
     block_sync();
+    stamp();
 
     // ---------------- conv4 + SimpleGate: first half kept in registers until the second half's MMAs are done ----------------
     uint32_t hold[32];
@@ -431,41 +479,39 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
       make_ln_params(eff, nx.ln1_w, nx.ln1_b, mrow, nx.mod_off, nx.mod_off + C, tid);
     }
     auto gate_half = [&](int h, uint32_t (&out)[32]) {  // 64 gated values of this row as 32 bf16x2
+      uint32_t r[4][32];
 #pragma unroll
-      for (int part = 0; part < 2; ++part) {
-        uint32_t r1[32], r2[32];
-        tmem_ld32(t_acc + part * 32, r1);
-        tmem_ld32(t_acc + 64 + part * 32, r2);
-        tmem_wait_ld();
-        const float* bias = bp.b4 + h * 128 + part * 32;
+      for (int c = 0; c < 4; ++c) tmem_ld32(t_acc + c * 32, r[c]);
+      tmem_wait_ld();
+      const float4* bias = reinterpret_cast<const float4*>(bp.b4 + h * 128);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float g0 = (__uint_as_float(r1[2 * i]) + __ldg(bias + 2 * i)) * (__uint_as_float(r2[2 * i]) + __ldg(bias + 64 + 2 * i));
-          const float g1 = (__uint_as_float(r1[2 * i + 1]) + __ldg(bias + 2 * i + 1)) *
-                           (__uint_as_float(r2[2 * i + 1]) + __ldg(bias + 64 + 2 * i + 1));
-          out[part * 16 + i] = pack_bf16x2(g0, g1);
-        }
+      for (int i = 0; i < 16; ++i) {  // gated values 4i .. 4i+3
+        const float4 p = __ldg(bias + i), q = __ldg(bias + 16 + i);
+        const uint32_t* x1 = &r[i >> 3][(i & 7) * 4];
+        const uint32_t* x2 = &r[2 + (i >> 3)][(i & 7) * 4];
+        out[2 * i] = pack_bf16x2((__uint_as_float(x1[0]) + p.x) * (__uint_as_float(x2[0]) + q.x),
+                                 (__uint_as_float(x1[1]) + p.y) * (__uint_as_float(x2[1]) + q.y));
+        out[2 * i + 1] = pack_bf16x2((__uint_as_float(x1[2]) + p.z) * (__uint_as_float(x2[2]) + q.z),
+                                     (__uint_as_float(x1[3]) + p.w) * (__uint_as_float(x2[3]) + q.w));
       }
     };
     auto store_half = [&](int h, const uint32_t (&in)[32]) {  // gated channels h*64 .. h*64+63 = k-block h of the A row
 #pragma unroll
       for (int q = 0; q < 8; ++q) sts128(sA + a_chunk_off(R, h * 8 + q), in[4 * q], in[4 * q + 1], in[4 * q + 2], in[4 * q + 3]);
     };
-    if (worker) {
-      mbar_wait(mma_bar, mph, args.status, 0xA31u);
-      tc_fence_after_sync();
-      gate_half(0, hold);
-      tc_fence_before_sync();
-    }
+    mbar_wait(mma_bar, mph, args.status, 0xA31u);
+    tc_fence_after_sync();
+    gate_half(0, hold);
+    tc_fence_before_sync();
     mph ^= 1u;
     block_sync();
     if (ctrl) {
       tc_fence_after_sync();
       issue(sT + 2 * TILE, ACC_COL, 0u);
     }
-    if (worker) {
-      mbar_wait(mma_bar, mph, args.status, 0xA32u);
-      tc_fence_after_sync();
+    mbar_wait(mma_bar, mph, args.status, 0xA32u);
+    tc_fence_after_sync();
+    {
       uint32_t g2[32];
       gate_half(1, g2);
       store_half(0, hold);
@@ -475,6 +521,7 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
     }
     mph ^= 1u;
     block_sync();
+    stamp();
 
     // ---------------- conv5 (+gamma) accumulated onto x; x += b5; next block's norm1 or the final store ----------------
     if (ctrl) {
@@ -486,37 +533,55 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
         load_w((b + 1) * 4 + 1, sW3, 1, 1);  // next block's W3
       }
     }
-    if (worker) {
-      mbar_wait(mma_bar, mph, args.status, 0xA42u);
-      tc_fence_after_sync();
+    mbar_wait(mma_bar, mph, args.status, 0xA42u);
+    tc_fence_after_sync();
+    {
+      uint32_t r[4][32];
 #pragma unroll
-      for (int c0 = 0; c0 < C; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(t_x + c0, r);
-        tmem_wait_ld();
+      for (int c = 0; c < 4; ++c) tmem_ld32(t_x + c * 32, r[c]);
+      tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          v[c0 + i] = __uint_as_float(r[i]) + __ldg(bp.b5 + c0 + i);
-          r[i] = __float_as_uint(v[c0 + i]);
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(bp.b5 + c * 32 + i));
+          v[c * 32 + i] = __uint_as_float(r[c][i]) + bb.x; v[c * 32 + i + 1] = __uint_as_float(r[c][i + 1]) + bb.y;
+          v[c * 32 + i + 2] = __uint_as_float(r[c][i + 2]) + bb.z; v[c * 32 + i + 3] = __uint_as_float(r[c][i + 3]) + bb.w;
         }
-        if (!last) tmem_st32(t_x + c0, r);
+        if (!last) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[c][i] = __float_as_uint(v[c * 32 + i]);
+          tmem_st32(t_x + c * 32, r[c]);
+        }
       }
       if (!last) {
         ln_row_to_a(v, eff, eff + C, sA, R);
         tmem_wait_st();
       } else {
-        float* xr = args.x + (static_cast<size_t>(face) * PX + R) * C;
+        // rows -> swizzled staging (A region / plane 0 are dead: every MMA has completed) -> coalesced row stores
+        const uint32_t srow = stage_row(R);
 #pragma unroll
-        for (int i = 0; i < C / 4; ++i)
-          *reinterpret_cast<float4*>(xr + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        for (int q = 0; q < 32; ++q)
+          sts128(srow + ((q ^ (R & 7)) << 4), __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
+                 __float_as_uint(v[4 * q + 3]));
       }
     }
     mph ^= 1u;
   }
+  block_sync();
+  {
+    float* xw = args.x + (static_cast<size_t>(face) * PX + warp * 32) * C + lane * 4;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      const int r = warp * 32 + i;
+      *reinterpret_cast<float4*>(xw + static_cast<size_t>(i) * C) = lds128(stage_row(r) + ((lane ^ (r & 7)) << 4));
+    }
+  }
 
   tc_fence_before_sync();
   block_sync();
-  if (warp == 8) {
+  stamp();
+  if (warp == 0) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
   }

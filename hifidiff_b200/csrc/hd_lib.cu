@@ -1035,6 +1035,24 @@ void add_face_blocks(hd_handle* h, Plan& P, size_t first, int count) {
   ti.ptr = a.x; ti.dtype = DT_F32; ti.C = c; ti.HW = rpf; ti.ld = c;
   std::string tap = h->blocks[first + count - 1].prefix;
   if (!tap.empty() && tap.back() == '.') tap.pop_back();
+  if (getenv("HD_FACE_TRACE") != nullptr) {  // diagnostics: phase timeline of CTA 0, printed after every eager launch
+    long long* tr = h->arena.get<long long>(64);
+    a.trace = tr;
+    const int n_st = 3 + 6 * count;
+    add_op(P, [=](cudaStream_t st) {
+      launch_k(fb::face_block_kernel, dim3(B), dim3(fb::THREADS), fb::SMEM_BYTES, st, a);
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(st, &cs);
+      if (cs != cudaStreamCaptureStatusNone) return;
+      long long hst[64];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(hst, tr, sizeof(hst), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[face_block trace, clocks since start]");
+      for (int i = 1; i < n_st; ++i) fprintf(stderr, " %lld", hst[i] - hst[0]);
+      fprintf(stderr, "\n");
+    }, tap, ti);
+    return;
+  }
   add_op(P, [=](cudaStream_t st) { launch_k(fb::face_block_kernel, dim3(B), dim3(fb::THREADS), fb::SMEM_BYTES, st, a); }, tap, ti);
 }
 
