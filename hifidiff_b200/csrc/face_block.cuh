@@ -58,7 +58,8 @@ struct Args {
   const int* mod_row_idx;
   int mod_stride;
   DeviceStatus* status;
-  long long* trace;                // optional: clock64 stamps of CTA 0's phase boundaries (diagnostics)
+  long long* trace;                // optional: clock64 stamps of one CTA's phase boundaries (diagnostics)
+  int trace_cta;
 };
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -111,6 +112,12 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
   return d;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // the controller lane / sub-warp branches rejoin their warps before the CTA barrier
 __device__ __forceinline__ void block_sync() {
   __syncwarp();
@@ -131,16 +138,20 @@ __device__ __forceinline__ uint32_t t_chunk_off(int px, int q) {
 // (eff_w, eff_b), written as the bf16 A operand row R.
 __device__ __forceinline__ void ln_row_to_a(const float (&v)[C], const float* eff_w, const float* eff_b, uint32_t a_base,
                                             int R) {
-  float s = 0.f;
+  float sa[8];  // 8 independent partial sums: a 16-deep dependency chain instead of 128
 #pragma unroll
-  for (int i = 0; i < C; ++i) s += v[i];
-  const float mu = s * (1.f / C);
-  float ss = 0.f;
+  for (int i = 0; i < 8; ++i) sa[i] = v[i];
+#pragma unroll
+  for (int i = 8; i < C; ++i) sa[i & 7] += v[i];
+  const float mu = (((sa[0] + sa[1]) + (sa[2] + sa[3])) + ((sa[4] + sa[5]) + (sa[6] + sa[7]))) * (1.f / C);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sa[i] = 0.f;
 #pragma unroll
   for (int i = 0; i < C; ++i) {
     const float d = v[i] - mu;
-    ss += d * d;
+    sa[i & 7] = fmaf(d, d, sa[i & 7]);
   }
+  const float ss = ((sa[0] + sa[1]) + (sa[2] + sa[3])) + ((sa[4] + sa[5]) + (sa[6] + sa[7]));
   const float rstd = 1.f / sqrtf(ss * (1.f / C) + 1e-6f);
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
@@ -182,7 +193,7 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
   const int nb = args.n_blocks;
   int n_stamp = 0;
   auto stamp = [&]() {
-    if (args.trace != nullptr && blockIdx.x == 0 && tid == 0) args.trace[n_stamp] = clock64();
+    if (args.trace != nullptr && blockIdx.x == args.trace_cta && tid == 0) args.trace[n_stamp] = clock64();
     ++n_stamp;
   };
 
@@ -233,6 +244,28 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
   if (ctrl) {
     load_w(0, sT + PLANE, 2, 0);  // W1 parks in plane 1 (plane 0 is written while its second half is still needed)
     load_w(1, sW3, 1, 1);
+    // everything else this kernel will need is pulled towards L2 now (cold after the rest of the step)
+    for (int i = 2; i < 4 * nb; ++i) {
+      const int halves = (i & 1) ? 1 : 2;
+      for (int h = 0; h < halves; ++h)
+        for (int kb = 0; kb < 2; ++kb) tma_prefetch_2d(args.maps + i, kb * BK, h * 128);
+    }
+  }
+  for (int b = 0; b < nb; ++b) {
+    const BlockParams bp = args.blocks[b];
+    prefetch_l2(bp.wsca_t + tid * 32);
+    prefetch_l2(bp.wsca_t + (256 + tid) * 32);
+    if (tid < 72) prefetch_l2(bp.dw_w + tid * 32);
+    if (tid >= 96 && tid < 104) prefetch_l2(bp.b1 + (tid - 96) * 32);
+    if (tid >= 104 && tid < 112) prefetch_l2(bp.b4 + (tid - 104) * 32);
+    if (tid >= 112 && tid < 120) prefetch_l2(bp.dw_b + (tid - 112) * 32);
+    if (tid >= 128 && tid < 132) prefetch_l2(bp.b3 + (tid - 128) * 32);
+    if (tid >= 132 && tid < 136) prefetch_l2(bp.b5 + (tid - 132) * 32);
+    if (tid >= 136 && tid < 140) prefetch_l2(bp.bsca + (tid - 136) * 32);
+    if (tid >= 140 && tid < 144) prefetch_l2(bp.ln1_w + (tid - 140) * 32);
+    if (tid >= 144 && tid < 148) prefetch_l2(bp.ln1_b + (tid - 144) * 32);
+    if (tid >= 148 && tid < 152) prefetch_l2(bp.ln2_w + (tid - 148) * 32);
+    if (tid >= 152 && tid < 156) prefetch_l2(bp.ln2_b + (tid - 152) * 32);
   }
   pdl_wait();
   stamp();
@@ -258,12 +291,14 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
     if (tid < C) make_ln_params(eff, bp.ln1_w, bp.ln1_b, mrow, bp.mod_off, bp.mod_off + C, tid);
     {
       const float* xw = args.x + (static_cast<size_t>(face) * PX + warp * 32) * C + lane * 4;
-#pragma unroll 8
+      float4 t[32];  // all 32 rows of this warp in flight at once
+#pragma unroll
+      for (int i = 0; i < 32; ++i) t[i] = *reinterpret_cast<const float4*>(xw + static_cast<size_t>(i) * C);
+#pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float4 t = *reinterpret_cast<const float4*>(xw + static_cast<size_t>(i) * C);
         const int r = warp * 32 + i;
-        sts128(stage_row(r) + ((lane ^ (r & 7)) << 4), __float_as_uint(t.x), __float_as_uint(t.y), __float_as_uint(t.z),
-               __float_as_uint(t.w));
+        sts128(stage_row(r) + ((lane ^ (r & 7)) << 4), __float_as_uint(t[i].x), __float_as_uint(t[i].y), __float_as_uint(t[i].z),
+               __float_as_uint(t[i].w));
       }
     }
     block_sync();
@@ -345,46 +380,53 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
         ax[k] = static_cast<uint32_t>((((lane >> 2) ^ k) << 4) + (lane & 3) * 4);
       }
       float ps0 = 0.f, ps1 = 0.f;
+      // two image rows at a time: 4 input rows per column feed 2 output pixels (fewer loads, 4 independent FMA chains)
 #pragma unroll 1
-      for (int y = strip * 4; y < strip * 4 + 4; ++y) {
-        const bool up = y > 0, dn = y < SP - 1;
-        const uint32_t trow = sT + static_cast<uint32_t>(y * SP) * 256u;                       // pixel (y, 0) in plane 0
-        const uint32_t arow = sA + static_cast<uint32_t>(((y >> 3) * 2 + cb) * TILE + (y & 7) * SP * 128);
-        uint64_t w1v[3][3], w2v[3][3];  // [column slot][dy]
-        auto load_col = [&](int x, uint64_t (&c1)[3], uint64_t (&c2)[3]) {
+      for (int y0 = strip * 4; y0 < strip * 4 + 4; y0 += 2) {
+        const bool up = y0 > 0, dn = y0 + 2 < SP;
+        const uint32_t trow = sT + static_cast<uint32_t>(y0 * SP) * 256u;                       // pixel (y0, 0) in plane 0
+        const uint32_t arow = sA + static_cast<uint32_t>(((y0 >> 3) * 2 + cb) * TILE + (y0 & 7) * SP * 128);
+        uint64_t w1v[3][4], w2v[3][4];  // [column slot][input row y0-1 .. y0+2]
+        auto load_col = [&](int x, uint64_t (&c1)[4], uint64_t (&c2)[4]) {
           const uint32_t a = trow + lx[x & 7] + x * 256;
           c1[0] = up ? bf2_to_f2(lds32(a - SP * 256)) : 0ull;
           c2[0] = up ? bf2_to_f2(lds32(a - SP * 256 + PLANE)) : 0ull;
           c1[1] = bf2_to_f2(lds32(a));
           c2[1] = bf2_to_f2(lds32(a + PLANE));
-          c1[2] = dn ? bf2_to_f2(lds32(a + SP * 256)) : 0ull;
-          c2[2] = dn ? bf2_to_f2(lds32(a + SP * 256 + PLANE)) : 0ull;
+          c1[2] = bf2_to_f2(lds32(a + SP * 256));
+          c2[2] = bf2_to_f2(lds32(a + SP * 256 + PLANE));
+          c1[3] = dn ? bf2_to_f2(lds32(a + 2 * SP * 256)) : 0ull;
+          c2[3] = dn ? bf2_to_f2(lds32(a + 2 * SP * 256 + PLANE)) : 0ull;
         };
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) w1v[0][dy] = w2v[0][dy] = 0ull;
+        for (int dy = 0; dy < 4; ++dy) w1v[0][dy] = w2v[0][dy] = 0ull;
         load_col(0, w1v[1], w2v[1]);
 #pragma unroll
         for (int x = 0; x < SP; ++x) {
-          uint64_t (&l1)[3] = w1v[x % 3], (&l2)[3] = w2v[x % 3];
-          uint64_t (&m1)[3] = w1v[(x + 1) % 3], (&m2)[3] = w2v[(x + 1) % 3];
-          uint64_t (&r1)[3] = w1v[(x + 2) % 3], (&r2)[3] = w2v[(x + 2) % 3];
+          uint64_t (&l1)[4] = w1v[x % 3], (&l2)[4] = w2v[x % 3];
+          uint64_t (&m1)[4] = w1v[(x + 1) % 3], (&m2)[4] = w2v[(x + 1) % 3];
+          uint64_t (&r1)[4] = w1v[(x + 2) % 3], (&r2)[4] = w2v[(x + 2) % 3];
           if (x + 1 < SP) {
             load_col(x + 1, r1, r2);
           } else {
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy) r1[dy] = r2[dy] = 0ull;
+            for (int dy = 0; dy < 4; ++dy) r1[dy] = r2[dy] = 0ull;
           }
-          uint64_t a1 = bz1, a2 = bz2;
+          uint64_t a1 = bz1, a2 = bz2, b1 = bz1, b2 = bz2;  // a: output row y0, b: output row y0 + 1
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
             a1 = ffma2(wk1[dy * 3 + 0], l1[dy], a1); a2 = ffma2(wk2[dy * 3 + 0], l2[dy], a2);
+            b1 = ffma2(wk1[dy * 3 + 0], l1[dy + 1], b1); b2 = ffma2(wk2[dy * 3 + 0], l2[dy + 1], b2);
             a1 = ffma2(wk1[dy * 3 + 1], m1[dy], a1); a2 = ffma2(wk2[dy * 3 + 1], m2[dy], a2);
+            b1 = ffma2(wk1[dy * 3 + 1], m1[dy + 1], b1); b2 = ffma2(wk2[dy * 3 + 1], m2[dy + 1], b2);
             a1 = ffma2(wk1[dy * 3 + 2], r1[dy], a1); a2 = ffma2(wk2[dy * 3 + 2], r2[dy], a2);
+            b1 = ffma2(wk1[dy * 3 + 2], r1[dy + 1], b1); b2 = ffma2(wk2[dy * 3 + 2], r2[dy + 1], b2);
           }
-          const float2 f1 = unpack_f2(a1), f2 = unpack_f2(a2);
-          const float g0 = f1.x * f2.x, g1 = f1.y * f2.y;
-          ps0 += g0; ps1 += g1;
-          sts32(arow + ax[x & 7] + x * 128, pack_bf16x2(g0, g1));
+          const float2 fa1 = unpack_f2(a1), fa2 = unpack_f2(a2), fb1 = unpack_f2(b1), fb2 = unpack_f2(b2);
+          const float ga0 = fa1.x * fa2.x, ga1 = fa1.y * fa2.y, gb0 = fb1.x * fb2.x, gb1 = fb1.y * fb2.y;
+          ps0 += ga0 + gb0; ps1 += ga1 + gb1;
+          sts32(arow + ax[x & 7] + x * 128, pack_bf16x2(ga0, ga1));
+          sts32(arow + ax[x & 7] + x * 128 + SP * 128, pack_bf16x2(gb0, gb1));
         }
       }
       *reinterpret_cast<float2*>(scr + strip * C + j) = make_float2(ps0, ps1);

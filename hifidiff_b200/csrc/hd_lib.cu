@@ -1038,6 +1038,7 @@ void add_face_blocks(hd_handle* h, Plan& P, size_t first, int count) {
   if (getenv("HD_FACE_TRACE") != nullptr) {  // diagnostics: phase timeline of CTA 0, printed after every eager launch
     long long* tr = h->arena.get<long long>(64);
     a.trace = tr;
+    a.trace_cta = atoi(getenv("HD_FACE_TRACE"));
     const int n_st = 3 + 6 * count;
     add_op(P, [=](cudaStream_t st) {
       launch_k(fb::face_block_kernel, dim3(B), dim3(fb::THREADS), fb::SMEM_BYTES, st, a);
