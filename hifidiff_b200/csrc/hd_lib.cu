@@ -17,6 +17,7 @@
 #include "gemm_tc.cuh"
 #include "chain.cuh"
 #include "face_block.cuh"
+#include "pair_block.cuh"
 
 using namespace hd;
 
@@ -60,6 +61,7 @@ bool g_use_pdl = true;  // HD_PDL=0 disables programmatic dependent launch
 bool g_bn256 = true;    // HD_BN256=0: 128x128 tiles for the dense 3x3 convs too
 int g_two_cta = 1;      // HD_TWO_CTA=0: never use cta_group::2 pairs; 2: wherever the shape allows (tests)
 bool g_face = true;     // HD_FACE=0: per-op kernels at the 16x16 level instead of the fused per-face block kernel
+bool g_pair = true;     // HD_PAIR=0: per-op kernels at the 8x8 level instead of the fused face-pair block kernel
 bool g_chain = false;   // HD_CHAIN=1: run the 1x1-level blocks as one persistent cooperative kernel (measured slower)
 int g_max_stages = 6;   // HD_MAX_STAGES=3: no 6-stage / 16-epilogue-warp variant (one CTA per SM)
 // HD_FUSE_LN=1 computes LayerNorm + modulation in the residual GEMM's epilogue where the tile holds the whole
@@ -132,6 +134,8 @@ struct BlockW {
   float *b1 = nullptr, *bsca = nullptr, *b3 = nullptr, *b4 = nullptr, *b5 = nullptr;
   float *dw_w = nullptr, *dw_b = nullptr;
   float* wsca_t = nullptr;  // 16x16 level: SCA weight transposed [k][n] fp32 for the fused face kernel's GEMV
+  void* wsca_tb = nullptr;  // 8x8 level: the same, bf16, for the fused face-pair kernel
+  std::vector<float> b3_h, b5_h;  // host copies of the folded conv3 / conv5 biases (cumulative residual bias)
   bool dw_folded = false;  // 1x1 level: depthwise 3x3 == per-channel scale, folded into conv1 (gate-packed)
   bool has_mod = true;     // false: unconditional NAFBlock of the FPG encoder (models/fpg/naf.py:105-126)
   bool dw_fused = false;   // 2x2..8x8 levels, bf16: depthwise 3x3 + gate + pool run in conv1's epilogue (gate-packed)
@@ -636,12 +640,26 @@ void load_block(hd_handle* h, BlockW& bw, int wdt) {
       for (int k = 0; k < c; ++k) t[static_cast<size_t>(k) * c + n] = w[static_cast<size_t>(n) * c + k];
     bw.wsca_t = upload_f32(h, t);
   }
+  if (c == pb::C && h->sp[bw.level] == pb::SP) {
+    auto w = host_vec(h, need(h, p + "sca.1.weight", {c, c}));
+    std::vector<uint16_t> t(w.size());
+    for (int n = 0; n < c; ++n)
+      for (int k = 0; k < c; ++k) {
+        uint32_t u;
+        memcpy(&u, &w[static_cast<size_t>(n) * c + k], 4);
+        u += 0x7FFFu + ((u >> 16) & 1u);  // round to nearest even (weights are finite)
+        t[static_cast<size_t>(k) * c + n] = static_cast<uint16_t>(u >> 16);
+      }
+    bw.wsca_tb = h->arena.alloc(t.size() * 2);
+    CUDA_CHECK(cudaMemcpy(bw.wsca_tb, t.data(), t.size() * 2, cudaMemcpyHostToDevice));
+  }
 
   {  // conv3 with beta folded: y = inp + beta * (W3 x + b3)
     auto b3 = host_vec(h, need(h, p + "conv3.bias", {c}));
     for (int i = 0; i < c; ++i) b3[i] *= beta[i];
     bw.w3 = pack_matrix(h, need(h, p + "conv3.weight", {c, c}), c, c, 1, nullptr, &beta, wdt);
     bw.b3 = upload_f32(h, b3);
+    bw.b3_h = b3;
   }
   {  // conv4, gate-packed: 128-row groups [64 x1 rows | 64 matching x2 rows]
     std::vector<int> perm(2 * c);
@@ -660,6 +678,7 @@ void load_block(hd_handle* h, BlockW& bw, int wdt) {
     for (int i = 0; i < c; ++i) b5[i] *= gamma[i];
     bw.w5 = pack_matrix(h, need(h, p + "conv5.weight", {c, c}), c, c, 1, nullptr, &gamma, wdt);
     bw.b5 = upload_f32(h, b5);
+    bw.b5_h = b5;
   }
   if (bw.has_mod) {
     // per-block time MLP rows go into the concatenated [mod_stride, 256] matrix
@@ -1057,6 +1076,77 @@ void add_face_blocks(hd_handle* h, Plan& P, size_t first, int count) {
   add_op(P, [=](cudaStream_t st) { launch_k(fb::face_block_kernel, dim3(B), dim3(fb::THREADS), fb::SMEM_BYTES, st, a); }, tap, ti);
 }
 
+// Fused face-pair kernel (pair_block.cuh) over the blocks [first, first + count) of the 8x8 level.
+bool pair_blocks_ok(hd_handle* h, size_t first, int count, bool debug) {
+  if (!g_pair || debug || !h->bf16 || count > pb::MAX_BLOCKS) return false;
+  for (int i = 0; i < count; ++i) {
+    const BlockW& bw = h->blocks[first + i];
+    if (bw.c != pb::C || h->sp[bw.level] != pb::SP || !bw.has_mod || bw.dw_fused || bw.dw_folded || bw.wsca_tb == nullptr) return false;
+  }
+  return true;
+}
+
+void add_pair_blocks(hd_handle* h, Plan& P, size_t first, int count) {
+  const int B = P.batch;
+  const int c = pb::C, rpf = pb::FPX;
+  std::vector<CUtensorMap> maps;
+  std::vector<pb::BlockParams> bps;
+  auto add_map = [&](const void* base, int N) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)c, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)c * 2};
+    cuuint32_t box[2] = {64, 128};
+    encode_map(h, &m, base, 2, dims, strides, box);
+    maps.push_back(m);
+  };
+  std::vector<float> cum(c, 0.f);
+  for (int i = 0; i < count; ++i) {
+    const BlockW& bw = h->blocks[first + i];
+    add_map(bw.w1, 2 * c);
+    add_map(bw.w3, c);
+    add_map(bw.w4, 2 * c);
+    add_map(bw.w5, c);
+    pb::BlockParams bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.ln1_w = bw.ln1_w; bp.ln1_b = bw.ln1_b; bp.ln2_w = bw.ln2_w; bp.ln2_b = bw.ln2_b;
+    bp.b1 = bw.b1; bp.dw_w = bw.dw_w; bp.dw_b = bw.dw_b; bp.wsca_t = static_cast<const bf16*>(bw.wsca_tb); bp.bsca = bw.bsca;
+    bp.b4 = bw.b4; bp.mod_off = bw.mod_off;
+    // the residual stream stays bias-free in tensor memory: x_true = x_tmem + (sum of the conv3 / conv5 biases so far)
+    for (int k = 0; k < c; ++k) cum[k] += bw.b3_h[k];
+    bp.cb3 = upload_f32(h, cum);
+    for (int k = 0; k < c; ++k) cum[k] += bw.b5_h[k];
+    bp.cb5 = upload_f32(h, cum);
+    bps.push_back(bp);
+    P.flops_per_face += 2.0 * rpf * 6.0 * c * c + 2.0 * c * c + 2.0 * 9 * 2 * c * rpf;
+  }
+  pb::Args a;
+  memset(&a, 0, sizeof(a));
+  CUtensorMap* d_maps = static_cast<CUtensorMap*>(h->arena.alloc(maps.size() * sizeof(CUtensorMap)));
+  pb::BlockParams* d_bps = static_cast<pb::BlockParams*>(h->arena.alloc(bps.size() * sizeof(pb::BlockParams)));
+  CUDA_CHECK(cudaMemcpy(d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(d_bps, bps.data(), bps.size() * sizeof(pb::BlockParams), cudaMemcpyHostToDevice));
+  a.maps = d_maps;
+  a.blocks = d_bps;
+  a.n_blocks = count;
+  a.n_faces = B;
+  a.x = h->resid[h->blocks[first].level];
+  a.mod_table = h->mod_table;
+  a.mod_row_idx = h->row_idx;
+  a.mod_stride = h->mod_stride;
+  a.status = h->d_status;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(pb::pair_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::SMEM_BYTES));
+    configured = true;
+  }
+  g_label = fmt("L%d c=%d pair_block x%d (%s)", h->blocks[first].level, c, count, h->blocks[first].prefix.c_str());
+  TapInfo ti;
+  ti.ptr = a.x; ti.dtype = DT_F32; ti.C = c; ti.HW = rpf; ti.ld = c;
+  std::string tap = h->blocks[first + count - 1].prefix;
+  if (!tap.empty() && tap.back() == '.') tap.pop_back();
+  add_op(P, [=](cudaStream_t st) { launch_k(pb::pair_block_kernel, dim3((B + 1) / 2), dim3(pb::THREADS), pb::SMEM_BYTES, st, a); }, tap, ti);
+}
+
 // Persistent chain over the blocks [first, first + count) of one 1x1-spatial level (see chain.cuh).
 // Expects blocks[first]'s norm1 output in act_a; leaves the level's residual stream finished in resid[level].
 void add_chain_1x1(hd_handle* h, Plan& P, size_t first, int count) {
@@ -1219,6 +1309,9 @@ Plan* get_plan(hd_handle* h, int B, bool debug = false) {
     if (face_blocks_ok(h, bi, kEncBlocks[l], debug)) {
       add_face_blocks(h, P, bi, kEncBlocks[l]);
       bi += kEncBlocks[l];
+    } else if (pair_blocks_ok(h, bi, kEncBlocks[l], debug)) {
+      add_pair_blocks(h, P, bi, kEncBlocks[l]);
+      bi += kEncBlocks[l];
     } else {
       for (int i = 0; i < kEncBlocks[l]; ++i, ++bi)
         add_block(h, P, h->blocks[bi], "encoders." + std::to_string(l) + "." + std::to_string(i),
@@ -1289,6 +1382,9 @@ Plan* get_plan(hd_handle* h, int B, bool debug = false) {
     add_gemm(h, P, d, static_cast<long long>(h->Bcap) * n * n, "ups." + std::to_string(L), ti);
     if (face_blocks_ok(h, bi, kDecBlocks[L], debug)) {
       add_face_blocks(h, P, bi, kDecBlocks[L]);
+      bi += kDecBlocks[L];
+    } else if (pair_blocks_ok(h, bi, kDecBlocks[L], debug)) {
+      add_pair_blocks(h, P, bi, kDecBlocks[L]);
       bi += kDecBlocks[L];
     } else {
       for (int i = 0; i < kDecBlocks[L]; ++i, ++bi)
@@ -1622,6 +1718,7 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   if (const char* e = getenv("HD_TWO_CTA")) g_two_cta = atoi(e);
   if (const char* e = getenv("HD_CHAIN")) g_chain = atoi(e) != 0;
   if (const char* e = getenv("HD_FACE")) g_face = atoi(e) != 0;
+  if (const char* e = getenv("HD_PAIR")) g_pair = atoi(e) != 0;
   if (const char* e = getenv("HD_MAX_STAGES")) g_max_stages = atoi(e);
   if (const char* e = getenv("HD_FUSE_LN")) g_fuse_ln = atoi(e) != 0;
   h = new hd_handle();
