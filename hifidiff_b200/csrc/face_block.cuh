@@ -118,6 +118,26 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, 
                : "memory");
 }
 
+// ---- code-size discipline --------------------------------------------------------------------------------------
+// These fused kernels are long straight-line programs; measured on B200, the first execution of every code region
+// after the rest of the step has flushed the instruction caches costs about as much as the work itself (the SM
+// fetches ~2-3 B of instructions per clock from L2).  So everything that is called from several places and does not
+// carry register arrays across the call lives in ONE non-inlined copy.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, DeviceStatus* st, uint32_t site) {
+  tc::mbar_wait(bar, parity, st, site);
+}
+__device__ __forceinline__ void mbar_wait_c(uint32_t bar, uint32_t parity, DeviceStatus* st, uint32_t site) {
+  if (!tc::mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, st, site);
+}
+// one 64-wide k-block: D[tmem] (+)= A tile (128 x 64) * B tile (N x 64)^T, four UMMA_K steps
+__device__ __noinline__ void issue_kblock(uint32_t a_tile, uint32_t b_tile, uint32_t tmem_d, uint32_t accumulate_first,
+                                          uint32_t idesc) {
+  const uint64_t da = tc::make_smem_desc(a_tile), db = tc::make_smem_desc(b_tile);
+#pragma unroll
+  for (int k = 0; k < tc::BK / tc::UMMA_K; ++k)
+    tc::umma_bf16(da + 2 * k, db + 2 * k, tmem_d, k == 0 ? accumulate_first : 1u, idesc);
+}
+
 // the controller lane / sub-warp branches rejoin their warps before the CTA barrier
 __device__ __forceinline__ void block_sync() {
   __syncwarp();

@@ -1129,6 +1129,7 @@ void add_pair_blocks(hd_handle* h, Plan& P, size_t first, int count) {
   a.blocks = d_bps;
   a.n_blocks = count;
   a.n_faces = B;
+  a.zero_bias = upload_f32(h, std::vector<float>(c, 0.f));
   a.x = h->resid[h->blocks[first].level];
   a.mod_table = h->mod_table;
   a.mod_row_idx = h->row_idx;
@@ -1144,6 +1145,25 @@ void add_pair_blocks(hd_handle* h, Plan& P, size_t first, int count) {
   ti.ptr = a.x; ti.dtype = DT_F32; ti.C = c; ti.HW = rpf; ti.ld = c;
   std::string tap = h->blocks[first + count - 1].prefix;
   if (!tap.empty() && tap.back() == '.') tap.pop_back();
+  if (getenv("HD_PAIR_TRACE") != nullptr) {  // diagnostics: phase timeline of one CTA, printed after every eager launch
+    long long* tr = h->arena.get<long long>(64);
+    a.trace = tr;
+    a.trace_cta = atoi(getenv("HD_PAIR_TRACE"));
+    const int n_st = 3 + 6 * count;
+    add_op(P, [=](cudaStream_t st) {
+      launch_k(pb::pair_block_kernel, dim3((B + 1) / 2), dim3(pb::THREADS), pb::SMEM_BYTES, st, a);
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(st, &cs);
+      if (cs != cudaStreamCaptureStatusNone) return;
+      long long hst[64];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(hst, tr, sizeof(hst), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[pair_block trace, clocks since start]");
+      for (int i = 1; i < n_st; ++i) fprintf(stderr, " %lld", hst[i] - hst[0]);
+      fprintf(stderr, "\n");
+    }, tap, ti);
+    return;
+  }
   add_op(P, [=](cudaStream_t st) { launch_k(pb::pair_block_kernel, dim3((B + 1) / 2), dim3(pb::THREADS), pb::SMEM_BYTES, st, a); }, tap, ti);
 }
 

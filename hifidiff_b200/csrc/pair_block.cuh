@@ -72,8 +72,78 @@ struct Args {
   const float* mod_table;
   const int* mod_row_idx;
   int mod_stride;
+  const float* zero_bias;          // 256 zeros (the stream carries no bias before the first conv3)
   DeviceStatus* status;
+  long long* trace;                // optional: clock64 stamps of one CTA's phase boundaries (diagnostics)
+  int trace_cta;
 };
+
+// LayerNorm2d + AdaLN modulation of residual row r, streamed from tensor memory (the row = x_tmem + cbias):
+// pass 1 takes the statistics over all 256 channels (shifted sums around the row's first element: one pass, no
+// cancellation), pass 2 re-reads this thread's half and writes it as k-blocks 2hf, 2hf+1 of the bf16 A operand.
+// Both threads of a row take the statistics redundantly, which is cheaper than exchanging them.
+__device__ __noinline__ void residual_ln(uint32_t t_row, int hf, int r, const float* __restrict__ cbias, const float* eff_w,
+                                         const float* eff_b, uint32_t sA) {
+  using namespace tc;
+  float shift, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    uint32_t t[32];
+    tmem_ld32(t_row + c * 32, t);
+    tmem_wait_ld();
+    const float4* bb = reinterpret_cast<const float4*>(cbias + c * 32);
+    if (c == 0) shift = __uint_as_float(t[0]) + __ldg(cbias);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b4 = __ldg(bb + i);
+      const float d0 = __uint_as_float(t[4 * i]) + b4.x - shift, d1 = __uint_as_float(t[4 * i + 1]) + b4.y - shift;
+      const float d2 = __uint_as_float(t[4 * i + 2]) + b4.z - shift, d3 = __uint_as_float(t[4 * i + 3]) + b4.w - shift;
+      s1[0] += d0; s1[1] += d1; s1[2] += d2; s1[3] += d3;
+      s2[0] = fmaf(d0, d0, s2[0]); s2[1] = fmaf(d1, d1, s2[1]); s2[2] = fmaf(d2, d2, s2[2]); s2[3] = fmaf(d3, d3, s2[3]);
+    }
+  }
+  const float S1 = (s1[0] + s1[1]) + (s1[2] + s1[3]), S2 = (s2[0] + s2[1]) + (s2[2] + s2[3]);
+  const float mu = shift + S1 * (1.f / C);
+  const float rstd = 1.f / sqrtf(fmaxf(S2 - S1 * S1 * (1.f / C), 0.f) * (1.f / C) + 1e-6f);
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    const int col = hf * 128 + c * 32;
+    uint32_t t[32];
+    tmem_ld32(t_row + col, t);
+    tmem_wait_ld();
+    const uint32_t arow = sA + static_cast<uint32_t>((hf * 2 + (c >> 1)) * TILE + r * 128);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(cbias + col + q * 8)), c1 = __ldg(reinterpret_cast<const float4*>(cbias + col + q * 8 + 4));
+      const float4 w0 = *reinterpret_cast<const float4*>(eff_w + col + q * 8), w1 = *reinterpret_cast<const float4*>(eff_w + col + q * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(eff_b + col + q * 8), b1 = *reinterpret_cast<const float4*>(eff_b + col + q * 8 + 4);
+      const float y0 = (__uint_as_float(t[q * 8 + 0]) + c0.x - mu) * rstd * w0.x + b0.x, y1 = (__uint_as_float(t[q * 8 + 1]) + c0.y - mu) * rstd * w0.y + b0.y;
+      const float y2 = (__uint_as_float(t[q * 8 + 2]) + c0.z - mu) * rstd * w0.z + b0.z, y3 = (__uint_as_float(t[q * 8 + 3]) + c0.w - mu) * rstd * w0.w + b0.w;
+      const float y4 = (__uint_as_float(t[q * 8 + 4]) + c1.x - mu) * rstd * w1.x + b1.x, y5 = (__uint_as_float(t[q * 8 + 5]) + c1.y - mu) * rstd * w1.y + b1.y;
+      const float y6 = (__uint_as_float(t[q * 8 + 6]) + c1.z - mu) * rstd * w1.z + b1.z, y7 = (__uint_as_float(t[q * 8 + 7]) + c1.w - mu) * rstd * w1.w + b1.w;
+      sts128(arow + ((((c & 1) * 4 + q) ^ (r & 7)) << 4), pack_bf16x2(y0, y1), pack_bf16x2(y2, y3), pack_bf16x2(y4, y5), pack_bf16x2(y6, y7));
+    }
+  }
+}
+
+// conv1 accumulator quarter -> bf16 plane: this thread's 64 columns of row r, + bias
+__device__ __noinline__ void drain_quarter(uint32_t acc, const float* __restrict__ bias_f, uint32_t prow, int hf, int r) {
+  using namespace tc;
+  uint32_t t[2][32];
+  tmem_ld32(acc + hf * 64, t[0]);
+  tmem_ld32(acc + hf * 64 + 32, t[1]);
+  tmem_wait_ld();
+  const float4* bias = reinterpret_cast<const float4*>(bias_f + hf * 64);
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    const float4 b0 = __ldg(bias + 2 * ch), b1 = __ldg(bias + 2 * ch + 1);
+    const uint32_t* rr = &t[ch >> 2][(ch & 3) * 8];
+    sts128(prow + (((hf * 8 + ch) ^ (r & 7)) << 4), pack_bf16x2(__uint_as_float(rr[0]) + b0.x, __uint_as_float(rr[1]) + b0.y),
+           pack_bf16x2(__uint_as_float(rr[2]) + b0.z, __uint_as_float(rr[3]) + b0.w),
+           pack_bf16x2(__uint_as_float(rr[4]) + b1.x, __uint_as_float(rr[5]) + b1.y),
+           pack_bf16x2(__uint_as_float(rr[6]) + b1.z, __uint_as_float(rr[7]) + b1.w));
+  }
+}
 
 __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args) {
   using namespace tc;
@@ -93,7 +163,13 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
   const uint32_t wbar = smem_u32(&bars[0]);
   const uint32_t mbar[2] = {smem_u32(&bars[5]), smem_u32(&bars[6])};
 
+  int n_stamp = 0;
+  auto stamp = [&]() {
+    if (args.trace != nullptr && blockIdx.x == args.trace_cta && tid == 0) args.trace[n_stamp] = clock64();
+    ++n_stamp;
+  };
   pdl_trigger();
+  stamp();
   if (tid == 0) {
     if ((sbase & 1023u) != 0u) {
       if (atomicCAS(&args.status->error, 0u, 3u) == 0u) args.status->where = 0xB00u;
@@ -131,28 +207,17 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
     tma_load_2d(slot_addr(s) + TILE, args.maps + map_idx, kb * BK, 128, b);
   };
   auto wait_slot = [&](int s) {
-    mbar_wait(wbar + s * 8, (wph >> s) & 1u, args.status, 0xB10u + s);
+    fb::mbar_wait_c(wbar + s * 8, (wph >> s) & 1u, args.status, 0xB10u + s);
     wph ^= 1u << s;
   };
   constexpr uint32_t idesc128 = make_idesc(128, 128), idesc256 = make_idesc(128, 256);
   // acc (+)= A[:, k-blocks 2*pair..2*pair+1] * Wq[:, same]^T    (N = 128)
   auto mma_pair = [&](int s, int pair, uint32_t acc_col, bool first) {
-#pragma unroll
-    for (int kk = 0; kk < 2; ++kk) {
-      const uint64_t da = make_smem_desc(sA + (pair * 2 + kk) * TILE);
-      const uint64_t db = make_smem_desc(slot_addr(s) + kk * TILE);
-#pragma unroll
-      for (int k = 0; k < BK / UMMA_K; ++k)
-        umma_bf16(da + 2 * k, db + 2 * k, tmem_base + acc_col, (first && kk == 0 && k == 0) ? 0u : 1u, idesc128);
-    }
+    fb::issue_kblock(sA + (pair * 2) * TILE, slot_addr(s), tmem_base + acc_col, first ? 0u : 1u, idesc128);
+    fb::issue_kblock(sA + (pair * 2 + 1) * TILE, slot_addr(s) + TILE, tmem_base + acc_col, 1u, idesc128);
   };
   // x += A[:, k-block kb] * W[:, kb]^T    (N = 256, accumulated onto the residual stream)
-  auto mma_kb = [&](int s, int kb) {
-    const uint64_t da = make_smem_desc(sA + kb * TILE);
-    const uint64_t db = make_smem_desc(slot_addr(s));
-#pragma unroll
-    for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(da + 2 * k, db + 2 * k, tmem_base + X_COL, 1u, idesc256);
-  };
+  auto mma_kb = [&](int s, int kb) { fb::issue_kblock(sA + kb * TILE, slot_addr(s), tmem_base + X_COL, 1u, idesc256); };
 
   if (ctrl) load_pair(0, 0, 0, P2), load_pair(0, 0, 1, P3);  // conv1 q0 of the first block (constants: before the wait)
   for (int b = 0; b < nb; ++b) {
@@ -164,6 +229,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
     if (tid < 144) prefetch_l2(bp.dw_w + tid * 32);
   }
   pdl_wait();
+  stamp();
 
   // ---- thread geometry ----
   const int r = (warp & 3) * 32 + lane;               // pixel row = TMEM lane
@@ -171,7 +237,6 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
   const int fl = r >> 6;                              // local face of this row
   const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const uint32_t t_x = tmem_base + lane_addr + X_COL + hf * 128;        // own half of the residual row
-  const uint32_t t_xp = tmem_base + lane_addr + X_COL + (1 - hf) * 128; // the partner thread's half (read-only: statistics)
   const uint32_t t_acc0 = tmem_base + lane_addr + ACC_COL;
   const bool face_ok[2] = {face0 < args.n_faces, face0 + 1 < args.n_faces};
   const float* mrow[2];
@@ -182,7 +247,6 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
   const int cb = warp & 3, df = warp >> 2, j = cb * 64 + lane * 2;
 
   uint32_t mph0 = 0, mph1 = 0;  // parities of the two MMA-done barriers (tracked by every thread)
-  float v[128];                 // this thread's half row of the residual stream
 
   // LayerNorm parameters of both faces -> R: eff_w = w (1 + scale), eff_b = b (1 + scale) + shift
   auto make_eff = [&](const float* lw, const float* lb, int shift_off, int scale_off) {
@@ -194,79 +258,9 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
       r_eff[(f * 2 + 1) * C + tid] = bb * sc + __ldg(mrow[f] + shift_off + tid);
     }
   };
-  // LayerNorm2d of row r over all 256 channels: the own half is in v, (ps1, ps2) are the partner half's shifted sums
-  // sum(p - c), sum((p - c)^2) with c = the own half's mean.  Writes the own 128 channels (k-blocks 2hf, 2hf+1) of A.
-  auto ln_to_a = [&](float c_own, float m2_own, float ps1, float ps2) {
-    const float mu = c_own + ps1 * (1.f / C);
-    const float m2 = m2_own + ps2 - ps1 * ps1 * (1.f / C);
-    const float rstd = 1.f / sqrtf(fmaxf(m2, 0.f) * (1.f / C) + 1e-6f);
-    const float* ew = r_eff + (fl * 2 + 0) * C + hf * 128;
-    const float* eb = r_eff + (fl * 2 + 1) * C + hf * 128;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const float4 w0 = *reinterpret_cast<const float4*>(ew + q * 8), w1 = *reinterpret_cast<const float4*>(ew + q * 8 + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(eb + q * 8), b1 = *reinterpret_cast<const float4*>(eb + q * 8 + 4);
-      const float y0 = (v[q * 8 + 0] - mu) * rstd * w0.x + b0.x, y1 = (v[q * 8 + 1] - mu) * rstd * w0.y + b0.y;
-      const float y2 = (v[q * 8 + 2] - mu) * rstd * w0.z + b0.z, y3 = (v[q * 8 + 3] - mu) * rstd * w0.w + b0.w;
-      const float y4 = (v[q * 8 + 4] - mu) * rstd * w1.x + b1.x, y5 = (v[q * 8 + 5] - mu) * rstd * w1.y + b1.y;
-      const float y6 = (v[q * 8 + 6] - mu) * rstd * w1.z + b1.z, y7 = (v[q * 8 + 7] - mu) * rstd * w1.w + b1.w;
-      const uint32_t a = sA + static_cast<uint32_t>((hf * 2 + (q >> 3)) * TILE + r * 128 + (((q & 7) ^ (r & 7)) << 4));
-      sts128(a, pack_bf16x2(y0, y1), pack_bf16x2(y2, y3), pack_bf16x2(y4, y5), pack_bf16x2(y6, y7));
-    }
-  };
-  // mean and centred second moment of the own half (two-pass, 8 independent partial sums)
-  auto own_stats = [&](float& c_own, float& m2_own) {
-    float sa[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sa[i] = v[i];
-#pragma unroll
-    for (int i = 8; i < 128; ++i) sa[i & 7] += v[i];
-    c_own = (((sa[0] + sa[1]) + (sa[2] + sa[3])) + ((sa[4] + sa[5]) + (sa[6] + sa[7]))) * (1.f / 128);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sa[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 128; ++i) {
-      const float d = v[i] - c_own;
-      sa[i & 7] = fmaf(d, d, sa[i & 7]);
-    }
-    m2_own = ((sa[0] + sa[1]) + (sa[2] + sa[3])) + ((sa[4] + sa[5]) + (sa[6] + sa[7]));
-  };
-  // own half of the residual row (x + cumulative bias) -> v; partner half -> shifted sums; then LayerNorm -> A
-  // (or, for the last block, v is left for the final store)
-  auto residual_epilogue = [&](const float* cbias, bool do_ln) {
-    {
-      uint32_t t[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(t_x + c * 32, t[c]);
-      tmem_wait_ld();
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(cbias + hf * 128 + c * 32 + i));
-          v[c * 32 + i] = __uint_as_float(t[c][i]) + bb.x; v[c * 32 + i + 1] = __uint_as_float(t[c][i + 1]) + bb.y;
-          v[c * 32 + i + 2] = __uint_as_float(t[c][i + 2]) + bb.z; v[c * 32 + i + 3] = __uint_as_float(t[c][i + 3]) + bb.w;
-        }
-    }
-    if (!do_ln) return;
-    float c_own, m2_own;
-    own_stats(c_own, m2_own);
-    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint32_t t[32];
-      tmem_ld32(t_xp + c * 32, t);
-      tmem_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(cbias + (1 - hf) * 128 + c * 32 + i));
-        const float d0 = __uint_as_float(t[i]) + bb.x - c_own, d1 = __uint_as_float(t[i + 1]) + bb.y - c_own;
-        const float d2 = __uint_as_float(t[i + 2]) + bb.z - c_own, d3 = __uint_as_float(t[i + 3]) + bb.w - c_own;
-        s1[0] += d0; s1[1] += d1; s1[2] += d2; s1[3] += d3;
-        s2[0] = fmaf(d0, d0, s2[0]); s2[1] = fmaf(d1, d1, s2[1]); s2[2] = fmaf(d2, d2, s2[2]); s2[3] = fmaf(d3, d3, s2[3]);
-      }
-    }
-    ln_to_a(c_own, m2_own, (s1[0] + s1[1]) + (s1[2] + s1[3]), (s2[0] + s2[1]) + (s2[2] + s2[3]));
+  const uint32_t t_row = tmem_base + lane_addr + X_COL;  // the whole residual row of this thread's pixel
+  auto ln_row = [&](const float* cbias) {
+    residual_ln(t_row, hf, r, cbias, r_eff + (fl * 2 + 0) * C, r_eff + (fl * 2 + 1) * C, sA);
   };
 
   // ---------------- prologue: x -> staging (coalesced) -> registers / TMEM; norm1 of the first block ----------------
@@ -292,62 +286,37 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
     }
     make_eff(bp.ln1_w, bp.ln1_b, bp.mod_off, bp.mod_off + C);
     block_sync();
-    float c_own, m2_own, ps1, ps2;
     {
       const uint32_t srow = sbase + r * 1024;
-#pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        const float4 t = lds128(srow + (((hf * 32 + q) ^ (r & 7)) << 4));
-        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-      }
-      own_stats(c_own, m2_own);
-      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        const float4 t = lds128(srow + ((((1 - hf) * 32 + q) ^ (r & 7)) << 4));
-        const float d0 = t.x - c_own, d1 = t.y - c_own, d2 = t.z - c_own, d3 = t.w - c_own;
-        s1[0] += d0; s1[1] += d1; s1[2] += d2; s1[3] += d3;
-        s2[0] = fmaf(d0, d0, s2[0]); s2[1] = fmaf(d1, d1, s2[1]); s2[2] = fmaf(d2, d2, s2[2]); s2[3] = fmaf(d3, d3, s2[3]);
-      }
-      ps1 = (s1[0] + s1[1]) + (s1[2] + s1[3]);
-      ps2 = (s2[0] + s2[1]) + (s2[2] + s2[3]);
-#pragma unroll
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 4; ++c0) {
         uint32_t t[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(v[c0 + i]);
-        fb::tmem_st32(t_x + c0, t);
+        for (int q = 0; q < 8; ++q) {
+          const float4 f = lds128(srow + (((hf * 32 + c0 * 8 + q) ^ (r & 7)) << 4));
+          t[4 * q] = __float_as_uint(f.x); t[4 * q + 1] = __float_as_uint(f.y); t[4 * q + 2] = __float_as_uint(f.z); t[4 * q + 3] = __float_as_uint(f.w);
+        }
+        fb::tmem_st32(t_x + c0 * 32, t);
       }
+      fb::tmem_wait_st();
     }
     fence_proxy_async_smem();
-    block_sync();  // every row has left the staging area
+    tc_fence_before_sync();
+    block_sync();  // every row has left the staging area and sits in tensor memory
+    tc_fence_after_sync();
     if (ctrl) load_pair(0, 1, 0, P1);  // conv1 q1, first pair (P1 was staging space)
-    ln_to_a(c_own, m2_own, ps1, ps2);
-    fb::tmem_wait_st();
+    ln_row(args.zero_bias);
   }
 
   for (int b = 0; b < nb; ++b) {
     const BlockParams bp = args.blocks[b];
     const bool last = b + 1 == nb;
     const int m1 = b * 4, m3 = b * 4 + 1, m4 = b * 4 + 2, m5 = b * 4 + 3;
+    stamp();  // A ready (norm1)
 
     // ---------------- conv1: four 128-column quarters, two accumulators, quarter q drained to plane q ----------------
     auto drain = [&](int q, uint32_t acc) {  // this thread's 64 columns of the quarter -> plane q, + bias, bf16
-      uint32_t t[2][32];
-      tmem_ld32(acc + hf * 64, t[0]);
-      tmem_ld32(acc + hf * 64 + 32, t[1]);
-      tmem_wait_ld();
-      const float4* bias = reinterpret_cast<const float4*>(bp.b1 + q * 128 + hf * 64);
-      const uint32_t prow = sP + static_cast<uint32_t>(q) * SLOT + static_cast<uint32_t>(r) * 256u;
-#pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        const float4 b0 = __ldg(bias + 2 * ch), b1 = __ldg(bias + 2 * ch + 1);
-        const uint32_t* rr = &t[ch >> 2][(ch & 3) * 8];
-        sts128(prow + (((hf * 8 + ch) ^ (r & 7)) << 4), pack_bf16x2(__uint_as_float(rr[0]) + b0.x, __uint_as_float(rr[1]) + b0.y),
-               pack_bf16x2(__uint_as_float(rr[2]) + b0.z, __uint_as_float(rr[3]) + b0.w),
-               pack_bf16x2(__uint_as_float(rr[4]) + b1.x, __uint_as_float(rr[5]) + b1.y),
-               pack_bf16x2(__uint_as_float(rr[6]) + b1.z, __uint_as_float(rr[7]) + b1.w));
-      }
+      drain_quarter(acc, bp.b1 + q * 128, sP + static_cast<uint32_t>(q) * SLOT + static_cast<uint32_t>(r) * 256u, hf, r);
     };
     fence_proxy_async_smem();
     tc_fence_before_sync();
@@ -362,7 +331,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
       mma_pair(P1, 0, ACC_COL + 128, true); mma_pair(RS, 1, ACC_COL + 128, false);
       umma_commit(mbar[1]);
     }
-    mbar_wait(mbar[0], mph0, args.status, 0xB20u); mph0 ^= 1u;  // q0 done
+    fb::mbar_wait_c(mbar[0], mph0, args.status, 0xB20u); mph0 ^= 1u;  // q0 done
     tc_fence_after_sync();
     if (ctrl) load_pair(m1, 2, 0, P2), load_pair(m1, 2, 1, P3);
     drain(0, t_acc0);
@@ -374,7 +343,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
       mma_pair(P2, 0, ACC_COL, true); mma_pair(P3, 1, ACC_COL, false);
       umma_commit(mbar[0]);
     }
-    mbar_wait(mbar[1], mph1, args.status, 0xB21u); mph1 ^= 1u;  // q1 done
+    fb::mbar_wait_c(mbar[1], mph1, args.status, 0xB21u); mph1 ^= 1u;  // q1 done
     tc_fence_after_sync();
     if (ctrl) load_pair(m1, 3, 0, RS);
     drain(1, t_acc0 + 128);
@@ -385,7 +354,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
       wait_slot(RS);
       mma_pair(RS, 0, ACC_COL + 128, true);
     }
-    mbar_wait(mbar[0], mph0, args.status, 0xB22u); mph0 ^= 1u;  // q2 done: P2, P3 are dead
+    fb::mbar_wait_c(mbar[0], mph0, args.status, 0xB22u); mph0 ^= 1u;  // q2 done: P2, P3 are dead
     tc_fence_after_sync();
     if (ctrl) {
       load_pair(m1, 3, 1, P3);
@@ -394,11 +363,12 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
       umma_commit(mbar[1]);
     }
     drain(2, t_acc0);
-    mbar_wait(mbar[1], mph1, args.status, 0xB23u); mph1 ^= 1u;  // q3 done
+    fb::mbar_wait_c(mbar[1], mph1, args.status, 0xB23u); mph1 ^= 1u;  // q3 done
     tc_fence_after_sync();
     drain(3, t_acc0 + 128);
     tc_fence_before_sync();
     block_sync();                                   // T complete, R free
+    stamp();
 
     // ---------------- depthwise 3x3 + bias + SimpleGate -> A operand; per-face means -> R ----------------
     {
@@ -479,6 +449,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
     for (int i = 0; i < 64; ++i) wv[i] = __ldg(wsrc + i * (C / 2));
     fence_proxy_async_smem();
     block_sync();                                   // T free; means visible
+    stamp();
     if (ctrl) {
       load_kb(m3, 0, P0); load_kb(m3, 1, P1); load_kb(m3, 2, P2); load_kb(m3, 3, P3);
     }
@@ -519,6 +490,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
       tc_fence_before_sync();
     }
     block_sync();                                   // A (gated, scaled) complete; R scratch dead
+    stamp();
 
     // ---------------- conv3 (+beta) accumulated onto x; norm2 + modulation -> A ----------------
     if (ctrl) {
@@ -532,16 +504,17 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
     }
     make_eff(bp.ln2_w, bp.ln2_b, bp.mod_off + 2 * C, bp.mod_off + 3 * C);
     block_sync();                                   // LayerNorm parameters visible
-    mbar_wait(mbar[0], mph0, args.status, 0xB30u); mph0 ^= 1u;
+    fb::mbar_wait_c(mbar[0], mph0, args.status, 0xB30u); mph0 ^= 1u;
     tc_fence_after_sync();
     if (ctrl) {
       load_pair(m4, 0, 0, P0); load_pair(m4, 0, 1, P1);
       load_pair(m4, 1, 0, P2); load_pair(m4, 1, 1, P3);
     }
-    residual_epilogue(bp.cb3, true);
+    ln_row(bp.cb3);
     fence_proxy_async_smem();
     tc_fence_before_sync();
     block_sync();                                   // A (norm2) complete; R free
+    stamp();
 
     // ---------------- conv4 + SimpleGate: gated values wait in registers until the last quarter's MMAs are done ----------------
     uint32_t hold[4][16];
@@ -570,7 +543,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
       mma_pair(P2, 0, ACC_COL + 128, true); mma_pair(P3, 1, ACC_COL + 128, false);
       umma_commit(mbar[1]);
     }
-    mbar_wait(mbar[0], mph0, args.status, 0xB40u); mph0 ^= 1u;  // q0 done: P0, P1 dead
+    fb::mbar_wait_c(mbar[0], mph0, args.status, 0xB40u); mph0 ^= 1u;  // q0 done: P0, P1 dead
     tc_fence_after_sync();
     if (ctrl) {
       load_pair(m4, 2, 1, P0);
@@ -585,7 +558,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
       mma_pair(RS, 0, ACC_COL, true); mma_pair(P0, 1, ACC_COL, false);
       umma_commit(mbar[0]);
     }
-    mbar_wait(mbar[1], mph1, args.status, 0xB41u); mph1 ^= 1u;  // q1 done: P2, P3 dead
+    fb::mbar_wait_c(mbar[1], mph1, args.status, 0xB41u); mph1 ^= 1u;  // q1 done: P2, P3 dead
     tc_fence_after_sync();
     if (ctrl) load_pair(m4, 3, 0, P2), load_pair(m4, 3, 1, P3);
     gate(1, t_acc0 + 128, hold[1]);
@@ -597,11 +570,11 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
       mma_pair(P2, 0, ACC_COL + 128, true); mma_pair(P3, 1, ACC_COL + 128, false);
       umma_commit(mbar[1]);
     }
-    mbar_wait(mbar[0], mph0, args.status, 0xB42u); mph0 ^= 1u;  // q2 done: R, P0 dead
+    fb::mbar_wait_c(mbar[0], mph0, args.status, 0xB42u); mph0 ^= 1u;  // q2 done: R, P0 dead
     tc_fence_after_sync();
     if (ctrl) load_kb(m5, 1, P0);
     gate(2, t_acc0, hold[2]);
-    mbar_wait(mbar[1], mph1, args.status, 0xB43u); mph1 ^= 1u;  // q3 done: every conv4 MMA has read A
+    fb::mbar_wait_c(mbar[1], mph1, args.status, 0xB43u); mph1 ^= 1u;  // q3 done: every conv4 MMA has read A
     tc_fence_after_sync();
     if (ctrl) load_kb(m5, 2, P2), load_kb(m5, 3, P3);
     gate(3, t_acc0 + 128, hold[3]);
@@ -618,6 +591,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
     fence_proxy_async_smem();
     tc_fence_before_sync();
     block_sync();                                   // A (gated) complete; LayerNorm parameters visible
+    stamp();
 
     // ---------------- conv5 (+gamma) accumulated onto x; next block's norm1 or the final store ----------------
     if (ctrl) {
@@ -628,22 +602,32 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
       wait_slot(P3); mma_kb(P3, 3);
       umma_commit(mbar[0]);
     }
-    mbar_wait(mbar[0], mph0, args.status, 0xB50u); mph0 ^= 1u;
+    fb::mbar_wait_c(mbar[0], mph0, args.status, 0xB50u); mph0 ^= 1u;
     tc_fence_after_sync();
     if (ctrl && !last) {
       load_pair(m1 + 4, 0, 0, P2); load_pair(m1 + 4, 0, 1, P3);
       load_pair(m1 + 4, 1, 0, P1);
     }
-    residual_epilogue(bp.cb5, !last);
+    if (!last) ln_row(bp.cb5);
   }
 
   // ---------------- final store: rows -> swizzled staging over [A | P0 | P1] -> coalesced global rows ----------------
   {
+    const float* cb = args.blocks[nb - 1].cb5;
     const uint32_t srow = sbase + r * 1024;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 4; ++c0) {
+      uint32_t t[32];
+      tmem_ld32(t_x + c0 * 32, t);
+      tmem_wait_ld();
 #pragma unroll
-    for (int q = 0; q < 32; ++q)
-      sts128(srow + (((hf * 32 + q) ^ (r & 7)) << 4), __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
-             __float_as_uint(v[4 * q + 3]));
+      for (int q = 0; q < 8; ++q) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(cb + hf * 128 + c0 * 32 + q * 4));
+        sts128(srow + (((hf * 32 + c0 * 8 + q) ^ (r & 7)) << 4), __float_as_uint(__uint_as_float(t[4 * q]) + bb.x),
+               __float_as_uint(__uint_as_float(t[4 * q + 1]) + bb.y), __float_as_uint(__uint_as_float(t[4 * q + 2]) + bb.z),
+               __float_as_uint(__uint_as_float(t[4 * q + 3]) + bb.w));
+      }
+    }
   }
   block_sync();
 #pragma unroll 8
@@ -656,6 +640,7 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
   }
   tc_fence_before_sync();
   block_sync();
+  stamp();
   if (warp == 0) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
