@@ -45,7 +45,8 @@ struct BlockParams {
   const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
   const float *b1, *dw_w, *dw_b;   // conv1 bias [256]; depthwise taps [9][256] and bias [256]
   const float *wsca_t, *bsca;      // SCA weight transposed [k][n] fp32, bias
-  const float *b3, *b4, *b5;       // beta*b3, gate-packed b4, gamma*b5
+  const float *b4;                 // gate-packed conv4 bias
+  const float *cb3, *cb5;          // cumulative residual bias after this block's conv3 / conv5 (the stream in TMEM is bias-free)
   int mod_off, pad;
 };
 
@@ -57,6 +58,7 @@ struct Args {
   const float* mod_table;
   const int* mod_row_idx;
   int mod_stride;
+  const float* zero_bias;          // 128 zeros (no bias before the first conv3)
   DeviceStatus* status;
   long long* trace;                // optional: clock64 stamps of one CTA's phase boundaries (diagnostics)
   int trace_cta;
@@ -195,6 +197,27 @@ __device__ __forceinline__ void make_ln_params(float* eff, const float* lw, cons
   eff[C + c] = __ldg(lb + c) * sc + __ldg(mrow + shift_off + c);
 }
 
+// residual row R (= x_tmem + cbias) -> LayerNorm2d + modulation -> bf16 A operand row; one copy for every call site
+__device__ __noinline__ void residual_ln(uint32_t t_x, int R, const float* __restrict__ cbias, const float* eff, uint32_t sA) {
+  using namespace tc;
+  float v[C];
+  {
+    uint32_t r[4][32];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_ld32(t_x + c * 32, r[c]);
+    tmem_wait_ld();
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(cbias + c * 32 + i));
+        v[c * 32 + i] = __uint_as_float(r[c][i]) + bb.x; v[c * 32 + i + 1] = __uint_as_float(r[c][i + 1]) + bb.y;
+        v[c * 32 + i + 2] = __uint_as_float(r[c][i + 2]) + bb.z; v[c * 32 + i + 3] = __uint_as_float(r[c][i + 3]) + bb.w;
+      }
+  }
+  ln_row_to_a(v, eff, eff + C, sA, R);
+}
+
 __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args) {
   using namespace tc;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -246,16 +269,10 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
   };
   constexpr uint32_t idesc = make_idesc(128, 128);
   auto issue = [&](uint32_t w_base, uint32_t d_col, uint32_t accumulate) {  // controller only: D[2 m-tiles] (+)= A W^T
-#pragma unroll
+#pragma unroll 1
     for (int mt = 0; mt < 2; ++mt) {
-#pragma unroll
-      for (int kb = 0; kb < 2; ++kb) {
-        const uint64_t da = make_smem_desc(sA + (mt * 2 + kb) * TILE);
-        const uint64_t db = make_smem_desc(w_base + kb * TILE);
-#pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k)
-          umma_bf16(da + 2 * k, db + 2 * k, tmem_base + d_col + mt * 128, accumulate | static_cast<uint32_t>((kb | k) != 0), idesc);
-      }
+      issue_kblock(sA + (mt * 2) * TILE, w_base, tmem_base + d_col + mt * 128, accumulate, idesc);
+      issue_kblock(sA + (mt * 2 + 1) * TILE, w_base + TILE, tmem_base + d_col + mt * 128, 1u, idesc);
     }
     umma_commit(mma_bar);
   };
@@ -279,8 +296,8 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
     if (tid >= 96 && tid < 104) prefetch_l2(bp.b1 + (tid - 96) * 32);
     if (tid >= 104 && tid < 112) prefetch_l2(bp.b4 + (tid - 104) * 32);
     if (tid >= 112 && tid < 120) prefetch_l2(bp.dw_b + (tid - 112) * 32);
-    if (tid >= 128 && tid < 132) prefetch_l2(bp.b3 + (tid - 128) * 32);
-    if (tid >= 132 && tid < 136) prefetch_l2(bp.b5 + (tid - 132) * 32);
+    if (tid >= 128 && tid < 132) prefetch_l2(bp.cb3 + (tid - 128) * 32);
+    if (tid >= 132 && tid < 136) prefetch_l2(bp.cb5 + (tid - 132) * 32);
     if (tid >= 136 && tid < 140) prefetch_l2(bp.bsca + (tid - 136) * 32);
     if (tid >= 140 && tid < 144) prefetch_l2(bp.ln1_w + (tid - 140) * 32);
     if (tid >= 144 && tid < 148) prefetch_l2(bp.ln1_b + (tid - 144) * 32);
@@ -304,7 +321,6 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
   auto stage_row = [&](int r) { return (r < 128 ? sA : sT - 128 * 512) + static_cast<uint32_t>(r) * 512u; };
 
   uint32_t mph = 0;  // parity of the MMA-done barrier
-  float v[C];        // this thread's pixel row of the residual stream
 
   {
     const BlockParams bp = args.blocks[0];
@@ -324,22 +340,20 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
     block_sync();
     {
       const uint32_t srow = stage_row(R);
-#pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        const float4 t = lds128(srow + ((q ^ (R & 7)) << 4));
-        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-      }
-#pragma unroll
-      for (int c0 = 0; c0 < C; c0 += 32) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 4; ++c0) {
         uint32_t r[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[c0 + i]);
-        tmem_st32(t_x + c0, r);
+        for (int q = 0; q < 8; ++q) {
+          const float4 f = lds128(srow + (((c0 * 8 + q) ^ (R & 7)) << 4));
+          r[4 * q] = __float_as_uint(f.x); r[4 * q + 1] = __float_as_uint(f.y); r[4 * q + 2] = __float_as_uint(f.z); r[4 * q + 3] = __float_as_uint(f.w);
+        }
+        tmem_st32(t_x + c0 * 32, r);
       }
+      tmem_wait_st();
     }
     block_sync();  // every row has left the staging area before the A operand is written over it
-    ln_row_to_a(v, eff, eff + C, sA, R);
-    tmem_wait_st();
+    residual_ln(t_x, R, args.zero_bias, eff, sA);
   }
 
   for (int b = 0; b < nb; ++b) {
@@ -356,10 +370,10 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
       block_sync();
       if (ctrl) {
         tc_fence_after_sync();
-        if (h == 0) mbar_wait(wbar0, wpar, args.status, 0xA10u);
+        if (h == 0) mbar_wait_c(wbar0, wpar, args.status, 0xA10u);
         issue(sT + PLANE + h * 2 * TILE, ACC_COL, 0u);
       }
-      mbar_wait(mma_bar, mph, args.status, 0xA11u);
+      mbar_wait_c(mma_bar, mph, args.status, 0xA11u);
       tc_fence_after_sync();
       {
         const uint32_t prow = sT + h * PLANE + static_cast<uint32_t>(R) * 256u;
@@ -496,35 +510,16 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
     // ---------------- conv3 (+beta) accumulated onto x; then x += b3, norm2 + modulation -> A ----------------
     if (ctrl) {
       tc_fence_after_sync();
-      mbar_wait(wbar0 + 8, wpar, args.status, 0xA20u);
+      mbar_wait_c(wbar0 + 8, wpar, args.status, 0xA20u);
       issue(sW3, X_COL, 1u);
-      mbar_wait(mma_bar, mph, args.status, 0xA21u);
+      mbar_wait_c(mma_bar, mph, args.status, 0xA21u);
       load_w(b * 4 + 3, sW3, 1, 3);  // W5 takes W3's place
     }
-    mbar_wait(mma_bar, mph, args.status, 0xA22u);
+    mbar_wait_c(mma_bar, mph, args.status, 0xA22u);
     tc_fence_after_sync();
-    {
-      uint32_t r[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(t_x + c * 32, r[c]);
-      tmem_wait_ld();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(bp.b3 + c * 32 + i));
-          v[c * 32 + i] = __uint_as_float(r[c][i]) + bb.x; v[c * 32 + i + 1] = __uint_as_float(r[c][i + 1]) + bb.y;
-          v[c * 32 + i + 2] = __uint_as_float(r[c][i + 2]) + bb.z; v[c * 32 + i + 3] = __uint_as_float(r[c][i + 3]) + bb.w;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) r[c][i] = __float_as_uint(v[c * 32 + i]);
-        tmem_st32(t_x + c * 32, r[c]);
-      }
-      ln_row_to_a(v, eff, eff + C, sA, R);
-      tmem_wait_st();
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-    }
+    residual_ln(t_x, R, bp.cb3, eff, sA);
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
     mph ^= 1u;
     block_sync();
     stamp();
@@ -533,7 +528,7 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
     uint32_t hold[32];
     if (ctrl) {
       tc_fence_after_sync();
-      mbar_wait(wbar0 + 16, wpar, args.status, 0xA30u);
+      mbar_wait_c(wbar0 + 16, wpar, args.status, 0xA30u);
       issue(sT, ACC_COL, 0u);
     }
     if (!last && tid < C) {
@@ -561,7 +556,7 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
 #pragma unroll
       for (int q = 0; q < 8; ++q) sts128(sA + a_chunk_off(R, h * 8 + q), in[4 * q], in[4 * q + 1], in[4 * q + 2], in[4 * q + 3]);
     };
-    mbar_wait(mma_bar, mph, args.status, 0xA31u);
+    mbar_wait_c(mma_bar, mph, args.status, 0xA31u);
     tc_fence_after_sync();
     gate_half(0, hold);
     tc_fence_before_sync();
@@ -571,7 +566,7 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
       tc_fence_after_sync();
       issue(sT + 2 * TILE, ACC_COL, 0u);
     }
-    mbar_wait(mma_bar, mph, args.status, 0xA32u);
+    mbar_wait_c(mma_bar, mph, args.status, 0xA32u);
     tc_fence_after_sync();
     {
       uint32_t g2[32];
@@ -588,44 +583,32 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
     // ---------------- conv5 (+gamma) accumulated onto x; x += b5; next block's norm1 or the final store ----------------
     if (ctrl) {
       tc_fence_after_sync();
-      mbar_wait(wbar0 + 24, wpar, args.status, 0xA40u);
+      mbar_wait_c(wbar0 + 24, wpar, args.status, 0xA40u);
       issue(sW3, X_COL, 1u);
       if (!last) {
-        mbar_wait(mma_bar, mph, args.status, 0xA41u);
+        mbar_wait_c(mma_bar, mph, args.status, 0xA41u);
         load_w((b + 1) * 4 + 1, sW3, 1, 1);  // next block's W3
       }
     }
-    mbar_wait(mma_bar, mph, args.status, 0xA42u);
+    mbar_wait_c(mma_bar, mph, args.status, 0xA42u);
     tc_fence_after_sync();
-    {
-      uint32_t r[4][32];
+    if (!last) {
+      residual_ln(t_x, R, bp.cb5, eff, sA);
+    } else {
+      // rows -> swizzled staging (A region / plane 0 are dead: every MMA has completed) -> coalesced row stores
+      const uint32_t srow = stage_row(R);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 4; ++c0) {
+        uint32_t r[32];
+        tmem_ld32(t_x + c0 * 32, r);
+        tmem_wait_ld();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(t_x + c * 32, r[c]);
-      tmem_wait_ld();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(bp.b5 + c * 32 + i));
-          v[c * 32 + i] = __uint_as_float(r[c][i]) + bb.x; v[c * 32 + i + 1] = __uint_as_float(r[c][i + 1]) + bb.y;
-          v[c * 32 + i + 2] = __uint_as_float(r[c][i + 2]) + bb.z; v[c * 32 + i + 3] = __uint_as_float(r[c][i + 3]) + bb.w;
+        for (int q = 0; q < 8; ++q) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(bp.cb5 + c0 * 32 + q * 4));
+          sts128(srow + (((c0 * 8 + q) ^ (R & 7)) << 4), __float_as_uint(__uint_as_float(r[4 * q]) + bb.x),
+                 __float_as_uint(__uint_as_float(r[4 * q + 1]) + bb.y), __float_as_uint(__uint_as_float(r[4 * q + 2]) + bb.z),
+                 __float_as_uint(__uint_as_float(r[4 * q + 3]) + bb.w));
         }
-        if (!last) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) r[c][i] = __float_as_uint(v[c * 32 + i]);
-          tmem_st32(t_x + c * 32, r[c]);
-        }
-      }
-      if (!last) {
-        ln_row_to_a(v, eff, eff + C, sA, R);
-        tmem_wait_st();
-      } else {
-        // rows -> swizzled staging (A region / plane 0 are dead: every MMA has completed) -> coalesced row stores
-        const uint32_t srow = stage_row(R);
-#pragma unroll
-        for (int q = 0; q < 32; ++q)
-          sts128(srow + ((q ^ (R & 7)) << 4), __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
-                 __float_as_uint(v[4 * q + 3]));
       }
     }
     mph ^= 1u;

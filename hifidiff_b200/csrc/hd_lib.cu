@@ -1007,6 +1007,7 @@ void add_face_blocks(hd_handle* h, Plan& P, size_t first, int count) {
   const int c = fb::C, rpf = fb::PX;
   std::vector<CUtensorMap> maps;
   std::vector<fb::BlockParams> bps;
+  std::vector<float> cum(fb::C, 0.f);
   auto add_map = [&](const void* base, int N) {
     CUtensorMap m;
     cuuint64_t dims[2] = {(cuuint64_t)c, (cuuint64_t)N};
@@ -1025,7 +1026,11 @@ void add_face_blocks(hd_handle* h, Plan& P, size_t first, int count) {
     memset(&bp, 0, sizeof(bp));
     bp.ln1_w = bw.ln1_w; bp.ln1_b = bw.ln1_b; bp.ln2_w = bw.ln2_w; bp.ln2_b = bw.ln2_b;
     bp.b1 = bw.b1; bp.dw_w = bw.dw_w; bp.dw_b = bw.dw_b; bp.wsca_t = bw.wsca_t; bp.bsca = bw.bsca;
-    bp.b3 = bw.b3; bp.b4 = bw.b4; bp.b5 = bw.b5; bp.mod_off = bw.mod_off;
+    bp.b4 = bw.b4; bp.mod_off = bw.mod_off;
+    for (int k = 0; k < c; ++k) cum[k] += bw.b3_h[k];
+    bp.cb3 = upload_f32(h, cum);
+    for (int k = 0; k < c; ++k) cum[k] += bw.b5_h[k];
+    bp.cb5 = upload_f32(h, cum);
     bps.push_back(bp);
     P.flops_per_face += 2.0 * rpf * 6.0 * c * c + 2.0 * c * c + 2.0 * 9 * 2 * c * rpf;
   }
@@ -1038,6 +1043,7 @@ void add_face_blocks(hd_handle* h, Plan& P, size_t first, int count) {
   a.maps = d_maps;
   a.blocks = d_bps;
   a.n_blocks = count;
+  a.zero_bias = upload_f32(h, std::vector<float>(c, 0.f));
   a.x = h->resid[h->blocks[first].level];
   a.mod_table = h->mod_table;
   a.mod_row_idx = h->row_idx;

@@ -54,6 +54,7 @@ constexpr uint32_t X_COL = 0, ACC_COL = 256;
 constexpr int R_EFF = 0;                  // [face 2][w|b][256] fp32 = 4 KB
 constexpr int R_MEAN = 4096;              // [face 2][256] fp32 = 2 KB
 constexpr int R_PART = 6144;              // [k-half 2][face 2][256] fp32 = 4 KB
+constexpr int R_XCHG = 12288;             // [half 2][row 128] (mean, M2) = 2 KB
 
 struct BlockParams {
   const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
@@ -78,51 +79,57 @@ struct Args {
   int trace_cta;
 };
 
-// LayerNorm2d + AdaLN modulation of residual row r, streamed from tensor memory (the row = x_tmem + cbias):
-// pass 1 takes the statistics over all 256 channels (shifted sums around the row's first element: one pass, no
-// cancellation), pass 2 re-reads this thread's half and writes it as k-blocks 2hf, 2hf+1 of the bf16 A operand.
-// Both threads of a row take the statistics redundantly, which is cheaper than exchanging them.
-__device__ __noinline__ void residual_ln(uint32_t t_row, int hf, int r, const float* __restrict__ cbias, const float* eff_w,
-                                         const float* eff_b, uint32_t sA) {
+// LayerNorm2d + AdaLN modulation of residual row r (= x_tmem + cbias).  The two threads of a row each hold one
+// 128-channel half in registers, take its mean / centred second moment (two-pass), swap them through shared memory
+// (one CTA barrier) and combine them exactly (Chan et al.); each then writes its half as k-blocks 2hf, 2hf+1 of the
+// bf16 A operand.  Must be called by all threads of the CTA.
+__device__ __noinline__ void residual_ln(uint32_t t_own, int hf, int r, const float* __restrict__ cbias_own, const float* eff_w,
+                                         const float* eff_b, uint32_t sA, float2* xchg) {
   using namespace tc;
-  float shift, s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-  for (int c = 0; c < 8; ++c) {
-    uint32_t t[32];
-    tmem_ld32(t_row + c * 32, t);
-    tmem_wait_ld();
-    const float4* bb = reinterpret_cast<const float4*>(cbias + c * 32);
-    if (c == 0) shift = __uint_as_float(t[0]) + __ldg(cbias);
+  float v[128];
+  {
+    uint32_t t[4][32];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 b4 = __ldg(bb + i);
-      const float d0 = __uint_as_float(t[4 * i]) + b4.x - shift, d1 = __uint_as_float(t[4 * i + 1]) + b4.y - shift;
-      const float d2 = __uint_as_float(t[4 * i + 2]) + b4.z - shift, d3 = __uint_as_float(t[4 * i + 3]) + b4.w - shift;
-      s1[0] += d0; s1[1] += d1; s1[2] += d2; s1[3] += d3;
-      s2[0] = fmaf(d0, d0, s2[0]); s2[1] = fmaf(d1, d1, s2[1]); s2[2] = fmaf(d2, d2, s2[2]); s2[3] = fmaf(d3, d3, s2[3]);
-    }
+    for (int c = 0; c < 4; ++c) tmem_ld32(t_own + c * 32, t[c]);
+    tmem_wait_ld();
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(cbias_own + c * 32 + i));
+        v[c * 32 + i] = __uint_as_float(t[c][i]) + bb.x; v[c * 32 + i + 1] = __uint_as_float(t[c][i + 1]) + bb.y;
+        v[c * 32 + i + 2] = __uint_as_float(t[c][i + 2]) + bb.z; v[c * 32 + i + 3] = __uint_as_float(t[c][i + 3]) + bb.w;
+      }
   }
-  const float S1 = (s1[0] + s1[1]) + (s1[2] + s1[3]), S2 = (s2[0] + s2[1]) + (s2[2] + s2[3]);
-  const float mu = shift + S1 * (1.f / C);
-  const float rstd = 1.f / sqrtf(fmaxf(S2 - S1 * S1 * (1.f / C), 0.f) * (1.f / C) + 1e-6f);
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    const int col = hf * 128 + c * 32;
-    uint32_t t[32];
-    tmem_ld32(t_row + col, t);
-    tmem_wait_ld();
-    const uint32_t arow = sA + static_cast<uint32_t>((hf * 2 + (c >> 1)) * TILE + r * 128);
+  float sa[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 c0 = __ldg(reinterpret_cast<const float4*>(cbias + col + q * 8)), c1 = __ldg(reinterpret_cast<const float4*>(cbias + col + q * 8 + 4));
-      const float4 w0 = *reinterpret_cast<const float4*>(eff_w + col + q * 8), w1 = *reinterpret_cast<const float4*>(eff_w + col + q * 8 + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(eff_b + col + q * 8), b1 = *reinterpret_cast<const float4*>(eff_b + col + q * 8 + 4);
-      const float y0 = (__uint_as_float(t[q * 8 + 0]) + c0.x - mu) * rstd * w0.x + b0.x, y1 = (__uint_as_float(t[q * 8 + 1]) + c0.y - mu) * rstd * w0.y + b0.y;
-      const float y2 = (__uint_as_float(t[q * 8 + 2]) + c0.z - mu) * rstd * w0.z + b0.z, y3 = (__uint_as_float(t[q * 8 + 3]) + c0.w - mu) * rstd * w0.w + b0.w;
-      const float y4 = (__uint_as_float(t[q * 8 + 4]) + c1.x - mu) * rstd * w1.x + b1.x, y5 = (__uint_as_float(t[q * 8 + 5]) + c1.y - mu) * rstd * w1.y + b1.y;
-      const float y6 = (__uint_as_float(t[q * 8 + 6]) + c1.z - mu) * rstd * w1.z + b1.z, y7 = (__uint_as_float(t[q * 8 + 7]) + c1.w - mu) * rstd * w1.w + b1.w;
-      sts128(arow + ((((c & 1) * 4 + q) ^ (r & 7)) << 4), pack_bf16x2(y0, y1), pack_bf16x2(y2, y3), pack_bf16x2(y4, y5), pack_bf16x2(y6, y7));
-    }
+  for (int i = 0; i < 8; ++i) sa[i] = v[i];
+#pragma unroll
+  for (int i = 8; i < 128; ++i) sa[i & 7] += v[i];
+  const float mean_h = (((sa[0] + sa[1]) + (sa[2] + sa[3])) + ((sa[4] + sa[5]) + (sa[6] + sa[7]))) * (1.f / 128);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sa[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 128; ++i) {
+    const float d = v[i] - mean_h;
+    sa[i & 7] = fmaf(d, d, sa[i & 7]);
+  }
+  const float m2_h = ((sa[0] + sa[1]) + (sa[2] + sa[3])) + ((sa[4] + sa[5]) + (sa[6] + sa[7]));
+  xchg[hf * 128 + r] = make_float2(mean_h, m2_h);
+  block_sync();
+  const float2 p = xchg[(1 - hf) * 128 + r];
+  const float mu = 0.5f * (mean_h + p.x), dm = mean_h - p.x;
+  const float rstd = 1.f / sqrtf((m2_h + p.y + dm * dm * 64.f) * (1.f / C) + 1e-6f);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const float4 w0 = *reinterpret_cast<const float4*>(eff_w + q * 8), w1 = *reinterpret_cast<const float4*>(eff_w + q * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(eff_b + q * 8), b1 = *reinterpret_cast<const float4*>(eff_b + q * 8 + 4);
+    const float y0 = (v[q * 8 + 0] - mu) * rstd * w0.x + b0.x, y1 = (v[q * 8 + 1] - mu) * rstd * w0.y + b0.y;
+    const float y2 = (v[q * 8 + 2] - mu) * rstd * w0.z + b0.z, y3 = (v[q * 8 + 3] - mu) * rstd * w0.w + b0.w;
+    const float y4 = (v[q * 8 + 4] - mu) * rstd * w1.x + b1.x, y5 = (v[q * 8 + 5] - mu) * rstd * w1.y + b1.y;
+    const float y6 = (v[q * 8 + 6] - mu) * rstd * w1.z + b1.z, y7 = (v[q * 8 + 7] - mu) * rstd * w1.w + b1.w;
+    const uint32_t a = sA + static_cast<uint32_t>((hf * 2 + (q >> 3)) * TILE + r * 128 + (((q & 7) ^ (r & 7)) << 4));
+    sts128(a, pack_bf16x2(y0, y1), pack_bf16x2(y2, y3), pack_bf16x2(y4, y5), pack_bf16x2(y6, y7));
   }
 }
 
@@ -258,9 +265,9 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
       r_eff[(f * 2 + 1) * C + tid] = bb * sc + __ldg(mrow[f] + shift_off + tid);
     }
   };
-  const uint32_t t_row = tmem_base + lane_addr + X_COL;  // the whole residual row of this thread's pixel
   auto ln_row = [&](const float* cbias) {
-    residual_ln(t_row, hf, r, cbias, r_eff + (fl * 2 + 0) * C, r_eff + (fl * 2 + 1) * C, sA);
+    residual_ln(t_x, hf, r, cbias + hf * 128, r_eff + (fl * 2 + 0) * C + hf * 128, r_eff + (fl * 2 + 1) * C + hf * 128, sA,
+                reinterpret_cast<float2*>(smem + R_OFF + R_XCHG));
   };
 
   // ---------------- prologue: x -> staging (coalesced) -> registers / TMEM; norm1 of the first block ----------------
