@@ -210,7 +210,7 @@ __device__ __noinline__ void residual_ln(uint32_t t_x, int R, const float* __res
     for (int c = 0; c < 4; ++c)
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(cbias + c * 32 + i));
+        const float4 bb = cbias != nullptr ? __ldg(reinterpret_cast<const float4*>(cbias + c * 32 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
         v[c * 32 + i] = __uint_as_float(r[c][i]) + bb.x; v[c * 32 + i + 1] = __uint_as_float(r[c][i + 1]) + bb.y;
         v[c * 32 + i + 2] = __uint_as_float(r[c][i + 2]) + bb.z; v[c * 32 + i + 3] = __uint_as_float(r[c][i + 3]) + bb.w;
       }
@@ -304,15 +304,15 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
     if (tid >= 148 && tid < 152) prefetch_l2(bp.ln2_w + (tid - 148) * 32);
     if (tid >= 152 && tid < 156) prefetch_l2(bp.ln2_b + (tid - 152) * 32);
   }
-  pdl_wait();
-  stamp();
-
   // worker geometry
   const int R = tid;                                  // pixel row (workers)
   const int quad = warp & 3, mt_own = (warp >> 2) & 1;
   const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
   const uint32_t t_x = tmem_base + lane_addr + X_COL + mt_own * 128;
   const uint32_t t_acc = tmem_base + lane_addr + ACC_COL + mt_own * 128;
+  pdl_wait();
+  stamp();
+
   const float* mrow = args.mod_table + static_cast<size_t>(__ldg(args.mod_row_idx + face)) * args.mod_stride;
   // depthwise geometry: warp -> (channel block, 4-row strip), lane -> channel pair
   const int cb = warp & 1, strip = (warp >> 1) & 3, j = cb * 64 + lane * 2;
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
       tmem_wait_st();
     }
     block_sync();  // every row has left the staging area before the A operand is written over it
-    residual_ln(t_x, R, args.zero_bias, eff, sA);
+    residual_ln(t_x, R, nullptr, eff, sA);
   }
 
   for (int b = 0; b < nb; ++b) {

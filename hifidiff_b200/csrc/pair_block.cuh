@@ -96,7 +96,7 @@ __device__ __noinline__ void residual_ln(uint32_t t_own, int hf, int r, const fl
     for (int c = 0; c < 4; ++c)
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(cbias_own + c * 32 + i));
+        const float4 bb = cbias_own != nullptr ? __ldg(reinterpret_cast<const float4*>(cbias_own + c * 32 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
         v[c * 32 + i] = __uint_as_float(t[c][i]) + bb.x; v[c * 32 + i + 1] = __uint_as_float(t[c][i + 1]) + bb.y;
         v[c * 32 + i + 2] = __uint_as_float(t[c][i + 2]) + bb.z; v[c * 32 + i + 3] = __uint_as_float(t[c][i + 3]) + bb.w;
       }
@@ -235,9 +235,6 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
     prefetch_l2(reinterpret_cast<const char*>(bp.wsca_t) + tid * 512 + 384);
     if (tid < 144) prefetch_l2(bp.dw_w + tid * 32);
   }
-  pdl_wait();
-  stamp();
-
   // ---- thread geometry ----
   const int r = (warp & 3) * 32 + lane;               // pixel row = TMEM lane
   const int hf = warp >> 2;                           // column half owned by this thread
@@ -245,6 +242,9 @@ __global__ void __launch_bounds__(THREADS, 1) pair_block_kernel(const Args args)
   const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const uint32_t t_x = tmem_base + lane_addr + X_COL + hf * 128;        // own half of the residual row
   const uint32_t t_acc0 = tmem_base + lane_addr + ACC_COL;
+  pdl_wait();
+  stamp();
+
   const bool face_ok[2] = {face0 < args.n_faces, face0 + 1 < args.n_faces};
   const float* mrow[2];
 #pragma unroll
