@@ -18,6 +18,7 @@
 #include "chain.cuh"
 #include "face_block.cuh"
 #include "pair_block.cuh"
+#include "quad_block.cuh"
 
 using namespace hd;
 
@@ -61,6 +62,7 @@ bool g_use_pdl = true;  // HD_PDL=0 disables programmatic dependent launch
 bool g_bn256 = true;    // HD_BN256=0: 128x128 tiles for the dense 3x3 convs too
 int g_two_cta = 1;      // HD_TWO_CTA=0: never use cta_group::2 pairs; 2: wherever the shape allows (tests)
 bool g_face = true;     // HD_FACE=0: per-op kernels at the 16x16 level instead of the fused per-face block kernel
+bool g_quad = true;     // HD_QUAD=0: per-op kernels at the 4x4 level instead of the 4-CTA-cluster block kernel
 bool g_pair = true;     // HD_PAIR=0: per-op kernels at the 8x8 level instead of the fused face-pair block kernel
 bool g_chain = false;   // HD_CHAIN=1: run the 1x1-level blocks as one persistent cooperative kernel (measured slower)
 int g_max_stages = 6;   // HD_MAX_STAGES=3: no 6-stage / 16-epilogue-warp variant (one CTA per SM)
@@ -640,7 +642,7 @@ void load_block(hd_handle* h, BlockW& bw, int wdt) {
       for (int k = 0; k < c; ++k) t[static_cast<size_t>(k) * c + n] = w[static_cast<size_t>(n) * c + k];
     bw.wsca_t = upload_f32(h, t);
   }
-  if (c == pb::C && h->sp[bw.level] == pb::SP) {
+  if ((c == pb::C && h->sp[bw.level] == pb::SP) || (c == qb::C && h->sp[bw.level] == qb::SP)) {
     auto w = host_vec(h, need(h, p + "sca.1.weight", {c, c}));
     std::vector<uint16_t> t(w.size());
     for (int n = 0; n < c; ++n)
@@ -1173,6 +1175,99 @@ void add_pair_blocks(hd_handle* h, Plan& P, size_t first, int count) {
   add_op(P, [=](cudaStream_t st) { launch_k(pb::pair_block_kernel, dim3((B + 1) / 2), dim3(pb::THREADS), pb::SMEM_BYTES, st, a); }, tap, ti);
 }
 
+// 4-CTA-cluster kernel (quad_block.cuh) over the blocks [first, first + count) of the 4x4 level.
+bool quad_blocks_ok(hd_handle* h, size_t first, int count, bool debug) {
+  if (!g_quad || debug || !h->bf16 || count > qb::MAX_BLOCKS) return false;
+  for (int i = 0; i < count; ++i) {
+    const BlockW& bw = h->blocks[first + i];
+    if (bw.c != qb::C || h->sp[bw.level] != qb::SP || !bw.has_mod || bw.dw_fused || bw.dw_folded || bw.wsca_tb == nullptr) return false;
+  }
+  return true;
+}
+
+void add_quad_blocks(hd_handle* h, Plan& P, size_t first, int count) {
+  const int B = P.batch;
+  const int c = qb::C, rpf = qb::FPX;
+  const int n_mtiles = cdiv(B, qb::FACES);
+  std::vector<CUtensorMap> maps;
+  std::vector<qb::BlockParams> bps;
+  auto add_map = [&](const void* base, int N) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)c, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)c * 2};
+    cuuint32_t box[2] = {64, 128};
+    encode_map(h, &m, base, 2, dims, strides, box);
+    maps.push_back(m);
+  };
+  std::vector<float> cum(c, 0.f);
+  for (int i = 0; i < count; ++i) {
+    const BlockW& bw = h->blocks[first + i];
+    add_map(bw.w1, 2 * c);
+    add_map(bw.w3, c);
+    add_map(bw.w4, 2 * c);
+    add_map(bw.w5, c);
+    qb::BlockParams bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.ln1_w = bw.ln1_w; bp.ln1_b = bw.ln1_b; bp.ln2_w = bw.ln2_w; bp.ln2_b = bw.ln2_b;
+    bp.b1 = bw.b1; bp.dw_w = bw.dw_w; bp.dw_b = bw.dw_b; bp.wsca_t = static_cast<const bf16*>(bw.wsca_tb); bp.bsca = bw.bsca;
+    bp.b4 = bw.b4; bp.mod_off = bw.mod_off;
+    for (int k = 0; k < c; ++k) cum[k] += bw.b3_h[k];
+    bp.cb3 = upload_f32(h, cum);
+    for (int k = 0; k < c; ++k) cum[k] += bw.b5_h[k];
+    bp.cb5 = upload_f32(h, cum);
+    bps.push_back(bp);
+    P.flops_per_face += 2.0 * rpf * 6.0 * c * c + 2.0 * c * c + 2.0 * 9 * 2 * c * rpf;
+  }
+  qb::Args a;
+  memset(&a, 0, sizeof(a));
+  CUtensorMap* d_maps = static_cast<CUtensorMap*>(h->arena.alloc(maps.size() * sizeof(CUtensorMap)));
+  qb::BlockParams* d_bps = static_cast<qb::BlockParams*>(h->arena.alloc(bps.size() * sizeof(qb::BlockParams)));
+  CUDA_CHECK(cudaMemcpy(d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(d_bps, bps.data(), bps.size() * sizeof(qb::BlockParams), cudaMemcpyHostToDevice));
+  a.maps = d_maps;
+  a.blocks = d_bps;
+  a.n_blocks = count;
+  a.n_faces = B;
+  a.n_mtiles = n_mtiles;
+  a.x = h->resid[h->blocks[first].level];
+  a.xa = static_cast<bf16*>(h->arena.alloc(static_cast<size_t>(2) * n_mtiles * 128 * c * 2));
+  a.stats = static_cast<float2*>(h->arena.alloc(static_cast<size_t>(n_mtiles) * qb::CL * 2 * 128 * sizeof(float2)));
+  a.means = h->arena.get<float>(static_cast<size_t>(n_mtiles) * qb::FACES * c);
+  a.zero_bias = upload_f32(h, std::vector<float>(c, 0.f));
+  a.mod_table = h->mod_table;
+  a.mod_row_idx = h->row_idx;
+  a.mod_stride = h->mod_stride;
+  a.status = h->d_status;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(qb::quad_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, qb::SMEM_BYTES));
+    configured = true;
+  }
+  g_label = fmt("L%d c=%d quad_block x%d (%s)", h->blocks[first].level, c, count, h->blocks[first].prefix.c_str());
+  TapInfo ti;
+  ti.ptr = a.x; ti.dtype = DT_F32; ti.C = c; ti.HW = rpf; ti.ld = c;
+  std::string tap = h->blocks[first + count - 1].prefix;
+  if (!tap.empty() && tap.back() == '.') tap.pop_back();
+  add_op(P, [=](cudaStream_t st) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(qb::CL * n_mtiles);
+    cfg.blockDim = dim3(qb::THREADS);
+    cfg.dynamicSmemBytes = qb::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = qb::CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, qb::quad_block_kernel, a);
+  }, tap, ti);
+}
+
 // Persistent chain over the blocks [first, first + count) of one 1x1-spatial level (see chain.cuh).
 // Expects blocks[first]'s norm1 output in act_a; leaves the level's residual stream finished in resid[level].
 void add_chain_1x1(hd_handle* h, Plan& P, size_t first, int count) {
@@ -1338,6 +1433,9 @@ Plan* get_plan(hd_handle* h, int B, bool debug = false) {
     } else if (pair_blocks_ok(h, bi, kEncBlocks[l], debug)) {
       add_pair_blocks(h, P, bi, kEncBlocks[l]);
       bi += kEncBlocks[l];
+    } else if (quad_blocks_ok(h, bi, kEncBlocks[l], debug)) {
+      add_quad_blocks(h, P, bi, kEncBlocks[l]);
+      bi += kEncBlocks[l];
     } else {
       for (int i = 0; i < kEncBlocks[l]; ++i, ++bi)
         add_block(h, P, h->blocks[bi], "encoders." + std::to_string(l) + "." + std::to_string(i),
@@ -1411,6 +1509,9 @@ Plan* get_plan(hd_handle* h, int B, bool debug = false) {
       bi += kDecBlocks[L];
     } else if (pair_blocks_ok(h, bi, kDecBlocks[L], debug)) {
       add_pair_blocks(h, P, bi, kDecBlocks[L]);
+      bi += kDecBlocks[L];
+    } else if (quad_blocks_ok(h, bi, kDecBlocks[L], debug)) {
+      add_quad_blocks(h, P, bi, kDecBlocks[L]);
       bi += kDecBlocks[L];
     } else {
       for (int i = 0; i < kDecBlocks[L]; ++i, ++bi)
@@ -1745,6 +1846,7 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   if (const char* e = getenv("HD_CHAIN")) g_chain = atoi(e) != 0;
   if (const char* e = getenv("HD_FACE")) g_face = atoi(e) != 0;
   if (const char* e = getenv("HD_PAIR")) g_pair = atoi(e) != 0;
+  if (const char* e = getenv("HD_QUAD")) g_quad = atoi(e) != 0;
   if (const char* e = getenv("HD_MAX_STAGES")) g_max_stages = atoi(e);
   if (const char* e = getenv("HD_FUSE_LN")) g_fuse_ln = atoi(e) != 0;
   h = new hd_handle();

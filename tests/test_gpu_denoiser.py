@@ -124,7 +124,7 @@ def test_fused_face_kernel_taps_and_plans_agree():
         cond = ([p.cuda() for p in priors], ident.cuda())
         t = torch.arange(batch) * 7 + 3 if batch == 3 else 321
         t_dev = t.cuda() if torch.is_tensor(t) else t
-        fast_names = ["encoders.0.1", "encoders.1.1", "decoders.2.1", "decoders.3.1"]
+        fast_names = ["encoders.0.1", "encoders.1.1", "encoders.2.3", "decoders.1.1", "decoders.2.1", "decoders.3.1"]
         out_fast, taps_fast = m.forward_with_taps(x.cuda(), t_dev, fast_names, *cond)
         out_dbg, taps_dbg = m.forward_with_taps(x.cuda(), t_dev, fast_names + ["intro"], *cond)
         plain = m(x.cuda(), t_dev, *cond).sample
