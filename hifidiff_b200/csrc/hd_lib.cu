@@ -62,7 +62,7 @@ bool g_use_pdl = true;  // HD_PDL=0 disables programmatic dependent launch
 bool g_bn256 = true;    // HD_BN256=0: 128x128 tiles for the dense 3x3 convs too
 int g_two_cta = 1;      // HD_TWO_CTA=0: never use cta_group::2 pairs; 2: wherever the shape allows (tests)
 bool g_face = true;     // HD_FACE=0: per-op kernels at the 16x16 level instead of the fused per-face block kernel
-bool g_quad = true;     // HD_QUAD=0: per-op kernels at the 4x4 level instead of the 4-CTA-cluster block kernel
+bool g_quad = false;    // HD_QUAD=1: 4-CTA-cluster block kernel at the 4x4 level (parity green; measured 35 us/step slower)
 bool g_pair = true;     // HD_PAIR=0: per-op kernels at the 8x8 level instead of the fused face-pair block kernel
 bool g_chain = false;   // HD_CHAIN=1: run the 1x1-level blocks as one persistent cooperative kernel (measured slower)
 int g_max_stages = 6;   // HD_MAX_STAGES=3: no 6-stage / 16-epilogue-warp variant (one CTA per SM)
@@ -1248,6 +1248,14 @@ void add_quad_blocks(hd_handle* h, Plan& P, size_t first, int count) {
   ti.ptr = a.x; ti.dtype = DT_F32; ti.C = c; ti.HW = rpf; ti.ld = c;
   std::string tap = h->blocks[first + count - 1].prefix;
   if (!tap.empty() && tap.back() == '.') tap.pop_back();
+  const bool tracing = getenv("HD_QUAD_TRACE") != nullptr;
+  long long* tr = nullptr;
+  if (tracing) {
+    tr = h->arena.get<long long>(64);
+    a.trace = tr;
+    a.trace_cta = atoi(getenv("HD_QUAD_TRACE"));
+  }
+  const int n_st = 3 + 11 * count;
   add_op(P, [=](cudaStream_t st) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1265,6 +1273,17 @@ void add_quad_blocks(hd_handle* h, Plan& P, size_t first, int count) {
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 2 : 1;
     cudaLaunchKernelEx(&cfg, qb::quad_block_kernel, a);
+    if (tracing) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(st, &cs);
+      if (cs != cudaStreamCaptureStatusNone) return;
+      long long hst[64];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(hst, tr, sizeof(hst), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[quad_block trace, clocks since start]");
+      for (int i = 1; i < n_st && i < 64; ++i) fprintf(stderr, " %lld", hst[i] - hst[0]);
+      fprintf(stderr, "\n");
+    }
   }, tap, ti);
 }
 

@@ -78,6 +78,8 @@ struct Args {
   const int* mod_row_idx;
   int mod_stride;
   DeviceStatus* status;
+  long long* trace;                // optional: clock64 stamps of one CTA's phase boundaries (diagnostics)
+  int trace_cta;
 };
 
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -152,13 +154,23 @@ __device__ __noinline__ void residual_ln(uint32_t t_own, int hf, int r, int rank
 
 // the other three CTAs' 128-channel slices of the A operand: exchange buffer (L2) -> local k-block tiles
 __device__ __noinline__ void gather_a(const bf16* xa_tile, int rank, uint32_t sA, int tid) {
-#pragma unroll 4
-  for (int it = 0; it < 24; ++it) {
-    const int idx = it * THREADS + tid;
-    const int cc = idx & 7, row = (idx >> 3) & 127, sel = idx >> 10;  // sel 0..5: the six foreign k-blocks
-    const int kb = sel + (sel >= rank * 2 ? 2 : 0);
-    const uint4 u = ldcg128(xa_tile + static_cast<size_t>(row) * C + kb * 64 + cc * 8);
-    sts128(sA + static_cast<uint32_t>(kb * TILE + row * 128 + ((cc ^ (row & 7)) << 4)), u.x, u.y, u.z, u.w);
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    uint4 u[12];  // twelve 16-byte loads in flight per thread: the L2 round trip is paid twice, not 24 times
+#pragma unroll
+    for (int it = 0; it < 12; ++it) {
+      const int idx = (half * 12 + it) * THREADS + tid;
+      const int cc = idx & 7, row = (idx >> 3) & 127, sel = idx >> 10;  // sel 0..5: the six foreign k-blocks
+      const int kb = sel + (sel >= rank * 2 ? 2 : 0);
+      u[it] = ldcg128(xa_tile + static_cast<size_t>(row) * C + kb * 64 + cc * 8);
+    }
+#pragma unroll
+    for (int it = 0; it < 12; ++it) {
+      const int idx = (half * 12 + it) * THREADS + tid;
+      const int cc = idx & 7, row = (idx >> 3) & 127, sel = idx >> 10;
+      const int kb = sel + (sel >= rank * 2 ? 2 : 0);
+      sts128(sA + static_cast<uint32_t>(kb * TILE + row * 128 + ((cc ^ (row & 7)) << 4)), u[it].x, u[it].y, u[it].z, u[it].w);
+    }
   }
 }
 
@@ -193,7 +205,13 @@ __global__ void __launch_bounds__(THREADS, 1) quad_block_kernel(const Args args)
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[3]);
   const uint32_t dbar[2] = {smem_u32(&bars[6]), smem_u32(&bars[7])};
 
+  int n_stamp = 0;
+  auto stamp = [&]() {
+    if (args.trace != nullptr && blockIdx.x == args.trace_cta && tid == 0) args.trace[n_stamp] = clock64();
+    ++n_stamp;
+  };
   pdl_trigger();
+  stamp();
   if (tid == 0) {
     if ((sbase & 1023u) != 0u) {
       if (atomicCAS(&args.status->error, 0u, 3u) == 0u) args.status->where = 0xC00u;
@@ -245,6 +263,7 @@ __global__ void __launch_bounds__(THREADS, 1) quad_block_kernel(const Args args)
   };
 
   pdl_wait();
+  stamp();
 
   // ---- thread geometry ----
   const int r = (warp & 3) * 32 + lane;               // pixel row = TMEM lane
@@ -323,6 +342,7 @@ __global__ void __launch_bounds__(THREADS, 1) quad_block_kernel(const Args args)
     const BlockParams bp = args.blocks[b];
     const bool last = b + 1 == nb;
     const int m1 = b * 4, m3 = b * 4 + 1, m4 = b * 4 + 2, m5 = b * 4 + 3;
+    stamp();  // 0: A ready (norm1 gathered)
 
     // ---------------- conv1: x1 quarter -> accumulator 0, x2 quarter -> accumulator 1 ----------------
     fence_proxy_async_smem();
@@ -365,6 +385,7 @@ __global__ void __launch_bounds__(THREADS, 1) quad_block_kernel(const Args args)
     put_plane(1, hold);
     tc_fence_before_sync();
     block_sync();                                   // conv1 tile complete
+    stamp();  // 1: conv1 done
 
     // ---------------- depthwise 3x3 + bias + SimpleGate -> own A k-blocks; per-face means -> exchange ----------------
     {
@@ -446,12 +467,17 @@ __global__ void __launch_bounds__(THREADS, 1) quad_block_kernel(const Args args)
     uint32_t wv[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) wv[i] = __ldg(wsrc + i * (C / 2));
+    stamp();  // 2: depthwise done
     cluster_sync_all();                             // every CTA's means are in the exchange buffer; conv1 tile dead
+    stamp();  // 3: means barrier
     // ---------------- SCA: s = Wsca mean + b for the own 128 outputs, all 8 faces ----------------
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
-      const int idx = it * THREADS + tid;           // 1024 float4 = [8 faces][512]
-      *reinterpret_cast<float4*>(p_mean + idx * 4) = __ldcg(reinterpret_cast<const float4*>(means_tile) + idx);
+      const int idx = it * THREADS + tid;           // 1024 float4 = [8 faces][512] -> staged as [k][8 faces]
+      const float4 m = __ldcg(reinterpret_cast<const float4*>(means_tile) + idx);
+      const int f = idx >> 7, k = (idx & 127) * 4;
+      p_mean[(k + 0) * FACES + f] = m.x; p_mean[(k + 1) * FACES + f] = m.y;
+      p_mean[(k + 2) * FACES + f] = m.z; p_mean[(k + 3) * FACES + f] = m.w;
     }
     block_sync();
     {
@@ -464,11 +490,12 @@ __global__ void __launch_bounds__(THREADS, 1) quad_block_kernel(const Args args)
         for (int i = 0; i < 64; ++i) {
           const float2 w = unpack_bf16x2(wv[i]);
           const int k = kq * 128 + half * 64 + i;
+          const float4 ma = *reinterpret_cast<const float4*>(p_mean + k * FACES), mb = *reinterpret_cast<const float4*>(p_mean + k * FACES + 4);
+          const float mm[FACES] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
 #pragma unroll
           for (int f = 0; f < FACES; ++f) {
-            const float m = p_mean[f * C + k];
-            acc[f][0] = fmaf(w.x, m, acc[f][0]);
-            acc[f][1] = fmaf(w.y, m, acc[f][1]);
+            acc[f][0] = fmaf(w.x, mm[f], acc[f][0]);
+            acc[f][1] = fmaf(w.y, mm[f], acc[f][1]);
           }
         }
         if (half == 0) {
@@ -501,8 +528,10 @@ __global__ void __launch_bounds__(THREADS, 1) quad_block_kernel(const Args args)
       }
     }
     block_sync();
+    stamp();  // 4: SCA + rescale done
     publish_a(xa_tile(), rank, sA, tid);
     exchange();
+    stamp();  // 5: gated operand gathered
     fence_proxy_async_smem();
     tc_fence_before_sync();
     block_sync();                                   // A (gated, scaled, all 512 channels) complete
@@ -516,9 +545,11 @@ __global__ void __launch_bounds__(THREADS, 1) quad_block_kernel(const Args args)
     fb::mbar_wait_c(dbar[0], dph0, args.status, 0xC30u); dph0 ^= 1u;
     tc_fence_after_sync();
     block_sync();                                   // ring idle in every thread's view: R is scratch again
+    stamp();  // 6: conv3 done
     eff_store();
     block_sync();
     ln_and_gather(bp.cb3);
+    stamp();  // 7: norm2 gathered
 
     // ---------------- conv4 + SimpleGate ----------------
     fence_proxy_async_smem();
@@ -561,10 +592,12 @@ __global__ void __launch_bounds__(THREADS, 1) quad_block_kernel(const Args args)
       *reinterpret_cast<uint4*>(xr) = make_uint4(g0[4 * ch], g0[4 * ch + 1], g0[4 * ch + 2], g0[4 * ch + 3]);
       *reinterpret_cast<uint4*>(xr + 64) = make_uint4(g1[4 * ch], g1[4 * ch + 1], g1[4 * ch + 2], g1[4 * ch + 3]);
     }
+    stamp();  // 8: conv4 + gate done
     exchange();
     fence_proxy_async_smem();
     tc_fence_before_sync();
     block_sync();                                   // A (gated, all 512 channels) complete
+    stamp();  // 9: gated operand gathered
 
     // ---------------- conv5 (+gamma) accumulated onto the x slice; next block's norm1 ----------------
     if (ctrl) {
@@ -577,6 +610,7 @@ __global__ void __launch_bounds__(THREADS, 1) quad_block_kernel(const Args args)
     }
     fb::mbar_wait_c(dbar[0], dph0, args.status, 0xC50u); dph0 ^= 1u;
     tc_fence_after_sync();
+    stamp();  // 10: conv5 done
     if (!last) {
       block_sync();                                 // ring idle: R is scratch again
       eff_store();
@@ -606,6 +640,7 @@ __global__ void __launch_bounds__(THREADS, 1) quad_block_kernel(const Args args)
   }
   tc_fence_before_sync();
   block_sync();
+  stamp();
   if (warp == 0) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);

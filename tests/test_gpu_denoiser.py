@@ -124,7 +124,7 @@ def test_fused_face_kernel_taps_and_plans_agree():
         cond = ([p.cuda() for p in priors], ident.cuda())
         t = torch.arange(batch) * 7 + 3 if batch == 3 else 321
         t_dev = t.cuda() if torch.is_tensor(t) else t
-        fast_names = ["encoders.0.1", "encoders.1.1", "encoders.2.3", "decoders.1.1", "decoders.2.1", "decoders.3.1"]
+        fast_names = ["encoders.0.1", "encoders.1.1", "decoders.2.1", "decoders.3.1"]
         out_fast, taps_fast = m.forward_with_taps(x.cuda(), t_dev, fast_names, *cond)
         out_dbg, taps_dbg = m.forward_with_taps(x.cuda(), t_dev, fast_names + ["intro"], *cond)
         plain = m(x.cuda(), t_dev, *cond).sample
@@ -139,6 +139,35 @@ def test_fused_face_kernel_taps_and_plans_agree():
         assert rel_l2(out_fast.sample, ref) <= 1e-2
         assert rel_l2(out_fast.sample, out_dbg.sample) <= 8e-3
     m.invalidate()
+
+
+@pytest.mark.parametrize("flag,names", [("HD_QUAD", ["encoders.2.3", "decoders.1.1"]), ("HD_CHAIN", [])])
+def test_experimental_kernels_keep_parity(flag, names):
+    """Kernels that are built but off by default (4-CTA-cluster block kernel at 4x4, persistent chain at 1x1)."""
+    import os
+    os.environ[flag] = "1"
+    try:
+        m, sd = build(H.FusedDenoiser, seed=2, precision="bf16", max_batch=64)
+        for batch in (3, 40):
+            x = inputs("latents", batch, seed=12)
+            priors, ident = testing.synthetic_condition(batch, 16, seed=12)
+            cond = ([p.cuda() for p in priors], ident.cuda())
+            t = torch.arange(batch) * 5 + 1 if batch == 3 else 700
+            t_dev = t.cuda() if torch.is_tensor(t) else t
+            if names:
+                out, taps = m.forward_with_taps(x.cuda(), t_dev, names, *cond)
+            else:
+                out, taps = m(x.cuda(), t_dev, *cond), {}
+            m.engine().synchronize()
+            ref_taps = {}
+            with torch.no_grad():
+                ref = denoiser_ref.fused_denoiser_forward(sd, x, t, priors, ident, ref_taps)
+            for k in names:
+                assert rel_l2(taps[k], ref_taps[k]) <= 1e-2, (flag, batch, k)
+            assert rel_l2(out.sample, ref) <= 1e-2, (flag, batch)
+        m.invalidate()
+    finally:
+        os.environ[flag] = "0"
 
 
 def test_errors_are_loud(denoiser):

@@ -5,7 +5,7 @@ import sys
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-if "HD_PAIR_TRACE" not in os.environ:
+if "HD_PAIR_TRACE" not in os.environ and "HD_QUAD_TRACE" not in os.environ:
     os.environ.setdefault("HD_FACE_TRACE", "0")
 import torch
 
