@@ -26,6 +26,8 @@ enum Epi : int {
   EPI_RESID_LN = 6, // EPI_RESID, and the following LayerNorm2d + AdaLN modulation of the same rows (N == 128)
   EPI_DWGATE = 7,   // conv1 + bias, then depthwise 3x3 + SimpleGate + per-face mean over the staged tile
                     // (gate-packed 128-column groups; tile = whole faces, spatial 2/4/8)
+  EPI_SCALE = 8,    // SCA: s[face,n] = acc + bias[n] (stored fp32), and scale_dst[row,n] = scale_src[row,n] * s[face,n] for the
+                    // rows_per_face rows of the face (conditional_naf.py:119 `x * self.sca(x)`), replacing scale_rows_kernel
 };
 
 enum AMode : int {
@@ -65,6 +67,10 @@ struct GemmDesc {
   const float* dw_w = nullptr;
   const float* dw_b = nullptr;
   void* pooled = nullptr;
+  // EPI_SCALE: bf16 [faces * rows_per_face, scale_ld] gated tensor in, scaled copy out
+  const void* scale_src = nullptr;
+  void* scale_dst = nullptr;
+  int scale_ld = 0;
 };
 
 // Device-side error word shared by all kernels of a handle (pipeline watchdog).

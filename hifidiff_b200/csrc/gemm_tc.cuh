@@ -48,6 +48,10 @@ struct TcArgs {
   const float* dw_w;
   const float* dw_b;
   bf16* pooled;
+  // EPI_SCALE
+  const bf16* scale_src;
+  bf16* scale_dst;
+  int scale_ld;
   long long* trace;           // optional per-CTA timeline (16 slots per CTA), nullptr in production
 };
 
@@ -524,6 +528,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       if (EPI == EPI_RESID || EPI == EPI_RESID_LN || EPI == EPI_PIXSHUF) { v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w; }
       if (okay) store4<TOut>(d + i * LPR * 4, v);
+      if (EPI == EPI_SCALE && okay) {
+        // (face, column) of this chunk from its address in the [faces, ldo] output; scale the face's pixel rows
+        const size_t off = static_cast<size_t>((d + i * LPR * 4) - reinterpret_cast<TOut*>(args.out));
+        const size_t face = off / static_cast<size_t>(args.ldo);
+        const size_t col = off - face * static_cast<size_t>(args.ldo);
+        const int rpf = args.rows_per_face;
+        for (int p = 0; p < rpf; ++p) {
+          const size_t o = (face * rpf + p) * static_cast<size_t>(args.scale_ld) + col;
+          const uint2 u = *reinterpret_cast<const uint2*>(args.scale_src + o);
+          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+          *reinterpret_cast<uint2*>(args.scale_dst + o) = make_uint2(pack_bf16x2(a.x * v.x, a.y * v.y), pack_bf16x2(b.x * v.z, b.y * v.w));
+        }
+      }
       return v;
     };
     // EPI_RESID_LN: the warp holds the whole 128-channel row (4 values per lane): LayerNorm2d statistics

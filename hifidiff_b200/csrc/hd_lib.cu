@@ -62,6 +62,7 @@ bool g_use_pdl = true;  // HD_PDL=0 disables programmatic dependent launch
 bool g_bn256 = true;    // HD_BN256=0: 128x128 tiles for the dense 3x3 convs too
 int g_two_cta = 1;      // HD_TWO_CTA=0: never use cta_group::2 pairs; 2: wherever the shape allows (tests)
 bool g_face = true;     // HD_FACE=0: per-op kernels at the 16x16 level instead of the fused per-face block kernel
+bool g_fuse_scale = false;  // HD_FUSE_SCALE=1: rescale the gated rows in the SCA GEMM epilogue (measured +83 us/step: too few CTAs)
 bool g_quad = false;    // HD_QUAD=1: 4-CTA-cluster block kernel at the 4x4 level (parity green; measured 35 us/step slower)
 bool g_pair = true;     // HD_PAIR=0: per-op kernels at the 8x8 level instead of the fused face-pair block kernel
 bool g_chain = false;   // HD_CHAIN=1: run the 1x1-level blocks as one persistent cooperative kernel (measured slower)
@@ -73,7 +74,7 @@ bool g_fuse_ln = false;
 // HD_FUSE_DW=1 runs depthwise 3x3 + gate + pool in conv1's epilogue at the 2x2..8x8 levels (EPI_DWGATE).
 // Measured on B200 at B=256: parity-equal but slower (2.75 vs 2.62 ms/step: the 9-tap stencil is
 // latency-bound on the 8 epilogue warps), so the standalone sliding-window kernel stays the default.
-bool g_fuse_dw = false;
+int g_fuse_dw = 0;       // HD_FUSE_DW: bit mask of spatial sizes (2 | 4 | 8) whose depthwise 3x3 runs in conv1's epilogue
 
 // Per-step kernel launch: programmatic stream serialization lets kernel N+1 be scheduled (and run its
 // prologue / weight prefetch) while kernel N drains; every such kernel executes pdl_wait() first.
@@ -395,6 +396,7 @@ void launch_tc(const TcLaunch& L, cudaStream_t st) {
     case EPI_GATE: launch_tc_inst<EPI_GATE, A_PLAIN, bf16>(L, st); break;
     case EPI_DWGATE: launch_tc_inst<EPI_DWGATE, A_PLAIN, bf16>(L, st); break;
     case EPI_PIXSHUF: launch_tc_inst<EPI_PIXSHUF, A_PLAIN, float>(L, st); break;
+    case EPI_SCALE: launch_tc_inst<EPI_SCALE, A_PLAIN, float>(L, st); break;
     default: break;
   }
 }
@@ -422,6 +424,7 @@ TcLaunch build_tc(hd_handle* h, const GemmDesc& d, long long a_rows_alloc) {
   a.mod_stride = d.mod_stride; a.ln_shift_off = d.ln_shift_off; a.ln_scale_off = d.ln_scale_off;
   a.rows_per_face = d.rows_per_face; a.ln_out = static_cast<bf16*>(d.ln_out);
   a.dw_w = d.dw_w; a.dw_b = d.dw_b; a.pooled = static_cast<bf16*>(d.pooled);
+  a.scale_src = static_cast<const bf16*>(d.scale_src); a.scale_dst = static_cast<bf16*>(d.scale_dst); a.scale_ld = d.scale_ld;
   a.trace = nullptr;
   if (d.a_mode == A_CONV3) {
     const int n = d.sp, C = d.C;
@@ -599,7 +602,7 @@ void load_block(hd_handle* h, BlockW& bw, int wdt) {
     bw.w1 = pack_matrix(h, need(h, p + "conv1.weight", {2 * c, c}), 2 * c, c, 1, &perm, &rs, wdt);
     bw.b1 = upload_f32(h, bp);
     bw.dw_folded = true;
-  } else if (g_fuse_dw && wdt == DT_BF16 && h->sp[bw.level] <= 8) {
+  } else if ((g_fuse_dw & h->sp[bw.level]) != 0 && wdt == DT_BF16 && h->sp[bw.level] <= 8) {
     // conv1 rows (and its bias, the depthwise taps and bias) in the gate-packed column order, so that the
     // depthwise 3x3 + SimpleGate + pool can run over conv1's staged accumulator tile (EPI_DWGATE)
     auto dw = host_vec(h, need(h, p + "conv2.weight", {2 * c, 9}));
@@ -791,7 +794,7 @@ void add_gemm(hd_handle* h, Plan& P, GemmDesc d, long long a_rows_alloc, const s
   const long long taps_exec = d.a_mode == A_CONV3 ? 1 : 1;
   (void)taps_exec;
   P.flops_per_face += 2.0 * d.M * static_cast<double>(d.N) * d.K / P.batch;
-  static const char* epi_names[] = {"bias", "relu", "sigmoid", "resid", "gate", "pixshuf", "resid+ln", "dw3x3+gate+pool"};
+  static const char* epi_names[] = {"bias", "relu", "sigmoid", "resid", "gate", "pixshuf", "resid+ln", "dw3x3+gate+pool", "bias+scale_rows"};
   const std::string what = g_label;
   if (tc_eligible(h, d)) {
     TcLaunch L = build_tc(h, d, a_rows_alloc);
@@ -859,6 +862,7 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
   float* sca_s = h->sca_s;
 
   const int has_mod = bw.has_mod ? 1 : 0;
+  const bool fuse_scale = g_fuse_scale && bf && rpf <= 16;
   auto ln = [=](const float* lw, const float* lb, int shift_off, int scale_off) {
     return [=](cudaStream_t st) {
       if (bf) launch_ln<bf16>(c, resid, lw, lb, static_cast<bf16*>(act_a), rows, rpf, mod, shift_off, scale_off, has_mod, st);
@@ -918,18 +922,23 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
     d.M = B; d.N = c; d.K = c; d.A = bw.dw_folded ? act_g : pooled; d.lda = c; d.a_dtype = adt;
     d.W = bw.wsca; d.ldw = c; d.w_dtype = adt; d.bias = bw.bsca; d.epi = EPI_BIAS;
     d.out = sca_s; d.ldo = c; d.out_dtype = DT_F32;
+    if (fuse_scale) {  // the face's rows are rescaled by the SCA GEMM's own epilogue, out of place into act_h
+      d.epi = EPI_SCALE; d.scale_src = act_g; d.scale_dst = act_h; d.scale_ld = c; d.rows_per_face = rpf;
+    }
     add_gemm(h, P, d, h->Bcap);
   }
-  g_label = L0 + "scale_rows";
-  add_op(P, [=](cudaStream_t st) {
-    const size_t total8 = static_cast<size_t>(rows) * c / 8;
-    if (bf) launch_k(scale_rows_kernel<bf16>, dim3(cdiv(total8, 256)), dim3(256), 0, st, static_cast<bf16*>(act_g), sca_s, total8, c, rpf);
-    else launch_k(scale_rows_kernel<float>, dim3(cdiv(total8, 256)), dim3(256), 0, st, static_cast<float*>(act_g), sca_s, total8, c, rpf);
-  });
+  if (!fuse_scale) {
+    g_label = L0 + "scale_rows";
+    add_op(P, [=](cudaStream_t st) {
+      const size_t total8 = static_cast<size_t>(rows) * c / 8;
+      if (bf) launch_k(scale_rows_kernel<bf16>, dim3(cdiv(total8, 256)), dim3(256), 0, st, static_cast<bf16*>(act_g), sca_s, total8, c, rpf);
+      else launch_k(scale_rows_kernel<float>, dim3(cdiv(total8, 256)), dim3(256), 0, st, static_cast<float*>(act_g), sca_s, total8, c, rpf);
+    });
+  }
   g_label = L0 + "conv3";
   {  // conv3 (+beta) + residual
     GemmDesc d;
-    d.M = rows; d.N = c; d.K = c; d.A = act_g; d.lda = c; d.a_dtype = adt;
+    d.M = rows; d.N = c; d.K = c; d.A = fuse_scale ? act_h : act_g; d.lda = c; d.a_dtype = adt;
     d.W = bw.w3; d.ldw = c; d.w_dtype = adt; d.bias = bw.b3; d.epi = EPI_RESID;
     d.out = resid; d.ldo = c; d.out_dtype = DT_F32; d.resid = resid; d.ldr = c;
     if (fuse_ln) fused_ln(d, bw.ln2_w, bw.ln2_b, bw.mod_off + 2 * c, bw.mod_off + 3 * c);
@@ -1859,13 +1868,14 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10) HD_THROW(HD_ERR_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
   if (const char* e = getenv("HD_PDL")) g_use_pdl = atoi(e) != 0;
-  if (const char* e = getenv("HD_FUSE_DW")) g_fuse_dw = atoi(e) != 0;
+  if (const char* e = getenv("HD_FUSE_DW")) g_fuse_dw = atoi(e) == 1 ? 14 : atoi(e);
   if (const char* e = getenv("HD_BN256")) g_bn256 = atoi(e) != 0;
   if (const char* e = getenv("HD_TWO_CTA")) g_two_cta = atoi(e);
   if (const char* e = getenv("HD_CHAIN")) g_chain = atoi(e) != 0;
   if (const char* e = getenv("HD_FACE")) g_face = atoi(e) != 0;
   if (const char* e = getenv("HD_PAIR")) g_pair = atoi(e) != 0;
   if (const char* e = getenv("HD_QUAD")) g_quad = atoi(e) != 0;
+  if (const char* e = getenv("HD_FUSE_SCALE")) g_fuse_scale = atoi(e) != 0;
   if (const char* e = getenv("HD_MAX_STAGES")) g_max_stages = atoi(e);
   if (const char* e = getenv("HD_FUSE_LN")) g_fuse_ln = atoi(e) != 0;
   h = new hd_handle();
