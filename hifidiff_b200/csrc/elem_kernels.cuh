@@ -39,9 +39,19 @@ __global__ void __launch_bounds__(256) intro_conv_kernel(const float* __restrict
   const int b = blockIdx.x;
   const int W2 = S + 2;
   pdl_trigger();
-  for (int i = threadIdx.x; i < 36 * 128; i += blockDim.x) {
-    const int k = i >> 7, o = i & 127;
-    s_w[i] = w[o * 36 + k];
+  // w is already [36][128] (host-side transpose): 4608 floats = 1152 float4, all loads of a thread in flight
+  {
+    float4 t[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int idx = i * 256 + threadIdx.x;
+      if (idx < 36 * 32) t[i] = __ldg(reinterpret_cast<const float4*>(w) + idx);
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int idx = i * 256 + threadIdx.x;
+      if (idx < 36 * 32) reinterpret_cast<float4*>(s_w)[idx] = t[i];
+    }
   }
   pdl_wait();
   for (int i = threadIdx.x; i < 4 * W2 * W2; i += blockDim.x) {
@@ -533,13 +543,34 @@ __global__ void __launch_bounds__(256) ending_conv_kernel(const TIn* __restrict_
   float* s_w = reinterpret_cast<float*>(s_end_raw + static_cast<size_t>(npix) * 128 * sizeof(TIn));
   const int face = blockIdx.x;
   pdl_trigger();
-  for (int i = threadIdx.x; i < 4 * 9 * 128; i += blockDim.x) s_w[i] = w[i];
+  {  // 4608 floats = 1152 float4, all loads of a thread in flight
+    float4 t[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int idx = i * 256 + threadIdx.x;
+      if (idx < 1152) t[i] = __ldg(reinterpret_cast<const float4*>(w) + idx);
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int idx = i * 256 + threadIdx.x;
+      if (idx < 1152) reinterpret_cast<float4*>(s_w)[idx] = t[i];
+    }
+  }
   pdl_wait();
   const TIn* xf = x + static_cast<size_t>(face) * npix * 128;
-  for (int i = threadIdx.x; i < npix * CPR; i += blockDim.x) {
-    const int r = i / CPR, ck = i % CPR;
-    const uint4 v = *reinterpret_cast<const uint4*>(xf + static_cast<size_t>(r) * 128 + ck * EPC);
-    *reinterpret_cast<uint4*>(tile + r * 128 + ((ck ^ (r % CPR)) * EPC)) = v;
+  for (int i0 = threadIdx.x; i0 < npix * CPR; i0 += 8 * blockDim.x) {  // 8 loads in flight per thread
+    uint4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < npix * CPR) v[u] = *reinterpret_cast<const uint4*>(xf + static_cast<size_t>(i / CPR) * 128 + (i % CPR) * EPC);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x;
+      const int r = i / CPR, ck = i % CPR;
+      if (i < npix * CPR) *reinterpret_cast<uint4*>(tile + r * 128 + ((ck ^ (r % CPR)) * EPC)) = v[u];
+    }
   }
   __syncthreads();
   for (int p = threadIdx.x; p < npix; p += blockDim.x) {

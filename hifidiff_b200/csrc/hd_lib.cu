@@ -573,6 +573,15 @@ std::vector<float> bn_scale(hd_handle* h, const std::string& p, int n, std::vect
   return rs;
 }
 
+// intro.weight [128, 4*9] -> [36][128] (tap-major, output channel minor): the kernel's shared-memory layout, so the
+// per-block fill is a straight coalesced copy
+std::vector<float> intro_taps_major(const std::vector<float>& w) {
+  std::vector<float> t(w.size());
+  for (int o = 0; o < kWidth; ++o)
+    for (int k = 0; k < 36; ++k) t[static_cast<size_t>(k) * kWidth + o] = w[static_cast<size_t>(o) * 36 + k];
+  return t;
+}
+
 void load_block(hd_handle* h, BlockW& bw, int wdt) {
   const std::string& p = bw.prefix;
   const int c = bw.c;
@@ -706,7 +715,7 @@ void load_weights_impl(hd_handle* h) {
   h->tm1_b = upload_f32(h, host_vec(h, need(h, "time_mlp.1.bias", {2 * kTimeDim})));
   h->tm3_w = upload_f32(h, host_vec(h, need(h, "time_mlp.3.weight", {kTimeDim, kTimeDim})));
   h->tm3_b = upload_f32(h, host_vec(h, need(h, "time_mlp.3.bias", {kTimeDim})));
-  h->intro_w = upload_f32(h, host_vec(h, need(h, "intro.weight", {kWidth, 36})));
+  h->intro_w = upload_f32(h, intro_taps_major(host_vec(h, need(h, "intro.weight", {kWidth, 36}))));
   h->intro_b = upload_f32(h, host_vec(h, need(h, "intro.bias", {kWidth})));
   h->end_w = static_cast<float*>(pack_matrix(h, need(h, "ending.weight", {4, kWidth, 9}), 4, 9 * kWidth, 9, nullptr,
                                              nullptr, DT_F32));
@@ -1581,7 +1590,7 @@ void load_fpg_impl(hd_handle* h) {
     }
   const int64_t keep = h->weight_elems_step;
   for (auto& b : F.blocks) load_block(h, b, wdt);
-  F.intro_w = upload_f32(h, host_vec(h, need(h, "intro.weight", {kWidth, 36})));
+  F.intro_w = upload_f32(h, intro_taps_major(host_vec(h, need(h, "intro.weight", {kWidth, 36}))));
   F.intro_b = upload_f32(h, host_vec(h, need(h, "intro.bias", {kWidth})));
   for (int l = 0; l < 4; ++l) {
     const int c = h->c[l];
