@@ -151,6 +151,7 @@ class FacialRefiner(nn.Module):
         self._cond_src = None
         self._cond: Optional[tuple] = None
         self.native_fpg = True   # run FPG on the sm_100a kernels (False: PyTorch eager)
+        self.native_idc = True   # run the IDC ResNet-50 on the sm_100a kernels (False: PyTorch/cuDNN eager)
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._drop_condition())
 
     def _drop_condition(self) -> None:
@@ -173,7 +174,13 @@ class FacialRefiner(nn.Module):
                     priors = eng.fpg_forward(cr_latent, self.denoiser.config.sample_size, self.denoiser.width)
                 else:
                     priors = self.fpg(cr_latent)
-                ident = self.idc(cr_face)
+                if self.native_idc and cr_face.device.type == "cuda" and cr_face.shape[-1] == 8 * self.denoiser.config.sample_size:
+                    eng = self.denoiser.engine(cr_face.shape[0])
+                    if not eng.idc_loaded:
+                        eng.load_idc_state(self.idc.state_dict())
+                    ident = eng.idc_forward(cr_face)
+                else:
+                    ident = self.idc(cr_face)
             self.train(was_training)
             self._cond = ([p.contiguous() for p in priors], ident.contiguous())
             self._cond_src = key

@@ -99,6 +99,7 @@ class _Engine:
         self.lib = lib
         self.handle = C.c_void_p()
         self.fpg_loaded = False
+        self.idc_loaded = False
         self.max_batch = max_batch
         self.max_steps = max_steps
         cfg = _lib.HdConfig(C.sizeof(_lib.HdConfig), model_kind, precision, latent_size,
@@ -171,6 +172,23 @@ class _Engine:
         with torch.cuda.device(x.device):
             self.check(self.lib.hd_fpg_forward(self.handle, x.data_ptr(), ptrs, b, _stream_ptr(x.device)), "hd_fpg_forward")
         return outs
+
+    def load_idc_state(self, state: dict) -> None:
+        descs, n, keep = self._descs(state)
+        self.check(self.lib.hd_load_idc_weights(self.handle, descs, n, None), "hd_load_idc_weights")
+        self.idc_loaded = True
+        del keep
+
+    def idc_forward(self, cr_face: torch.Tensor) -> torch.Tensor:
+        """ResNet50.forward (models/idc/model.py:123-136) on the sm_100a kernels -> (B,2048,1,1) fp32."""
+        x = cr_face.to(torch.float32).contiguous()
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != x.shape[3]:
+            raise ValueError(f"cr_face must be (B,3,H,H), got {tuple(x.shape)}")
+        out = torch.empty((x.shape[0], 2048, 1, 1), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            self.check(self.lib.hd_idc_forward(self.handle, x.data_ptr(), x.shape[2], out.data_ptr(), x.shape[0],
+                                               _stream_ptr(x.device)), "hd_idc_forward")
+        return out
 
     def info(self) -> "_lib.HdInfo":
         info = _lib.HdInfo()

@@ -126,6 +126,17 @@ int32_t hd_load_fpg_weights(hd_handle* h, const hd_tensor_desc* tensors, int32_t
 int32_t hd_fpg_forward(hd_handle* h, const float* cr_latent, float* const priors_out[5], int32_t batch,
                        void* stream);
 
+/* IDC identity network on the same kernels (SURVEY.md §8f "next" row 2).  hd_load_idc_weights takes the
+ * ResNet-50 module's state_dict (conv1.weight, batch_norm1.*, layerL.i.{conv1,conv2,conv3}.{weight,bias},
+ * layerL.i.batch_normK.*, layerL.0.i_downsample.{0,1}.*; replaces idc.load_state_dict, refiner.py:18-20) and
+ * folds every eval-mode BatchNorm into its conv.  hd_idc_forward replaces ResNet.forward
+ * (models/idc/model.py:123-136) as called at refiner.py:34: cr_face (B,3,image_size,image_size) fp32, device or
+ * host, image_size == 8 * latent_size -> identity_out (B,2048,1,1) fp32 device buffer.  Any batch >= 1 (faces are
+ * processed in chunks of 64). */
+int32_t hd_load_idc_weights(hd_handle* h, const hd_tensor_desc* tensors, int32_t n, void* stream);
+int32_t hd_idc_forward(hd_handle* h, const float* cr_face, int32_t image_size, float* identity_out,
+                       int32_t batch, void* stream);
+
 /* Condition-only work, hoisted out of the timestep loop (it depends on neither x_t nor t):
  * idc_conv(identity) (model.py:245-246) and the five HCA channel/spatial gates computed from
  * the priors (hca.py:33-48).  priors[j]: (B, C_j, n_j, n_j) with C = 2048,1024,512,256,128 and
