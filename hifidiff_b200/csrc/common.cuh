@@ -71,6 +71,8 @@ struct GemmDesc {
   const void* scale_src = nullptr;
   void* scale_dst = nullptr;
   int scale_ld = 0;
+  // split-K until the grid has at least this many CTAs (one chain of a split region gets its share of the SMs)
+  int cta_target = 120;
 };
 
 // Device-side error word shared by all kernels of a handle (pipeline watchdog).

@@ -67,6 +67,15 @@ bool g_fuse_scale = false;  // HD_FUSE_SCALE=1: rescale the gated rows in the SC
 bool g_quad = false;    // HD_QUAD=1: 4-CTA-cluster block kernel at the 4x4 level (parity green; measured 35 us/step slower)
 bool g_pair = true;     // HD_PAIR=0: per-op kernels at the 8x8 level instead of the fused face-pair block kernel
 bool g_chain = false;   // HD_CHAIN=1: run the 1x1-level blocks as one persistent cooperative kernel (measured slower)
+// HD_SPLIT=n: the 4x4 / 2x2 / 1x1 levels (latency-bound: ~120 GEMMs of 7-10 us that cannot fill the chip) run as n
+// independent face-range chains on n streams, forked and joined inside the step's CUDA graph, each GEMM sized
+// for 1/n of the SMs so the chains' kernels co-reside.  1 = off (default).  Measured on B200 at B=256: 2.21 ms/step
+// with 2 chains, 2.41 with 3, 2.37 with 4, against 2.16 unsplit — these kernels are latency-bound, so a
+// half-size kernel takes as long as a full-size one and concurrency buys nothing.
+int g_split = 1;
+int g_cta_target = 120;  // HD_CTA_TARGET: split-K until a GEMM's grid has at least this many CTAs
+int g_sca_target = 120;  // HD_SCA_TARGET: the same for the SCA GEMMs (M = faces)
+constexpr int kMaxSplit = 4;
 int g_max_stages = 6;   // HD_MAX_STAGES=3: no 6-stage / 16-epilogue-warp variant (one CTA per SM)
 // HD_FUSE_LN=1 computes LayerNorm + modulation in the residual GEMM's epilogue where the tile holds the whole
 // row (c = 128).  Measured on B200 at B=256: the fused epilogue costs 31.6 us against 14.2 us (GEMM) + 10.2 us
@@ -198,6 +207,16 @@ struct Op {
   std::string tap;
   TapInfo info;
   std::string label;  // kernel kind + shape, for hd_profile_step
+  int chain = 0;      // stream the op is issued on: 0 = the handle's stream, j > 0 = side stream j - 1
+  bool fork = false;  // before this op: side streams wait for everything issued so far
+  bool join = false;  // after this op: the handle's stream waits for the side streams
+};
+
+// Face range an op builder works on.  Default: the whole batch in the shared workspace.  Inside a split
+// region each chain owns faces [f0, f0 + nf) of the per-level tensors and slab `id` of every scratch buffer.
+struct ChainCx {
+  int id = 0, f0 = 0, nf = -1, nslab = 1;
+  int cta_target = 120;  // split-K until a GEMM's grid has at least this many CTAs
 };
 
 thread_local std::string g_label;  // label picked up by the next add_op
@@ -210,6 +229,8 @@ struct Plan {
   int64_t graph_first = 0;
   const float* graph_noise = nullptr;
   double flops_per_face = 0;
+  ChainCx cx;        // context the op builders are working in (reset to the whole batch once the plan is built)
+  int n_chains = 1;  // > 1: the plan has a split region (fork / join ops)
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -234,6 +255,10 @@ struct hd_handle {
   int mod_stride = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaStream_t side[kMaxSplit - 1] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxSplit - 1] = {};
+  size_t act_bytes = 0, pooled_rows = 0;
+  int split = 1;  // HD_SPLIT at hd_create
   EncodeTiledFn encode = nullptr;
   Arena arena;
   DeviceStatus* d_status = nullptr;
@@ -501,7 +526,7 @@ TcLaunch build_tc(hd_handle* h, const GemmDesc& d, long long a_rows_alloc) {
   // split-K over a (1,1,S) cluster until the grid can cover the chip (>= 120 CTAs)
   const int tiles = cdiv(d.M, 128) * (d.N / bn);
   int split = 1;
-  while (tiles * split < 120 && split < 8 && a.num_kb % (2 * split) == 0 && a.num_kb / (2 * split) >= 2) split *= 2;
+  while (tiles * split < d.cta_target && split < 8 && a.num_kb % (2 * split) == 0 && a.num_kb / (2 * split) >= 2) split *= 2;
   if (d.epi == EPI_RESID_LN || d.epi == EPI_DWGATE) split = 1;  // these epilogues need the finished tile in one CTA
   L.grid = dim3(cdiv(d.M, 128), d.N / bn, split);
   const int local_kb = a.num_kb / split;
@@ -822,6 +847,7 @@ void add_op(Plan& P, std::function<void(cudaStream_t)> fn, const std::string& ta
   op.tap = tap;
   op.info = info;
   op.label = g_label;
+  op.chain = P.cx.id;
   P.ops.push_back(std::move(op));
 }
 
@@ -830,6 +856,7 @@ void add_gemm(hd_handle* h, Plan& P, GemmDesc d, long long a_rows_alloc, const s
   const long long taps_exec = d.a_mode == A_CONV3 ? 1 : 1;
   (void)taps_exec;
   P.flops_per_face += 2.0 * d.M * static_cast<double>(d.N) * d.K / P.batch;
+  if (d.cta_target == 120) d.cta_target = P.cx.nslab > 1 ? P.cx.cta_target : g_cta_target;
   static const char* epi_names[] = {"bias", "relu", "sigmoid", "resid", "gate", "pixshuf", "resid+ln", "dw3x3+gate+pool", "bias+scale_rows"};
   const std::string what = g_label;
   if (tc_eligible(h, d)) {
@@ -883,19 +910,37 @@ void launch_ln(int c, const float* x, const float* lw, const float* lb, T* out, 
   }
 }
 
+// Chain context helpers: batch / first face of the current chain, its slab of a scratch buffer, and the row
+// capacity a GEMM A operand living in that slab may claim (a multiple of 128 >= the rows actually used).
+int cx_batch(const Plan& P) { return P.cx.nf >= 0 ? P.cx.nf : P.batch; }
+void* cx_slab(const Plan& P, void* base, size_t bytes) {
+  if (P.cx.nslab <= 1) return base;
+  return static_cast<char*>(base) + static_cast<size_t>(P.cx.id) * ((bytes / P.cx.nslab) & ~static_cast<size_t>(1023));
+}
+long long cx_rows_alloc(const hd_handle* h, const Plan& P, int rpf) {
+  if (P.cx.nslab <= 1) return static_cast<long long>(h->Bcap) * rpf;
+  return static_cast<long long>(cdiv(static_cast<long long>(cx_batch(P)) * rpf, 128LL)) * 128;
+}
+
 // next_ln1: the block that follows at the same level (its norm1 can be fused into this block's conv5
 // epilogue); skip_ln1: this block's norm1 output was already produced by its predecessor.
 void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapname, const BlockW* next_ln1 = nullptr,
                bool skip_ln1 = false) {
-  const int B = P.batch, l = bw.level, c = bw.c, sp = h->sp[l];
+  const int B = cx_batch(P), f0 = P.cx.f0, l = bw.level, c = bw.c, sp = h->sp[l];
   const int rows = B * sp * sp, rpf = sp * sp;
-  const long long rows_alloc = static_cast<long long>(h->Bcap) * rpf;
+  const long long rows_alloc = cx_rows_alloc(h, P, rpf);
   const int adt = h->bf16 ? DT_BF16 : DT_F32;
-  float* resid = h->resid[l];
-  ModRef mod{h->mod_table, h->row_idx, h->mod_stride};
+  const size_t as = esize(adt);
+  float* resid = h->resid[l] + static_cast<size_t>(f0) * rpf * c;
+  const int* row_idx = h->row_idx + f0;
+  ModRef mod{h->mod_table, row_idx, h->mod_stride};
   const bool bf = h->bf16;
-  void *act_a = h->act_a, *act_h = h->act_h, *act_g = h->act_g, *pooled = h->pooled;
-  float* sca_s = h->sca_s;
+  void *act_a = cx_slab(P, h->act_a, h->act_bytes), *act_h = cx_slab(P, h->act_h, 2 * h->act_bytes),
+       *act_g = cx_slab(P, h->act_g, h->act_bytes);
+  // per-face vectors: slab stride = the chain's face capacity rounded up to whole 128-row tiles
+  const size_t pool_off = P.cx.nslab <= 1 ? 0 : static_cast<size_t>(P.cx.id) * cx_rows_alloc(h, P, 1) * 2048;
+  void* pooled = static_cast<char*>(h->pooled) + pool_off * as;
+  float* sca_s = h->sca_s + pool_off;
 
   const int has_mod = bw.has_mod ? 1 : 0;
   const bool fuse_scale = g_fuse_scale && bf && rpf <= 16;
@@ -911,7 +956,7 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
   const bool fuse_ln = g_fuse_ln && bf && c == 128 && bw.has_mod;
   auto fused_ln = [&](GemmDesc& d, const float* lw, const float* lb, int shift_off, int scale_off) {
     d.epi = EPI_RESID_LN;
-    d.ln_w = lw; d.ln_b = lb; d.mod_table = h->mod_table; d.mod_row_idx = h->row_idx; d.mod_stride = h->mod_stride;
+    d.ln_w = lw; d.ln_b = lb; d.mod_table = h->mod_table; d.mod_row_idx = row_idx; d.mod_stride = h->mod_stride;
     d.ln_shift_off = shift_off; d.ln_scale_off = scale_off; d.rows_per_face = rpf; d.ln_out = act_a;
   };
   if (!(fuse_ln && skip_ln1)) {
@@ -958,10 +1003,11 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
     d.M = B; d.N = c; d.K = c; d.A = bw.dw_folded ? act_g : pooled; d.lda = c; d.a_dtype = adt;
     d.W = bw.wsca; d.ldw = c; d.w_dtype = adt; d.bias = bw.bsca; d.epi = EPI_BIAS;
     d.out = sca_s; d.ldo = c; d.out_dtype = DT_F32;
+    if (P.cx.nslab <= 1) d.cta_target = g_sca_target;
     if (fuse_scale) {  // the face's rows are rescaled by the SCA GEMM's own epilogue, out of place into act_h
       d.epi = EPI_SCALE; d.scale_src = act_g; d.scale_dst = act_h; d.scale_ld = c; d.rows_per_face = rpf;
     }
-    add_gemm(h, P, d, h->Bcap);
+    add_gemm(h, P, d, cx_rows_alloc(h, P, 1));
   }
   if (!fuse_scale) {
     g_label = L0 + "scale_rows";
@@ -1009,14 +1055,15 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
 
 void add_hca(hd_handle* h, Plan& P, int j, int level) {
   const HcaW& w = h->hca[j];
-  const int B = P.batch, d = w.d, sp = w.sp, rpf = sp * sp, rows = B * rpf;
-  const long long rows_alloc = static_cast<long long>(h->Bcap) * rpf;
+  const int B = cx_batch(P), f0 = P.cx.f0, d = w.d, sp = w.sp, rpf = sp * sp, rows = B * rpf;
+  const long long rows_alloc = cx_rows_alloc(h, P, rpf);
   const int adt = h->bf16 ? DT_BF16 : DT_F32;
   const bool bf = h->bf16;
-  const float* fd = h->resid[level];
-  const float *wc = w.wc, *ws = w.ws;
-  const float* idc = j == 0 ? h->idc_add : nullptr;
-  void* act_a = h->act_a;
+  const float* fd = h->resid[level] + static_cast<size_t>(f0) * rpf * d;
+  const float *wc = w.wc + static_cast<size_t>(f0) * d, *ws = w.ws + static_cast<size_t>(f0) * rpf;
+  const float* idc = j == 0 ? h->idc_add + static_cast<size_t>(f0) * d : nullptr;
+  void* act_a = cx_slab(P, h->act_a, h->act_bytes);
+  void* hca_out = cx_slab(P, h->hca_out, h->act_bytes);
   g_label = fmt("hca%d apply", j);
   add_op(P, [=](cudaStream_t st) {
     const size_t total8 = static_cast<size_t>(rows) * d / 8;
@@ -1025,7 +1072,7 @@ void add_hca(hd_handle* h, Plan& P, int j, int level) {
   });
   GemmDesc g;
   g.M = rows; g.N = d; g.A = act_a; g.a_dtype = adt; g.w_dtype = adt; g.bias = w.bf; g.epi = EPI_RELU;
-  g.out = h->hca_out; g.ldo = d; g.out_dtype = adt; g.ldw = 9 * d;
+  g.out = hca_out; g.ldo = d; g.out_dtype = adt; g.ldw = 9 * d;
   if (sp == 1) {  // only the centre tap sees a pixel
     g.a_mode = A_PLAIN; g.K = d; g.lda = d;
     g.W = static_cast<const char*>(w.wf) + static_cast<size_t>(4) * d * esize(adt);
@@ -1033,7 +1080,7 @@ void add_hca(hd_handle* h, Plan& P, int j, int level) {
     g.a_mode = A_CONV3; g.K = 9 * d; g.sp = sp; g.C = d; g.lda = d; g.W = w.wf;
   }
   TapInfo ti;
-  ti.ptr = h->hca_out; ti.dtype = adt; ti.C = d; ti.HW = rpf; ti.ld = d;
+  ti.ptr = hca_out; ti.dtype = adt; ti.C = d; ti.HW = rpf; ti.ld = d;
   g_label = fmt("hca%d conv3x3", j);
   add_gemm(h, P, g, rows_alloc, "hcas." + std::to_string(j), ti);
 }
@@ -1489,69 +1536,46 @@ Plan* get_plan(hd_handle* h, int B, bool debug = false) {
     }, "intro", ti);
     P.flops_per_face += 2.0 * 36 * 128 * S * S;
   }
-  size_t bi = 0;
-  for (int l = 0; l < 4; ++l) {
-    if (face_blocks_ok(h, bi, kEncBlocks[l], debug)) {
-      add_face_blocks(h, P, bi, kEncBlocks[l]);
-      bi += kEncBlocks[l];
-    } else if (pair_blocks_ok(h, bi, kEncBlocks[l], debug)) {
-      add_pair_blocks(h, P, bi, kEncBlocks[l]);
-      bi += kEncBlocks[l];
-    } else if (quad_blocks_ok(h, bi, kEncBlocks[l], debug)) {
-      add_quad_blocks(h, P, bi, kEncBlocks[l]);
-      bi += kEncBlocks[l];
-    } else {
-      for (int i = 0; i < kEncBlocks[l]; ++i, ++bi)
-        add_block(h, P, h->blocks[bi], "encoders." + std::to_string(l) + "." + std::to_string(i),
-                  i + 1 < kEncBlocks[l] ? &h->blocks[bi + 1] : nullptr, i > 0);
-    }
-    // down: 2x2 stride-2 conv as space-to-depth + GEMM
-    const int c = h->c[l], n = h->sp[l], rows_out = B * (n / 2) * (n / 2);
-    const float* src = h->resid[l];
-    void* act_a = h->act_a;
+  // ---- builders for one UNet stage; each works on the current chain context (P.cx) ----
+  auto emit_blocks = [&](size_t first, int count, const std::string& prefix) {
+    const bool whole = P.cx.nslab <= 1;  // the fused kernels address the whole batch
+    if (whole && face_blocks_ok(h, first, count, debug)) { add_face_blocks(h, P, first, count); return; }
+    if (whole && pair_blocks_ok(h, first, count, debug)) { add_pair_blocks(h, P, first, count); return; }
+    if (whole && quad_blocks_ok(h, first, count, debug)) { add_quad_blocks(h, P, first, count); return; }
+    for (int i = 0; i < count; ++i)
+      add_block(h, P, h->blocks[first + i], prefix + std::to_string(i), i + 1 < count ? &h->blocks[first + i + 1] : nullptr, i > 0);
+  };
+  auto emit_down = [&](int l) {  // 2x2 stride-2 conv as space-to-depth + GEMM: resid[l] -> resid[l + 1]
+    const int Bq = cx_batch(P), f0 = P.cx.f0;
+    const int c = h->c[l], n = h->sp[l], rows_out = Bq * (n / 2) * (n / 2);
+    const float* src = h->resid[l] + static_cast<size_t>(f0) * n * n * c;
+    void* act_a = cx_slab(P, h->act_a, h->act_bytes);
     g_label = fmt("down%d s2d", l);
     add_op(P, [=](cudaStream_t st) {
       const size_t total8 = static_cast<size_t>(rows_out) * 4 * c / 8;
-      if (bf) launch_k(s2d_kernel<bf16>, dim3(cdiv(total8, 256)), dim3(256), 0, st, src, static_cast<bf16*>(act_a), B, n, c);
-      else launch_k(s2d_kernel<float>, dim3(cdiv(total8, 256)), dim3(256), 0, st, src, static_cast<float*>(act_a), B, n, c);
+      if (bf) launch_k(s2d_kernel<bf16>, dim3(cdiv(total8, 256)), dim3(256), 0, st, src, static_cast<bf16*>(act_a), Bq, n, c);
+      else launch_k(s2d_kernel<float>, dim3(cdiv(total8, 256)), dim3(256), 0, st, src, static_cast<float*>(act_a), Bq, n, c);
     });
+    float* out = h->resid[l + 1] + static_cast<size_t>(f0) * (n / 2) * (n / 2) * 2 * c;
     GemmDesc d;
     d.M = rows_out; d.N = 2 * c; d.K = 4 * c; d.A = act_a; d.lda = 4 * c; d.a_dtype = adt;
     d.W = h->down_w[l]; d.ldw = 4 * c; d.w_dtype = adt; d.bias = h->down_b[l]; d.epi = EPI_BIAS;
-    d.out = h->resid[l + 1]; d.ldo = 2 * c; d.out_dtype = DT_F32;
+    d.out = out; d.ldo = 2 * c; d.out_dtype = DT_F32;
     TapInfo ti;
-    ti.ptr = h->resid[l + 1]; ti.dtype = DT_F32; ti.C = 2 * c; ti.HW = (n / 2) * (n / 2); ti.ld = 2 * c;
+    ti.ptr = out; ti.dtype = DT_F32; ti.C = 2 * c; ti.HW = (n / 2) * (n / 2); ti.ld = 2 * c;
     g_label = fmt("down%d", l);
-    add_gemm(h, P, d, static_cast<long long>(h->Bcap) * (n / 2) * (n / 2), "downs." + std::to_string(l), ti);
-  }
-  if (g_chain && !debug && bf && h->sp[4] == 1 && h->blocks[bi].dw_folded) {
-    // the 8 bottleneck blocks as one persistent cooperative kernel (chain.cuh); norm1 of the first block first
-    const BlockW& b0 = h->blocks[bi];
-    const int c = b0.c, rows = B;
-    const float* resid = h->resid[4];
-    void* act_a = h->act_a;
-    ModRef mod{h->mod_table, h->row_idx, h->mod_stride};
-    const float *lw = b0.ln1_w, *lb = b0.ln1_b;
-    const int so = b0.mod_off, co = b0.mod_off + c;
-    g_label = "L4 chain ln1";
-    add_op(P, [=](cudaStream_t st) { launch_ln<bf16>(c, resid, lw, lb, static_cast<bf16*>(act_a), rows, 1, mod, so, co, 1, st); });
-    add_chain_1x1(h, P, bi, kMidBlocks);
-    bi += kMidBlocks;
-  } else {
-    for (int i = 0; i < kMidBlocks; ++i, ++bi)
-      add_block(h, P, h->blocks[bi], "middle_blks." + std::to_string(i), i + 1 < kMidBlocks ? &h->blocks[bi + 1] : nullptr,
-                i > 0);
-  }
-  if (h->fused) add_hca(h, P, 0, 4);
-  for (int L = 0; L < 4; ++L) {
+    add_gemm(h, P, d, cx_rows_alloc(h, P, (n / 2) * (n / 2)), "downs." + std::to_string(l), ti);
+  };
+  auto emit_up = [&](int L) {  // 1x1 conv + PixelShuffle(2) + skip add: level 4 - L -> resid[3 - L] (in place on the skip)
+    const int Bq = cx_batch(P), f0 = P.cx.f0;
     const int lin = 4 - L, lout = 3 - L;
-    const int cin = h->c[lin], n = h->sp[lin], rows_in = B * n * n;
+    const int cin = h->c[lin], n = h->sp[lin], rows_in = Bq * n * n;
     const void* a_ptr;
     if (h->fused) {
-      a_ptr = h->hca_out;
+      a_ptr = cx_slab(P, h->hca_out, h->act_bytes);
     } else {
-      const float* src = h->resid[lin];
-      void* act_a = h->act_a;
+      const float* src = h->resid[lin] + static_cast<size_t>(f0) * n * n * cin;
+      void* act_a = cx_slab(P, h->act_a, h->act_bytes);
       a_ptr = act_a;
       g_label = fmt("up%d cast", L);
       add_op(P, [=](cudaStream_t st) {
@@ -1560,30 +1584,97 @@ Plan* get_plan(hd_handle* h, int B, bool debug = false) {
         else launch_k(cast_kernel<float>, dim3(cdiv(total8, 256)), dim3(256), 0, st, src, static_cast<float*>(act_a), total8);
       });
     }
+    float* out = h->resid[lout] + static_cast<size_t>(f0) * 4 * n * n * (cin / 2);
     GemmDesc d;
     d.M = rows_in; d.N = 2 * cin; d.K = cin; d.A = a_ptr; d.lda = cin; d.a_dtype = adt;
     d.W = h->up_w[L]; d.ldw = cin; d.w_dtype = adt; d.bias = nullptr; d.epi = EPI_PIXSHUF; d.sp = n;
-    d.out = h->resid[lout]; d.ldo = cin / 2; d.out_dtype = DT_F32;
+    d.out = out; d.ldo = cin / 2; d.out_dtype = DT_F32;
     TapInfo ti;
-    ti.ptr = h->resid[lout]; ti.dtype = DT_F32; ti.C = cin / 2; ti.HW = 4 * n * n; ti.ld = cin / 2;
+    ti.ptr = out; ti.dtype = DT_F32; ti.C = cin / 2; ti.HW = 4 * n * n; ti.ld = cin / 2;
     g_label = fmt("up%d", L);
-    add_gemm(h, P, d, static_cast<long long>(h->Bcap) * n * n, "ups." + std::to_string(L), ti);
-    if (face_blocks_ok(h, bi, kDecBlocks[L], debug)) {
-      add_face_blocks(h, P, bi, kDecBlocks[L]);
-      bi += kDecBlocks[L];
-    } else if (pair_blocks_ok(h, bi, kDecBlocks[L], debug)) {
-      add_pair_blocks(h, P, bi, kDecBlocks[L]);
-      bi += kDecBlocks[L];
-    } else if (quad_blocks_ok(h, bi, kDecBlocks[L], debug)) {
-      add_quad_blocks(h, P, bi, kDecBlocks[L]);
-      bi += kDecBlocks[L];
+    add_gemm(h, P, d, cx_rows_alloc(h, P, n * n), "ups." + std::to_string(L), ti);
+  };
+  auto emit_mid = [&](size_t first) {
+    if (P.cx.nslab <= 1 && g_chain && !debug && bf && h->sp[4] == 1 && h->blocks[first].dw_folded) {
+      // the 8 bottleneck blocks as one persistent cooperative kernel (chain.cuh); norm1 of the first block first
+      const BlockW& b0 = h->blocks[first];
+      const int c = b0.c, rows = B;
+      const float* resid = h->resid[4];
+      void* act_a = h->act_a;
+      ModRef mod{h->mod_table, h->row_idx, h->mod_stride};
+      const float *lw = b0.ln1_w, *lb = b0.ln1_b;
+      const int so = b0.mod_off, co = b0.mod_off + c;
+      g_label = "L4 chain ln1";
+      add_op(P, [=](cudaStream_t st) { launch_ln<bf16>(c, resid, lw, lb, static_cast<bf16*>(act_a), rows, 1, mod, so, co, 1, st); });
+      add_chain_1x1(h, P, first, kMidBlocks);
     } else {
-      for (int i = 0; i < kDecBlocks[L]; ++i, ++bi)
-        add_block(h, P, h->blocks[bi], "decoders." + std::to_string(L) + "." + std::to_string(i),
-                  i + 1 < kDecBlocks[L] ? &h->blocks[bi + 1] : nullptr, i > 0);
+      emit_blocks(first, kMidBlocks, "middle_blks.");
     }
-    if (h->fused) add_hca(h, P, L + 1, lout);
+  };
+  // block index of the first block of each stage, in execution order
+  size_t enc_first[4], dec_first[4], mid_first;
+  {
+    size_t bi = 0;
+    for (int l = 0; l < 4; ++l) { enc_first[l] = bi; bi += kEncBlocks[l]; }
+    mid_first = bi; bi += kMidBlocks;
+    for (int L = 0; L < 4; ++L) { dec_first[L] = bi; bi += kDecBlocks[L]; }
   }
+  // Split region (HD_SPLIT): everything from down1 to up2 — the 4x4, 2x2 and 1x1 levels — built once per
+  // face-range chain.  Chains touch disjoint faces of the per-level tensors and private slabs of the scratch
+  // buffers, so they are independent between the fork (after the 8x8 encoder) and the join (before the 8x8
+  // decoder); the ops are interleaved round-robin so plain launches alternate streams too.
+  const int n_chains = (!debug && bf && h->split > 1 && B >= 16 * h->split) ? h->split : 1;
+  P.n_chains = n_chains;
+  auto emit_inner = [&]() {
+    emit_down(1);
+    emit_blocks(enc_first[2], kEncBlocks[2], "encoders.2.");
+    emit_down(2);
+    emit_blocks(enc_first[3], kEncBlocks[3], "encoders.3.");
+    emit_down(3);
+    emit_mid(mid_first);
+    if (h->fused) add_hca(h, P, 0, 4);
+    emit_up(0);
+    emit_blocks(dec_first[0], kDecBlocks[0], "decoders.0.");
+    if (h->fused) add_hca(h, P, 1, 3);
+    emit_up(1);
+    emit_blocks(dec_first[1], kDecBlocks[1], "decoders.1.");
+    if (h->fused) add_hca(h, P, 2, 2);
+    emit_up(2);
+  };
+  emit_blocks(enc_first[0], kEncBlocks[0], "encoders.0.");
+  emit_down(0);
+  emit_blocks(enc_first[1], kEncBlocks[1], "encoders.1.");
+  if (n_chains == 1) {
+    emit_inner();
+  } else {
+    const size_t region_begin = P.ops.size();
+    std::vector<std::vector<Op>> per_chain(n_chains);
+    const int per = cdiv(B, n_chains);
+    const double flops_before = P.flops_per_face;
+    for (int j = 0; j < n_chains; ++j) {
+      P.cx.id = j; P.cx.nslab = n_chains; P.cx.f0 = j * per; P.cx.nf = std::min(per, B - j * per);
+      P.cx.cta_target = std::max(120 / n_chains, 24);
+      emit_inner();
+      per_chain[j].assign(std::make_move_iterator(P.ops.begin() + region_begin), std::make_move_iterator(P.ops.end()));
+      P.ops.resize(region_begin);
+      for (auto& op : per_chain[j]) op.tap.clear();  // a chain sees only its faces: taps come from the per-op plan
+    }
+    P.cx = ChainCx();
+    // add_gemm divides by the whole batch, so the chains' shares already add up to one face
+    (void)flops_before;
+    size_t longest = 0;
+    for (auto& v : per_chain) longest = std::max(longest, v.size());
+    for (size_t i = 0; i < longest; ++i)
+      for (int j = 0; j < n_chains; ++j)
+        if (i < per_chain[j].size()) P.ops.push_back(std::move(per_chain[j][i]));
+    P.ops[region_begin].fork = true;
+    P.ops.back().join = true;
+  }
+  emit_blocks(dec_first[2], kDecBlocks[2], "decoders.2.");
+  if (h->fused) add_hca(h, P, 3, 1);
+  emit_up(3);
+  emit_blocks(dec_first[3], kDecBlocks[3], "decoders.3.");
+  if (h->fused) add_hca(h, P, 4, 0);
   {  // ending
     const float *w = h->end_w, *b = h->end_b;
     const void* in = h->fused ? h->hca_out : static_cast<const void*>(h->resid[0]);
@@ -1976,10 +2067,26 @@ void join_out(hd_handle* h, void* user_stream) {
   CUDA_CHECK(cudaStreamWaitEvent(us, h->ev_out, 0));
 }
 
+// Issues one op of a plan: ops of a split region go to their chain's stream; the fork / join edges are event
+// waits, which stream capture turns into parallel branches of the step's CUDA graph.
+void exec_op(hd_handle* h, const Op& op, cudaStream_t st, int n_chains) {
+  if (op.fork) {
+    cudaEventRecord(h->ev_fork, st);
+    for (int j = 0; j + 1 < n_chains; ++j) cudaStreamWaitEvent(h->side[j], h->ev_fork, 0);
+  }
+  op.fn(op.chain == 0 ? st : h->side[op.chain - 1]);
+  if (op.join) {
+    for (int j = 0; j + 1 < n_chains; ++j) {
+      cudaEventRecord(h->ev_join[j], h->side[j]);
+      cudaStreamWaitEvent(st, h->ev_join[j], 0);
+    }
+  }
+}
+
 void run_plan(hd_handle* h, Plan* P, cudaStream_t st, const char* const* tap_names, float* const* tap_out, int n_taps,
               int B) {
   for (auto& op : P->ops) {
-    op.fn(st);
+    exec_op(h, op, st, P->n_chains);
     if (n_taps > 0 && !op.tap.empty()) {
       for (int i = 0; i < n_taps; ++i) {
         if (op.tap != tap_names[i]) continue;
@@ -2087,6 +2194,11 @@ void hd_destroy(hd_handle* h) {
   h->arena.release();
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int j = 0; j < kMaxSplit - 1; ++j) {
+    if (h->ev_join[j]) cudaEventDestroy(h->ev_join[j]);
+    if (h->side[j]) cudaStreamDestroy(h->side[j]);
+  }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -2111,6 +2223,9 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10) HD_THROW(HD_ERR_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
   if (const char* e = getenv("HD_PDL")) g_use_pdl = atoi(e) != 0;
+  if (const char* e = getenv("HD_CTA_TARGET")) g_cta_target = std::max(atoi(e), 1);
+  if (const char* e = getenv("HD_SCA_TARGET")) g_sca_target = std::max(atoi(e), 1);
+  if (const char* e = getenv("HD_SPLIT")) g_split = std::min(std::max(atoi(e), 1), kMaxSplit);
   if (const char* e = getenv("HD_FUSE_DW")) g_fuse_dw = atoi(e) == 1 ? 14 : atoi(e);
   if (const char* e = getenv("HD_BN256")) g_bn256 = atoi(e) != 0;
   if (const char* e = getenv("HD_TWO_CTA")) g_two_cta = atoi(e);
@@ -2124,6 +2239,7 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   h = new hd_handle();
   struct Guard { hd_handle*& p; bool armed = true; ~Guard() { if (armed && p) { hd_destroy(p); p = nullptr; } } } guard{h};
   h->cfg = *cfg;
+  h->split = g_split;
   h->fused = cfg->model == HD_MODEL_FUSED;
   h->bf16 = cfg->precision == HD_PRECISION_BF16;
   h->S = cfg->latent_size;
@@ -2134,6 +2250,11 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  for (int j = 0; j < kMaxSplit - 1; ++j) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&h->side[j], cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_join[j], cudaEventDisableTiming));
+  }
   {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -2173,12 +2294,14 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
     h->resid[l] = A.get<float>(pc);
     max_pc = std::max(max_pc, pc);
   }
+  h->act_bytes = max_pc * as;
   h->act_a = A.alloc(max_pc * as);
   h->act_h = A.alloc(2 * max_pc * as);
   h->act_g = A.alloc(max_pc * as);
   h->hca_out = A.alloc(max_pc * as);
-  h->pooled = A.alloc(Bc * 2048 * as);
-  h->sca_s = A.get<float>(Bc * 2048);
+  h->pooled_rows = Bc + 128 * kMaxSplit;  // split chains round their face capacity up to whole 128-row tiles
+  h->pooled = A.alloc(h->pooled_rows * 2048 * as);
+  h->sca_s = A.get<float>(h->pooled_rows * 2048);
   if (!h->bf16) h->gate_tmp = A.get<float>(2 * max_pc);
   const size_t xe = Bc * 4 * h->S * h->S;
   h->x_state = A.get<float>(xe);
@@ -2388,7 +2511,7 @@ int32_t hd_sample(hd_handle* h, float* x_inout, const hd_step_coef* coef, int32_
   int* ridx = h->row_idx;
   const int Bcap = h->Bcap;
   auto one_step = [&](cudaStream_t s) {
-    for (auto& op : P->ops) op.fn(s);
+    for (auto& op : P->ops) exec_op(h, op, s, P->n_chains);
     launch_k(sampler_update_kernel, dim3(cdiv(threads, 256)), dim3(256), 0, s, xs, eb, cf, ss, 0, noise, seed, first_face, B, epf);
     launch_k(advance_rows_kernel, dim3(1), dim3(256), 0, s, ss, ridx, Bcap);
   };
