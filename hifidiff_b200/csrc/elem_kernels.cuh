@@ -419,6 +419,92 @@ __global__ void __launch_bounds__(256, 2) dwconv_gate_pool_kernel(const T* __res
   }
 }
 
+// The same op at the 2x2 and 4x4 levels, where a face is 4 / 16 pixels: one thread owns 4 gate channels of one
+// face, holds all of the face's pixels in registers (x1 pass, then x2 pass multiplied in), and needs no shared
+// memory, no halo and no cross-thread reduction for the pool.  A warp reads 128 consecutive channels per pixel
+// (256 B of bf16).  Same FMA and summation order as dwconv_gate_pool_kernel (zero-padding taps are skipped:
+// they add exact zeros), so both kernels produce the same bits.
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void ld4(const bf16* p, float (&v)[4]) {
+  const uint2 a = *reinterpret_cast<const uint2*>(p);
+  float2 f = unpack_bf16x2(a.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16x2(a.y); v[2] = f.x; v[3] = f.y;
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void st4(bf16* p, const float (&v)[4]) {
+  uint2 a;
+  a.x = pack_bf16x2(v[0], v[1]);
+  a.y = pack_bf16x2(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = a;
+}
+
+template <typename T, int SP>
+__global__ void __launch_bounds__(256) dwconv_small_kernel(const T* __restrict__ h, const float* __restrict__ w9,
+                                                           const float* __restrict__ bias, T* __restrict__ g,
+                                                           T* __restrict__ pooled, int c, int faces) {
+  constexpr int NP = SP * SP, CH = 4;
+  pdl_trigger();
+  const int per_face = c / CH;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int face = static_cast<int>(i / per_face);
+  const int j = static_cast<int>(i - static_cast<size_t>(face) * per_face) * CH;
+  const int C2 = 2 * c;
+  pdl_wait();
+  if (face >= faces) return;
+  float res[NP][CH];
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    float in[NP][CH], wt[9][CH], b[CH];
+    const T* src = h + static_cast<size_t>(face) * NP * C2 + hf * c + j;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) ld4(src + static_cast<size_t>(p) * C2, in[p]);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) ld4(w9 + t * C2 + hf * c + j, wt[t]);
+    ld4(bias + hf * c + j, b);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const int y = p / SP, x = p % SP;
+      float a[CH];
+#pragma unroll
+      for (int e = 0; e < CH; ++e) a[e] = b[e];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int yy = y + r - 1, xx = x + k - 1;
+          if (yy < 0 || yy >= SP || xx < 0 || xx >= SP) continue;
+#pragma unroll
+          for (int e = 0; e < CH; ++e) a[e] = fmaf(in[yy * SP + xx][e], wt[r * 3 + k][e], a[e]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < CH; ++e) res[p][e] = hf == 0 ? a[e] : res[p][e] * a[e];
+    }
+  }
+  float tot[CH] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int x = 0; x < SP; ++x) {
+    float s[CH] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int y = 0; y < SP; ++y)
+#pragma unroll
+      for (int e = 0; e < CH; ++e) s[e] += res[y * SP + x][e];
+#pragma unroll
+    for (int e = 0; e < CH; ++e) tot[e] += s[e];
+  }
+  T* dst = g + static_cast<size_t>(face) * NP * c + j;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) st4(dst + static_cast<size_t>(p) * c, res[p]);
+#pragma unroll
+  for (int e = 0; e < CH; ++e) tot[e] = tot[e] / static_cast<float>(NP);
+  st4(pooled + static_cast<size_t>(face) * c + j, tot);
+}
+
 // g[m, k] *= s[face(m), k]   (the SCA channel scale, conditional_naf.py:119)
 template <typename T>
 __global__ void __launch_bounds__(256) scale_rows_kernel(T* __restrict__ g, const float* __restrict__ s, size_t total8,

@@ -73,6 +73,7 @@ bool g_chain = false;   // HD_CHAIN=1: run the 1x1-level blocks as one persisten
 // with 2 chains, 2.41 with 3, 2.37 with 4, against 2.16 unsplit — these kernels are latency-bound, so a
 // half-size kernel takes as long as a full-size one and concurrency buys nothing.
 int g_split = 1;
+bool g_dw_small = true;  // HD_DW_SMALL=0: the generic tiled depthwise kernel at the 2x2 / 4x4 levels too
 int g_cta_target = 120;  // HD_CTA_TARGET: split-K until a GEMM's grid has at least this many CTAs
 int g_sca_target = 120;  // HD_SCA_TARGET: the same for the SCA GEMMs (M = faces)
 constexpr int kMaxSplit = 4;
@@ -987,6 +988,15 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
   g_label = L0 + "dwconv_gate_pool";
   if (!bw.dw_folded && !bw.dw_fused) {  // depthwise 3x3 + SimpleGate + pool
     const float *dw_w = bw.dw_w, *dw_b = bw.dw_b;
+    if (g_dw_small && (sp == 2 || sp == 4) && c % 4 == 0) {  // register-resident faces (dwconv_small_kernel)
+      add_op(P, [=](cudaStream_t st) {
+        const dim3 grid(cdiv(static_cast<size_t>(B) * (c / 4), 256));
+        if (bf && sp == 2) launch_k(dwconv_small_kernel<bf16, 2>, grid, dim3(256), 0, st, static_cast<const bf16*>(act_h), dw_w, dw_b, static_cast<bf16*>(act_g), static_cast<bf16*>(pooled), c, B);
+        else if (bf) launch_k(dwconv_small_kernel<bf16, 4>, grid, dim3(256), 0, st, static_cast<const bf16*>(act_h), dw_w, dw_b, static_cast<bf16*>(act_g), static_cast<bf16*>(pooled), c, B);
+        else if (sp == 2) launch_k(dwconv_small_kernel<float, 2>, grid, dim3(256), 0, st, static_cast<const float*>(act_h), dw_w, dw_b, static_cast<float*>(act_g), static_cast<float*>(pooled), c, B);
+        else launch_k(dwconv_small_kernel<float, 4>, grid, dim3(256), 0, st, static_cast<const float*>(act_h), dw_w, dw_b, static_cast<float*>(act_g), static_cast<float*>(pooled), c, B);
+      });
+    } else
     add_op(P, [=](cudaStream_t st) {
       const int tile_px = sp >= 16 ? sp * sp : 64;   // whole faces per tile; small tiles below 16x16 for parallelism
       dim3 grid(c / 64, cdiv(rows, tile_px));
@@ -2223,6 +2233,7 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10) HD_THROW(HD_ERR_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
   if (const char* e = getenv("HD_PDL")) g_use_pdl = atoi(e) != 0;
+  if (const char* e = getenv("HD_DW_SMALL")) g_dw_small = atoi(e) != 0;
   if (const char* e = getenv("HD_CTA_TARGET")) g_cta_target = std::max(atoi(e), 1);
   if (const char* e = getenv("HD_SCA_TARGET")) g_sca_target = std::max(atoi(e), 1);
   if (const char* e = getenv("HD_SPLIT")) g_split = std::min(std::max(atoi(e), 1), kMaxSplit);
