@@ -20,6 +20,7 @@
 #include "pair_block.cuh"
 #include "quad_block.cuh"
 #include "idc_kernels.cuh"
+#include "sca_kernel.cuh"
 
 using namespace hd;
 
@@ -73,6 +74,10 @@ bool g_chain = false;   // HD_CHAIN=1: run the 1x1-level blocks as one persisten
 // with 2 chains, 2.41 with 3, 2.37 with 4, against 2.16 unsplit — these kernels are latency-bound, so a
 // half-size kernel takes as long as a full-size one and concurrency buys nothing.
 int g_split = 1;
+// HD_SCA_FUSED=1: SCA GEMM + rescale as one mma.sync kernel (sca_kernel.cuh).  Parity-green, measured slower at
+// B=256 (9.4 / 10.1 / 17.4 us at the 4x4 / 2x2 / 1x1 levels against 8.0 / 10.3 / 10.7 for the split-K tcgen05 GEMM
+// + rescale): 64x32 tiles without split-K make every CTA ingest its whole A and W panels at ~60 B/clk/SM.
+bool g_sca_fused = false;
 bool g_dw_small = true;  // HD_DW_SMALL=0: the generic tiled depthwise kernel at the 2x2 / 4x4 levels too
 int g_cta_target = 120;  // HD_CTA_TARGET: split-K until a GEMM's grid has at least this many CTAs
 int g_sca_target = 120;  // HD_SCA_TARGET: the same for the SCA GEMMs (M = faces)
@@ -1007,30 +1012,48 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
     });
     P.flops_per_face += 2.0 * 9 * 2 * c * rpf;
   }
-  g_label = L0 + "sca";
-  {  // SCA 1x1 on the pooled vector
-    GemmDesc d;
-    d.M = B; d.N = c; d.K = c; d.A = bw.dw_folded ? act_g : pooled; d.lda = c; d.a_dtype = adt;
-    d.W = bw.wsca; d.ldw = c; d.w_dtype = adt; d.bias = bw.bsca; d.epi = EPI_BIAS;
-    d.out = sca_s; d.ldo = c; d.out_dtype = DT_F32;
-    if (P.cx.nslab <= 1) d.cta_target = g_sca_target;
-    if (fuse_scale) {  // the face's rows are rescaled by the SCA GEMM's own epilogue, out of place into act_h
-      d.epi = EPI_SCALE; d.scale_src = act_g; d.scale_dst = act_h; d.scale_ld = c; d.rows_per_face = rpf;
+  const bool sca_fused = bf && g_sca_fused && !fuse_scale && c % sca::BK == 0 && rpf <= 16;  // 4x4, 2x2, 1x1 levels
+  if (sca_fused) {  // SCA GEMM + rescale of the face's rows in one mma.sync kernel, out of place into act_h
+    const bf16* a_src = static_cast<const bf16*>(bw.dw_folded ? act_g : pooled);
+    const bf16* wsca = static_cast<const bf16*>(bw.wsca);
+    const float* bsca = bw.bsca;
+    static bool configured = false;
+    if (!configured) {
+      CUDA_CHECK(cudaFuncSetAttribute(sca::sca_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sca::SMEM_BYTES));
+      configured = true;
     }
-    add_gemm(h, P, d, cx_rows_alloc(h, P, 1));
-  }
-  if (!fuse_scale) {
-    g_label = L0 + "scale_rows";
+    g_label = L0 + fmt("sca+scale mma.sync M=%d N=%d K=%d grid=(%d,%d)", B, c, c, c / sca::BN, cdiv(B, sca::BM));
     add_op(P, [=](cudaStream_t st) {
-      const size_t total8 = static_cast<size_t>(rows) * c / 8;
-      if (bf) launch_k(scale_rows_kernel<bf16>, dim3(cdiv(total8, 256)), dim3(256), 0, st, static_cast<bf16*>(act_g), sca_s, total8, c, rpf);
-      else launch_k(scale_rows_kernel<float>, dim3(cdiv(total8, 256)), dim3(256), 0, st, static_cast<float*>(act_g), sca_s, total8, c, rpf);
+      launch_k(sca::sca_scale_kernel, dim3(c / sca::BN, cdiv(B, sca::BM)), dim3(sca::THREADS), sca::SMEM_BYTES, st, a_src, wsca, bsca,
+               static_cast<const bf16*>(act_g), static_cast<bf16*>(act_h), sca_s, B, c, rpf);
     });
+    P.flops_per_face += 2.0 * c * static_cast<double>(c);
+  } else {
+    g_label = L0 + "sca";
+    {  // SCA 1x1 on the pooled vector
+      GemmDesc d;
+      d.M = B; d.N = c; d.K = c; d.A = bw.dw_folded ? act_g : pooled; d.lda = c; d.a_dtype = adt;
+      d.W = bw.wsca; d.ldw = c; d.w_dtype = adt; d.bias = bw.bsca; d.epi = EPI_BIAS;
+      d.out = sca_s; d.ldo = c; d.out_dtype = DT_F32;
+      if (P.cx.nslab <= 1) d.cta_target = g_sca_target;
+      if (fuse_scale) {  // the face's rows are rescaled by the SCA GEMM's own epilogue, out of place into act_h
+        d.epi = EPI_SCALE; d.scale_src = act_g; d.scale_dst = act_h; d.scale_ld = c; d.rows_per_face = rpf;
+      }
+      add_gemm(h, P, d, cx_rows_alloc(h, P, 1));
+    }
+    if (!fuse_scale) {
+      g_label = L0 + "scale_rows";
+      add_op(P, [=](cudaStream_t st) {
+        const size_t total8 = static_cast<size_t>(rows) * c / 8;
+        if (bf) launch_k(scale_rows_kernel<bf16>, dim3(cdiv(total8, 256)), dim3(256), 0, st, static_cast<bf16*>(act_g), sca_s, total8, c, rpf);
+        else launch_k(scale_rows_kernel<float>, dim3(cdiv(total8, 256)), dim3(256), 0, st, static_cast<float*>(act_g), sca_s, total8, c, rpf);
+      });
+    }
   }
   g_label = L0 + "conv3";
   {  // conv3 (+beta) + residual
     GemmDesc d;
-    d.M = rows; d.N = c; d.K = c; d.A = fuse_scale ? act_h : act_g; d.lda = c; d.a_dtype = adt;
+    d.M = rows; d.N = c; d.K = c; d.A = (fuse_scale || sca_fused) ? act_h : act_g; d.lda = c; d.a_dtype = adt;
     d.W = bw.w3; d.ldw = c; d.w_dtype = adt; d.bias = bw.b3; d.epi = EPI_RESID;
     d.out = resid; d.ldo = c; d.out_dtype = DT_F32; d.resid = resid; d.ldr = c;
     if (fuse_ln) fused_ln(d, bw.ln2_w, bw.ln2_b, bw.mod_off + 2 * c, bw.mod_off + 3 * c);
@@ -2233,6 +2256,7 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10) HD_THROW(HD_ERR_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
   if (const char* e = getenv("HD_PDL")) g_use_pdl = atoi(e) != 0;
+  if (const char* e = getenv("HD_SCA_FUSED")) g_sca_fused = atoi(e) != 0;
   if (const char* e = getenv("HD_DW_SMALL")) g_dw_small = atoi(e) != 0;
   if (const char* e = getenv("HD_CTA_TARGET")) g_cta_target = std::max(atoi(e), 1);
   if (const char* e = getenv("HD_SCA_TARGET")) g_sca_target = std::max(atoi(e), 1);

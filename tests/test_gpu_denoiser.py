@@ -141,9 +141,11 @@ def test_fused_face_kernel_taps_and_plans_agree():
     m.invalidate()
 
 
-@pytest.mark.parametrize("flag,names", [("HD_QUAD", ["encoders.2.3", "decoders.1.1"]), ("HD_CHAIN", [])])
+@pytest.mark.parametrize("flag,names", [("HD_QUAD", ["encoders.2.3", "decoders.1.1"]), ("HD_CHAIN", []),
+                                        ("HD_SCA_FUSED", ["encoders.2.3", "encoders.3.7", "middle_blks.7"])])
 def test_experimental_kernels_keep_parity(flag, names):
-    """Kernels that are built but off by default (4-CTA-cluster block kernel at 4x4, persistent chain at 1x1)."""
+    """Kernels that are built but off by default (4-CTA-cluster block kernel at 4x4, persistent chain at 1x1,
+    mma.sync SCA + rescale kernel at 4x4..1x1)."""
     import os
     os.environ[flag] = "1"
     try:
