@@ -306,6 +306,50 @@ def main():
     ms_e2e, _ = timed(step_e2e, args.steps)
     model.engine().synchronize()
 
+    # the condition networks of the refiner cascade (FPG over the CR latent, IDC ResNet-50 over the CR face), native,
+    # once per batch of faces and outside the timed sampling pass: reported for BASELINE.json configs[4]
+    cond_nets = None
+    if rank == 0 and args.precision == "bf16":
+        try:
+            from hifidiff_b200.conditioning import FacialPriorGuidance, ResNet50
+            eng = model.engine()
+
+            def rand_state(mod, seed):
+                with torch.device("meta"):
+                    mm = mod()
+                s0 = mm.state_dict()
+                return {k: v.to(dev) for k, v in testing.random_state({k: v.shape for k, v in s0.items()},
+                                                                      {k: v.dtype for k, v in s0.items()}, seed=seed).items()}
+            if not eng.fpg_loaded:
+                eng.load_fpg_state(rand_state(FacialPriorGuidance, 7))
+            if not eng.idc_loaded:
+                eng.load_idc_state(rand_state(ResNet50, 8))
+            face_h = torch.rand((B, 3, 128, 128), generator=torch.Generator().manual_seed(5)).pin_memory()
+            lat_h = torch.randn((B, 4, 16, 16), generator=torch.Generator().manual_seed(6)).pin_memory()
+
+            def cond_pass():
+                f = face_h.to(dev, non_blocking=True)
+                l = lat_h.to(dev, non_blocking=True)
+                return eng.fpg_forward(l), eng.idc_forward(f)
+            cond_pass()
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            for _ in range(3):
+                f = face_h.to(dev, non_blocking=True)
+                idn = eng.idc_forward(f)
+            ev[1].record()
+            for _ in range(3):
+                pri = eng.fpg_forward(lat_h.to(dev, non_blocking=True))
+            ev[2].record()
+            torch.cuda.synchronize()
+            cond_nets = {"faces": B, "idc_resnet50_ms": ev[0].elapsed_time(ev[1]) / 3, "fpg_ms": ev[1].elapsed_time(ev[2]) / 3,
+                         "h2d_bytes": face_h.numel() * 4 + lat_h.numel() * 4,
+                         "finite": bool(torch.isfinite(idn).all().item() and all(torch.isfinite(p).all().item() for p in pri)),
+                         "note": "hd_idc_forward / hd_fpg_forward from pinned host inputs, once per batch of faces (t-invariant)"}
+        except Exception as exc:  # the headline number must not depend on this side measurement
+            cond_nets = {"error": str(exc)[:200]}
+
     info = model.engine().info()
     if rank == 0:
         peaks = load_peaks()
@@ -341,6 +385,7 @@ def main():
             },
             "clocks": clock_info,
             "finite": finite,
+            "condition_nets": cond_nets,
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args)

@@ -11,6 +11,6 @@ timeout 600 ncu --metrics $M --clock-control none --profile-from-start off --csv
     --log-file gpurun_out/${tag}_launches_metrics_B256.csv python tools/profile_sampler_step.py 256 > gpurun_out/ncu1.log 2>&1
 echo "ncu launches rc=$?"
 python tools/summarize_metrics.py gpurun_out/${tag}_launches_metrics_B256.csv gpurun_out/${tag}_traffic.json > gpurun_out/${tag}_launches_metrics_B256.summary.txt; head -30 gpurun_out/${tag}_launches_metrics_B256.summary.txt
-timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:$kre -c 1 \
+timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k "regex:$kre" -c 1 \
     -f -o gpurun_out/${tag}_prof_full python tools/profile_sampler_step.py 256 > gpurun_out/ncu2.log 2>&1
 echo "ncu full rc=$?"
