@@ -119,3 +119,35 @@ def test_ddpm_trajectory_matches_oracle_loop():
                              xT, o, 20, noise_fn=lambda i, t: z[i].reshape(2, 4, 16, 16))
     assert psnr(got, want) >= 80.0
     m.invalidate()
+
+
+@pytest.mark.parametrize("prec,min_psnr", [("fp32", 80.0), ("bf16", 35.0)])
+def test_refiner_cascade_trajectory(prec, min_psnr):
+    """BASELINE.json configs[4] scaled down: the whole cascade through the sampler call the reference makes
+    (`ddim_sample(refiner, ..., cr_face, cr_latent)`, train_refiner.py:86-125 between x_T and the VAE decode) —
+    IDC ResNet-50 + FPG + FusedDenoiser all native, 10 DDIM steps, 3 faces, against the oracle's cascade; then the
+    same faces sharded 2 + 1 with the condition recomputed per shard."""
+    from oracle import cond_ref
+    m, sd = build(H.FacialRefiner, seed=3, precision=prec, eps_gain=TRAJ_EPS_GAIN, max_batch=4, max_steps=10, args=())
+    sched = H.DDIMScheduler(num_train_timesteps=1000, beta_schedule="scaled_linear", prediction_type="epsilon",
+                            clip_sample=False)
+    xT = inputs("latents", 3, seed=21)
+    cr_face, cr_latent = inputs("cr_face", 3), inputs("cr_latent", 3)
+    x0 = H.ddim_sample(m, xT.cuda(), sched, 10, cr_face=cr_face.cuda(), cr_latent=cr_latent.cuda())
+    m.denoiser.engine().synchronize()
+    with torch.no_grad():
+        priors = cond_ref.fpg_forward(sd, cr_latent, "fpg.")
+        ident = cond_ref.idc_forward(sd, cr_face, "idc.")
+        want = R.sample_loop(lambda xx, tt: denoiser_ref.fused_denoiser_forward(sd, xx, tt, priors, ident, prefix="denoiser."),
+                             xT, R.DDIMSchedulerRef(clip_sample=False), 10)
+    q = psnr(x0, want)
+    print(f"refiner cascade DDIM-10 {prec}: PSNR vs oracle x0 = {q:.2f} dB, rel-L2 {rel_l2(x0, want):.3e}")
+    assert q >= min_psnr
+    lo = H.ddim_sample(m, xT[:2].contiguous().cuda(), sched, 10, cr_face=cr_face[:2].contiguous().cuda(),
+                       cr_latent=cr_latent[:2].contiguous().cuda())
+    hi = H.ddim_sample(m, xT[2:].contiguous().cuda(), sched, 10, cr_face=cr_face[2:].contiguous().cuda(),
+                       cr_latent=cr_latent[2:].contiguous().cuda(), first_face=2)
+    m.denoiser.engine().synchronize()
+    # split-K depth may differ with the number of row tiles, so shards agree to round-off, not always to the bit
+    assert rel_l2(torch.cat([lo, hi]), x0) <= 2e-3
+    m.denoiser.invalidate()
