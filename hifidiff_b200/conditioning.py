@@ -4,12 +4,13 @@
   ResNet50 (IDC)       <- models/idc/model.py:10-55,102-166
   FacialRefiner        <- models/refiner.py:10-38
 
-These are SURVEY.md §8(f) "next" rows 1-2: they depend on neither x_t nor t, cost ~3.7 GFLOP per
-face against >= 104 GFLOP for the sampling loop, and for now run as ordinary PyTorch/cuDNN eager
-modules with the reference's exact `state_dict()` layout.  What *is* native is everything the
-per-timestep loop touches: `FacialRefiner` computes the priors and the identity embedding once
-per (cr_face, cr_latent) pair and hands them to the sm_100a `FusedDenoiser`, instead of
-recomputing them at every step as refiner.py:33-34 does (same result: they are t-invariant).
+These are SURVEY.md §8(f) "next" rows 1-2: they depend on neither x_t nor t and cost ~5 GFLOP per face
+against >= 104 GFLOP for the sampling loop.  The nn.Modules below keep the reference's exact
+`state_dict()` layout (and a PyTorch eager `forward` used by the parity tests); on a CUDA device
+`FacialRefiner.condition` runs both networks on the sm_100a kernels instead (`hd_fpg_forward`,
+`hd_idc_forward`; switches `native_fpg` / `native_idc`), once per (cr_face, cr_latent) pair, and hands
+the priors and the identity embedding to the sm_100a `FusedDenoiser` — instead of recomputing them at
+every step as refiner.py:33-34 does (same result: they are t-invariant).
 """
 from __future__ import annotations
 
