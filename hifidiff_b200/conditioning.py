@@ -175,7 +175,13 @@ class FacialRefiner(nn.Module):
                     priors = eng.fpg_forward(cr_latent, self.denoiser.config.sample_size, self.denoiser.width)
                 else:
                     priors = self.fpg(cr_latent)
-                if self.native_idc and cr_face.device.type == "cuda" and cr_face.shape[-1] == 8 * self.denoiser.config.sample_size:
+                if self.native_idc and cr_face.device.type == "cuda":
+                    want = 8 * self.denoiser.config.sample_size
+                    if cr_face.shape[-1] != want or cr_face.shape[-2] != want:
+                        # no silent detour through PyTorch: the native ResNet-50 is built for the pipeline's face size
+                        raise ValueError(f"cr_face must be (B,3,{want},{want}) for latent size "
+                                         f"{self.denoiser.config.sample_size}; set native_idc=False to run the "
+                                         f"PyTorch module on other sizes")
                     eng = self.denoiser.engine(cr_face.shape[0])
                     if not eng.idc_loaded:
                         eng.load_idc_state(self.idc.state_dict())
