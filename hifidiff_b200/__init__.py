@@ -6,9 +6,10 @@ the C ABI in `include/hifidiff_b200.h`.  See DESIGN.md.
 """
 from .modules import Denoiser, FusedDenoiser, UNet2DOutput
 from .conditioning import FacialPriorGuidance, FacialRefiner, ResNet50
+from .restoration import CoarseRestoration
 from .schedulers import DDIMScheduler, DDPMScheduler
 from .sampler import ddim_sample, ddpm_sample, sample, sample_sharded, shard_bounds
 
-__all__ = ["Denoiser", "FusedDenoiser", "UNet2DOutput", "FacialPriorGuidance", "FacialRefiner", "ResNet50",
+__all__ = ["Denoiser", "FusedDenoiser", "UNet2DOutput", "FacialPriorGuidance", "FacialRefiner", "ResNet50", "CoarseRestoration",
            "DDIMScheduler", "DDPMScheduler", "ddim_sample", "ddpm_sample", "sample", "sample_sharded",
            "shard_bounds"]

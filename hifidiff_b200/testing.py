@@ -42,6 +42,10 @@ def random_state(shapes: Dict[str, torch.Size], dtypes: Dict[str, torch.dtype], 
             t = torch.rand(shape, generator=g) + 0.5
         elif leaf == "running_mean":
             t = torch.randn(shape, generator=g) * 0.1
+        elif name.endswith("fc_loc.2.bias"):        # STN affine (models/cr/stn.py:36-40): near the identity transform,
+            t = torch.tensor([1.0, 0.0, 0.0, 0.0, 1.0, 0.0]) + torch.randn(shape, generator=g) * 0.05
+        elif name.endswith("fc_loc.2.weight"):      # so the sampled grid stays inside the image
+            t = (torch.rand(shape, generator=g) * 2 - 1) * 0.05 * math.sqrt(3.0 / shape[1])
         elif len(shape) == 1:                       # biases, LayerNorm / BatchNorm affine
             is_norm_weight = leaf == "weight"
             t = torch.randn(shape, generator=g) * 0.1 + (1.0 if is_norm_weight else 0.0)

@@ -39,8 +39,9 @@ def load():
     from models.fpg.model import FacialPriorGuidance  # type: ignore
     from models.idc.model import ResNet50  # type: ignore
     from models.refiner import FacialRefiner  # type: ignore
+    from models.cr.model import CoarseRestoration  # type: ignore
     return types.SimpleNamespace(Denoiser=Denoiser, FusedDenoiser=FusedDenoiser,
                                  ConditionalNAFBlock=ConditionalNAFBlock,
                                  HybridCrossAttention=HybridCrossAttention,
                                  FacialPriorGuidance=FacialPriorGuidance, ResNet50=ResNet50,
-                                 FacialRefiner=FacialRefiner)
+                                 FacialRefiner=FacialRefiner, CoarseRestoration=CoarseRestoration)

@@ -42,6 +42,8 @@ def inputs(kind, batch, seed=0):
         return torch.rand((batch, 3, 128, 128), generator=gen(200 + seed))
     if kind == "cr_latent":
         return torch.randn((batch, 4, 16, 16), generator=gen(300 + seed))
+    if kind == "ln_face":   # CoarseRestoration input, same as tests/golden/make_golden_cr.py::cr_input
+        return torch.rand((batch, 3, 128, 128), generator=gen(600 + seed))
     raise KeyError(kind)
 
 
