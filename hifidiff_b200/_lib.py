@@ -24,7 +24,7 @@ HD_PRECISION_FP32 = 1
 EXPORTED_SYMBOLS = (
     "hd_abi_version", "hd_create", "hd_destroy", "hd_last_error", "hd_get_info", "hd_load_weights",
     "hd_set_time_frequencies", "hd_set_condition", "hd_denoise_step", "hd_denoise_step_taps",
-    "hd_sample", "hd_sampler_update", "hd_debug_gemm", "hd_synchronize", "hd_profile_step", "hd_debug_gemm_trace", "hd_load_fpg_weights", "hd_fpg_forward", "hd_load_idc_weights", "hd_idc_forward", "hd_debug_gemm_time",
+    "hd_sample", "hd_sampler_update", "hd_debug_gemm", "hd_synchronize", "hd_profile_step", "hd_debug_gemm_trace", "hd_load_fpg_weights", "hd_fpg_forward", "hd_load_idc_weights", "hd_idc_forward", "hd_load_cr_weights", "hd_cr_forward", "hd_debug_gemm_time",
 )
 
 
@@ -104,6 +104,10 @@ def load() -> C.CDLL:
     lib.hd_load_idc_weights.argtypes = [vp, C.POINTER(HdTensorDesc), i32, vp]
     lib.hd_idc_forward.restype = i32
     lib.hd_idc_forward.argtypes = [vp, vp, i32, vp, i32, vp]
+    lib.hd_load_cr_weights.restype = i32
+    lib.hd_load_cr_weights.argtypes = [vp, C.POINTER(HdTensorDesc), i32, vp]
+    lib.hd_cr_forward.restype = i32
+    lib.hd_cr_forward.argtypes = [vp, vp, i32, vp, i32, vp]
     lib.hd_debug_gemm_time.restype = i32
     lib.hd_debug_gemm_time.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, C.POINTER(C.c_float)]
     lib.hd_synchronize.restype = i32

@@ -1,0 +1,285 @@
+// CoarseRestoration (reference models/cr/model.py:8-88, models/cr/stn.py:9-52): the kernels that are not GEMMs.
+// CR runs once per face before the sampling loop, in fp32 throughout (the spatial transformers resample the
+// residual stream with data-dependent coordinates, so this stage keeps the fp32 arithmetic of the reference; its
+// 1x1 / 2x2 convolutions run on the FFMA GEMM, gemm_simt.cuh).  Activations are NHWC fp32.
+#pragma once
+#include "common.cuh"
+
+namespace hd {
+
+// intro: 3x3 conv 3 -> 32, pad 1 (cr/model.py:41-49,78).  x NCHW [B][3][H][H] -> out NHWC [B][H][H][32].
+// w [27][32] (k = (c*3 + ky)*3 + kx), thread = one pixel x 8 output channels.
+__global__ void __launch_bounds__(256) cr_intro_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ b, float* __restrict__ out, int B, int H) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * H * H * 4) return;
+  const int cg = static_cast<int>(i & 3);
+  size_t r = i >> 2;
+  const int px = static_cast<int>(r % H); r /= H;
+  const int py = static_cast<int>(r % H);
+  const int face = static_cast<int>(r / H);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = b[cg * 8 + j];
+  for (int c = 0; c < 3; ++c)
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = py + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = px + kx - 1;
+        if (xx < 0 || xx >= H) continue;
+        const float v = x[((static_cast<size_t>(face) * 3 + c) * H + yy) * H + xx];
+        const float* wr = w + ((c * 3 + ky) * 3 + kx) * 32 + cg * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+      }
+    }
+  store8(out + ((static_cast<size_t>(face) * H + py) * H + px) * 32 + cg * 8, acc);
+}
+
+// outro: 3x3 conv 32 -> 3, pad 1 (cr/model.py:50-58,86).  x NHWC [B][H][H][32] -> out NCHW [B][3][H][H].
+// w [3][9][32], thread = one pixel.
+__global__ void __launch_bounds__(256) cr_outro_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ b, float* __restrict__ out, int B, int H) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * H * H) return;
+  size_t r = i;
+  const int px = static_cast<int>(r % H); r /= H;
+  const int py = static_cast<int>(r % H);
+  const int face = static_cast<int>(r / H);
+  float acc[3] = {b[0], b[1], b[2]};
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = py + ky - 1;
+    if (yy < 0 || yy >= H) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = px + kx - 1;
+      if (xx < 0 || xx >= H) continue;
+      const float* src = x + ((static_cast<size_t>(face) * H + yy) * H + xx) * 32;
+      const int tap = ky * 3 + kx;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 v = *reinterpret_cast<const float4*>(src + c4 * 4);
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          const float4 ww = __ldg(reinterpret_cast<const float4*>(w + (o * 9 + tap) * 32 + c4 * 4));
+          acc[o] = fmaf(v.x, ww.x, acc[o]); acc[o] = fmaf(v.y, ww.y, acc[o]);
+          acc[o] = fmaf(v.z, ww.z, acc[o]); acc[o] = fmaf(v.w, ww.w, acc[o]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 3; ++o) out[((static_cast<size_t>(face) * 3 + o) * H + py) * H + px] = acc[o];
+}
+
+// depthwise 3x3 (pad 1, bias) + SimpleGate at any spatial size (cr/naf.py:34-42,113-114): h [B][n][n][2c] ->
+// g [B][n][n][c] = dw(x1) * dw(x2).  Neighbours come straight from global memory (L1/L2): thread = one pixel x 4
+// gate channels.  w9 [9][2c], bias [2c].
+__global__ void __launch_bounds__(256) cr_dwconv_gate_kernel(const float* __restrict__ h, const float* __restrict__ w9,
+                                                             const float* __restrict__ bias, float* __restrict__ g, int B,
+                                                             int n, int c) {
+  pdl_trigger();
+  pdl_wait();
+  const int c4 = c / 4, C2 = 2 * c;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * n * n * c4) return;
+  const int j = static_cast<int>(i % c4) * 4;
+  size_t r = i / c4;
+  const int px = static_cast<int>(r % n); r /= n;
+  const int py = static_cast<int>(r % n);
+  const int face = static_cast<int>(r / n);
+  float4 a1 = *reinterpret_cast<const float4*>(bias + j), a2 = *reinterpret_cast<const float4*>(bias + c + j);
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+    if (yy < 0 || yy >= n || xx < 0 || xx >= n) continue;
+    const float* src = h + ((static_cast<size_t>(face) * n + yy) * n + xx) * C2;
+    const float4 x1 = *reinterpret_cast<const float4*>(src + j), x2 = *reinterpret_cast<const float4*>(src + c + j);
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w9 + t * C2 + j));
+    const float4 w2 = __ldg(reinterpret_cast<const float4*>(w9 + t * C2 + c + j));
+    a1.x = fmaf(x1.x, w1.x, a1.x); a1.y = fmaf(x1.y, w1.y, a1.y); a1.z = fmaf(x1.z, w1.z, a1.z); a1.w = fmaf(x1.w, w1.w, a1.w);
+    a2.x = fmaf(x2.x, w2.x, a2.x); a2.y = fmaf(x2.y, w2.y, a2.y); a2.z = fmaf(x2.z, w2.z, a2.z); a2.w = fmaf(x2.w, w2.w, a2.w);
+  }
+  *reinterpret_cast<float4*>(g + ((static_cast<size_t>(face) * n + py) * n + px) * c + j) =
+      make_float4(a1.x * a2.x, a1.y * a2.y, a1.z * a2.z, a1.w * a2.w);
+}
+
+// per-face channel mean (AdaptiveAvgPool2d(1), cr/naf.py:57): g [B][HW][c] -> pooled [B][c].
+// grid (c/32, B), block 256: lane = channel, 8 row lanes, fixed-order reduction.
+__global__ void __launch_bounds__(256) cr_pool_kernel(const float* __restrict__ g, float* __restrict__ pooled, int HW, int c) {
+  __shared__ float red[8][32];
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + lane, face = blockIdx.y;
+  const float* src = g + static_cast<size_t>(face) * HW * c + ch;
+  float s = 0.f;
+  for (int p = rl; p < HW; p += 8) s += src[static_cast<size_t>(p) * c];
+  red[rl][lane] = s;
+  __syncthreads();
+  if (rl == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += red[k][lane];
+    pooled[static_cast<size_t>(face) * c + ch] = tot / static_cast<float>(HW);
+  }
+}
+
+// SimpleGate on a plain [rows][2c] tensor (cr/naf.py:120-121; utils.py:57-60): out[r][k] = in[r][k] * in[r][c + k].
+__global__ void __launch_bounds__(256) cr_gate_kernel(const float* __restrict__ in, float* __restrict__ out, size_t rows, int c) {
+  pdl_trigger();
+  pdl_wait();
+  const int c4 = c / 4;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * c4) return;
+  const size_t r = i / c4;
+  const int j = static_cast<int>(i - r * c4) * 4;
+  const float4 a = *reinterpret_cast<const float4*>(in + r * 2 * c + j);
+  const float4 b = *reinterpret_cast<const float4*>(in + r * 2 * c + c + j);
+  *reinterpret_cast<float4*>(out + r * c + j) = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+}
+
+// a += b  (the skip add in front of the first decoder, cr/model.py:83)
+__global__ void __launch_bounds__(256) cr_add_kernel(float* __restrict__ a, const float* __restrict__ b, size_t total4) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  float4 x = reinterpret_cast<float4*>(a)[i];
+  const float4 y = reinterpret_cast<const float4*>(b)[i];
+  x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+  reinterpret_cast<float4*>(a)[i] = x;
+}
+
+__global__ void __launch_bounds__(256) cr_zero_kernel(float* __restrict__ a, size_t total4) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < total4) reinterpret_cast<float4*>(a)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// STN localisation stage (stn.py:20-27): valid k x k conv (Cin -> Cout <= 10) + MaxPool2d(2,2) + ReLU, fused.
+//   in NHWC [B][n][n][Cin], w [Cout][k][k][Cin], out NHWC [B][no][no][Cout], no = (n - k + 1) / 2.
+// Thread = one pooled pixel, all output channels: the 2x2 conv outputs under the pool window share their inputs.
+template <int COUT>
+__global__ void __launch_bounds__(128) cr_stn_conv_pool_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                               const float* __restrict__ b, float* __restrict__ out, int B,
+                                                               int n, int Cin, int k, int no) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * no * no) return;
+  size_t r = i;
+  const int px = static_cast<int>(r % no); r /= no;
+  const int py = static_cast<int>(r % no);
+  const int face = static_cast<int>(r / no);
+  float acc[4][COUT];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[q][o] = 0.f;
+  const float* base = in + (static_cast<size_t>(face) * n + 2 * py) * n * Cin + static_cast<size_t>(2 * px) * Cin;
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx) {
+      const float* wk = w + (ky * k + kx) * Cin;
+      const float* s00 = base + (static_cast<size_t>(ky) * n + kx) * Cin;
+      for (int c = 0; c < Cin; c += 4) {
+        const float4 v00 = *reinterpret_cast<const float4*>(s00 + c);
+        const float4 v01 = *reinterpret_cast<const float4*>(s00 + Cin + c);
+        const float4 v10 = *reinterpret_cast<const float4*>(s00 + static_cast<size_t>(n) * Cin + c);
+        const float4 v11 = *reinterpret_cast<const float4*>(s00 + static_cast<size_t>(n) * Cin + Cin + c);
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+          const float4 ww = __ldg(reinterpret_cast<const float4*>(wk + static_cast<size_t>(o) * k * k * Cin + c));
+          acc[0][o] = fmaf(v00.x, ww.x, acc[0][o]); acc[0][o] = fmaf(v00.y, ww.y, acc[0][o]);
+          acc[0][o] = fmaf(v00.z, ww.z, acc[0][o]); acc[0][o] = fmaf(v00.w, ww.w, acc[0][o]);
+          acc[1][o] = fmaf(v01.x, ww.x, acc[1][o]); acc[1][o] = fmaf(v01.y, ww.y, acc[1][o]);
+          acc[1][o] = fmaf(v01.z, ww.z, acc[1][o]); acc[1][o] = fmaf(v01.w, ww.w, acc[1][o]);
+          acc[2][o] = fmaf(v10.x, ww.x, acc[2][o]); acc[2][o] = fmaf(v10.y, ww.y, acc[2][o]);
+          acc[2][o] = fmaf(v10.z, ww.z, acc[2][o]); acc[2][o] = fmaf(v10.w, ww.w, acc[2][o]);
+          acc[3][o] = fmaf(v11.x, ww.x, acc[3][o]); acc[3][o] = fmaf(v11.y, ww.y, acc[3][o]);
+          acc[3][o] = fmaf(v11.z, ww.z, acc[3][o]); acc[3][o] = fmaf(v11.w, ww.w, acc[3][o]);
+        }
+      }
+    }
+  float* o_ptr = out + i * COUT;
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) {
+    const float m = fmaxf(fmaxf(acc[0][o], acc[1][o]), fmaxf(acc[2][o], acc[3][o])) + b[o];  // bias commutes with max
+    o_ptr[o] = fmaxf(m, 0.f);
+  }
+}
+
+// STN regressor (stn.py:29-33,45-47): theta = W2 relu(W1 xs + b1) + b2, one block per face.
+//   xs [fc] (NHWC order of the localisation output; W1's columns are permuted to match at load), W1 [hid][fc],
+//   W2 [6][hid] -> theta [B][6].  hid <= 96.
+__global__ void __launch_bounds__(256) cr_stn_fc_kernel(const float* __restrict__ xs, const float* __restrict__ w1,
+                                                        const float* __restrict__ b1, const float* __restrict__ w2,
+                                                        const float* __restrict__ b2, float* __restrict__ theta, int fc,
+                                                        int hid) {
+  __shared__ float hbuf[96];
+  pdl_trigger();
+  pdl_wait();
+  const int face = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* x = xs + static_cast<size_t>(face) * fc;
+  for (int j = warp; j < hid; j += 8) {
+    const float* wr = w1 + static_cast<size_t>(j) * fc;
+    float s = 0.f;
+    for (int k = lane; k < fc; k += 32) s = fmaf(x[k], wr[k], s);
+    s = warp_sum(s);
+    if (lane == 0) hbuf[j] = fmaxf(s + b1[j], 0.f);
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float s = b2[threadIdx.x];
+    for (int k = 0; k < hid; ++k) s = fmaf(hbuf[k], w2[threadIdx.x * hid + k], s);
+    theta[face * 6 + threadIdx.x] = s;
+  }
+}
+
+// affine_grid + grid_sample (bilinear, zeros padding, align_corners=False; stn.py:49-50) on the NHWC stream.
+// Base grid as torch builds it: linspace(-1, 1, W) * (W - 1) / W, the linspace evaluated from both ends.
+__device__ __forceinline__ float cr_base_coord(int i, int W) {
+  const float step = 2.f / static_cast<float>(W - 1);
+  const float v = i < W / 2 ? -1.f + step * static_cast<float>(i) : 1.f - step * static_cast<float>(W - 1 - i);
+  return v * static_cast<float>(W - 1) / static_cast<float>(W);
+}
+__global__ void __launch_bounds__(256) cr_stn_sample_kernel(const float* __restrict__ in, const float* __restrict__ theta,
+                                                            float* __restrict__ out, int B, int n, int c) {
+  pdl_trigger();
+  pdl_wait();
+  const int c4 = c / 4;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * n * n * c4) return;
+  const int j = static_cast<int>(i % c4) * 4;
+  size_t r = i / c4;
+  const int px = static_cast<int>(r % n); r /= n;
+  const int py = static_cast<int>(r % n);
+  const int face = static_cast<int>(r / n);
+  const float* th = theta + face * 6;
+  const float xb = cr_base_coord(px, n), yb = cr_base_coord(py, n);
+  const float gx = xb * th[0] + yb * th[1] + th[2];
+  const float gy = xb * th[3] + yb * th[4] + th[5];
+  const float ix = ((gx + 1.f) * static_cast<float>(n) - 1.f) / 2.f;
+  const float iy = ((gy + 1.f) * static_cast<float>(n) - 1.f) / 2.f;
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+  const float wx1 = ix - fx, wx0 = (fx + 1.f) - ix, wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+  const float wgt[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};  // nw, ne, sw, se
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* fbase = in + static_cast<size_t>(face) * n * n * c + j;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int xx = x0 + (q & 1), yy = y0 + (q >> 1);
+    if (xx < 0 || xx >= n || yy < 0 || yy >= n) continue;
+    const float4 v = *reinterpret_cast<const float4*>(fbase + (static_cast<size_t>(yy) * n + xx) * c);
+    acc.x += v.x * wgt[q]; acc.y += v.y * wgt[q]; acc.z += v.z * wgt[q]; acc.w += v.w * wgt[q];
+  }
+  *reinterpret_cast<float4*>(out + ((static_cast<size_t>(face) * n + py) * n + px) * c + j) = acc;
+}
+
+}  // namespace hd

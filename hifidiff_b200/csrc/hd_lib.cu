@@ -21,6 +21,7 @@
 #include "quad_block.cuh"
 #include "idc_kernels.cuh"
 #include "sca_kernel.cuh"
+#include "cr_kernels.cuh"
 
 using namespace hd;
 
@@ -194,6 +195,34 @@ struct IdcW {
   double flops_per_face = 0;
 };
 
+// CoarseRestoration (models/cr/model.py:8-88): fp32 throughout, plain (unpacked) weights for the FFMA GEMM
+struct CrBlockW {
+  int c = 0;
+  float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr;
+  float *w1 = nullptr, *b1 = nullptr, *dw_w = nullptr, *dw_b = nullptr, *wsca = nullptr, *bsca = nullptr;
+  float *w3 = nullptr, *b3 = nullptr, *w4 = nullptr, *b4 = nullptr, *w5 = nullptr, *b5 = nullptr;  // beta / gamma folded
+};
+struct CrStnW {
+  int k1 = 0, k2 = 0, n1 = 0, n2 = 0, fc = 0, hid = 0;
+  float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;      // localisation convs, [Cout][k][k][Cin]
+  float *f1 = nullptr, *fb1 = nullptr, *f2 = nullptr, *fb2 = nullptr;    // regressor, f1 columns in NHWC order
+};
+struct CrStageW {
+  int c = 0, res = 0, sampling = 0;  // 0 none, 1 down (2x2 s2 conv), 2 up (1x1 conv + PixelShuffle)
+  std::vector<CrBlockW> blocks;
+  CrStnW stn;
+  float *samp_w = nullptr, *samp_b = nullptr;
+};
+struct CrW {
+  bool loaded = false;
+  int H = 128, cap = 8;
+  float *intro_w = nullptr, *intro_b = nullptr, *outro_w = nullptr, *outro_b = nullptr;
+  std::vector<CrStageW> stages;  // 4 encoders, middle, 4 decoders
+  // workspace for one chunk of faces (all fp32)
+  float *r[5] = {}, *sk[5] = {}, *ln_out = nullptr, *act_h = nullptr, *act_g = nullptr, *tmp = nullptr;
+  float *pooled = nullptr, *sca_s = nullptr, *loc1 = nullptr, *loc2 = nullptr, *theta = nullptr, *stage = nullptr;
+};
+
 struct HcaW {
   int d = 0, sp = 0;
   void* wf = nullptr;  // [d, 9d] fused 3x3, BN folded
@@ -303,6 +332,10 @@ struct hd_handle {
   std::map<int, std::unique_ptr<Plan>> idc_plans;
   const float* idc_in = nullptr;
   float* idc_out = nullptr;
+  CrW cr;
+  std::map<int, std::unique_ptr<Plan>> cr_plans;
+  const float* cr_in = nullptr;
+  float* cr_out = nullptr;
   size_t workspace_bytes = 0;
 
   // transient during load
@@ -907,6 +940,8 @@ void launch_ln(int c, const float* x, const float* lw, const float* lb, T* out, 
   const int lpr = std::min(32, c / 16);
   const int grid = cdiv(rows, 4 * (32 / lpr));  // 4 warps per block, 32/lpr rows per warp
   switch (c) {
+    case 32: launch_k(ln_mod_kernel<32, T>, dim3(grid), dim3(128), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
+    case 64: launch_k(ln_mod_kernel<64, T>, dim3(grid), dim3(128), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
     case 128: launch_k(ln_mod_kernel<128, T>, dim3(grid), dim3(128), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
     case 256: launch_k(ln_mod_kernel<256, T>, dim3(grid), dim3(128), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
     case 512: launch_k(ln_mod_kernel<512, T>, dim3(grid), dim3(128), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
@@ -2048,6 +2083,285 @@ Plan* get_idc_plan(hd_handle* h, int B) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// CoarseRestoration: NAFNet U-Net with a spatial transformer after every stage
+// (models/cr/model.py:8-88, models/cr/stn.py:9-52), once per face before the sampling loop, fp32 throughout.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCrChunk = 8;  // faces per pass (~14 MB of fp32 workspace per face)
+constexpr int kCrC[5] = {32, 64, 128, 256, 512};
+constexpr int kCrRes[5] = {128, 64, 32, 16, 8};
+
+float* cr_mat(hd_handle* h, const std::string& name, int N, int Kd, int taps, const std::vector<int>* perm,
+              const std::vector<float>* rs) {
+  return static_cast<float*>(pack_matrix(h, need(h, name, {N, Kd}), N, Kd, taps, perm, rs, DT_F32));
+}
+float* cr_vec(hd_handle* h, const std::string& name, int n) { return upload_f32(h, host_vec(h, need(h, name, {n}))); }
+
+void load_cr_block(hd_handle* h, CrBlockW& b, const std::string& p, int c) {
+  b.c = c;
+  b.ln1_w = cr_vec(h, p + "norm1.weight", c); b.ln1_b = cr_vec(h, p + "norm1.bias", c);
+  b.ln2_w = cr_vec(h, p + "norm2.weight", c); b.ln2_b = cr_vec(h, p + "norm2.bias", c);
+  auto beta = host_vec(h, need(h, p + "beta", {c}));
+  auto gamma = host_vec(h, need(h, p + "gamma", {c}));
+  b.w1 = cr_mat(h, p + "conv1.weight", 2 * c, c, 1, nullptr, nullptr);
+  b.b1 = cr_vec(h, p + "conv1.bias", 2 * c);
+  {  // depthwise 3x3: [2c,1,3,3] -> [9][2c]
+    auto w = host_vec(h, need(h, p + "conv2.weight", {2 * c, 9}));
+    std::vector<float> t(static_cast<size_t>(18) * c);
+    for (int ch = 0; ch < 2 * c; ++ch)
+      for (int tap = 0; tap < 9; ++tap) t[static_cast<size_t>(tap) * 2 * c + ch] = w[static_cast<size_t>(ch) * 9 + tap];
+    b.dw_w = upload_f32(h, t);
+    b.dw_b = cr_vec(h, p + "conv2.bias", 2 * c);
+  }
+  b.wsca = cr_mat(h, p + "sca.1.weight", c, c, 1, nullptr, nullptr);
+  b.bsca = cr_vec(h, p + "sca.1.bias", c);
+  auto b3 = host_vec(h, need(h, p + "conv3.bias", {c}));
+  auto b5 = host_vec(h, need(h, p + "conv5.bias", {c}));
+  for (int i = 0; i < c; ++i) { b3[i] *= beta[i]; b5[i] *= gamma[i]; }
+  b.w3 = cr_mat(h, p + "conv3.weight", c, c, 1, nullptr, &beta);   // y = inp + beta * (W3 x + b3)
+  b.b3 = upload_f32(h, b3);
+  b.w4 = cr_mat(h, p + "conv4.weight", 2 * c, c, 1, nullptr, nullptr);
+  b.b4 = cr_vec(h, p + "conv4.bias", 2 * c);
+  b.w5 = cr_mat(h, p + "conv5.weight", c, c, 1, nullptr, &gamma);
+  b.b5 = upload_f32(h, b5);
+}
+
+// conv weight OIHW [O][I][k][k] -> [O][k][k][I] (channels innermost, as the NHWC kernels read them)
+float* cr_conv_ohwi(hd_handle* h, const std::string& name, int O, int I, int k) {
+  auto w = host_vec(h, need(h, name, {O, I, k * k}));
+  std::vector<float> t(w.size());
+  for (int o = 0; o < O; ++o)
+    for (int i = 0; i < I; ++i)
+      for (int q = 0; q < k * k; ++q) t[(static_cast<size_t>(o) * k * k + q) * I + i] = w[(static_cast<size_t>(o) * I + i) * k * k + q];
+  return upload_f32(h, t);
+}
+
+void load_cr_stn(hd_handle* h, CrStnW& s, const std::string& p, int c, int res) {
+  // kernel sizes and regressor width as STNBlock.__init__ derives them (stn.py:13-22,29-33)
+  if (res <= 8) { s.k1 = 3; s.k2 = 1; } else if (res <= 16) { s.k1 = 5; s.k2 = 3; } else if (res <= 32) { s.k1 = 7; s.k2 = 5; } else { s.k1 = 9; s.k2 = 7; }
+  s.n1 = (res - s.k1 + 1) / 2;
+  s.n2 = (s.n1 - s.k2 + 1) / 2;
+  s.fc = 10 * s.n2 * s.n2;
+  s.hid = static_cast<int>(std::sqrt(static_cast<double>(s.fc)));
+  if (s.hid > 96) HD_THROW(HD_ERR_UNSUPPORTED, "STN regressor width %d", s.hid);
+  s.w1 = cr_conv_ohwi(h, p + "localization.0.weight", 8, c, s.k1);
+  s.b1 = cr_vec(h, p + "localization.0.bias", 8);
+  s.w2 = cr_conv_ohwi(h, p + "localization.3.weight", 10, 8, s.k2);
+  s.b2 = cr_vec(h, p + "localization.3.bias", 10);
+  {  // fc_loc.0: columns from the reference's (C,H,W) flattening to the kernels' (H,W,C)
+    auto w = host_vec(h, need(h, p + "fc_loc.0.weight", {s.hid, s.fc}));
+    std::vector<float> t(w.size());
+    const int hw = s.n2 * s.n2;
+    for (int j = 0; j < s.hid; ++j)
+      for (int q = 0; q < hw; ++q)
+        for (int o = 0; o < 10; ++o) t[static_cast<size_t>(j) * s.fc + q * 10 + o] = w[static_cast<size_t>(j) * s.fc + o * hw + q];
+    s.f1 = upload_f32(h, t);
+  }
+  s.fb1 = cr_vec(h, p + "fc_loc.0.bias", s.hid);
+  s.f2 = upload_f32(h, host_vec(h, need(h, p + "fc_loc.2.weight", {6, s.hid})));
+  s.fb2 = cr_vec(h, p + "fc_loc.2.bias", 6);
+}
+
+void load_cr_impl(hd_handle* h) {
+  CrW& R = h->cr;
+  R.H = 8 * h->S;
+  if (R.H != 128) HD_THROW(HD_ERR_UNSUPPORTED, "CoarseRestoration is built for 128x128 faces (latent size 16)");
+  R.cap = kCrChunk;
+  {  // intro (32,3,3,3) -> [27][32]; outro (3,32,3,3) -> [3][9][32]
+    auto w = host_vec(h, need(h, "intro.weight", {32, 27}));
+    std::vector<float> t(27 * 32);
+    for (int o = 0; o < 32; ++o)
+      for (int k = 0; k < 27; ++k) t[static_cast<size_t>(k) * 32 + o] = w[static_cast<size_t>(o) * 27 + k];
+    R.intro_w = upload_f32(h, t);
+    R.intro_b = cr_vec(h, "intro.bias", 32);
+    R.outro_w = cr_conv_ohwi(h, "outro.weight", 3, 32, 3);
+    R.outro_b = cr_vec(h, "outro.bias", 3);
+  }
+  R.stages.clear();
+  const int enc_naf[4] = {2, 2, 4, 8};
+  auto add_stage = [&](const std::string& p, int level, int num_naf, int sampling) {
+    CrStageW st;
+    st.c = kCrC[level]; st.res = kCrRes[level]; st.sampling = sampling;
+    st.blocks.resize(num_naf);
+    for (int i = 0; i < num_naf; ++i) load_cr_block(h, st.blocks[i], p + "nfbs." + std::to_string(i) + ".", st.c);
+    load_cr_stn(h, st.stn, p + "stn.", st.c, st.res);
+    const int c = st.c;
+    if (sampling == 1) {  // Conv2d(c, 2c, 2, 2): K order (dy, dx, c) of the space-to-depth rows
+      st.samp_w = cr_mat(h, p + "sampling.weight", 2 * c, 4 * c, 4, nullptr, nullptr);
+      st.samp_b = cr_vec(h, p + "sampling.bias", 2 * c);
+    } else if (sampling == 2) {  // Conv2d(c, 2c, 1, bias=False) + PixelShuffle(2): rows grouped by quadrant
+      const int N = 2 * c, quarter = N / 4;
+      std::vector<int> perm(N);
+      for (int n = 0; n < N; ++n) perm[n] = 4 * (n % quarter) + n / quarter;
+      st.samp_w = cr_mat(h, p + "sampling.0.weight", N, c, 1, &perm, nullptr);
+    }
+    R.stages.push_back(std::move(st));
+  };
+  for (int i = 0; i < 4; ++i) add_stage("encoders." + std::to_string(i) + ".", i, enc_naf[i], 1);
+  add_stage("middle_blocks.", 4, 8, 0);
+  for (int j = 0; j < 4; ++j) add_stage("decoders." + std::to_string(j) + ".", 4 - j, 2, 2);
+  // workspace
+  const size_t cap = R.cap;
+  size_t e[5];
+  for (int l = 0; l < 5; ++l) e[l] = static_cast<size_t>(kCrRes[l]) * kCrRes[l] * kCrC[l];
+  for (int l = 0; l < 5; ++l) R.r[l] = h->arena.get<float>(cap * e[l]);
+  for (int l = 1; l < 5; ++l) R.sk[l] = h->arena.get<float>(cap * e[l]);
+  R.ln_out = h->arena.get<float>(cap * e[0]);
+  R.act_h = h->arena.get<float>(cap * 2 * e[0]);
+  R.act_g = h->arena.get<float>(cap * e[0]);
+  R.tmp = h->arena.get<float>(cap * e[0]);
+  R.pooled = h->arena.get<float>(cap * 512);
+  R.sca_s = h->arena.get<float>(cap * 512);
+  R.loc1 = h->arena.get<float>(cap * 60 * 60 * 8);
+  R.loc2 = h->arena.get<float>(cap * 27 * 27 * 10);
+  R.theta = h->arena.get<float>(cap * 6);
+  R.stage = h->arena.get<float>(cap * 3 * R.H * R.H);
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  for (void* p : h->temp_dev) cudaFree(p);
+  h->temp_dev.clear();
+  h->src.clear();
+  R.loaded = true;
+  h->cr_plans.clear();
+}
+
+Plan* get_cr_plan(hd_handle* h, int B) {
+  auto it = h->cr_plans.find(B);
+  if (it != h->cr_plans.end()) return it->second.get();
+  std::unique_ptr<Plan> up(new Plan());
+  Plan& P = *up;
+  P.batch = B;
+  const CrW& R = h->cr;
+  const int H = R.H;
+  auto gemm = [&](int M, int N, int K, const float* A, int lda, const float* W, const float* bias, int epi, float* out, int ldo,
+                  const float* resid, int sp, const std::string& label) {
+    GemmDesc d;
+    d.M = M; d.N = N; d.K = K; d.A = A; d.lda = lda; d.a_dtype = DT_F32; d.W = W; d.ldw = K; d.w_dtype = DT_F32;
+    d.bias = bias; d.epi = epi; d.out = out; d.ldo = ldo; d.out_dtype = DT_F32; d.resid = resid; d.ldr = ldo; d.sp = sp;
+    g_label = label + fmt(" gemm_ffma M=%d N=%d K=%d", M, N, K);
+    add_op(P, [d](cudaStream_t st) { launch_simt(d, st); });
+    P.flops_per_face += 2.0 * M * static_cast<double>(N) * K / P.batch;
+  };
+  auto ew = [&](size_t total, int per_block = 256) { return dim3(static_cast<unsigned>(cdiv(total, static_cast<size_t>(per_block)))); };
+  auto naf_block = [&](const CrBlockW& b, float* x, int n, const std::string& L0) {
+    const int c = b.c, rpf = n * n, rows = B * rpf;
+    float *ln_out = R.ln_out, *act_h = R.act_h, *act_g = R.act_g, *pooled = R.pooled, *sca_s = R.sca_s;
+    ModRef nomod{nullptr, nullptr, 0};
+    const float *l1w = b.ln1_w, *l1b = b.ln1_b, *l2w = b.ln2_w, *l2b = b.ln2_b;
+    g_label = L0 + "ln1";
+    add_op(P, [=](cudaStream_t st) { launch_ln<float>(c, x, l1w, l1b, ln_out, rows, rpf, nomod, 0, 0, 0, st); });
+    gemm(rows, 2 * c, c, ln_out, c, b.w1, b.b1, EPI_BIAS, act_h, 2 * c, nullptr, 0, L0 + "conv1");
+    const float *dw_w = b.dw_w, *dw_b = b.dw_b;
+    g_label = L0 + "dwconv+gate";
+    add_op(P, [=](cudaStream_t st) {
+      launch_k(cr_dwconv_gate_kernel, ew(static_cast<size_t>(rows) * (c / 4)), dim3(256), 0, st, static_cast<const float*>(act_h), dw_w, dw_b, act_g, B, n, c);
+    });
+    g_label = L0 + "pool";
+    add_op(P, [=](cudaStream_t st) {
+      launch_k(cr_pool_kernel, dim3(c / 32, B), dim3(256), 0, st, static_cast<const float*>(act_g), pooled, rpf, c);
+    });
+    gemm(B, c, c, pooled, c, b.wsca, b.bsca, EPI_BIAS, sca_s, c, nullptr, 0, L0 + "sca");
+    g_label = L0 + "scale_rows";
+    add_op(P, [=](cudaStream_t st) {
+      const size_t total8 = static_cast<size_t>(rows) * c / 8;
+      launch_k(scale_rows_kernel<float>, ew(total8), dim3(256), 0, st, act_g, static_cast<const float*>(sca_s), total8, c, rpf);
+    });
+    gemm(rows, c, c, act_g, c, b.w3, b.b3, EPI_RESID, x, c, x, 0, L0 + "conv3");
+    g_label = L0 + "ln2";
+    add_op(P, [=](cudaStream_t st) { launch_ln<float>(c, x, l2w, l2b, ln_out, rows, rpf, nomod, 0, 0, 0, st); });
+    gemm(rows, 2 * c, c, ln_out, c, b.w4, b.b4, EPI_BIAS, act_h, 2 * c, nullptr, 0, L0 + "conv4");
+    g_label = L0 + "gate";
+    add_op(P, [=](cudaStream_t st) {
+      launch_k(cr_gate_kernel, ew(static_cast<size_t>(rows) * (c / 4)), dim3(256), 0, st, static_cast<const float*>(act_h), act_g, static_cast<size_t>(rows), c);
+    });
+    gemm(rows, c, c, act_g, c, b.w5, b.b5, EPI_RESID, x, c, x, 0, L0 + "conv5");
+    P.flops_per_face += 2.0 * 9 * 2 * c * rpf;
+  };
+  auto stn = [&](const CrStnW& s, const float* x, float* out, int n, int c, const std::string& L0) {
+    float *loc1 = R.loc1, *loc2 = R.loc2, *theta = R.theta;
+    const float *w1 = s.w1, *b1 = s.b1, *w2 = s.w2, *b2 = s.b2, *f1 = s.f1, *fb1 = s.fb1, *f2 = s.f2, *fb2 = s.fb2;
+    const int k1 = s.k1, k2 = s.k2, n1 = s.n1, n2 = s.n2, fc = s.fc, hid = s.hid;
+    g_label = L0 + fmt("stn conv%dx%d+pool+relu", k1, k1);
+    add_op(P, [=](cudaStream_t st) {
+      launch_k(cr_stn_conv_pool_kernel<8>, ew(static_cast<size_t>(B) * n1 * n1, 128), dim3(128), 0, st, x, w1, b1, loc1, B, n, c, k1, n1);
+    });
+    g_label = L0 + fmt("stn conv%dx%d+pool+relu", k2, k2);
+    add_op(P, [=](cudaStream_t st) {
+      launch_k(cr_stn_conv_pool_kernel<10>, ew(static_cast<size_t>(B) * n2 * n2, 128), dim3(128), 0, st, static_cast<const float*>(loc1), w2, b2, loc2, B, n1, 8, k2, n2);
+    });
+    g_label = L0 + "stn fc";
+    add_op(P, [=](cudaStream_t st) {
+      launch_k(cr_stn_fc_kernel, dim3(B), dim3(256), 0, st, static_cast<const float*>(loc2), f1, fb1, f2, fb2, theta, fc, hid);
+    });
+    g_label = L0 + "stn affine_grid+grid_sample";
+    add_op(P, [=](cudaStream_t st) {
+      launch_k(cr_stn_sample_kernel, ew(static_cast<size_t>(B) * n * n * (c / 4)), dim3(256), 0, st, x, static_cast<const float*>(theta), out, B, n, c);
+    });
+    P.flops_per_face += 2.0 * (static_cast<double>(k1) * k1 * c * 8 * (2 * n1) * (2 * n1) + static_cast<double>(k2) * k2 * 80 * (2 * n2) * (2 * n2));
+  };
+  auto copy = [&](const float* src, float* dst, size_t elems, const std::string& label) {
+    g_label = label;
+    add_op(P, [=](cudaStream_t st) { launch_k(cast_kernel<float>, ew(elems / 8), dim3(256), 0, st, src, dst, elems / 8); });
+  };
+  {  // intro
+    const float *w = R.intro_w, *b = R.intro_b;
+    float* out = R.r[0];
+    g_label = "cr intro conv3x3";
+    add_op(P, [=](cudaStream_t st) { launch_k(cr_intro_kernel, ew(static_cast<size_t>(B) * H * H * 4), dim3(256), 0, st, h->cr_in, w, b, out, B, H); });
+  }
+  float* tmp = R.tmp;
+  for (int i = 0; i < 4; ++i) {  // encoders: NAF blocks, STN, 2x2 stride-2 conv; the result is also the skip (model.py:79-81)
+    const CrStageW& S = R.stages[i];
+    const int n = S.res, c = S.c;
+    const std::string L0 = fmt("cr enc%d c=%d ", i, c);
+    for (size_t k = 0; k < S.blocks.size(); ++k) naf_block(S.blocks[k], R.r[i], n, L0 + fmt("b%d ", static_cast<int>(k)));
+    stn(S.stn, R.r[i], tmp, n, c, L0);
+    float* s2d = R.act_h;
+    const int rows_out = B * (n / 2) * (n / 2);
+    g_label = L0 + "down s2d";
+    add_op(P, [=](cudaStream_t st) {
+      const size_t total8 = static_cast<size_t>(rows_out) * 4 * c / 8;
+      launch_k(s2d_kernel<float>, ew(total8), dim3(256), 0, st, static_cast<const float*>(tmp), s2d, B, n, c);
+    });
+    gemm(rows_out, 2 * c, 4 * c, s2d, 4 * c, S.samp_w, S.samp_b, EPI_BIAS, R.r[i + 1], 2 * c, nullptr, 0, L0 + "down");
+    copy(R.r[i + 1], R.sk[i + 1], static_cast<size_t>(rows_out) * 2 * c, L0 + "skip copy");
+  }
+  {  // middle: NAF blocks + STN, no sampling; then x + enc_skips[3] for the first decoder (model.py:82-84)
+    const CrStageW& S = R.stages[4];
+    const int n = S.res, c = S.c;
+    const std::string L0 = fmt("cr mid c=%d ", c);
+    for (size_t k = 0; k < S.blocks.size(); ++k) naf_block(S.blocks[k], R.r[4], n, L0 + fmt("b%d ", static_cast<int>(k)));
+    stn(S.stn, R.r[4], tmp, n, c, L0);
+    float *a = R.sk[4];
+    const size_t total4 = static_cast<size_t>(B) * n * n * c / 4;
+    g_label = L0 + "add skip";   // sk[4] <- stn(middle) + enc_skips[3]: the first decoder's stream
+    add_op(P, [=](cudaStream_t st) { launch_k(cr_add_kernel, ew(total4), dim3(256), 0, st, a, static_cast<const float*>(tmp), total4); });
+  }
+  for (int j = 0; j < 4; ++j) {  // decoders: stream = (up-sampled previous stage + skip), accumulated in the skip buffer
+    const CrStageW& S = R.stages[5 + j];
+    const int l = 4 - j, n = S.res, c = S.c;
+    const std::string L0 = fmt("cr dec%d c=%d ", j, c);
+    float* x = R.sk[l];
+    for (size_t k = 0; k < S.blocks.size(); ++k) naf_block(S.blocks[k], x, n, L0 + fmt("b%d ", static_cast<int>(k)));
+    stn(S.stn, x, tmp, n, c, L0);
+    float* target = l - 1 >= 1 ? R.sk[l - 1] : R.r[0];
+    if (l - 1 == 0) {  // the last up-sampling has no skip to land on: start from zeros
+      const size_t total4 = static_cast<size_t>(B) * H * H * 32 / 4;
+      g_label = L0 + "zero";
+      add_op(P, [=](cudaStream_t st) { launch_k(cr_zero_kernel, ew(total4), dim3(256), 0, st, target, total4); });
+    }
+    gemm(B * n * n, 2 * c, c, tmp, c, S.samp_w, nullptr, EPI_PIXSHUF, target, c / 2, nullptr, n, L0 + "up");
+  }
+  {  // outro
+    const float *w = R.outro_w, *b = R.outro_b;
+    const float* in = R.r[0];
+    g_label = "cr outro conv3x3";
+    add_op(P, [=](cudaStream_t st) { launch_k(cr_outro_kernel, ew(static_cast<size_t>(B) * H * H), dim3(256), 0, st, in, w, b, h->cr_out, B, H); });
+  }
+  Plan* raw = up.get();
+  h->cr_plans[B] = std::move(up);
+  return raw;
+}
+
+// ------------------------------------------------------------------------------------------------
 // time-modulation table: rows r -> all 32 blocks' [shift_att, scale_att, shift_ffn, scale_ffn]
 // (model.py:22-29,46-51 ; conditional_naf.py:18-22,103-106) — fp32 FFMA, depends on t only
 // ------------------------------------------------------------------------------------------------
@@ -2682,6 +2996,58 @@ int32_t hd_idc_forward(hd_handle* h, const float* cr_face, int32_t image_size, f
   CUDA_CHECK(cudaGetLastError());
   if (!in_dev) CUDA_CHECK(cudaStreamSynchronize(st));
   if (!in_dev) check_device_status(h);
+  join_out(h, stream);
+  HD_API_END(h)
+}
+
+int32_t hd_load_cr_weights(hd_handle* h, const hd_tensor_desc* tensors, int32_t n, void* stream) {
+  HD_API_BEGIN
+  if (!h || !tensors || n <= 0) HD_THROW(HD_ERR_INVALID, "null argument");
+  if (h->cr.loaded) HD_THROW(HD_ERR_STATE, "CR weights already loaded; create a new handle to reload");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  (void)stream;
+  CUDA_CHECK(cudaDeviceSynchronize());
+  h->src.clear();
+  for (int i = 0; i < n; ++i) {
+    const hd_tensor_desc& t = tensors[i];
+    if (!t.name || !t.data) continue;
+    SrcTensor s;
+    s.data = t.data; s.dtype = t.dtype;
+    s.numel = 1;
+    for (int k = 0; k < t.ndim && k < 4; ++k) { s.shape.push_back(t.shape[k]); s.numel *= static_cast<size_t>(t.shape[k]); }
+    h->src[t.name] = s;
+  }
+  load_cr_impl(h);
+  HD_API_END(h)
+}
+
+int32_t hd_cr_forward(hd_handle* h, const float* ln_face, int32_t image_size, float* cr_face_out, int32_t B, void* stream) {
+  HD_API_BEGIN
+  if (!h || !ln_face || !cr_face_out) HD_THROW(HD_ERR_INVALID, "null argument");
+  if (!h->cr.loaded) HD_THROW(HD_ERR_STATE, "hd_load_cr_weights has not been called");
+  if (B < 1) HD_THROW(HD_ERR_INVALID, "batch %d < 1", B);
+  const CrW& R = h->cr;
+  if (image_size != R.H) HD_THROW(HD_ERR_INVALID, "ln_face must be (B,3,%d,%d), got %d", R.H, R.H, image_size);
+  if (!is_device_ptr(cr_face_out)) HD_THROW(HD_ERR_INVALID, "hd_cr_forward writes a device buffer");
+  CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  join_in(h, stream);
+  cudaStream_t st = h->stream;
+  const bool in_dev = is_device_ptr(ln_face);
+  const size_t per_face = static_cast<size_t>(3) * R.H * R.H;
+  for (int off = 0; off < B; off += R.cap) {
+    const int bc = std::min(R.cap, B - off);
+    if (in_dev) {
+      h->cr_in = ln_face + off * per_face;
+    } else {
+      CUDA_CHECK(cudaMemcpyAsync(R.stage, ln_face + off * per_face, bc * per_face * 4, cudaMemcpyHostToDevice, st));
+      h->cr_in = R.stage;
+    }
+    h->cr_out = cr_face_out + off * per_face;
+    Plan* P = get_cr_plan(h, bc);
+    for (auto& op : P->ops) op.fn(st);
+  }
+  CUDA_CHECK(cudaGetLastError());
+  if (!in_dev) CUDA_CHECK(cudaStreamSynchronize(st));
   join_out(h, stream);
   HD_API_END(h)
 }

@@ -100,6 +100,7 @@ class _Engine:
         self.handle = C.c_void_p()
         self.fpg_loaded = False
         self.idc_loaded = False
+        self.cr_loaded = False
         self.max_batch = max_batch
         self.max_steps = max_steps
         cfg = _lib.HdConfig(C.sizeof(_lib.HdConfig), model_kind, precision, latent_size,
@@ -188,6 +189,23 @@ class _Engine:
         with torch.cuda.device(x.device):
             self.check(self.lib.hd_idc_forward(self.handle, x.data_ptr(), x.shape[2], out.data_ptr(), x.shape[0],
                                                _stream_ptr(x.device)), "hd_idc_forward")
+        return out
+
+    def load_cr_state(self, state: dict) -> None:
+        descs, n, keep = self._descs(state)
+        self.check(self.lib.hd_load_cr_weights(self.handle, descs, n, None), "hd_load_cr_weights")
+        self.cr_loaded = True
+        del keep
+
+    def cr_forward(self, ln_face: torch.Tensor) -> torch.Tensor:
+        """CoarseRestoration.forward (models/cr/model.py:75-88) on CUDA kernels -> (B,3,128,128) fp32."""
+        x = ln_face.to(torch.float32).contiguous()
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != x.shape[3]:
+            raise ValueError(f"ln_face must be (B,3,H,H), got {tuple(x.shape)}")
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            self.check(self.lib.hd_cr_forward(self.handle, x.data_ptr(), x.shape[2], out.data_ptr(), x.shape[0],
+                                              _stream_ptr(x.device)), "hd_cr_forward")
         return out
 
     def info(self) -> "_lib.HdInfo":

@@ -1,14 +1,17 @@
 """CoarseRestoration (CR) — the stage BEFORE the sampling loop (reference
 models/cr/model.py:8-88, models/cr/stn.py:9-52, call site train_refiner.py:106).
 
-Status: boundary + oracle only.  This module reproduces the reference's constructor, `forward(x)` contract
-((B,3,128,128) low-quality face -> (B,3,128,128) coarse frontal face) and `state_dict()` layout exactly (checked
-against the unmodified reference by tests/golden/make_golden_cr.py: same keys, order, shapes, dtypes and seeded
-default init), so checkpoints load unchanged.  Its arithmetic is ordinary PyTorch ops for now — it is NOT yet on
-the sm_100a kernels and is not part of any parity or throughput claim; the kernel plan is DESIGN.md §6 item 4.
+This module reproduces the reference's constructor, `forward(x)` contract ((B,3,128,128) low-quality face ->
+(B,3,128,128) coarse frontal face) and `state_dict()` layout exactly (checked against the unmodified reference by
+tests/golden/make_golden_cr.py: same keys, order, shapes, dtypes and seeded default init), so checkpoints load
+unchanged.  On a CUDA device `forward` runs on the library's own kernels (`hd_load_cr_weights` / `hd_cr_forward`:
+fp32 NHWC, NAF blocks on the FFMA GEMM, fused localisation conv + pool, affine-grid bilinear resampling) — a first,
+fp32-only native version of this once-per-face stage; `native = False` (or a CPU tensor) runs the plain PyTorch
+arithmetic below, which is what the CPU parity tests exercise.
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 from typing import Optional
 
@@ -16,8 +19,9 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from . import _lib
 from .conditioning import _naf_block
-from .modules import _NAFBlockParams
+from .modules import _Engine, _NAFBlockParams
 
 
 class _STNBlock(nn.Module):
@@ -74,8 +78,50 @@ class CoarseRestoration(nn.Module):
         self.middle_blocks = _NAFSTNBlock(16 * w, 8, 8)
         self.decoders = nn.Sequential(_NAFSTNBlock(16 * w, 8, 2, "up"), _NAFSTNBlock(8 * w, 16, 2, "up"),
                                       _NAFSTNBlock(4 * w, 32, 2, "up"), _NAFSTNBlock(2 * w, 64, 2, "up"))
+        self.native = True      # CUDA inputs run on the library's kernels (False: PyTorch ops)
+        self._engine = None
+        self._engine_dev = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
+
+    def invalidate(self) -> None:
+        """Drop the library's packed copy of the weights; the next CUDA call re-reads the parameters."""
+        if self._engine is not None:
+            self._engine.close()
+        self._engine = None
+        self._engine_dev = None
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate()
+        return out
+
+    def engine(self) -> _Engine:
+        p = next(self.parameters())
+        if p.device.type != "cuda":
+            raise RuntimeError("the native CoarseRestoration path runs only on CUDA (sm_100a)")
+        if self._engine is None or self._engine_dev != p.device:
+            self.invalidate()
+            with torch.cuda.device(p.device):
+                torch.cuda.synchronize()
+                eng = _Engine(_lib.HD_MODEL_DENOISER, 16, _lib.HD_PRECISION_FP32, p.device, 1, 1, False)
+                eng.load_cr_state(self.state_dict())
+            self._engine, self._engine_dev = eng, p.device
+        return self._engine
+
+    @torch.no_grad()
+    def _forward_native(self, x: torch.Tensor) -> torch.Tensor:
+        if tuple(x.shape[1:]) != (3, 128, 128):
+            raise ValueError(f"the native CoarseRestoration takes (B,3,128,128) faces, got {tuple(x.shape)}; "
+                             f"set native=False for other sizes")
+        return self.engine().cr_forward(x)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.native and x.is_cuda:
+            # inference (the reference calls CR under no_grad with frozen weights, train_refiner.py:380-381,86);
+            # anything that needs autograd goes through the PyTorch ops below
+            needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+            if not needs_grad:
+                return self._forward_native(x)
         skips = []
         x = self.intro(x)
         for enc in self.encoders:

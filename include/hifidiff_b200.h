@@ -137,6 +137,17 @@ int32_t hd_load_idc_weights(hd_handle* h, const hd_tensor_desc* tensors, int32_t
 int32_t hd_idc_forward(hd_handle* h, const float* cr_face, int32_t image_size, float* identity_out,
                        int32_t batch, void* stream);
 
+/* CoarseRestoration on CUDA kernels (SURVEY.md §8f "next" row 3), the stage before the sampling loop.
+ * hd_load_cr_weights takes the CR module's state_dict (intro.*, outro.*, {encoders.i,middle_blocks,decoders.j}.
+ * {nfbs.k.*, stn.localization.{0,3}.*, stn.fc_loc.{0,2}.*, sampling.*}; replaces cr_module.load_state_dict,
+ * train_refiner.py:377-379).  hd_cr_forward replaces CoarseRestoration.forward (models/cr/model.py:75-88) as
+ * called at train_refiner.py:106: ln_face (B,3,128,128) fp32, device or host -> cr_face_out (B,3,128,128) fp32
+ * device buffer.  fp32 arithmetic in both precision modes (the spatial transformers resample with data-dependent
+ * coordinates); any batch >= 1 (faces are processed in chunks of 8). */
+int32_t hd_load_cr_weights(hd_handle* h, const hd_tensor_desc* tensors, int32_t n, void* stream);
+int32_t hd_cr_forward(hd_handle* h, const float* ln_face, int32_t image_size, float* cr_face_out, int32_t batch,
+                      void* stream);
+
 /* Condition-only work, hoisted out of the timestep loop (it depends on neither x_t nor t):
  * idc_conv(identity) (model.py:245-246) and the five HCA channel/spatial gates computed from
  * the priors (hca.py:33-48).  priors[j]: (B, C_j, n_j, n_j) with C = 2048,1024,512,256,128 and
