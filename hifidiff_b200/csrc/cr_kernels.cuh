@@ -109,22 +109,23 @@ __global__ void __launch_bounds__(256) cr_dwconv_gate_kernel(const float* __rest
 }
 
 // per-face channel mean (AdaptiveAvgPool2d(1), cr/naf.py:57): g [B][HW][c] -> pooled [B][c].
-// grid (c/32, B), block 256: lane = channel, 8 row lanes, fixed-order reduction.
-__global__ void __launch_bounds__(256) cr_pool_kernel(const float* __restrict__ g, float* __restrict__ pooled, int HW, int c) {
-  __shared__ float red[8][32];
+// grid (c/32, B), block 1024: lane = channel, 32 row lanes, fixed-order reduction.
+constexpr int kCrPoolLanes = 32;
+__global__ void __launch_bounds__(1024) cr_pool_kernel(const float* __restrict__ g, float* __restrict__ pooled, int HW, int c) {
+  __shared__ float red[kCrPoolLanes][32];
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int ch = blockIdx.x * 32 + lane, face = blockIdx.y;
   const float* src = g + static_cast<size_t>(face) * HW * c + ch;
   float s = 0.f;
-  for (int p = rl; p < HW; p += 8) s += src[static_cast<size_t>(p) * c];
+  for (int p = rl; p < HW; p += kCrPoolLanes) s += src[static_cast<size_t>(p) * c];
   red[rl][lane] = s;
   __syncthreads();
   if (rl == 0) {
     float tot = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) tot += red[k][lane];
+    for (int k = 0; k < kCrPoolLanes; ++k) tot += red[k][lane];
     pooled[static_cast<size_t>(face) * c + ch] = tot / static_cast<float>(HW);
   }
 }
@@ -164,28 +165,32 @@ __global__ void __launch_bounds__(256) cr_zero_kernel(float* __restrict__ a, siz
 
 // STN localisation stage (stn.py:20-27): valid k x k conv (Cin -> Cout <= 10) + MaxPool2d(2,2) + ReLU, fused.
 //   in NHWC [B][n][n][Cin], w [Cout][k][k][Cin], out NHWC [B][no][no][Cout], no = (n - k + 1) / 2.
-// Thread = one pooled pixel, all output channels: the 2x2 conv outputs under the pool window share their inputs.
-template <int COUT>
+// Thread = one pooled pixel x OG output channels (COUT / OG groups): the 2x2 conv outputs under the pool window
+// share their inputs.
+template <int COUT, int OG>
 __global__ void __launch_bounds__(128) cr_stn_conv_pool_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                                const float* __restrict__ b, float* __restrict__ out, int B,
                                                                int n, int Cin, int k, int no) {
   pdl_trigger();
   pdl_wait();
+  constexpr int NG = COUT / OG;
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= static_cast<size_t>(B) * no * no) return;
-  size_t r = i;
+  if (i >= static_cast<size_t>(B) * no * no * NG) return;
+  const int og = static_cast<int>(i % NG) * OG;
+  size_t r = i / NG;
+  const size_t pix = r;
   const int px = static_cast<int>(r % no); r /= no;
   const int py = static_cast<int>(r % no);
   const int face = static_cast<int>(r / no);
-  float acc[4][COUT];
+  float acc[4][OG];
 #pragma unroll
   for (int q = 0; q < 4; ++q)
 #pragma unroll
-    for (int o = 0; o < COUT; ++o) acc[q][o] = 0.f;
+    for (int o = 0; o < OG; ++o) acc[q][o] = 0.f;
   const float* base = in + (static_cast<size_t>(face) * n + 2 * py) * n * Cin + static_cast<size_t>(2 * px) * Cin;
   for (int ky = 0; ky < k; ++ky)
     for (int kx = 0; kx < k; ++kx) {
-      const float* wk = w + (ky * k + kx) * Cin;
+      const float* wk = w + (static_cast<size_t>(og) * k * k + ky * k + kx) * Cin;
       const float* s00 = base + (static_cast<size_t>(ky) * n + kx) * Cin;
       for (int c = 0; c < Cin; c += 4) {
         const float4 v00 = *reinterpret_cast<const float4*>(s00 + c);
@@ -193,7 +198,7 @@ __global__ void __launch_bounds__(128) cr_stn_conv_pool_kernel(const float* __re
         const float4 v10 = *reinterpret_cast<const float4*>(s00 + static_cast<size_t>(n) * Cin + c);
         const float4 v11 = *reinterpret_cast<const float4*>(s00 + static_cast<size_t>(n) * Cin + Cin + c);
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) {
+        for (int o = 0; o < OG; ++o) {
           const float4 ww = __ldg(reinterpret_cast<const float4*>(wk + static_cast<size_t>(o) * k * k * Cin + c));
           acc[0][o] = fmaf(v00.x, ww.x, acc[0][o]); acc[0][o] = fmaf(v00.y, ww.y, acc[0][o]);
           acc[0][o] = fmaf(v00.z, ww.z, acc[0][o]); acc[0][o] = fmaf(v00.w, ww.w, acc[0][o]);
@@ -206,10 +211,10 @@ __global__ void __launch_bounds__(128) cr_stn_conv_pool_kernel(const float* __re
         }
       }
     }
-  float* o_ptr = out + i * COUT;
+  float* o_ptr = out + pix * COUT + og;
 #pragma unroll
-  for (int o = 0; o < COUT; ++o) {
-    const float m = fmaxf(fmaxf(acc[0][o], acc[1][o]), fmaxf(acc[2][o], acc[3][o])) + b[o];  // bias commutes with max
+  for (int o = 0; o < OG; ++o) {
+    const float m = fmaxf(fmaxf(acc[0][o], acc[1][o]), fmaxf(acc[2][o], acc[3][o])) + b[og + o];  // bias commutes with max
     o_ptr[o] = fmaxf(m, 0.f);
   }
 }

@@ -215,7 +215,7 @@ struct CrStageW {
 };
 struct CrW {
   bool loaded = false;
-  int H = 128, cap = 8;
+  int H = 128, cap = 32;
   float *intro_w = nullptr, *intro_b = nullptr, *outro_w = nullptr, *outro_b = nullptr;
   std::vector<CrStageW> stages;  // 4 encoders, middle, 4 decoders
   // workspace for one chunk of faces (all fp32)
@@ -2086,7 +2086,7 @@ Plan* get_idc_plan(hd_handle* h, int B) {
 // CoarseRestoration: NAFNet U-Net with a spatial transformer after every stage
 // (models/cr/model.py:8-88, models/cr/stn.py:9-52), once per face before the sampling loop, fp32 throughout.
 // ------------------------------------------------------------------------------------------------
-constexpr int kCrChunk = 8;  // faces per pass (~14 MB of fp32 workspace per face)
+constexpr int kCrChunk = 32;  // faces per pass (~14 MB of fp32 workspace per face)
 constexpr int kCrC[5] = {32, 64, 128, 256, 512};
 constexpr int kCrRes[5] = {128, 64, 32, 16, 8};
 
@@ -2256,7 +2256,7 @@ Plan* get_cr_plan(hd_handle* h, int B) {
     });
     g_label = L0 + "pool";
     add_op(P, [=](cudaStream_t st) {
-      launch_k(cr_pool_kernel, dim3(c / 32, B), dim3(256), 0, st, static_cast<const float*>(act_g), pooled, rpf, c);
+      launch_k(cr_pool_kernel, dim3(c / 32, B), dim3(1024), 0, st, static_cast<const float*>(act_g), pooled, rpf, c);
     });
     gemm(B, c, c, pooled, c, b.wsca, b.bsca, EPI_BIAS, sca_s, c, nullptr, 0, L0 + "sca");
     g_label = L0 + "scale_rows";
@@ -2281,11 +2281,11 @@ Plan* get_cr_plan(hd_handle* h, int B) {
     const int k1 = s.k1, k2 = s.k2, n1 = s.n1, n2 = s.n2, fc = s.fc, hid = s.hid;
     g_label = L0 + fmt("stn conv%dx%d+pool+relu", k1, k1);
     add_op(P, [=](cudaStream_t st) {
-      launch_k(cr_stn_conv_pool_kernel<8>, ew(static_cast<size_t>(B) * n1 * n1, 128), dim3(128), 0, st, x, w1, b1, loc1, B, n, c, k1, n1);
+      launch_k(cr_stn_conv_pool_kernel<8, 2>, ew(static_cast<size_t>(B) * n1 * n1 * 4, 128), dim3(128), 0, st, x, w1, b1, loc1, B, n, c, k1, n1);
     });
     g_label = L0 + fmt("stn conv%dx%d+pool+relu", k2, k2);
     add_op(P, [=](cudaStream_t st) {
-      launch_k(cr_stn_conv_pool_kernel<10>, ew(static_cast<size_t>(B) * n2 * n2, 128), dim3(128), 0, st, static_cast<const float*>(loc1), w2, b2, loc2, B, n1, 8, k2, n2);
+      launch_k(cr_stn_conv_pool_kernel<10, 5>, ew(static_cast<size_t>(B) * n2 * n2 * 2, 128), dim3(128), 0, st, static_cast<const float*>(loc1), w2, b2, loc2, B, n1, 8, k2, n2);
     });
     g_label = L0 + "stn fc";
     add_op(P, [=](cudaStream_t st) {
