@@ -345,10 +345,30 @@ def main():
                 pri = eng.fpg_forward(lat_h.to(dev, non_blocking=True))
             ev[2].record()
             torch.cuda.synchronize()
+            # the stage before the loop: CoarseRestoration on its own fp32 kernels (hd_cr_forward)
+            with torch.device("meta"):
+                crm = H.CoarseRestoration()
+            s0 = crm.state_dict()
+            crm = crm.to_empty(device=dev)
+            crm.load_state_dict(testing.random_state({k: v.shape for k, v in s0.items()}, {k: v.dtype for k, v in s0.items()}, seed=4))
+            crm.eval()
+            with torch.no_grad():
+                crm(face_h[:8].to(dev))
+                torch.cuda.synchronize()
+                ev_c = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                ev_c[0].record()
+                cr_out = crm(face_h.to(dev, non_blocking=True))
+                ev_c[1].record()
+                torch.cuda.synchronize()
+            cr_ms = ev_c[0].elapsed_time(ev_c[1])
+            cr_finite = bool(torch.isfinite(cr_out).all().item())
+            crm.invalidate()
+            del crm, cr_out
             cond_nets = {"faces": B, "idc_resnet50_ms": ev[0].elapsed_time(ev[1]) / 3, "fpg_ms": ev[1].elapsed_time(ev[2]) / 3,
+                         "coarse_restoration_ms": cr_ms, "coarse_restoration_finite": cr_finite,
                          "h2d_bytes": face_h.numel() * 4 + lat_h.numel() * 4,
                          "finite": bool(torch.isfinite(idn).all().item() and all(torch.isfinite(p).all().item() for p in pri)),
-                         "note": "hd_idc_forward / hd_fpg_forward from pinned host inputs, once per batch of faces (t-invariant)"}
+                         "note": "hd_idc_forward / hd_fpg_forward / hd_cr_forward from pinned host inputs, once per batch of faces (t-invariant)"}
         except Exception as exc:  # the headline number must not depend on this side measurement
             cond_nets = {"error": str(exc)[:200]}
 
