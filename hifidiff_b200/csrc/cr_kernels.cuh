@@ -163,6 +163,32 @@ __global__ void __launch_bounds__(256) cr_zero_kernel(float* __restrict__ a, siz
   if (i < total4) reinterpret_cast<float4*>(a)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// fp32 -> three bf16 column blocks for the split-precision tensor-core GEMM: x = hi + lo with hi = bf16(x),
+// lo = bf16(x - hi).  Activations (mode 0) are laid out [hi | lo | hi] and weights (mode 1) [hi | hi | lo], so one
+// bf16 GEMM over K' = 3K accumulates a_hi w_hi + a_lo w_hi + a_hi w_lo in fp32 — everything but the lo*lo term
+// (2^-16 relative), i.e. fp32-grade products on the tcgen05 pipe.  in [rows][K] -> out [rows][3K].
+__global__ void __launch_bounds__(256) cr_split3_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t rows, int K,
+                                                        int mode) {
+  pdl_trigger();
+  pdl_wait();
+  const int k8 = K / 8;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * k8) return;
+  const size_t r = i / k8;
+  const int k0 = static_cast<int>(i - r * k8) * 8;
+  float v[8], hi[8], lo[8];
+  load8(in + r * K + k0, v);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    hi[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
+    lo[e] = v[e] - hi[e];
+  }
+  bf16* o = out + r * 3 * K + k0;
+  store8(o, hi);
+  store8(o + K, mode == 0 ? lo : hi);
+  store8(o + 2 * K, mode == 0 ? hi : lo);
+}
+
 // STN localisation stage (stn.py:20-27): valid k x k conv (Cin -> Cout <= 10) + MaxPool2d(2,2) + ReLU, fused.
 //   in NHWC [B][n][n][Cin], w [Cout][k][k][Cin], out NHWC [B][no][no][Cout], no = (n - k + 1) / 2.
 // Thread = one pooled pixel x OG output channels (COUT / OG groups): the 2x2 conv outputs under the pool window

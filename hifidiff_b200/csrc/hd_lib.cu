@@ -79,6 +79,7 @@ int g_split = 1;
 // B=256 (9.4 / 10.1 / 17.4 us at the 4x4 / 2x2 / 1x1 levels against 8.0 / 10.3 / 10.7 for the split-K tcgen05 GEMM
 // + rescale): 64x32 tiles without split-K make every CTA ingest its whole A and W panels at ~60 B/clk/SM.
 bool g_sca_fused = false;
+bool g_cr_tc = true;     // HD_CR_TC=0: every CoarseRestoration GEMM on the FFMA kernel (no split-precision tcgen05 path)
 bool g_dw_small = true;  // HD_DW_SMALL=0: the generic tiled depthwise kernel at the 2x2 / 4x4 levels too
 int g_cta_target = 120;  // HD_CTA_TARGET: split-K until a GEMM's grid has at least this many CTAs
 int g_sca_target = 120;  // HD_SCA_TARGET: the same for the SCA GEMMs (M = faces)
@@ -201,6 +202,7 @@ struct CrBlockW {
   float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr;
   float *w1 = nullptr, *b1 = nullptr, *dw_w = nullptr, *dw_b = nullptr, *wsca = nullptr, *bsca = nullptr;
   float *w3 = nullptr, *b3 = nullptr, *w4 = nullptr, *b4 = nullptr, *w5 = nullptr, *b5 = nullptr;  // beta / gamma folded
+  bf16 *w1s = nullptr, *w3s = nullptr, *w4s = nullptr, *w5s = nullptr;  // c >= 128: [N][3K] bf16 hi|hi|lo for the split-precision tcgen05 GEMM
 };
 struct CrStnW {
   int k1 = 0, k2 = 0, n1 = 0, n2 = 0, fc = 0, hid = 0;
@@ -221,6 +223,8 @@ struct CrW {
   // workspace for one chunk of faces (all fp32)
   float *r[5] = {}, *sk[5] = {}, *ln_out = nullptr, *act_h = nullptr, *act_g = nullptr, *tmp = nullptr;
   float *pooled = nullptr, *sca_s = nullptr, *loc1 = nullptr, *loc2 = nullptr, *theta = nullptr, *stage = nullptr;
+  bf16* a3 = nullptr;  // split-precision A operand [rows][3K]
+  bool use_tc = true;
 };
 
 struct HcaW {
@@ -2123,6 +2127,16 @@ void load_cr_block(hd_handle* h, CrBlockW& b, const std::string& p, int c) {
   b.b4 = cr_vec(h, p + "conv4.bias", 2 * c);
   b.w5 = cr_mat(h, p + "conv5.weight", c, c, 1, nullptr, &gamma);
   b.b5 = upload_f32(h, b5);
+  if (c >= 128 && h->bf16 && g_cr_tc) {
+    auto split = [&](const float* w, int N, int K) {
+      bf16* out = h->arena.get<bf16>(static_cast<size_t>(N) * 3 * K);
+      const size_t total = static_cast<size_t>(N) * (K / 8);
+      cr_split3_kernel<<<cdiv(total, 256), 256, 0, h->stream>>>(w, out, static_cast<size_t>(N), K, 1);
+      CUDA_CHECK(cudaGetLastError());
+      return out;
+    };
+    b.w1s = split(b.w1, 2 * c, c); b.w3s = split(b.w3, c, c); b.w4s = split(b.w4, 2 * c, c); b.w5s = split(b.w5, c, c);
+  }
 }
 
 // conv weight OIHW [O][I][k][k] -> [O][k][k][I] (channels innermost, as the NHWC kernels read them)
@@ -2215,6 +2229,8 @@ void load_cr_impl(hd_handle* h) {
   R.loc2 = h->arena.get<float>(cap * 27 * 27 * 10);
   R.theta = h->arena.get<float>(cap * 6);
   R.stage = h->arena.get<float>(cap * 3 * R.H * R.H);
+  R.use_tc = h->bf16 && g_cr_tc;
+  if (R.use_tc) R.a3 = h->arena.get<bf16>(cap * 3 * e[2]);  // levels with c >= 128: rows x c <= e[2]
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   for (void* p : h->temp_dev) cudaFree(p);
   h->temp_dev.clear();
@@ -2241,14 +2257,31 @@ Plan* get_cr_plan(hd_handle* h, int B) {
     P.flops_per_face += 2.0 * M * static_cast<double>(N) * K / P.batch;
   };
   auto ew = [&](size_t total, int per_block = 256) { return dim3(static_cast<unsigned>(cdiv(total, static_cast<size_t>(per_block)))); };
+  // split-precision tensor-core GEMM (c >= 128): A fp32 -> [hi | lo | hi] bf16, W pre-split [hi | hi | lo], K' = 3K,
+  // fp32 accumulate in TMEM: a_hi w_hi + a_lo w_hi + a_hi w_lo
+  auto gemm_tc3 = [&](int M, int N, int K, const float* A, const bf16* Ws, const float* bias, int epi, float* out, int ldo,
+                      const float* resid, long long rows_alloc, const std::string& label) {
+    bf16* a3 = R.a3;
+    const size_t total = static_cast<size_t>(M) * (K / 8);
+    g_label = label + " split3";
+    add_op(P, [=](cudaStream_t st) { launch_k(cr_split3_kernel, ew(total), dim3(256), 0, st, A, a3, static_cast<size_t>(M), K, 0); });
+    GemmDesc d;
+    d.M = M; d.N = N; d.K = 3 * K; d.A = a3; d.lda = 3 * K; d.a_dtype = DT_BF16; d.W = Ws; d.ldw = 3 * K; d.w_dtype = DT_BF16;
+    d.bias = bias; d.epi = epi; d.out = out; d.ldo = ldo; d.out_dtype = DT_F32; d.resid = resid; d.ldr = ldo;
+    g_label = label + " (3xbf16)";
+    add_gemm(h, P, d, rows_alloc);
+  };
   auto naf_block = [&](const CrBlockW& b, float* x, int n, const std::string& L0) {
     const int c = b.c, rpf = n * n, rows = B * rpf;
+    const bool tc = R.use_tc && b.w1s != nullptr;
+    const long long rows_alloc = static_cast<long long>(R.cap) * rpf;
     float *ln_out = R.ln_out, *act_h = R.act_h, *act_g = R.act_g, *pooled = R.pooled, *sca_s = R.sca_s;
     ModRef nomod{nullptr, nullptr, 0};
     const float *l1w = b.ln1_w, *l1b = b.ln1_b, *l2w = b.ln2_w, *l2b = b.ln2_b;
     g_label = L0 + "ln1";
     add_op(P, [=](cudaStream_t st) { launch_ln<float>(c, x, l1w, l1b, ln_out, rows, rpf, nomod, 0, 0, 0, st); });
-    gemm(rows, 2 * c, c, ln_out, c, b.w1, b.b1, EPI_BIAS, act_h, 2 * c, nullptr, 0, L0 + "conv1");
+    if (tc) gemm_tc3(rows, 2 * c, c, ln_out, b.w1s, b.b1, EPI_BIAS, act_h, 2 * c, nullptr, rows_alloc, L0 + "conv1");
+    else gemm(rows, 2 * c, c, ln_out, c, b.w1, b.b1, EPI_BIAS, act_h, 2 * c, nullptr, 0, L0 + "conv1");
     const float *dw_w = b.dw_w, *dw_b = b.dw_b;
     g_label = L0 + "dwconv+gate";
     add_op(P, [=](cudaStream_t st) {
@@ -2264,15 +2297,18 @@ Plan* get_cr_plan(hd_handle* h, int B) {
       const size_t total8 = static_cast<size_t>(rows) * c / 8;
       launch_k(scale_rows_kernel<float>, ew(total8), dim3(256), 0, st, act_g, static_cast<const float*>(sca_s), total8, c, rpf);
     });
-    gemm(rows, c, c, act_g, c, b.w3, b.b3, EPI_RESID, x, c, x, 0, L0 + "conv3");
+    if (tc) gemm_tc3(rows, c, c, act_g, b.w3s, b.b3, EPI_RESID, x, c, x, rows_alloc, L0 + "conv3");
+    else gemm(rows, c, c, act_g, c, b.w3, b.b3, EPI_RESID, x, c, x, 0, L0 + "conv3");
     g_label = L0 + "ln2";
     add_op(P, [=](cudaStream_t st) { launch_ln<float>(c, x, l2w, l2b, ln_out, rows, rpf, nomod, 0, 0, 0, st); });
-    gemm(rows, 2 * c, c, ln_out, c, b.w4, b.b4, EPI_BIAS, act_h, 2 * c, nullptr, 0, L0 + "conv4");
+    if (tc) gemm_tc3(rows, 2 * c, c, ln_out, b.w4s, b.b4, EPI_BIAS, act_h, 2 * c, nullptr, rows_alloc, L0 + "conv4");
+    else gemm(rows, 2 * c, c, ln_out, c, b.w4, b.b4, EPI_BIAS, act_h, 2 * c, nullptr, 0, L0 + "conv4");
     g_label = L0 + "gate";
     add_op(P, [=](cudaStream_t st) {
       launch_k(cr_gate_kernel, ew(static_cast<size_t>(rows) * (c / 4)), dim3(256), 0, st, static_cast<const float*>(act_h), act_g, static_cast<size_t>(rows), c);
     });
-    gemm(rows, c, c, act_g, c, b.w5, b.b5, EPI_RESID, x, c, x, 0, L0 + "conv5");
+    if (tc) gemm_tc3(rows, c, c, act_g, b.w5s, b.b5, EPI_RESID, x, c, x, rows_alloc, L0 + "conv5");
+    else gemm(rows, c, c, act_g, c, b.w5, b.b5, EPI_RESID, x, c, x, 0, L0 + "conv5");
     P.flops_per_face += 2.0 * 9 * 2 * c * rpf;
   };
   auto stn = [&](const CrStnW& s, const float* x, float* out, int n, int c, const std::string& L0) {
@@ -2571,6 +2607,7 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   if (prop.major != 10) HD_THROW(HD_ERR_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
   if (const char* e = getenv("HD_PDL")) g_use_pdl = atoi(e) != 0;
   if (const char* e = getenv("HD_SCA_FUSED")) g_sca_fused = atoi(e) != 0;
+  if (const char* e = getenv("HD_CR_TC")) g_cr_tc = atoi(e) != 0;
   if (const char* e = getenv("HD_DW_SMALL")) g_dw_small = atoi(e) != 0;
   if (const char* e = getenv("HD_CTA_TARGET")) g_cta_target = std::max(atoi(e), 1);
   if (const char* e = getenv("HD_SCA_TARGET")) g_sca_target = std::max(atoi(e), 1);

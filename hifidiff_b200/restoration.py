@@ -79,6 +79,7 @@ class CoarseRestoration(nn.Module):
         self.decoders = nn.Sequential(_NAFSTNBlock(16 * w, 8, 2, "up"), _NAFSTNBlock(8 * w, 16, 2, "up"),
                                       _NAFSTNBlock(4 * w, 32, 2, "up"), _NAFSTNBlock(2 * w, 64, 2, "up"))
         self.native = True      # CUDA inputs run on the library's kernels (False: PyTorch ops)
+        self.tensor_cores = True  # 1x1 convs at c >= 128 as split-precision (3 x bf16) tcgen05 GEMMs; False: FFMA everywhere
         self._engine = None
         self._engine_dev = None
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
@@ -103,7 +104,8 @@ class CoarseRestoration(nn.Module):
             self.invalidate()
             with torch.cuda.device(p.device):
                 torch.cuda.synchronize()
-                eng = _Engine(_lib.HD_MODEL_DENOISER, 16, _lib.HD_PRECISION_FP32, p.device, 1, 1, False)
+                eng = _Engine(_lib.HD_MODEL_DENOISER, 16, _lib.HD_PRECISION_BF16 if self.tensor_cores else _lib.HD_PRECISION_FP32,
+                              p.device, 1, 1, False)
                 eng.load_cr_state(self.state_dict())
             self._engine, self._engine_dev = eng, p.device
         return self._engine

@@ -142,8 +142,9 @@ int32_t hd_idc_forward(hd_handle* h, const float* cr_face, int32_t image_size, f
  * {nfbs.k.*, stn.localization.{0,3}.*, stn.fc_loc.{0,2}.*, sampling.*}; replaces cr_module.load_state_dict,
  * train_refiner.py:377-379).  hd_cr_forward replaces CoarseRestoration.forward (models/cr/model.py:75-88) as
  * called at train_refiner.py:106: ln_face (B,3,128,128) fp32, device or host -> cr_face_out (B,3,128,128) fp32
- * device buffer.  fp32 arithmetic in both precision modes (the spatial transformers resample with data-dependent
- * coordinates); any batch >= 1 (faces are processed in chunks of 32). */
+ * device buffer.  The residual stream and the spatial transformers are fp32 in both precision modes; with
+ * HD_PRECISION_BF16 the 1x1 convs at c >= 128 run as split-precision (3 x bf16, fp32 accumulate) tcgen05 GEMMs,
+ * with HD_PRECISION_FP32 every GEMM is FFMA.  Any batch >= 1 (faces are processed in chunks of 32). */
 int32_t hd_load_cr_weights(hd_handle* h, const hd_tensor_desc* tensors, int32_t n, void* stream);
 int32_t hd_cr_forward(hd_handle* h, const float* ln_face, int32_t image_size, float* cr_face_out, int32_t batch,
                       void* stream);

@@ -11,20 +11,22 @@ from util import golden, inputs, rel_l2, state_for
 
 pytestmark = pytest.mark.gpu
 
-# fp32 kernels; nine data-dependent bilinear resamplings amplify round-off in the affine parameters.  Measured:
-# 7.9e-5 on the fixture, 3.2e-4 on the worst of 11 faces (a later run: see the printed line) — PyTorch's own CUDA path (TF32 convs, its default) is at
-# 3.4e-2 from the same CPU arithmetic.
-TOL = 5e-4
+# Nine data-dependent bilinear resamplings amplify round-off in the affine parameters.  Measured against the CPU
+# arithmetic of the reference: FFMA everywhere 7.3e-5 on the fixture / 2.2e-4 on the worst of 37 faces; with the
+# 1x1 convs at c >= 128 on the tensor cores as split-precision (3 x bf16) GEMMs 6.1e-4 / 1.0e-3.  PyTorch's own
+# CUDA path (TF32 convs, its default) is at 3.4e-2.
+TOL = {True: 2e-3, False: 5e-4}
 
 
-@pytest.fixture(scope="module")
-def cr():
+@pytest.fixture(scope="module", params=[True, False], ids=["tcgen05-3xbf16", "ffma"])
+def cr(request):
     with torch.device("meta"):
         m = H.CoarseRestoration()
     sd = state_for(m, seed=4)
     m = m.to_empty(device="cuda")
     m.load_state_dict(sd)
     m.eval()
+    m.tensor_cores = request.param
     yield m, sd
     m.invalidate()
 
@@ -36,9 +38,9 @@ def test_cr_native_matches_reference_fixture(cr):
         y = m(inputs("ln_face", 2).cuda())
     torch.cuda.synchronize()
     e = rel_l2(y, g["y"])
-    print(f"CR native vs reference fixture: rel-L2 {e:.3e}")
+    print(f"CR native (tensor_cores={m.tensor_cores}) vs reference fixture: rel-L2 {e:.3e}")
     assert tuple(y.shape) == (2, 3, 128, 128) and torch.isfinite(y).all()
-    assert e <= TOL
+    assert e <= TOL[m.tensor_cores]
 
 
 def test_cr_native_ragged_chunks_and_host_input(cr):
@@ -52,8 +54,8 @@ def test_cr_native_ragged_chunks_and_host_input(cr):
         m.native = True
     torch.cuda.synchronize()
     worst = max(rel_l2(y[i], want[i]) for i in range(37))
-    print(f"CR native B=37: rel-L2 {rel_l2(y, want):.3e} (worst face {worst:.3e}); torch-on-GPU vs CPU oracle {rel_l2(y_torch, want):.3e}")
-    assert worst <= TOL
+    print(f"CR native (tensor_cores={m.tensor_cores}) B=37: rel-L2 {rel_l2(y, want):.3e} (worst face {worst:.3e}); torch-on-GPU vs CPU oracle {rel_l2(y_torch, want):.3e}")
+    assert worst <= TOL[m.tensor_cores]
     eng = m.engine()
     out_h = torch.empty_like(y)
     eng.check(eng.lib.hd_cr_forward(eng.handle, x.contiguous().data_ptr(), 128, out_h.data_ptr(), 37, None), "hd_cr_forward")
