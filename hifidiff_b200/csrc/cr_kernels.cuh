@@ -245,6 +245,76 @@ __global__ void __launch_bounds__(128) cr_stn_conv_pool_kernel(const float* __re
   }
 }
 
+// The same stage for wide inputs (Cin % 16 == 0: the first localisation conv): the channel reduction is split over
+// CS = 4 adjacent lanes, each doing all COUT output channels for a quarter of the channels (4 input + COUT weight
+// loads per 16 * COUT FMAs, and a pixel's 4 lanes read 64 contiguous bytes), combined with two shuffles at the end.
+// The one-thread-per-pixel form above is bound by L1 bandwidth at 6 loads per 32 FMAs.
+template <int COUT>
+__global__ void __launch_bounds__(128) cr_stn_conv_pool_cs_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                                  const float* __restrict__ b, float* __restrict__ out, int B,
+                                                                  int n, int Cin, int k, int no) {
+  constexpr int CS = 4;
+  pdl_trigger();
+  pdl_wait();
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int slice = static_cast<int>(i % CS);
+  const size_t npix = static_cast<size_t>(B) * no * no;
+  const bool valid = i / CS < npix;
+  const size_t pix = valid ? i / CS : npix - 1;   // out-of-range lanes redo the last pixel (all lanes stay in the shuffles)
+  size_t r = pix;
+  const int px = static_cast<int>(r % no); r /= no;
+  const int py = static_cast<int>(r % no);
+  const int face = static_cast<int>(r / no);
+  const int cper = Cin / CS, cbeg = slice * cper;
+  float acc[4][COUT];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[q][o] = 0.f;
+  const float* base = in + (static_cast<size_t>(face) * n + 2 * py) * n * Cin + static_cast<size_t>(2 * px) * Cin + cbeg;
+  const size_t wstride = static_cast<size_t>(k) * k * Cin;
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx) {
+      const float* wk = w + static_cast<size_t>(ky * k + kx) * Cin + cbeg;
+      const float* s00 = base + (static_cast<size_t>(ky) * n + kx) * Cin;
+      for (int c = 0; c < cper; c += 4) {
+        const float4 v00 = *reinterpret_cast<const float4*>(s00 + c);
+        const float4 v01 = *reinterpret_cast<const float4*>(s00 + Cin + c);
+        const float4 v10 = *reinterpret_cast<const float4*>(s00 + static_cast<size_t>(n) * Cin + c);
+        const float4 v11 = *reinterpret_cast<const float4*>(s00 + static_cast<size_t>(n) * Cin + Cin + c);
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+          const float4 ww = __ldg(reinterpret_cast<const float4*>(wk + o * wstride + c));
+          acc[0][o] = fmaf(v00.x, ww.x, acc[0][o]); acc[0][o] = fmaf(v00.y, ww.y, acc[0][o]);
+          acc[0][o] = fmaf(v00.z, ww.z, acc[0][o]); acc[0][o] = fmaf(v00.w, ww.w, acc[0][o]);
+          acc[1][o] = fmaf(v01.x, ww.x, acc[1][o]); acc[1][o] = fmaf(v01.y, ww.y, acc[1][o]);
+          acc[1][o] = fmaf(v01.z, ww.z, acc[1][o]); acc[1][o] = fmaf(v01.w, ww.w, acc[1][o]);
+          acc[2][o] = fmaf(v10.x, ww.x, acc[2][o]); acc[2][o] = fmaf(v10.y, ww.y, acc[2][o]);
+          acc[2][o] = fmaf(v10.z, ww.z, acc[2][o]); acc[2][o] = fmaf(v10.w, ww.w, acc[2][o]);
+          acc[3][o] = fmaf(v11.x, ww.x, acc[3][o]); acc[3][o] = fmaf(v11.y, ww.y, acc[3][o]);
+          acc[3][o] = fmaf(v11.z, ww.z, acc[3][o]); acc[3][o] = fmaf(v11.w, ww.w, acc[3][o]);
+        }
+      }
+    }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+      float v = acc[q][o];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      acc[q][o] = v;
+    }
+  if (slice == 0 && valid) {
+    float* o_ptr = out + pix * COUT;
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+      const float m = fmaxf(fmaxf(acc[0][o], acc[1][o]), fmaxf(acc[2][o], acc[3][o])) + b[o];
+      o_ptr[o] = fmaxf(m, 0.f);
+    }
+  }
+}
+
 // STN regressor (stn.py:29-33,45-47): theta = W2 relu(W1 xs + b1) + b2, one block per face.
 //   xs [fc] (NHWC order of the localisation output; W1's columns are permuted to match at load), W1 [hid][fc],
 //   W2 [6][hid] -> theta [B][6].  hid <= 96.

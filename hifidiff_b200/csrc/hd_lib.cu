@@ -79,6 +79,7 @@ int g_split = 1;
 // B=256 (9.4 / 10.1 / 17.4 us at the 4x4 / 2x2 / 1x1 levels against 8.0 / 10.3 / 10.7 for the split-K tcgen05 GEMM
 // + rescale): 64x32 tiles without split-K make every CTA ingest its whole A and W panels at ~60 B/clk/SM.
 bool g_sca_fused = false;
+bool g_cr_stn_cs = true;  // HD_CR_STN_CS=0: one thread per (pixel, 2 output channels) in the first STN localisation conv
 bool g_cr_tc = true;     // HD_CR_TC=0: every CoarseRestoration GEMM on the FFMA kernel (no split-precision tcgen05 path)
 bool g_dw_small = true;  // HD_DW_SMALL=0: the generic tiled depthwise kernel at the 2x2 / 4x4 levels too
 int g_cta_target = 120;  // HD_CTA_TARGET: split-K until a GEMM's grid has at least this many CTAs
@@ -2317,7 +2318,8 @@ Plan* get_cr_plan(hd_handle* h, int B) {
     const int k1 = s.k1, k2 = s.k2, n1 = s.n1, n2 = s.n2, fc = s.fc, hid = s.hid;
     g_label = L0 + fmt("stn conv%dx%d+pool+relu", k1, k1);
     add_op(P, [=](cudaStream_t st) {
-      launch_k(cr_stn_conv_pool_kernel<8, 2>, ew(static_cast<size_t>(B) * n1 * n1 * 4, 128), dim3(128), 0, st, x, w1, b1, loc1, B, n, c, k1, n1);
+      if (g_cr_stn_cs) launch_k(cr_stn_conv_pool_cs_kernel<8>, ew(static_cast<size_t>(B) * n1 * n1 * 4, 128), dim3(128), 0, st, x, w1, b1, loc1, B, n, c, k1, n1);
+      else launch_k(cr_stn_conv_pool_kernel<8, 2>, ew(static_cast<size_t>(B) * n1 * n1 * 4, 128), dim3(128), 0, st, x, w1, b1, loc1, B, n, c, k1, n1);
     });
     g_label = L0 + fmt("stn conv%dx%d+pool+relu", k2, k2);
     add_op(P, [=](cudaStream_t st) {
@@ -2607,6 +2609,7 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   if (prop.major != 10) HD_THROW(HD_ERR_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
   if (const char* e = getenv("HD_PDL")) g_use_pdl = atoi(e) != 0;
   if (const char* e = getenv("HD_SCA_FUSED")) g_sca_fused = atoi(e) != 0;
+  if (const char* e = getenv("HD_CR_STN_CS")) g_cr_stn_cs = atoi(e) != 0;
   if (const char* e = getenv("HD_CR_TC")) g_cr_tc = atoi(e) != 0;
   if (const char* e = getenv("HD_DW_SMALL")) g_dw_small = atoi(e) != 0;
   if (const char* e = getenv("HD_CTA_TARGET")) g_cta_target = std::max(atoi(e), 1);

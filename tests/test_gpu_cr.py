@@ -12,7 +12,7 @@ from util import golden, inputs, rel_l2, state_for
 pytestmark = pytest.mark.gpu
 
 # Nine data-dependent bilinear resamplings amplify round-off in the affine parameters.  Measured against the CPU
-# arithmetic of the reference: FFMA everywhere 7.3e-5 on the fixture / 2.2e-4 on the worst of 37 faces; with the
+# arithmetic of the reference: FFMA everywhere 3.3e-5 on the fixture / 2.2e-4 on the worst of 37 faces; with the
 # 1x1 convs at c >= 128 on the tensor cores as split-precision (3 x bf16) GEMMs 6.1e-4 / 1.0e-3.  PyTorch's own
 # CUDA path (TF32 convs, its default) is at 3.4e-2.
 TOL = {True: 2e-3, False: 5e-4}
