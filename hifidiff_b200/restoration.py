@@ -6,8 +6,9 @@ This module reproduces the reference's constructor, `forward(x)` contract ((B,3,
 tests/golden/make_golden_cr.py: same keys, order, shapes, dtypes and seeded default init), so checkpoints load
 unchanged.  On a CUDA device `forward` runs on the library's own kernels (`hd_load_cr_weights` / `hd_cr_forward`:
 fp32 NHWC, NAF blocks on the FFMA GEMM, fused localisation conv + pool, affine-grid bilinear resampling) — a first,
-fp32-only native version of this once-per-face stage; `native = False` (or a CPU tensor) runs the plain PyTorch
-arithmetic below, which is what the CPU parity tests exercise.
+native version of this once-per-face stage.  There is no implicit fallback: a CPU tensor or a call that needs
+autograd raises; `native = False` is the explicit opt-out to the plain PyTorch arithmetic below (training, and the
+CPU tests that pin this module's layout and arithmetic against the reference).
 """
 from __future__ import annotations
 
@@ -118,12 +119,16 @@ class CoarseRestoration(nn.Module):
         return self.engine().cr_forward(x)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if self.native and x.is_cuda:
-            # inference (the reference calls CR under no_grad with frozen weights, train_refiner.py:380-381,86);
-            # anything that needs autograd goes through the PyTorch ops below
-            needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
-            if not needs_grad:
-                return self._forward_native(x)
+        if self.native:
+            # the library path: CUDA, inference (the reference calls CR under no_grad with frozen weights,
+            # train_refiner.py:380-381,86).  No silent detour: anything else must opt out with native=False.
+            if not x.is_cuda:
+                raise RuntimeError("hifidiff_b200.CoarseRestoration runs on CUDA (sm_100a); there is no CPU path. "
+                                   "Set native=False to evaluate the plain PyTorch arithmetic instead.")
+            if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+                raise RuntimeError("the native CoarseRestoration is inference-only: call it under torch.no_grad() "
+                                   "(or freeze the weights), or set native=False for the autograd-capable PyTorch ops")
+            return self._forward_native(x)
         skips = []
         x = self.intro(x)
         for enc in self.encoders:

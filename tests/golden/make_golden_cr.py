@@ -58,6 +58,7 @@ def main():
     r.eval()
     m.load_state_dict(sd)
     m.eval()
+    m.native = False   # the module's PyTorch arithmetic (the library path is CUDA-only)
     x = cr_input(2)
     taps = {}
     with torch.no_grad():

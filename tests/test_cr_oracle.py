@@ -44,6 +44,9 @@ def test_cr_module_layout_and_forward(cr_state):
     m = H.CoarseRestoration()
     m.load_state_dict(cr_state)          # strict: every key of the reference layout, nothing else
     m.eval()
+    with pytest.raises(RuntimeError), torch.no_grad():
+        m(inputs("ln_face", 1))          # the library path has no CPU fallback
+    m.native = False                     # explicit opt-out: the module's PyTorch arithmetic
     with torch.no_grad():
         y = m(inputs("ln_face", 2))
     g = golden("cr_forward.npz")
@@ -55,6 +58,7 @@ def test_cr_stn_default_init_is_identity():
     """Reference init (stn.py:36-40): zero weight + identity bias in the last FC, so a fresh STN is a no-op resample."""
     torch.manual_seed(0)
     m = H.CoarseRestoration().eval()
+    m.native = False
     x = torch.randn(1, 32, 128, 128)
     with torch.no_grad():
         y = m.encoders[0].stn(x)

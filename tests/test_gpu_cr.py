@@ -63,3 +63,5 @@ def test_cr_native_ragged_chunks_and_host_input(cr):
     assert torch.equal(out_h, y)
     with pytest.raises(ValueError), torch.no_grad():
         m(torch.rand(1, 3, 64, 64).cuda())
+    with pytest.raises(RuntimeError):                      # inference-only: no silent switch to autograd-capable ops
+        m(torch.rand(1, 3, 128, 128).cuda())
