@@ -11,7 +11,7 @@ from hifidiff_b200.sampler import _coef_array
 from oracle import denoiser_ref, philox, schedulers_ref as R
 
 from gpu_util import RawHandle, build
-from util import TRAJ_EPS_GAIN, gen, golden, inputs, psnr, rel_l2
+from util import TRAJ_EPS_GAIN, gen, golden, inputs, psnr, rel_l2, state_for
 
 pytestmark = pytest.mark.gpu
 
@@ -150,4 +150,67 @@ def test_refiner_cascade_trajectory(prec, min_psnr):
     m.denoiser.engine().synchronize()
     # split-K depth may differ with the number of row tiles, so shards agree to round-off, not always to the bit
     assert rel_l2(torch.cat([lo, hi]), x0) <= 2e-3
+    m.denoiser.invalidate()
+
+
+class _StubVAE:
+    """Stands in for diffusers' AutoencoderKL (unavailable offline): a fixed linear 8x down / up map with the same
+    call surface (`encode(x).latent_dist.sample()`, `decode(z).sample`), deterministic so both sides see the same z."""
+
+    class _Out:
+        def __init__(self, t):
+            self.sample = t
+            self.latent_dist = self
+
+    def __init__(self):
+        g = gen(77)
+        self.enc = torch.randn(4, 3, generator=g) * 8.0    # latents of roughly unit scale after scaling_factor, like a real VAE
+        self.dec = torch.randn(3, 4, generator=g) * 0.02   # decoded images stay inside (0, 1): the clamp must not decide the test
+
+    def encode(self, x):
+        z = torch.nn.functional.avg_pool2d(x, 8)
+        z = torch.einsum("oc,bchw->bohw", self.enc.to(x.device), z)
+        out = self._Out(z)
+        out.sample = lambda: z
+        return out
+
+    def decode(self, z):
+        y = torch.einsum("oc,bchw->bohw", self.dec.to(z.device), z)
+        return self._Out(torch.nn.functional.interpolate(y, scale_factor=8, mode="nearest"))
+
+
+@pytest.mark.parametrize("cr_tensor_cores", [True, False])
+def test_pixel_pipeline_matches_oracle_pipeline(cr_tensor_cores):
+    """The reference's whole `ddim_sample` (train_refiner.py:86-125) at the pixel level: native CoarseRestoration ->
+    VAE encode (stub) -> native IDC + FPG + 10 DDIM steps -> VAE decode (stub), against the same pipeline assembled
+    from the CPU oracles."""
+    from oracle import cond_ref, cr_ref
+    vae = _StubVAE()
+    with torch.device("meta"):
+        crm = H.CoarseRestoration()
+    sd_cr = state_for(crm, seed=4)
+    crm = crm.to_empty(device="cuda")
+    crm.load_state_dict(sd_cr)
+    crm.eval()
+    crm.tensor_cores = cr_tensor_cores
+    m, sd = build(H.FacialRefiner, seed=3, precision="bf16", eps_gain=TRAJ_EPS_GAIN, max_batch=4, max_steps=10, args=())
+    sched = H.DDIMScheduler(num_train_timesteps=1000, beta_schedule="scaled_linear", prediction_type="epsilon",
+                            clip_sample=False)
+    ln_face = inputs("ln_face", 2, seed=9)
+    xT = inputs("latents", 2, seed=23)
+    images = H.ddim_sample_images(ln_face.cuda(), m, vae, crm, sched, 0.18215, 10, x_T=xT.cuda())
+    m.denoiser.engine().synchronize()
+    with torch.no_grad():
+        cr_face = cr_ref.cr_forward(sd_cr, ln_face)
+        cr_latent = vae.encode(H.to_vae_range(cr_face)).latent_dist.sample() * 0.18215
+        priors = cond_ref.fpg_forward(sd, cr_latent, "fpg.")
+        ident = cond_ref.idc_forward(sd, cr_face, "idc.")
+        x0 = R.sample_loop(lambda xx, tt: denoiser_ref.fused_denoiser_forward(sd, xx, tt, priors, ident, prefix="denoiser."),
+                           xT, R.DDIMSchedulerRef(clip_sample=False), 10)
+        want = H.from_vae_range(vae.decode(x0 / 0.18215).sample)
+    q = psnr(images, want)
+    print(f"pixel pipeline (CR tensor_cores={cr_tensor_cores} + VAE stub + refiner cascade, DDIM-10): PSNR vs oracle pipeline {q:.2f} dB")
+    assert tuple(images.shape) == (2, 3, 128, 128) and float(images.min()) >= 0.0 and float(images.max()) <= 1.0
+    assert q >= 35.0, q
+    crm.invalidate()
     m.denoiser.invalidate()
