@@ -63,3 +63,22 @@ def test_cr_stn_default_init_is_identity():
     with torch.no_grad():
         y = m.encoders[0].stn(x)
     assert rel_l2(y, x) < 1e-5
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference tree not mounted")
+def test_cr_oracle_against_live_reference_stage():
+    """One NAF_STN_Block of the unmodified reference (different seed, batch 3, the 16x16 stage with its 5x5 / 3x3
+    localisation convs) against the oracle's restatement."""
+    from oracle import ref_shim
+    import sys
+    ref_shim.load()
+    from models.cr.model import NAF_STN_Block  # type: ignore  # noqa: E402  (path set by ref_shim)
+    blk = NAF_STN_Block(256, 16, num_naf=2, sampling="up").eval()
+    sd = state_for(blk, seed=123)
+    blk.load_state_dict(sd)
+    x = torch.randn(3, 256, 16, 16, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        want = blk(x)
+        got = cr_ref.naf_stn_block(sd, "", x, 2, "up")
+    assert tuple(got.shape) == (3, 128, 32, 32)
+    assert rel_l2(got, want) < TOL
