@@ -12,7 +12,6 @@ CPU tests that pin this module's layout and arithmetic against the reference).
 """
 from __future__ import annotations
 
-import ctypes as C
 import math
 from typing import Optional
 

@@ -70,7 +70,6 @@ def test_cr_oracle_against_live_reference_stage():
     """One NAF_STN_Block of the unmodified reference (different seed, batch 3, the 16x16 stage with its 5x5 / 3x3
     localisation convs) against the oracle's restatement."""
     from oracle import ref_shim
-    import sys
     ref_shim.load()
     from models.cr.model import NAF_STN_Block  # type: ignore  # noqa: E402  (path set by ref_shim)
     blk = NAF_STN_Block(256, 16, num_naf=2, sampling="up").eval()
