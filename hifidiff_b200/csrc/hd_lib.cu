@@ -302,6 +302,9 @@ struct hd_handle {
   EncodeTiledFn encode = nullptr;
   Arena arena;
   DeviceStatus* d_status = nullptr;
+  DeviceStatus* status_host = nullptr;  // pinned mirror of d_status, refreshed asynchronously after every enqueued call
+  cudaEvent_t ev_status = nullptr;
+  bool status_posted = false;
 
   // weights
   std::vector<BlockW> blocks;  // execution order
@@ -2441,13 +2444,36 @@ void check_device_status(hd_handle* h) {
   }
 }
 
+// Deferred watchdog report for the asynchronous entry points: every call that enqueues kernels ends with an async
+// copy of the 8-byte status word into pinned memory (post_status); the NEXT call on the handle, and hd_synchronize,
+// look at it once the copy has completed (poll_status).  A tripped tcgen05 pipeline therefore surfaces as
+// HD_ERR_KERNEL on the following call instead of staying silent until somebody calls hd_synchronize.
+void post_status(hd_handle* h) {
+  cudaMemcpyAsync(h->status_host, h->d_status, sizeof(DeviceStatus), cudaMemcpyDeviceToHost, h->stream);
+  cudaEventRecord(h->ev_status, h->stream);
+  h->status_posted = true;
+}
+void poll_status(hd_handle* h) {
+  if (!h->status_posted || cudaEventQuery(h->ev_status) != cudaSuccess) { cudaGetLastError(); return; }
+  h->status_posted = false;
+  if (h->status_host->error != 0) {
+    const unsigned int where = h->status_host->where;
+    DeviceStatus z{0, 0};
+    *h->status_host = z;
+    cudaMemcpy(h->d_status, &z, sizeof(z), cudaMemcpyHostToDevice);
+    HD_THROW(HD_ERR_KERNEL, "tcgen05 pipeline watchdog tripped in an earlier call (site 0x%x)", where);
+  }
+}
+
 void join_in(hd_handle* h, void* user_stream) {
+  poll_status(h);
   cudaStream_t us = static_cast<cudaStream_t>(user_stream);
   CUDA_CHECK(cudaEventRecord(h->ev_in, us));
   CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_in, 0));
 }
 void join_out(hd_handle* h, void* user_stream) {
   cudaStream_t us = static_cast<cudaStream_t>(user_stream);
+  post_status(h);
   CUDA_CHECK(cudaEventRecord(h->ev_out, h->stream));
   CUDA_CHECK(cudaStreamWaitEvent(us, h->ev_out, 0));
 }
@@ -2580,6 +2606,8 @@ void hd_destroy(hd_handle* h) {
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_status) cudaEventDestroy(h->ev_status);
+  if (h->status_host) cudaFreeHost(h->status_host);
   for (int j = 0; j < kMaxSplit - 1; ++j) {
     if (h->ev_join[j]) cudaEventDestroy(h->ev_join[j]);
     if (h->side[j]) cudaStreamDestroy(h->side[j]);
@@ -2677,6 +2705,9 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   const size_t as = h->bf16 ? 2 : 4;
   const size_t Bc = h->Bcap;
   h->d_status = A.get<DeviceStatus>(1);
+  CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&h->status_host), sizeof(DeviceStatus), cudaHostAllocDefault));
+  memset(h->status_host, 0, sizeof(DeviceStatus));
+  CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_status, cudaEventDisableTiming));
   size_t max_pc = 0;
   for (int l = 0; l < kNumLevels; ++l) {
     const size_t pc = Bc * h->sp[l] * h->sp[l] * h->c[l];
@@ -2790,6 +2821,7 @@ int32_t hd_set_condition(hd_handle* h, const float* const priors[5], const float
   CUDA_CHECK(cudaSetDevice(h->cfg.device));
   join_in(h, stream);
   cudaStream_t st = h->stream;
+  bool staged = false;  // a host-pointer input went through cond_stage
   for (int j = 0; j < kNumLevels; ++j) {
     HcaW& w = h->hca[j];
     const int d = w.d, hw = w.sp * w.sp, rows = B * hw;
@@ -2797,8 +2829,10 @@ int32_t hd_set_condition(hd_handle* h, const float* const priors[5], const float
     const float* src = priors[j];
     if (!src) HD_THROW(HD_ERR_INVALID, "priors[%d] is null", j);
     if (!is_device_ptr(src)) {
+      if (staged) CUDA_CHECK(cudaStreamSynchronize(st));  // the previous prior still owns the staging buffer
       CUDA_CHECK(cudaMemcpyAsync(h->cond_stage, src, total * 4, cudaMemcpyHostToDevice, st));
       src = h->cond_stage;
+      staged = true;
     }
     nchw_to_nhwc_kernel<<<cdiv(total, 256), 256, 0, st>>>(src, h->cond_nhwc, B, d, hw);
     // channel gate (hca.py:33-43)
@@ -2812,13 +2846,17 @@ int32_t hd_set_condition(hd_handle* h, const float* const priors[5], const float
   {  // idc_conv(identity) (model.py:245), identity is (B,2048,1,1) == (B,2048)
     const float* src = identity;
     if (!is_device_ptr(src)) {
+      if (staged) CUDA_CHECK(cudaStreamSynchronize(st));
       CUDA_CHECK(cudaMemcpyAsync(h->cond_stage, src, static_cast<size_t>(B) * 2048 * 4, cudaMemcpyHostToDevice, st));
       src = h->cond_stage;
+      staged = true;
     }
     simt_f32(B, 2048, 2048, src, h->idc_w, h->idc_b, h->idc_add, EPI_BIAS, st);
   }
   CUDA_CHECK(cudaGetLastError());
-  CUDA_CHECK(cudaStreamSynchronize(st));  // staging buffers are reused by the next call
+  // Device-pointer inputs: fully asynchronous (every buffer written above is consumed in stream order).  Host-pointer
+  // inputs were copied from pageable memory the caller may free on return: wait for those copies.
+  if (staged) CUDA_CHECK(cudaStreamSynchronize(st));
   h->condition_set = true;
   join_out(h, stream);
   HD_API_END(h)

@@ -459,15 +459,18 @@ class FusedDenoiser(_DenoiserBase):
         with torch.cuda.device(ident.device):
             eng.check(eng.lib.hd_set_condition(eng.handle, ptrs, ident.data_ptr(), b, _stream_ptr(ident.device)),
                       "hd_set_condition")
-        self._cond_key = self._key_of(facial_priors, identity_embedding)
-
-    @staticmethod
-    def _key_of(priors, ident):
-        return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in list(priors) + [ident])
+        # strong references: the storage of a cached tensor cannot be recycled for a fresh one while the key is alive
+        self._cond_key = tuple((t, t._version) for t in list(facial_priors) + [identity_embedding])
 
     def _ensure_condition(self, priors, ident, batch: int) -> None:
+        """Re-runs `set_condition` unless the SAME tensor objects, unmodified, were used last time."""
+        if priors is None or ident is None:
+            raise ValueError("FusedDenoiser needs facial_priors and identity_embedding")
         self.engine(batch)  # may invalidate the condition if the engine is rebuilt
-        if self._cond_key is None or self._cond_key != self._key_of(priors, ident):
+        cur = list(priors) + [ident]
+        key = self._cond_key
+        if (key is None or len(key) != len(cur)
+                or not all(k[0] is t and k[1] == t._version for k, t in zip(key, cur))):
             self.set_condition(priors, ident)
 
     def forward(self, latents, timesteps, facial_priors, identity_embedding):

@@ -22,8 +22,8 @@ from .schedulers import _SchedulerBase
 
 
 def to_vae_range(x: torch.Tensor) -> torch.Tensor:
-    """[0, 1] -> [-1, 1] (train_refiner.py:56-61)."""
-    return x * 2.0 - 1.0
+    """[0, 1] -> [-1, 1], clamped first (train_refiner.py:56-61: `x.clamp(0, 1) * 2.0 - 1.0`)."""
+    return x.clamp(0, 1) * 2.0 - 1.0
 
 
 def from_vae_range(x: torch.Tensor) -> torch.Tensor:
@@ -40,19 +40,30 @@ def encode_latent(vae, images: torch.Tensor, scaling_factor: float, image_res: i
     return vae.encode(to_vae_range(images)).latent_dist.sample() * scaling_factor
 
 
+def initial_noise(n_faces: int, latent_res: int = 16, seed: int = 0, first_face: int = 0) -> torch.Tensor:
+    """x_T for faces [first_face, first_face + n_faces): face i is drawn from its own generator keyed by
+    (seed, global face index), so any sharding of a set of faces over ranks starts every face from the same noise
+    (the reference draws one batch tensor from the global RNG, train_refiner.py:101-104)."""
+    out = torch.empty((n_faces, 4, latent_res, latent_res), dtype=torch.float32)
+    for i in range(n_faces):
+        g = torch.Generator(device="cpu").manual_seed((int(seed) * 0x9E3779B1 + first_face + i) & 0x7FFFFFFFFFFFFFFF)
+        out[i] = torch.randn((4, latent_res, latent_res), generator=g)
+    return out
+
+
 @torch.no_grad()
 def ddim_sample_images(ln_face: torch.Tensor, unet: FacialRefiner, vae, cr_module, scheduler: _SchedulerBase,
                        scaling_factor: float = 0.18215, num_inference_steps: int = 50, *, image_res: int = 128,
                        x_T: Optional[torch.Tensor] = None, seed: int = 0, first_face: int = 0) -> torch.Tensor:
     """The reference's `ddim_sample(ln_face, unet, vae, cr_module, scheduler, accelerator, scaling_factor,
     num_inference_steps)` (train_refiner.py:86-125) without the accelerator argument.  `x_T` replaces the draw from
-    the global RNG (:101-104) so that runs are reproducible and shardable; when omitted it is drawn here."""
+    the global RNG (:101-104) so that runs are reproducible; when omitted it is drawn per global face index
+    (`initial_noise`), so shards of one set of faces (same seed, their own first_face) see the same noise."""
     if ln_face.device.type != "cuda":
         raise RuntimeError("hifidiff_b200 has no CPU path: ln_face must be a CUDA tensor")
     bs, latent_res = ln_face.shape[0], image_res // 8
     if x_T is None:
-        g = torch.Generator(device="cpu").manual_seed(seed)
-        x_T = torch.randn((bs, 4, latent_res, latent_res), generator=g).to(ln_face.device)
+        x_T = initial_noise(bs, latent_res, seed, first_face).to(ln_face.device)
     cr_face = cr_module(ln_face)
     cr_latent = encode_latent(vae, cr_face, scaling_factor, image_res).to(torch.float32).contiguous()
     latents = sample(unet, x_T, scheduler, num_inference_steps, cr_face=cr_face, cr_latent=cr_latent, seed=seed,

@@ -34,6 +34,17 @@ class _SchedulerBase:
     def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 1e-4, beta_end: float = 2e-2,
                  beta_schedule: str = "linear", prediction_type: str = "epsilon", clip_sample: bool = True,
                  clip_sample_range: float = 1.0, **unused):
+        # diffusers kwargs this restatement implements only at their default value: anything else must not be
+        # silently ignored (it would sample with leading / offset-0 / fixed_small behaviour regardless)
+        supported_defaults = {"trained_betas": None, "set_alpha_to_one": True, "steps_offset": 0,
+                              "timestep_spacing": "leading", "thresholding": False, "rescale_betas_zero_snr": False,
+                              "variance_type": "fixed_small", "dynamic_thresholding_ratio": 0.995,
+                              "sample_max_value": 1.0}
+        for k, v in unused.items():
+            if k not in supported_defaults:
+                raise TypeError(f"unexpected scheduler argument '{k}'")
+            if v != supported_defaults[k]:
+                raise NotImplementedError(f"{k}={v!r}: only the diffusers default {supported_defaults[k]!r} is implemented")
         if prediction_type != "epsilon":
             raise NotImplementedError("only prediction_type='epsilon' (the reference's setting)")
         if beta_schedule == "scaled_linear":

@@ -14,7 +14,12 @@
  *   - Data pointers may be device pointers (on the handle's device) or host pointers; host
  *     buffers are staged through the library's own pinned/device buffers on `stream`.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
- *     enqueued on it; calls do not synchronise unless a host pointer has to be written.
+ *     enqueued on it; calls do not synchronise unless a host pointer has to be read or written
+ *     (host inputs come from pageable memory the caller may free on return).
+ *   - Device-side faults (the tcgen05 pipeline watchdog) are reported late, never dropped: every
+ *     call that enqueues kernels ends with an asynchronous copy of the 8-byte status word into
+ *     pinned memory; the NEXT call on the handle, and hd_synchronize(), return HD_ERR_KERNEL if
+ *     that word is set.
  *   - One handle per (process, device); a handle is not thread-safe.
  *   - The caller owns every buffer it passes; the library owns only its packed-weight arena,
  *     activation workspace and time-modulation tables.
@@ -185,7 +190,8 @@ int32_t hd_sampler_update(hd_handle* h, float* x_inout, const float* eps, const 
                           const float* noise, void* stream);
 
 /* Waits for all work the handle has enqueued and reports a tripped device-side watchdog
- * (HD_ERR_KERNEL) or a sticky CUDA error.  The asynchronous entry points above do not check. */
+ * (HD_ERR_KERNEL) or a sticky CUDA error.  The asynchronous entry points report a fault of an earlier
+ * call when they are entered (see Conventions); this is the call that reports it for the last one. */
 int32_t hd_synchronize(hd_handle* h);
 
 /* Times every kernel of one denoise step (plain launches, CUDA events between launches, warm L2),

@@ -98,3 +98,48 @@ def test_product_add_noise_and_ctor_kwargs():
     x0, n = torch.randn(3, 4, 16, 16, generator=g), torch.randn(3, 4, 16, 16, generator=g)
     t = torch.tensor([0, 500, 999])
     assert torch.equal(p.add_noise(x0, n, t), o.add_noise(x0, n, t))
+
+
+def test_unsupported_diffusers_kwargs_raise():
+    """Non-default spacing / offset / variance options are not silently ignored."""
+    S.DDIMScheduler(num_train_timesteps=1000, beta_schedule="scaled_linear", timestep_spacing="leading", steps_offset=0,
+                    set_alpha_to_one=True)
+    for kw in ({"timestep_spacing": "trailing"}, {"steps_offset": 1}, {"set_alpha_to_one": False},
+               {"variance_type": "fixed_large"}, {"thresholding": True}, {"rescale_betas_zero_snr": True}):
+        with pytest.raises(NotImplementedError):
+            S.DDPMScheduler(beta_schedule="scaled_linear", **kw)
+    with pytest.raises(TypeError):
+        S.DDIMScheduler(not_a_diffusers_argument=1)
+
+
+def test_oracle_against_the_published_formulas_in_float64():
+    """Independent anchor for the (parity-unpinned) scheduler oracle: the closed forms of the papers, evaluated in
+    numpy float64 from the beta schedule alone — Ho et al. 2020 eq. 6-7 (posterior mean / beta-tilde), Song et al.
+    2021 eq. 12 (DDIM) — against the fp32 op-by-op restatement of diffusers' step()."""
+    T = 1000
+    betas = np.linspace(1e-4 ** 0.5, 2e-2 ** 0.5, T, dtype=np.float64) ** 2
+    abar = np.cumprod(1.0 - betas)
+    g = torch.Generator().manual_seed(4)
+    x, eps, z = (torch.randn(2, 4, 16, 16, generator=g) for _ in range(3))
+    xd, ed, zd = x.double().numpy(), eps.double().numpy(), z.double().numpy()
+    for n in (50, 1000):
+        ddpm, ddim = R.DDPMSchedulerRef(clip_sample=False), R.DDIMSchedulerRef(clip_sample=False)
+        ddpm.set_timesteps(n)
+        ddim.set_timesteps(n)
+        stride = T // n
+        for t in (T - stride, 25 * stride, stride, 0):
+            a_t = abar[t]
+            a_p = abar[t - stride] if t - stride >= 0 else 1.0
+            x0 = (xd - np.sqrt(1 - a_t) * ed) / np.sqrt(a_t)
+            # DDIM, sigma = 0
+            want = np.sqrt(a_p) * x0 + np.sqrt(1 - a_p) * ed
+            got = ddim.step(eps, t, x).double().numpy()
+            assert np.abs(got - want).max() <= 2e-5 * max(1.0, np.abs(want).max()), ("ddim", n, t)
+            # DDPM posterior q(x_{t-1} | x_t, x0) with the strided alpha_t = abar_t / abar_prev
+            alpha = a_t / a_p
+            mean = np.sqrt(a_p) * (1 - alpha) / (1 - a_t) * x0 + np.sqrt(alpha) * (1 - a_p) / (1 - a_t) * xd
+            var = (1 - a_p) / (1 - a_t) * (1 - alpha)
+            want = mean + (np.sqrt(var) * zd if t > 0 else 0.0)
+            got = ddpm.step(eps, t, x, variance_noise=z).double().numpy()
+            # 1 - abar_t cancels in fp32 as t -> 0 (abar_1 = 0.99978): diffusers' op order carries ~6e-5 there
+            assert np.abs(got - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), ("ddpm", n, t)
