@@ -128,7 +128,7 @@ def _fused_sched():
                            clip_sample=False)
 
 
-@pytest.mark.parametrize("prec,min_psnr", [("fp32", 120.0), ("bf16", 50.0)])
+@pytest.mark.parametrize("prec,min_psnr", [("fp32", 133.0), ("bf16", 55.0)])   # measured on B200: 139.6 / 61.6 dB
 def test_fused_ddim50_trajectory_vs_reference(prec, min_psnr):
     """FusedDenoiser, 50 DDIM steps, synthetic priors / identity: final latent against the trajectory the
     reference's own module produced (tests/golden/fused_ddim50.npz, written by make_golden.py section 5)."""
@@ -169,7 +169,7 @@ def test_ddpm1000_bf16_trajectory_vs_oracle():
     print(f"DDPM-1000 bf16, 2 faces: PSNR vs fp32 oracle loop = {q:.2f} dB, rel-L2 {rel_l2(got, want):.3e} "
           f"(oracle loop {time.time() - t0:.0f} s on {torch.get_num_threads()} threads)")
     assert torch.isfinite(got).all()
-    assert q >= 45.0
+    assert q >= 54.0                        # measured on B200: 60.0 dB
     m.invalidate()
 
 
@@ -315,15 +315,16 @@ def test_two_successive_batches_each_get_their_own_condition():
     assert cross < 30.0                     # the two batches really differ
     # the module API, called like the reference's loop body (refiner.py:32-38), on fresh tensors per batch
     eps = []
-    for ln_face in faces:
-        cr_face = crm(ln_face.cuda())
+    with torch.no_grad():
+        for ln_face in faces:
+            cr_face = crm(ln_face.cuda())
+            cr_latent = H.encode_latent(vae, cr_face, 0.18215, 128).float().contiguous()
+            eps.append(m(xT.cuda(), 500, cr_face, cr_latent).sample.cpu())
+            del cr_face, cr_latent
+        fresh, _ = build(H.FacialRefiner, seed=3, precision="bf16", eps_gain=TRAJ_EPS_GAIN, max_batch=4, max_steps=10, args=())
+        cr_face = crm(faces[1].cuda())
         cr_latent = H.encode_latent(vae, cr_face, 0.18215, 128).float().contiguous()
-        eps.append(m(xT.cuda(), 500, cr_face, cr_latent).sample.cpu())
-        del cr_face, cr_latent
-    fresh, _ = build(H.FacialRefiner, seed=3, precision="bf16", eps_gain=TRAJ_EPS_GAIN, max_batch=4, max_steps=10, args=())
-    cr_face = crm(faces[1].cuda())
-    cr_latent = H.encode_latent(vae, cr_face, 0.18215, 128).float().contiguous()
-    want2 = fresh(xT.cuda(), 500, cr_face, cr_latent).sample.cpu()
+        want2 = fresh(xT.cuda(), 500, cr_face, cr_latent).sample.cpu()
     assert torch.equal(eps[1], want2)       # batch 2 through the used module == batch 2 through a fresh module
     assert not torch.equal(eps[0], eps[1])
     crm.invalidate()
