@@ -16,6 +16,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "chain.cuh"
+#include "level_chain.cuh"
 #include "face_block.cuh"
 #include "pair_block.cuh"
 #include "quad_block.cuh"
@@ -93,6 +94,10 @@ bool g_fuse_ln = false;
 // HD_FUSE_DW=1 runs depthwise 3x3 + gate + pool in conv1's epilogue at the 2x2..8x8 levels (EPI_DWGATE).
 // Measured on B200 at B=256: parity-equal but slower (2.75 vs 2.62 ms/step: the 9-tap stencil is
 // latency-bound on the 8 epilogue warps), so the standalone sliding-window kernel stays the default.
+// HD_LV: bit mask of UNet levels (bit l = level l) whose NAF-block runs execute as ONE persistent level-chain kernel
+// (level_chain.cuh) instead of nine launches per block.  HD_LV_COOP=0 launches it without the cooperative attribute.
+int g_lv = 1 << 4;
+bool g_lv_coop = true;
 int g_fuse_dw = 0;       // HD_FUSE_DW: bit mask of spatial sizes (2 | 4 | 8) whose depthwise 3x3 runs in conv1's epilogue
 
 // Per-step kernel launch: programmatic stream serialization lets kernel N+1 be scheduled (and run its
@@ -1590,6 +1595,184 @@ void add_chain_1x1(hd_handle* h, Plan& P, size_t first, int count) {
   });
 }
 
+
+// Persistent level chain (level_chain.cuh) over the blocks [first, first + count) of one small-spatial level.
+// Expects blocks[first]'s norm1 output in act_a; leaves the finished residual stream in resid[level].
+bool level_chain_ok(hd_handle* h, size_t first, int count, bool debug) {
+  if (debug || !h->bf16 || count < 1) return false;
+  const BlockW& b0 = h->blocks[first];
+  if (((g_lv >> b0.level) & 1) == 0) return false;
+  if (h->sp[b0.level] != 1) return false;  // 1x1 spatial: depthwise folded into conv1, pooled mean == the tensor
+  for (int i = 0; i < count; ++i) {
+    const BlockW& bw = h->blocks[first + i];
+    if (bw.level != b0.level || !bw.dw_folded || !bw.has_mod || bw.c % 128 != 0 || bw.c / 128 > 32) return false;
+  }
+  return true;
+}
+
+void add_level_chain(hd_handle* h, Plan& P, size_t first, int count) {
+  const int B = P.batch;
+  const BlockW& b0 = h->blocks[first];
+  const int c = b0.c, level = b0.level, rpf = h->sp[level] * h->sp[level];
+  const int rows = B * rpf;
+  const int m_tiles = cdiv(rows, 128);
+  const long long rows_alloc = static_cast<long long>(h->Bcap) * rpf;
+  std::vector<lv::Phase> phases;
+  std::vector<CUtensorMap> maps;
+  auto add_map = [&](const void* base, int K, long long nrows, int ld) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)nrows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, 128};
+    encode_map(h, &m, base, 2, dims, strides, box);
+    maps.push_back(m);
+    return static_cast<int>(maps.size()) - 1;
+  };
+  bf16* act_a = static_cast<bf16*>(h->act_a);
+  bf16* act_g = static_cast<bf16*>(h->act_g);
+  bf16* act_h = static_cast<bf16*>(h->act_h);
+  float* x = h->resid[level];
+  const int map_a = add_map(act_a, c, rows_alloc, c);
+  const int map_g = add_map(act_g, c, rows_alloc, c);
+  const int map_h = add_map(act_h, c, rows_alloc, c);
+  auto gemm = [&](int kind, int mapA, const void* W, int N, int K, const float* bias) {
+    lv::Phase ph;
+    memset(&ph, 0, sizeof(ph));
+    ph.kind = kind;
+    ph.map_a = mapA;
+    ph.map_w = add_map(W, K, N, K);
+    ph.m_tiles = m_tiles;
+    ph.n_tiles = N / 128;
+    ph.num_kb = K / 64;
+    ph.N = N;
+    ph.bias = bias;
+    int split = 1;
+    while (split < lv::CL && m_tiles * ph.n_tiles * split * 2 <= lv::GRID && ph.num_kb % (2 * split) == 0 &&
+           ph.num_kb / (2 * split) >= 2)
+      split *= 2;
+    ph.split = split;
+    P.flops_per_face += 2.0 * rows * static_cast<double>(N) * K / P.batch;
+    return ph;
+  };
+  for (int i = 0; i < count; ++i) {
+    const BlockW& bw = h->blocks[first + i];
+    const BlockW* nx = i + 1 < count ? &h->blocks[first + i + 1] : nullptr;
+    {  // conv1 (+ folded depthwise) -> SimpleGate -> g            conditional_naf.py:116-118
+      lv::Phase ph = gemm(lv::LV_GATE, map_a, bw.w1, 2 * c, c, bw.b1);
+      ph.out = act_g;
+      phases.push_back(ph);
+    }
+    {  // SCA: g2 = g * (Wsca g + b)                                conditional_naf.py:119
+      lv::Phase ph = gemm(lv::LV_MUL, map_g, bw.wsca, c, c, bw.bsca);
+      ph.mul = act_g; ph.out = act_h;
+      phases.push_back(ph);
+    }
+    {  // conv3 (+beta) + residual, then norm2 + modulation          conditional_naf.py:120-127
+      lv::Phase ph = gemm(lv::LV_RESID, map_h, bw.w3, c, c, bw.b3);
+      ph.x = x; ph.ln = 1; ph.out = act_a; ph.ln_w = bw.ln2_w; ph.ln_b = bw.ln2_b;
+      ph.shift_off = bw.mod_off + 2 * c; ph.scale_off = bw.mod_off + 3 * c;
+      phases.push_back(ph);
+    }
+    {  // conv4 -> SimpleGate                                       conditional_naf.py:128-129
+      lv::Phase ph = gemm(lv::LV_GATE, map_a, bw.w4, 2 * c, c, bw.b4);
+      ph.out = act_g;
+      phases.push_back(ph);
+    }
+    {  // conv5 (+gamma) + residual, then the next block's norm1     conditional_naf.py:130-134,114-115
+      lv::Phase ph = gemm(lv::LV_RESID, map_g, bw.w5, c, c, bw.b5);
+      ph.x = x;
+      if (nx != nullptr) {
+        ph.ln = 1; ph.out = act_a; ph.ln_w = nx->ln1_w; ph.ln_b = nx->ln1_b;
+        ph.shift_off = nx->mod_off; ph.scale_off = nx->mod_off + c;
+      }
+      phases.push_back(ph);
+    }
+  }
+  lv::Phase* d_ph = static_cast<lv::Phase*>(h->arena.alloc(phases.size() * sizeof(lv::Phase)));
+  CUtensorMap* d_maps = static_cast<CUtensorMap*>(h->arena.alloc(maps.size() * sizeof(CUtensorMap)));
+  CUDA_CHECK(cudaMemcpy(d_ph, phases.data(), phases.size() * sizeof(lv::Phase), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  lv::Args a;
+  memset(&a, 0, sizeof(a));
+  a.phases = d_ph;
+  a.n_phases = static_cast<int>(phases.size());
+  a.maps = d_maps;
+  a.rows = rows;
+  a.rows_per_face = rpf;
+  a.stats = static_cast<float2*>(h->arena.alloc(static_cast<size_t>(m_tiles) * 128 * 32 * sizeof(float2)));
+  a.sync = h->arena.get<unsigned int>(64);
+  a.mod_table = h->mod_table;
+  a.mod_row_idx = h->row_idx;
+  a.mod_stride = h->mod_stride;
+  a.status = h->d_status;
+  const int n_ph = a.n_phases;
+  const bool tracing = getenv("HD_LV_TRACE") != nullptr;
+  if (tracing) a.trace = h->arena.get<long long>(static_cast<size_t>(lv::GRID) * n_ph * 8);
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(lv::level_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lv::SMEM_BYTES));
+    configured = true;
+  }
+  g_label = fmt("L%d c=%d level_chain x%d blocks: %d phases, grid %d x cluster %d", level, c, count, n_ph, lv::GRID, lv::CL);
+  TapInfo ti;
+  ti.ptr = x; ti.dtype = DT_F32; ti.C = c; ti.HW = rpf; ti.ld = c;
+  std::string tap = h->blocks[first + count - 1].prefix;
+  if (!tap.empty() && tap.back() == '.') tap.pop_back();
+  const bool coop = g_lv_coop;
+  add_op(P, [=](cudaStream_t st) {
+    cudaMemsetAsync(a.sync, 0, 64 * sizeof(unsigned int), st);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(lv::GRID);
+    cfg.blockDim = dim3(lv::THREADS);
+    cfg.dynamicSmemBytes = lv::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the grid barriers cannot deadlock
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = coop ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, lv::level_chain_kernel, a);
+    if (tracing) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(st, &cs);
+      if (cs != cudaStreamCaptureStatusNone) return;
+      cudaStreamSynchronize(st);
+      std::vector<long long> tr(static_cast<size_t>(lv::GRID) * n_ph * 8);
+      cudaMemcpy(tr.data(), a.trace, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      // medians over CTAs of the per-phase intervals (clocks): barrier pass -> accumulator ready -> staged+handshake ->
+      // reduce/epilogue done -> (LN barrier) -> phase arrive; and phase-to-phase period
+      static const char* names[] = {"gemm_gate", "gemm_mul", "gemm_resid"};
+      fprintf(stderr, "[level_chain trace] phase kind split: bar->acc acc->drained drained->handshake handshake->epi epi->lnbar epi|lnbar->arrive | period (median clocks over %d CTAs)\n", lv::GRID);
+      for (int p = 0; p < n_ph && p < 12; ++p) {
+        auto med = [&](int from, int to) {
+          std::vector<long long> v;
+          for (int cta = 0; cta < lv::GRID; ++cta) {
+            const long long* t = tr.data() + (static_cast<size_t>(cta) * n_ph + p) * 8;
+            if (t[from] != 0 && t[to] != 0) v.push_back(t[to] - t[from]);
+          }
+          if (v.empty()) return -1ll;
+          std::sort(v.begin(), v.end());
+          return v[v.size() / 2];
+        };
+        long long period = -1;
+        if (p + 1 < n_ph) {
+          std::vector<long long> v;
+          for (int cta = 0; cta < lv::GRID; ++cta) {
+            const long long* t0 = tr.data() + (static_cast<size_t>(cta) * n_ph + p) * 8;
+            const long long* t1 = tr.data() + (static_cast<size_t>(cta) * n_ph + p + 1) * 8;
+            if (t0[5] != 0 && t1[5] != 0) v.push_back(t1[5] - t0[5]);
+          }
+          if (!v.empty()) { std::sort(v.begin(), v.end()); period = v[v.size() / 2]; }
+        }
+        const bool has_ln = phases[p].kind == lv::LV_RESID && phases[p].ln;
+        fprintf(stderr, "  %2d %-10s S=%d: %6lld %6lld %6lld %6lld %6lld %6lld | %6lld\n", p, names[phases[p].kind], phases[p].split,
+                med(0, 1), med(1, 6), med(6, 2), med(2, 3), has_ln ? med(3, 4) : -1ll, has_ln ? med(4, 5) : med(3, 5), period);
+      }
+    }
+  }, tap, ti);
+}
+
 Plan* get_plan(hd_handle* h, int B, bool debug = false) {
   auto& cache = debug ? h->plans_dbg : h->plans;
   auto it = cache.find(B);
@@ -1671,7 +1854,19 @@ Plan* get_plan(hd_handle* h, int B, bool debug = false) {
     add_gemm(h, P, d, cx_rows_alloc(h, P, n * n), "ups." + std::to_string(L), ti);
   };
   auto emit_mid = [&](size_t first) {
-    if (P.cx.nslab <= 1 && g_chain && !debug && bf && h->sp[4] == 1 && h->blocks[first].dw_folded) {
+    if (P.cx.nslab <= 1 && level_chain_ok(h, first, kMidBlocks, debug)) {
+      // the 8 bottleneck blocks as one persistent level-chain kernel (level_chain.cuh); norm1 of the first block first
+      const BlockW& b0 = h->blocks[first];
+      const int c = b0.c, rows = B;
+      const float* resid = h->resid[4];
+      void* act_a = h->act_a;
+      ModRef mod{h->mod_table, h->row_idx, h->mod_stride};
+      const float *lw = b0.ln1_w, *lb = b0.ln1_b;
+      const int so = b0.mod_off, co = b0.mod_off + c;
+      g_label = "L4 level_chain ln1";
+      add_op(P, [=](cudaStream_t st) { launch_ln<bf16>(c, resid, lw, lb, static_cast<bf16*>(act_a), rows, 1, mod, so, co, 1, st); });
+      add_level_chain(h, P, first, kMidBlocks);
+    } else if (P.cx.nslab <= 1 && g_chain && !debug && bf && h->sp[4] == 1 && h->blocks[first].dw_folded) {
       // the 8 bottleneck blocks as one persistent cooperative kernel (chain.cuh); norm1 of the first block first
       const BlockW& b0 = h->blocks[first];
       const int c = b0.c, rows = B;
@@ -2653,6 +2848,8 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   if (const char* e = getenv("HD_FUSE_SCALE")) g_fuse_scale = atoi(e) != 0;
   if (const char* e = getenv("HD_MAX_STAGES")) g_max_stages = atoi(e);
   if (const char* e = getenv("HD_FUSE_LN")) g_fuse_ln = atoi(e) != 0;
+  if (const char* e = getenv("HD_LV")) g_lv = atoi(e);
+  if (const char* e = getenv("HD_LV_COOP")) g_lv_coop = atoi(e) != 0;
   h = new hd_handle();
   struct Guard { hd_handle*& p; bool armed = true; ~Guard() { if (armed && p) { hd_destroy(p); p = nullptr; } } } guard{h};
   h->cfg = *cfg;

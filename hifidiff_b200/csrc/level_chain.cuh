@@ -11,9 +11,10 @@
 //               this phase is still in its epilogue / barrier — and the A cursor waits at every phase boundary for the
 //               grid barrier (the A operand is the previous phase's output).
 //   warp 1      MMA issuer: tcgen05.mma M=128 N=128 K=16 from separate A / W rings into one of two TMEM accumulators.
-//   warps 2-9   epilogue: TMEM -> fp32 staging tile in shared memory; the CTAs that split K for the same output tile
-//               are cluster-mates and exchange partial tiles over distributed shared memory (fixed summation order:
-//               deterministic); bias + SimpleGate / SCA multiply / residual add; LayerNorm2d + AdaLN modulation of the
+//   warps 2-9   epilogue: the CTAs that split K for the same output tile are cluster-mates; each pushes the rows another
+//               CTA finishes straight from TMEM registers into that CTA's shared memory (st.async over distributed
+//               shared memory, completion counted on the receiver's mbarrier) and adds the partial rows it received
+//               in fixed order (deterministic); bias + SimpleGate / SCA multiply / residual add; LayerNorm2d + AdaLN modulation of the
 //               finished residual rows (per-tile (mean, M2) statistics merged across the N tiles after one extra grid
 //               barrier); the next GEMM's bf16 A operand is written to global memory (L2-resident).
 //
@@ -133,6 +134,22 @@ __device__ __forceinline__ bool wait_counter(const unsigned int* counter, unsign
     }
   }
 }
+// 16-byte store into the shared memory of a cluster-mate; completes 16 bytes on that CTA's mbarrier
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(remote_addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t map_shared_rank(uint32_t local_addr, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  return remote;
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory"); }
 
 // One unit of GEMM work of this CTA: (phase, iteration) -> tile and K range.  Both producer cursors, the MMA issuer
@@ -163,6 +180,9 @@ __device__ __forceinline__ Unit make_unit(const Phase& P, int iter) {
 struct Cursor {
   int ph, it, kb;
   Unit u;
+  const CUtensorMap* map;  // this cursor's operand of the current phase
+  int row0;                // first row of the operand tile (A: mt * 128, W: nt * 128)
+  bool is_w;
   bool done;
 };
 __device__ __forceinline__ void cursor_settle(Cursor& c, const Args& a) {
@@ -172,7 +192,11 @@ __device__ __forceinline__ void cursor_settle(Cursor& c, const Args& a) {
     const int iters = phase_iters(P);
     while (c.it < iters) {
       c.u = make_unit(P, c.it);
-      if (c.u.valid) return;
+      if (c.u.valid) {
+        c.map = a.maps + (c.is_w ? P.map_w : P.map_a);
+        c.row0 = (c.is_w ? c.u.nt : c.u.mt) * 128;
+        return;
+      }
       ++c.it;
     }
     ++c.ph;
@@ -180,8 +204,8 @@ __device__ __forceinline__ void cursor_settle(Cursor& c, const Args& a) {
   }
   c.done = true;
 }
-__device__ __forceinline__ void cursor_init(Cursor& c, const Args& a) {
-  c.ph = 0; c.it = 0; c.kb = 0; c.done = false;
+__device__ __forceinline__ void cursor_init(Cursor& c, const Args& a, bool is_w) {
+  c.ph = 0; c.it = 0; c.kb = 0; c.done = false; c.is_w = is_w; c.map = nullptr; c.row0 = 0;
   cursor_settle(c, a);
 }
 __device__ __forceinline__ void cursor_next(Cursor& c, const Args& a) {
@@ -191,7 +215,7 @@ __device__ __forceinline__ void cursor_next(Cursor& c, const Args& a) {
   cursor_settle(c, a);
 }
 
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) level_chain_kernel(const Args args) {
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(320, 1) level_chain_kernel(const Args args) {
   using namespace tc;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -204,7 +228,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) level_c
   uint64_t* tmem_empty = tmem_full + 2;     // [2]
   uint64_t* stage_ready = tmem_empty + 2;   // all CL cluster-mates have staged their partial tile
   uint64_t* reads_done = stage_ready + 1;   // all CL cluster-mates have finished reading the staged tiles
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(reads_done + 1);
+  uint64_t* phase_go = reads_done + 1;      // the producer has seen the grid barrier that opens the next phase
+  uint64_t* recv_full = phase_go + 1;       // the cluster-mates' partial rows have landed in this CTA's receive slots
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(recv_full + 1);
   float* stage = reinterpret_cast<float*>(smem + OFF_STG);
 
   const int warp = threadIdx.x >> 5;
@@ -219,6 +245,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) level_c
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tmem_full[s]), 1); mbar_init(smem_u32(&tmem_empty[s]), EW); }
     mbar_init(smem_u32(stage_ready), CL);
     mbar_init(smem_u32(reads_done), CL);
+    mbar_init(smem_u32(phase_go), 1);
+    mbar_init(smem_u32(recv_full), 1);
     fence_barrier_init();
     fence_proxy_async_smem();
   }
@@ -236,76 +264,79 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) level_c
   if (warp == 0) {
     if (lane == 0) {
       // ================= TMA producer: W cursor ahead of A cursor =================
+      // The only thread of the CTA that polls the grid-barrier counter (polling from every warp slows the arrivals
+      // down); the epilogue warps wait on the local phase_go barrier it signals.
+      for (int i = 0; i < 3; ++i) prefetch_tensormap(args.maps + i);
       Cursor ca, cw;
-      cursor_init(ca, args);
-      cursor_init(cw, args);
-      uint32_t a_it = 0, w_it = 0;   // k-blocks pushed into each ring
-      uint32_t seq_a = 0, seq_w = 0; // items issued by each cursor
-      int synced = 0;                // phases [0, synced) are known complete grid-wide
+      cursor_init(ca, args, false);
+      cursor_init(cw, args, true);
+      uint32_t a_slot = 0, a_par = 0, a_fills = 0;   // A ring: next slot, its parity, fills so far
+      uint32_t w_slot = 0, w_par = 0, w_fills = 0;
+      uint32_t seq_a = 0, seq_w = 0;                 // items issued by each cursor
+      const CUtensorMap* w_map_seen = nullptr;
       auto issue_w = [&](bool blocking) -> bool {
         if (cw.done) return false;
-        const int s = w_it % NW;
-        const uint32_t ph = (w_it / NW) & 1;
-        const uint32_t eb = smem_u32(&empty_w[s]);
-        if (w_it >= static_cast<uint32_t>(NW)) {
-          if (blocking) { if (!mbar_wait(eb, ph ^ 1u, status, 0xA10u)) { cw.done = true; return false; } }
-          else if (!mbar_try_wait(eb, ph ^ 1u)) return false;
+        const uint32_t eb = smem_u32(&empty_w[w_slot]);
+        if (w_fills >= static_cast<uint32_t>(NW)) {
+          if (blocking) mbar_wait(eb, w_par ^ 1u, status, 0xA10u);
+          else if (!mbar_try_wait(eb, w_par ^ 1u)) return false;
         }
-        const int map_w = args.phases[cw.ph].map_w;
-        const uint32_t fb = smem_u32(&full_w[s]);
+        if (cw.map != w_map_seen) {  // the descriptor of the phase after this one: fetched a whole phase ahead
+          w_map_seen = cw.map;
+          if (cw.ph + 1 < args.n_phases) prefetch_tensormap(args.maps + args.phases[cw.ph + 1].map_w);
+        }
+        const uint32_t fb = smem_u32(&full_w[w_slot]);
         mbar_expect_tx(fb, TILE_BYTES);
-        tma_load_2d(smem_u32(smem + OFF_W + s * TILE_BYTES), args.maps + map_w, (cw.u.kb_begin + cw.kb) * BK, cw.u.nt * 128, fb);
-        ++w_it; ++seq_w;
+        tma_load_2d(smem_u32(smem + OFF_W + w_slot * TILE_BYTES), cw.map, (cw.u.kb_begin + cw.kb) * BK, cw.row0, fb);
+        ++w_fills; ++seq_w;
+        if (++w_slot == static_cast<uint32_t>(NW)) { w_slot = 0; w_par ^= 1u; }
         cursor_next(cw, args);
         return true;
       };
-      while (!ca.done) {
-        if (ca.ph > synced) {
-          // the A operand of phase ca.ph is written by the epilogues of phase ca.ph - 1: wait for the whole grid,
+      for (int ph = 0; ph < args.n_phases; ++ph) {
+        if (ph > 0) {
+          // the A operand of phase ph is written by the epilogues of phase ph - 1: wait for the whole grid,
           // streaming as many weight tiles as the W ring takes first
           while (issue_w(false)) {}
-          if (!wait_counter(bar_phase, static_cast<unsigned int>(GRID) * ca.ph, status, 0xA20u)) break;
-          __threadfence();
+          wait_counter(bar_phase, static_cast<unsigned int>(GRID) * ph, status, 0xA20u);
           fence_proxy_async_all();
-          synced = ca.ph;
-          if (trace != nullptr) trace[ca.ph * 8 + 0] = clock64();
+          mbar_arrive_local(smem_u32(phase_go));
+          if (trace != nullptr) trace[ph * 8 + 0] = clock64();
         }
-        while (seq_w <= seq_a) { if (!issue_w(true)) break; }  // this item's W tile is in flight
-        const int s = a_it % NA;
-        const uint32_t ph = (a_it / NA) & 1;
-        const uint32_t eb = smem_u32(&empty_a[s]);
-        if (a_it >= static_cast<uint32_t>(NA) && !mbar_try_wait(eb, ph ^ 1u)) {
-          while (issue_w(false)) {}
-          if (!mbar_wait(eb, ph ^ 1u, status, 0xA30u)) break;
+        while (!ca.done && ca.ph == ph) {
+          while (seq_w <= seq_a) { if (!issue_w(true)) break; }  // this item's W tile is in flight
+          const uint32_t eb = smem_u32(&empty_a[a_slot]);
+          if (a_fills >= static_cast<uint32_t>(NA) && !mbar_try_wait(eb, a_par ^ 1u)) {
+            while (issue_w(false)) {}
+            mbar_wait(eb, a_par ^ 1u, status, 0xA30u);
+          }
+          const uint32_t fb = smem_u32(&full_a[a_slot]);
+          mbar_expect_tx(fb, TILE_BYTES);
+          tma_load_2d(smem_u32(smem + OFF_A + a_slot * TILE_BYTES), ca.map, (ca.u.kb_begin + ca.kb) * BK, ca.row0, fb);
+          ++a_fills; ++seq_a;
+          if (++a_slot == static_cast<uint32_t>(NA)) { a_slot = 0; a_par ^= 1u; }
+          cursor_next(ca, args);
+          issue_w(false);
         }
-        const int map_a = args.phases[ca.ph].map_a;
-        const uint32_t fb = smem_u32(&full_a[s]);
-        mbar_expect_tx(fb, TILE_BYTES);
-        tma_load_2d(smem_u32(smem + OFF_A + s * TILE_BYTES), args.maps + map_a, (ca.u.kb_begin + ca.kb) * BK, ca.u.mt * 128, fb);
-        ++a_it; ++seq_a;
-        cursor_next(ca, args);
-        issue_w(false);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ================= MMA issuer =================
       constexpr uint32_t idesc = make_idesc(BM, 128);
-      uint32_t a_it = 0, w_it = 0, acc_it = 0;
-      bool ok = true;
-      for (int ph = 0; ph < args.n_phases && ok; ++ph) {
+      uint32_t sa = 0, pa = 0, sw = 0, pw = 0, acc_it = 0;
+      for (int ph = 0; ph < args.n_phases; ++ph) {
         const Phase P = args.phases[ph];
         const int iters = phase_iters(P);
-        for (int it = 0; it < iters && ok; ++it) {
+        for (int it = 0; it < iters; ++it) {
           const Unit u = make_unit(P, it);
           if (!u.valid) continue;
           const uint32_t buf = acc_it & 1u;
-          ok = mbar_wait(smem_u32(&tmem_empty[buf]), ((acc_it >> 1) & 1u) ^ 1u, status, 0xB10u);
+          mbar_wait(smem_u32(&tmem_empty[buf]), ((acc_it >> 1) & 1u) ^ 1u, status, 0xB10u);
           tc_fence_after_sync();
-          for (int kb = 0; kb < u.kb_count && ok; ++kb) {
-            const int sa = a_it % NA, sw = w_it % NW;
-            ok = mbar_wait(smem_u32(&full_w[sw]), (w_it / NW) & 1u, status, 0xB20u) &&
-                 mbar_wait(smem_u32(&full_a[sa]), (a_it / NA) & 1u, status, 0xB30u);
+          for (int kb = 0; kb < u.kb_count; ++kb) {
+            mbar_wait(smem_u32(&full_w[sw]), pw, status, 0xB20u);
+            mbar_wait(smem_u32(&full_a[sa]), pa, status, 0xB30u);
             tc_fence_after_sync();
             const uint64_t da = make_smem_desc(smem_u32(smem + OFF_A + sa * TILE_BYTES));
             const uint64_t db = make_smem_desc(smem_u32(smem + OFF_W + sw * TILE_BYTES));
@@ -313,7 +344,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) level_c
             for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(da + 2 * k, db + 2 * k, tmem_base + buf * 128u, (kb | k) != 0 ? 1u : 0u, idesc);
             umma_commit(smem_u32(&empty_a[sa]));
             umma_commit(smem_u32(&empty_w[sw]));
-            ++a_it; ++w_it;
+            if (++sa == static_cast<uint32_t>(NA)) { sa = 0; pa ^= 1u; }
+            if (++sw == static_cast<uint32_t>(NW)) { sw = 0; pw ^= 1u; }
           }
           umma_commit(smem_u32(&tmem_full[buf]));
           ++acc_it;
@@ -325,11 +357,18 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) level_c
     // Control flow here never depends on whether a wait succeeded: a tripped watchdog sets the status word, every
     // later wait then gives up at once, and all warps still meet at every barrier (garbage out, HD_ERR_KERNEL on
     // the host) instead of hanging the GPU.
+    //
+    // K-split reduction by PUSH: the staging buffer is S receive slots of 128/S rows.  The CTA with split rank z
+    // finishes rows [z * 128/S, (z+1) * 128/S) of the tile; every CTA of the group sends those rows of ITS partial
+    // accumulator straight from registers into slot (its own z) of that CTA — st.async over distributed shared
+    // memory, counted in bytes on the receiver's mbarrier — and keeps its own rows with plain stores.  The receiver
+    // then adds the S slots in slot order (fixed: deterministic) out of its own shared memory.  (Pulling the partial
+    // tiles with ld.shared::cluster instead measured 8-10 k clocks per 128x128 tile: remote loads are latency-bound.)
     const int ew = warp - 2;                 // 0..7
     const int quad = warp & 3;               // TMEM lane quadrant this warp may read
     const int chalf = ew >> 2;               // which 64 accumulator columns this warp drains
-    uint32_t acc_it = 0, hs_it = 0;          // accumulators consumed; cluster handshakes done
-    bool hs_pending = false;                 // peers may still be reading this CTA's staging tile
+    uint32_t acc_it = 0, rx_it = 0, hs_it = 0;   // accumulators consumed; receive phases; read-done handshakes
+    bool hs_pending = false;                 // cluster-mates may still be reading... writing: see reads_done below
     unsigned int ln_target = 0;
     const uint32_t stage_u32 = smem_u32(stage);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -338,21 +377,20 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) level_c
       const int iters = phase_iters(P);
       const int S = P.split;
       const int rows_mine = 128 / S;
+      const uint32_t slot_bytes = static_cast<uint32_t>(STG_BYTES / S);
       const uint32_t gbase = (crank / S) * S;   // first cluster rank of this CTA's K-split group
       const bool gate = P.kind == LV_GATE;
-      // cross-CTA data of the previous phase (mul source, residual rows) must be visible to this warp's loads
-      if (ph > 0) {
-        if (lane == 0) wait_counter(bar_phase, static_cast<unsigned int>(GRID) * ph, status, 0xC10u);
-        __syncwarp();
-      }
+      // cross-CTA data of the previous phase (mul source, residual rows) is visible once the producer saw the barrier
+      if (ph > 0) mbar_wait(smem_u32(phase_go), (ph - 1) & 1u, status, 0xC10u);
       for (int it = 0; it < iters; ++it) {
         const Unit u = make_unit(P, it);
         const int ncol = u.nt * 128;
         const int row_base = u.z * rows_mine;
         // rows of the non-gate epilogues: one row per warp pass, lanes along the 32 four-column chunks
-        constexpr int MAXP = 16;
-        const int passes = rows_mine / EW;       // non-gate: 4 / 8 / 16
+        constexpr int MAXP = 8;
+        const int passes = rows_mine / EW;       // non-gate: 4 / 8 (split 4 / 2)
         float4 e_pre[MAXP];
+        if (u.valid && S > 1 && threadIdx.x == 64) mbar_expect_tx(smem_u32(recv_full), (S - 1) * slot_bytes);
         if (u.valid && !gate) {
           // residual rows / SCA multiplicand of this CTA's rows: fetched while the MMAs are still running
 #pragma unroll
@@ -361,9 +399,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) level_c
             const int m = u.mt * 128 + row_base + p * EW + ew;
             if (p < passes && m < args.rows) {
               if (P.kind == LV_RESID) {
-                e_pre[p] = *reinterpret_cast<const float4*>(P.x + static_cast<size_t>(m) * P.N + ncol + lane * 4);
+                e_pre[p] = __ldcg(reinterpret_cast<const float4*>(P.x + static_cast<size_t>(m) * P.N + ncol + lane * 4));
               } else {
-                const uint2 g = *reinterpret_cast<const uint2*>(P.mul + static_cast<size_t>(m) * P.N + ncol + lane * 4);
+                const uint2 g = __ldcg(reinterpret_cast<const uint2*>(P.mul + static_cast<size_t>(m) * P.N + ncol + lane * 4));
                 const float2 g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y);
                 e_pre[p] = make_float4(g0.x, g0.y, g1.x, g1.y);
               }
@@ -372,18 +410,23 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) level_c
         }
         if (u.valid) {
           const uint32_t buf = acc_it & 1u;
-          if (hs_pending) {  // peers finished reading the previous partial tile staged here
+          if (hs_pending) {  // (several units per phase only) the group has consumed the previous unit's slots
             mbar_wait_cluster(smem_u32(reads_done), (hs_it - 1u) & 1u, status, 0xC20u);
             hs_pending = false;
           }
           mbar_wait(smem_u32(&tmem_full[buf]), (acc_it >> 1) & 1u, status, 0xC30u);
           tc_fence_after_sync();
           if (trace != nullptr && threadIdx.x == 64) trace[ph * 8 + 1] = clock64();
-          // ---- TMEM -> staging (16-byte chunks XOR-swizzled by row) ----
+          // ---- TMEM -> receive slots: own rows locally, the other rows into their owners' shared memory ----
           {
-            const int r = quad * 32 + lane;
+            const int r = quad * 32 + lane;                 // accumulator row of this thread
+            const int zdst = r / rows_mine;                 // split rank that finishes this row
+            const int rl = r - zdst * rows_mine;            // row inside its owner's slot
+            const uint32_t off = static_cast<uint32_t>(u.z) * slot_bytes + static_cast<uint32_t>(rl) * 512u;
+            const bool local = zdst == u.z;
+            const uint32_t dst_base = local ? stage_u32 + off : map_shared_rank(stage_u32 + off, gbase + zdst);
+            const uint32_t dst_bar = local ? 0u : map_shared_rank(smem_u32(recv_full), gbase + zdst);
             const uint32_t taddr = tmem_base + buf * 128u + (static_cast<uint32_t>(quad * 32) << 16);
-            float* srow = stage + r * 128;
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 32) {
               uint32_t v[32];
@@ -391,8 +434,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) level_c
               tmem_wait_ld();
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const int ck = ((chalf * 64 + c0) >> 2) + j;
-                *reinterpret_cast<uint4*>(srow + ((ck ^ (r & 7)) << 2)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                const uint32_t ck = static_cast<uint32_t>(((chalf * 64 + c0) >> 2) + j);
+                const uint32_t a = dst_base + ((ck ^ static_cast<uint32_t>(rl & 7)) << 4);
+                if (local) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
+                else st_async_v4(a, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], dst_bar);
               }
             }
           }
@@ -400,15 +445,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) level_c
           __syncwarp();
           if (lane == 0) mbar_arrive_local(smem_u32(&tmem_empty[buf]));
           ++acc_it;
+          if (trace != nullptr && threadIdx.x == 64) trace[ph * 8 + 6] = clock64();
         }
-        // ---- all staged: CTA-wide, then cluster-wide when K is split ----
+        // ---- own rows staged by every warp of this CTA; the cluster-mates' rows have landed ----
         epi_bar_sync();
-        if (S > 1) {
-          if (threadIdx.x == 64) {
-#pragma unroll
-            for (uint32_t r = 0; r < static_cast<uint32_t>(CL); ++r) mbar_arrive_remote(smem_u32(stage_ready), r);
-          }
-          mbar_wait_cluster(smem_u32(stage_ready), hs_it & 1u, status, 0xC40u);
+        if (u.valid && S > 1) {
+          mbar_wait_cluster(smem_u32(recv_full), rx_it & 1u, status, 0xC40u);
+          ++rx_it;
         }
         if (trace != nullptr && threadIdx.x == 64) trace[ph * 8 + 2] = clock64();
         if (u.valid && gate) {
@@ -422,21 +465,21 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) level_c
             float4 part[2][CL], part2[2][CL];
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-              const int r = row_base + ((p0 + q) * EW + ew) * 2 + sub;
-              const uint32_t a1 = stage_u32 + static_cast<uint32_t>((r * 128 + ((sl ^ (r & 7)) << 2)) * 4);
-              const uint32_t a2 = stage_u32 + static_cast<uint32_t>((r * 128 + (((sl + 16) ^ (r & 7)) << 2)) * 4);
+              const int rl = ((p0 + q) * EW + ew) * 2 + sub;
+              const uint32_t a1 = stage_u32 + static_cast<uint32_t>(rl * 512 + ((sl ^ (rl & 7)) << 4));
+              const uint32_t a2 = stage_u32 + static_cast<uint32_t>(rl * 512 + (((sl + 16) ^ (rl & 7)) << 4));
 #pragma unroll
               for (int s = 0; s < CL; ++s) {
                 if (s < S) {
-                  part[q][s] = ld_dsmem_f4(a1, gbase + s);
-                  part2[q][s] = ld_dsmem_f4(a2, gbase + s);
+                  part[q][s] = ld_shared_f4(a1 + s * slot_bytes);
+                  part2[q][s] = ld_shared_f4(a2 + s * slot_bytes);
                 }
               }
             }
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-              const int r = row_base + ((p0 + q) * EW + ew) * 2 + sub;
-              const int m = u.mt * 128 + r;
+              const int rl = ((p0 + q) * EW + ew) * 2 + sub;
+              const int m = u.mt * 128 + row_base + rl;
               float4 v = zero4, w = zero4;
 #pragma unroll
               for (int s = 0; s < CL; ++s) {
@@ -459,16 +502,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) level_c
               float4 part[4][CL];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const int r = row_base + (p0 + q) * EW + ew;
-                const uint32_t a1 = stage_u32 + static_cast<uint32_t>((r * 128 + ((lane ^ (r & 7)) << 2)) * 4);
+                const int rl = (p0 + q) * EW + ew;
+                const uint32_t a1 = stage_u32 + static_cast<uint32_t>(rl * 512 + ((lane ^ (rl & 7)) << 4));
 #pragma unroll
                 for (int s = 0; s < CL; ++s)
-                  if (s < S) part[q][s] = ld_dsmem_f4(a1, gbase + s);
+                  if (s < S) part[q][s] = ld_shared_f4(a1 + s * slot_bytes);
               }
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const int r = row_base + (p0 + q) * EW + ew;
-                const int m = u.mt * 128 + r;
+                const int rl = (p0 + q) * EW + ew;
+                const int m = u.mt * 128 + row_base + rl;
                 const bool live = m < args.rows;
                 float4 v = zero4;
 #pragma unroll
@@ -495,8 +538,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) level_c
           }
         }
         if (trace != nullptr && threadIdx.x == 64) trace[ph * 8 + 3] = clock64();
-        if (S > 1) {
-          epi_bar_sync();  // every warp of this CTA is done with its remote reads
+        if (S > 1 && iters > 1) {
+          // another unit of this phase follows without a grid barrier in between: the group agrees that everybody
+          // has read its slots before anybody pushes the next partial rows
+          epi_bar_sync();
           if (threadIdx.x == 64) {
 #pragma unroll
             for (uint32_t r = 0; r < static_cast<uint32_t>(CL); ++r) mbar_arrive_remote(smem_u32(reads_done), r);
@@ -505,19 +550,24 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) level_c
           ++hs_it;
         }
       }
+      if (hs_pending) {  // leave the phase with the handshake barrier consumed
+        mbar_wait_cluster(smem_u32(reads_done), (hs_it - 1u) & 1u, status, 0xC25u);
+        hs_pending = false;
+      }
       if (P.kind == LV_RESID && P.ln) {
         // ---- grid barrier among the epilogue warps, then LayerNorm2d + modulation of the finished rows ----
-        __threadfence();
+        // (bar.sync orders every warp's stores before thread 64's gpu-scope fence: one fence releases them all)
         epi_bar_sync();
         ln_target += GRID;
         if (threadIdx.x == 64) {
+          __threadfence();
           atomicAdd(bar_ln, 1u);
           wait_counter(bar_ln, ln_target, status, 0xC50u);
-          __threadfence();
         }
         epi_bar_sync();
         if (trace != nullptr && threadIdx.x == 64) trace[ph * 8 + 4] = clock64();
         const int T = P.n_tiles;
+        const float inv_t = 1.f / static_cast<float>(T);
         const float inv_n = 1.f / static_cast<float>(P.N);
         for (int it = 0; it < iters; ++it) {
           const Unit u = make_unit(P, it);
@@ -525,33 +575,47 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) level_c
           const int ncol = u.nt * 128 + lane * 4;
           const float4 w4 = __ldg(reinterpret_cast<const float4*>(P.ln_w + ncol));
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.ln_b + ncol));
-          for (int rr = ew; rr < rows_mine; rr += EW) {
-            const int m = u.mt * 128 + u.z * rows_mine + rr;
-            if (m >= args.rows) continue;
-            const float4 xv = *reinterpret_cast<const float4*>(P.x + static_cast<size_t>(m) * P.N + ncol);
-            float2 st = make_float2(0.f, 0.f);
-            if (lane < T) st = __ldcg(args.stats + static_cast<size_t>(m) * 32 + lane);
-            const float mu = warp_sum(st.x) / static_cast<float>(T);
-            const float dm = lane < T ? st.x - mu : 0.f;
-            const float m2 = warp_sum(st.y + 128.f * dm * dm);
-            const float denom = sqrtf(m2 * inv_n + 1e-6f);
-            const float* mrow = args.mod_table + static_cast<size_t>(args.mod_row_idx[m / args.rows_per_face]) * args.mod_stride;
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(mrow + P.scale_off + ncol));
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(mrow + P.shift_off + ncol));
-            float4 y;
-            y.x = (w4.x * ((xv.x - mu) / denom) + b4.x) * (sc.x + 1.f) + sh.x;
-            y.y = (w4.y * ((xv.y - mu) / denom) + b4.y) * (sc.y + 1.f) + sh.y;
-            y.z = (w4.z * ((xv.z - mu) / denom) + b4.z) * (sc.z + 1.f) + sh.z;
-            y.w = (w4.w * ((xv.w - mu) / denom) + b4.w) * (sc.w + 1.f) + sh.w;
-            store4<bf16>(P.out + static_cast<size_t>(m) * P.N + ncol, y);
+          // four rows per batch: all loads of the batch are issued before the first reduction
+#pragma unroll 1
+          for (int rr0 = ew; rr0 < rows_mine; rr0 += 4 * EW) {
+            float4 xv[4], sc[4], sh[4];
+            float2 st[4];
+            int mrow[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int rr = rr0 + q * EW;
+              const int m = u.mt * 128 + u.z * rows_mine + rr;
+              mrow[q] = (rr < rows_mine && m < args.rows) ? m : -1;
+              xv[q] = zero4; sc[q] = zero4; sh[q] = zero4; st[q] = make_float2(0.f, 0.f);
+              if (mrow[q] >= 0) {
+                xv[q] = __ldcg(reinterpret_cast<const float4*>(P.x + static_cast<size_t>(m) * P.N + ncol));
+                if (lane < T) st[q] = __ldcg(args.stats + static_cast<size_t>(m) * 32 + lane);
+                const float* mr = args.mod_table + static_cast<size_t>(args.mod_row_idx[m / args.rows_per_face]) * args.mod_stride;
+                sc[q] = __ldg(reinterpret_cast<const float4*>(mr + P.scale_off + ncol));
+                sh[q] = __ldg(reinterpret_cast<const float4*>(mr + P.shift_off + ncol));
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float mu = warp_sum(st[q].x) * inv_t;
+              const float dm = lane < T ? st[q].x - mu : 0.f;
+              const float m2 = warp_sum(st[q].y + 128.f * dm * dm);
+              const float denom = sqrtf(m2 * inv_n + 1e-6f);
+              float4 y;
+              y.x = (w4.x * ((xv[q].x - mu) / denom) + b4.x) * (sc[q].x + 1.f) + sh[q].x;
+              y.y = (w4.y * ((xv[q].y - mu) / denom) + b4.y) * (sc[q].y + 1.f) + sh[q].y;
+              y.z = (w4.z * ((xv[q].z - mu) / denom) + b4.z) * (sc[q].z + 1.f) + sh[q].z;
+              y.w = (w4.w * ((xv[q].w - mu) / denom) + b4.w) * (sc[q].w + 1.f) + sh[q].w;
+              if (mrow[q] >= 0) store4<bf16>(P.out + static_cast<size_t>(mrow[q]) * P.N + ncol, y);
+            }
           }
         }
       }
       // ---- end of phase: this CTA's global writes are published, one arrival on the grid counter ----
-      fence_proxy_async_all();
-      __threadfence();
+      fence_proxy_async_all();  // this thread's generic-proxy stores vs. the TMA (async-proxy) reads of the next phase
       epi_bar_sync();
       if (threadIdx.x == 64) {
+        __threadfence();
         atomicAdd(bar_phase, 1u);
         if (trace != nullptr) trace[ph * 8 + 5] = clock64();
       }

@@ -124,7 +124,7 @@ def test_fused_face_kernel_taps_and_plans_agree():
         cond = ([p.cuda() for p in priors], ident.cuda())
         t = torch.arange(batch) * 7 + 3 if batch == 3 else 321
         t_dev = t.cuda() if torch.is_tensor(t) else t
-        fast_names = ["encoders.0.1", "encoders.1.1", "decoders.2.1", "decoders.3.1"]
+        fast_names = ["encoders.0.1", "encoders.1.1", "middle_blks.7", "decoders.2.1", "decoders.3.1"]
         out_fast, taps_fast = m.forward_with_taps(x.cuda(), t_dev, fast_names, *cond)
         out_dbg, taps_dbg = m.forward_with_taps(x.cuda(), t_dev, fast_names + ["intro"], *cond)
         plain = m(x.cuda(), t_dev, *cond).sample
@@ -138,6 +138,38 @@ def test_fused_face_kernel_taps_and_plans_agree():
             assert rel_l2(taps_fast[k], taps_dbg[k]) <= 6e-3, (batch, k)
         assert rel_l2(out_fast.sample, ref) <= 1e-2
         assert rel_l2(out_fast.sample, out_dbg.sample) <= 8e-3
+    m.invalidate()
+
+
+@pytest.mark.parametrize("batch", [5, 130, 256])
+def test_level_chain_against_per_op_plan(batch):
+    """The persistent level-chain kernel (level_chain.cuh: the eight 2048-channel bottleneck blocks in one launch,
+    K split over cluster-mates, LayerNorm statistics merged across N tiles) against the one-kernel-per-op plan at
+    the tap it exposes and at eps, for one, two (ragged) and two full 128-row tiles; the small batch also against
+    the CPU oracle."""
+    m, sd = build(H.FusedDenoiser, seed=2, precision="bf16", max_batch=256)
+    x = inputs("latents", batch, seed=13)
+    priors, ident = testing.synthetic_condition(batch, 16, seed=13)
+    cond = ([p.cuda() for p in priors], ident.cuda())
+    t = (torch.arange(batch) * 3 + 1) % 1000
+    out_fast, taps_fast = m.forward_with_taps(x.cuda(), t.cuda(), ["middle_blks.7"], *cond)
+    out_dbg, taps_dbg = m.forward_with_taps(x.cuda(), t.cuda(), ["middle_blks.7", "middle_blks.3"], *cond)
+    again = m(x.cuda(), t.cuda(), *cond).sample
+    m.engine().synchronize()
+    info = m.engine().info()
+    print(f"level chain B={batch}: {info.launches_per_step} launches/step; middle_blks.7 fast vs per-op "
+          f"{rel_l2(taps_fast['middle_blks.7'], taps_dbg['middle_blks.7']):.3e}, eps {rel_l2(out_fast.sample, out_dbg.sample):.3e}")
+    assert torch.isfinite(out_fast.sample).all()
+    assert torch.equal(again, out_fast.sample)                                  # deterministic (fixed split-K order)
+    # two independent bf16 evaluation orders of the same 8 blocks (each <= 1e-2 from the fp32 oracle)
+    assert rel_l2(taps_fast["middle_blks.7"], taps_dbg["middle_blks.7"]) <= 8e-3
+    assert rel_l2(out_fast.sample, out_dbg.sample) <= 8e-3
+    if batch <= 8:
+        ref_taps = {}
+        with torch.no_grad():
+            ref = denoiser_ref.fused_denoiser_forward(sd, x, t, priors, ident, ref_taps)
+        assert rel_l2(taps_fast["middle_blks.7"], ref_taps["middle_blks.7"]) <= 1e-2
+        assert rel_l2(out_fast.sample, ref) <= 1e-2
     m.invalidate()
 
 
