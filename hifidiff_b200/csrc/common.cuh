@@ -23,11 +23,8 @@ enum Epi : int {
   EPI_RESID = 3,    // out[m,n] = resid[m,n] + acc + bias[n]         (fp32 residual stream)
   EPI_GATE = 4,     // packed 128-column groups: out[m, g*64+i] = (acc[m,g*128+i]+b) * (acc[m,g*128+64+i]+b)
   EPI_PIXSHUF = 5,  // 1x1 up-conv + PixelShuffle(2) + skip add, in place on the fp32 skip buffer
-  EPI_RESID_LN = 6, // EPI_RESID, and the following LayerNorm2d + AdaLN modulation of the same rows (N == 128)
-  EPI_DWGATE = 7,   // conv1 + bias, then depthwise 3x3 + SimpleGate + per-face mean over the staged tile
-                    // (gate-packed 128-column groups; tile = whole faces, spatial 2/4/8)
-  EPI_SCALE = 8,    // SCA: s[face,n] = acc + bias[n] (stored fp32), and scale_dst[row,n] = scale_src[row,n] * s[face,n] for the
-                    // rows_per_face rows of the face (conditional_naf.py:119 `x * self.sca(x)`), replacing scale_rows_kernel
+  EPI_MUL = 6,      // out[m,n] = (acc + bias[n]) * mul[m,n]: SCA at 1x1 spatial, where the pooled mean is the gated tensor
+                    // itself and a face is one row (conditional_naf.py:119 `x * self.sca(x)`); mul is bf16, passed as `resid`
 };
 
 enum AMode : int {
@@ -53,24 +50,8 @@ struct GemmDesc {
   void* out = nullptr;
   int ldo = 0;
   int out_dtype = DT_F32;
-  const float* resid = nullptr;
+  const float* resid = nullptr;  // EPI_RESID / EPI_PIXSHUF: fp32 [M, ldr]; EPI_MUL: bf16 [M, ldr] multiplicand
   int ldr = 0;
-  // EPI_RESID_LN: the consumer's LayerNorm affine, where its modulation vectors sit in the table row,
-  // and the bf16 output that replaces a separate ln_mod_kernel launch
-  const float* ln_w = nullptr;
-  const float* ln_b = nullptr;
-  const float* mod_table = nullptr;
-  const int* mod_row_idx = nullptr;
-  int mod_stride = 0, ln_shift_off = 0, ln_scale_off = 0, rows_per_face = 1;
-  void* ln_out = nullptr;
-  // EPI_DWGATE: depthwise taps [9][N] and bias [N] in the packed column order, pooled means out (bf16 [faces, N/2])
-  const float* dw_w = nullptr;
-  const float* dw_b = nullptr;
-  void* pooled = nullptr;
-  // EPI_SCALE: bf16 [faces * rows_per_face, scale_ld] gated tensor in, scaled copy out
-  const void* scale_src = nullptr;
-  void* scale_dst = nullptr;
-  int scale_ld = 0;
   // split-K until the grid has at least this many CTAs (one chain of a split region gets its share of the SMs)
   int cta_target = 120;
 };

@@ -37,21 +37,6 @@ struct TcArgs {
   int kb_per_tap;             // A_CONV3: C / 64
   int conv_bh, conv_bb;       // A_CONV3: box rows in h and in batch (conv_bh * sp * conv_bb == 128)
   DeviceStatus* status;
-  // EPI_RESID_LN
-  const float* ln_w;
-  const float* ln_b;
-  const float* mod_table;
-  const int* mod_row_idx;
-  int mod_stride, ln_shift_off, ln_scale_off, rows_per_face;
-  bf16* ln_out;
-  // EPI_DWGATE
-  const float* dw_w;
-  const float* dw_b;
-  bf16* pooled;
-  // EPI_SCALE
-  const bf16* scale_src;
-  bf16* scale_dst;
-  int scale_ld;
   long long* trace;           // optional per-CTA timeline (16 slots per CTA), nullptr in production
 };
 
@@ -62,8 +47,7 @@ template <int BN, int STAGES, int EW = 8> struct TileCfg {
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr int STAGING_BYTES = BM * BN * 4;  // fp32 accumulator tile, aliases the ring after the mainloop
   static_assert(RING_BYTES >= STAGING_BYTES, "epilogue staging must fit in the operand ring");
-  static constexpr int SEG_BYTES = 32 * 64 * 4;        // EPI_DWGATE: per-segment channel sums for the pooled mean
-  static constexpr int BAR_BYTES = 256 + SEG_BYTES;
+  static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = RING_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;               // power of two >= 32
   // co-resident CTAs per SM (228 KB shared memory, 512 TMEM columns): short-K GEMMs are dominated by
@@ -250,8 +234,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   static_assert(BN / (EW / 4) >= 32, "each epilogue warp drains at least one 32-column TMEM chunk");
   static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
   static_assert(EPI != EPI_GATE || BN == 128, "gate epilogue needs 128-column packed groups");
-  static_assert(EPI != EPI_RESID_LN || BN == 128, "fused LayerNorm needs the whole 128-channel row in one tile");
-  static_assert(EPI != EPI_DWGATE || BN == 128, "depthwise+gate epilogue needs 128-column packed groups");
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment (same offset in every CTA of the cluster)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -406,79 +388,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (nsplit > 1) cluster_sync_all(); else __syncthreads();
   if (trace != nullptr && threadIdx.x == 64) trace[6] = clock64();
 
-  if (EPI == EPI_DWGATE) {
-    // ---------------- epilogue phase B': depthwise 3x3 + SimpleGate + pooled mean over the staged tile ----------------
-    // The tile holds whole faces (128 % sp^2 == 0).  A lane owns 2 gate channels (2 x1 + 2 x2 columns) with
-    // its 36 taps in registers; a warp walks 128/EW consecutive pixel rows.  conv1's output never leaves
-    // the SM and is never rounded (reference: conditional_naf.py:116-119).
-    float* s_seg = reinterpret_cast<float*>(bar_base + 256);  // [<=32 segments][64 channels]
-    if (warp >= 2) {
-      const int ew = warp - 2;
-      const int sp = args.sp, npix = sp * sp;
-      constexpr int RPW = BM / NUM_EPI_WARPS;                  // rows per warp
-      const int seg_len = npix < RPW ? npix : RPW;             // rows whose sums a warp keeps in registers
-      const int col1 = 2 * lane, col2 = 64 + 2 * lane;         // packed columns: x1 | x2
-      float w1[9][2], w2[9][2], bd1[2], bd2[2], bc1[2], bc2[2];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const float2 a = __ldg(reinterpret_cast<const float2*>(args.dw_w + static_cast<size_t>(t) * args.N + n0 + col1));
-        const float2 b = __ldg(reinterpret_cast<const float2*>(args.dw_w + static_cast<size_t>(t) * args.N + n0 + col2));
-        w1[t][0] = a.x; w1[t][1] = a.y; w2[t][0] = b.x; w2[t][1] = b.y;
-      }
-      {
-        const float2 a = __ldg(reinterpret_cast<const float2*>(args.dw_b + n0 + col1));
-        const float2 b = __ldg(reinterpret_cast<const float2*>(args.dw_b + n0 + col2));
-        const float2 c = __ldg(reinterpret_cast<const float2*>(args.bias + n0 + col1));
-        const float2 d = __ldg(reinterpret_cast<const float2*>(args.bias + n0 + col2));
-        bd1[0] = a.x; bd1[1] = a.y; bd2[0] = b.x; bd2[1] = b.y;
-        bc1[0] = c.x; bc1[1] = c.y; bc2[0] = d.x; bc2[1] = d.y;
-      }
-      const int ck1 = lane >> 1, ck2 = 16 + (lane >> 1), sub2 = (lane & 1) * 2;
-      bf16* gout = reinterpret_cast<bf16*>(args.out);
-      float ps0 = 0.f, ps1 = 0.f;
-#pragma unroll 1
-      for (int rr = 0; rr < RPW; ++rr) {
-        const int r = ew * RPW + rr;
-        const int pf = r % npix;
-        const int py = pf / sp, px = pf - py * sp;
-        float a1[2] = {bd1[0], bd1[1]}, a2[2] = {bd2[0], bd2[1]};
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const int dy = t / 3 - 1, dx = t % 3 - 1;
-          const int yy = py + dy, xx = px + dx;
-          if (yy < 0 || yy >= sp || xx < 0 || xx >= sp) continue;
-          const int r2 = r + dy * sp + dx;
-          const float* row2 = stage + r2 * BN;
-          const float2 x1 = *reinterpret_cast<const float2*>(row2 + ((ck1 ^ (r2 & 7)) << 2) + sub2);
-          const float2 x2 = *reinterpret_cast<const float2*>(row2 + ((ck2 ^ (r2 & 7)) << 2) + sub2);
-          a1[0] = fmaf(x1.x + bc1[0], w1[t][0], a1[0]);
-          a1[1] = fmaf(x1.y + bc1[1], w1[t][1], a1[1]);
-          a2[0] = fmaf(x2.x + bc2[0], w2[t][0], a2[0]);
-          a2[1] = fmaf(x2.y + bc2[1], w2[t][1], a2[1]);
-        }
-        const float o0 = a1[0] * a2[0], o1 = a1[1] * a2[1];
-        ps0 += o0; ps1 += o1;
-        const int m = m0 + r;
-        if (m < args.M)
-          *reinterpret_cast<uint32_t*>(gout + static_cast<size_t>(m) * args.ldo + (n0 >> 1) + 2 * lane) = pack_bf16x2(o0, o1);
-        if ((rr + 1) % seg_len == 0) {
-          *reinterpret_cast<float2*>(s_seg + (r / seg_len) * 64 + 2 * lane) = make_float2(ps0, ps1);
-          ps0 = 0.f; ps1 = 0.f;
-        }
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
-      // per-face means, segments added in fixed order (deterministic)
-      const int faces_in_tile = BM / npix, segs_per_face = npix / seg_len;
-      for (int i = threadIdx.x - 64; i < faces_in_tile * 64; i += 32 * NUM_EPI_WARPS) {
-        const int f = i >> 6, ch = i & 63;
-        const int face = m0 / npix + f;
-        if (face * npix >= args.M) continue;
-        float sum = 0.f;
-        for (int q = 0; q < segs_per_face; ++q) sum += s_seg[(f * segs_per_face + q) * 64 + ch];
-        args.pooled[static_cast<size_t>(face) * args.ldo + (n0 >> 1) + ch] = __float2bfloat16_rn(sum / static_cast<float>(npix));
-      }
-    }
-  } else
   if (warp >= 2) {
     // ---------------- epilogue phase B: lanes along columns, coalesced global traffic ----------------
     constexpr int CH = (EPI == EPI_GATE) ? BN / 8 : BN / 4;  // output 4-column chunks per row
@@ -526,43 +435,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         v.x = 1.f / (1.f + __expf(-v.x)); v.y = 1.f / (1.f + __expf(-v.y));
         v.z = 1.f / (1.f + __expf(-v.z)); v.w = 1.f / (1.f + __expf(-v.w));
       }
-      if (EPI == EPI_RESID || EPI == EPI_RESID_LN || EPI == EPI_PIXSHUF) { v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w; }
+      if (EPI == EPI_RESID || EPI == EPI_PIXSHUF) { v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w; }
+      if (EPI == EPI_MUL) { v.x *= e.x; v.y *= e.y; v.z *= e.z; v.w *= e.w; }
       if (okay) store4<TOut>(d + i * LPR * 4, v);
-      if (EPI == EPI_SCALE && okay) {
-        // (face, column) of this chunk from its address in the [faces, ldo] output; scale the face's pixel rows
-        const size_t off = static_cast<size_t>((d + i * LPR * 4) - reinterpret_cast<TOut*>(args.out));
-        const size_t face = off / static_cast<size_t>(args.ldo);
-        const size_t col = off - face * static_cast<size_t>(args.ldo);
-        const int rpf = args.rows_per_face;
-        for (int p = 0; p < rpf; ++p) {
-          const size_t o = (face * rpf + p) * static_cast<size_t>(args.scale_ld) + col;
-          const uint2 u = *reinterpret_cast<const uint2*>(args.scale_src + o);
-          const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-          *reinterpret_cast<uint2*>(args.scale_dst + o) = make_uint2(pack_bf16x2(a.x * v.x, a.y * v.y), pack_bf16x2(b.x * v.z, b.y * v.w));
-        }
-      }
       return v;
     };
-    // EPI_RESID_LN: the warp holds the whole 128-channel row (4 values per lane): LayerNorm2d statistics
-    // by warp shuffles (two-pass, as utils.py:16-24), affine, AdaLN modulation, bf16 store
-    auto layer_norm_row = [&](float4 v, int mc, bool okay) {
-      const float mu = warp_sum(v.x + v.y + v.z + v.w) * (1.f / 128.f);
-      const float d0 = v.x - mu, d1 = v.y - mu, d2 = v.z - mu, d3 = v.w - mu;
-      const float var = warp_sum(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3) * (1.f / 128.f);
-      const float denom = sqrtf(var + 1e-6f);
-      const int c0 = sl * 4;
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(args.ln_w + c0));
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.ln_b + c0));
-      const float* mrow = args.mod_table + static_cast<size_t>(args.mod_row_idx[mc / args.rows_per_face]) * args.mod_stride;
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(mrow + args.ln_scale_off + c0));
-      const float4 sh = __ldg(reinterpret_cast<const float4*>(mrow + args.ln_shift_off + c0));
-      float4 y;
-      y.x = (w4.x * (d0 / denom) + b4.x) * (sc.x + 1.f) + sh.x;
-      y.y = (w4.y * (d1 / denom) + b4.y) * (sc.y + 1.f) + sh.y;
-      y.z = (w4.z * (d2 / denom) + b4.z) * (sc.z + 1.f) + sh.z;
-      y.w = (w4.w * (d3 / denom) + b4.w) * (sc.w + 1.f) + sh.w;
-      if (okay) store4<bf16>(args.ln_out + static_cast<size_t>(mc) * 128 + c0, y);
+    // EPI_MUL: the bf16 multiplicand of one 4-column chunk
+    auto load_mul = [&](const bf16* p) -> float4 {
+      const uint2 u = *reinterpret_cast<const uint2*>(p);
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+      return make_float4(a.x, a.y, b.x, b.y);
     };
+    const bf16* mul_src = reinterpret_cast<const bf16*>(args.resid);
     // row bookkeeping shared by both paths
     auto locate = [&](int pass, bool& okay, int& rc, int& mc, TOut*& d) {
       const int rl = (pass * NUM_EPI_WARPS + ew) * RPI + sub;  // row within this CTA's slice
@@ -594,8 +478,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int swz = r0 & 7;
       const float* sbase = stage + r0 * BN;
       TOut* dbase = reinterpret_cast<TOut*>(args.out) + static_cast<size_t>(m0 + r0) * args.ldo + out_col0 + sl * 4;
-      const float* rbase = (EPI == EPI_RESID || EPI == EPI_RESID_LN)
-                               ? args.resid + static_cast<size_t>(m0 + r0) * args.ldr + n0 + sl * 4 : nullptr;
+      const float* rbase = EPI == EPI_RESID ? args.resid + static_cast<size_t>(m0 + r0) * args.ldr + n0 + sl * 4 : nullptr;
+      const bf16* mbase = EPI == EPI_MUL ? mul_src + static_cast<size_t>(m0 + r0) * args.ldr + n0 + sl * 4 : nullptr;
       const size_t dstep = static_cast<size_t>(STEP) * args.ldo, rstep = static_cast<size_t>(STEP) * args.ldr;
       int soff[CPL], soff2[CPL];
 #pragma unroll
@@ -617,16 +501,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             acc2[u][i] = zero4;
             ext[u][i] = zero4;
             if (EPI == EPI_GATE) acc2[u][i] = *reinterpret_cast<const float4*>(sbase + p * (STEP * BN) + soff2[i]);
-            if ((EPI == EPI_RESID || EPI == EPI_RESID_LN) && ok[u])
-              ext[u][i] = *reinterpret_cast<const float4*>(rbase + p * rstep + i * LPR * 4);
+            if (EPI == EPI_RESID && ok[u]) ext[u][i] = *reinterpret_cast<const float4*>(rbase + p * rstep + i * LPR * 4);
+            if (EPI == EPI_MUL && ok[u]) ext[u][i] = load_mul(mbase + p * rstep + i * LPR * 4);
           }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
           for (int i = 0; i < CPL; ++i) {
-            const float4 r = finish(acc[u][i], acc2[u][i], ext[u][i], i, dbase + (it0 + u) * dstep, ok[u]);
-            if (EPI == EPI_RESID_LN) layer_norm_row(r, m0 + r0 + (it0 + u) * STEP, ok[u]);
+            finish(acc[u][i], acc2[u][i], ext[u][i], i, dbase + (it0 + u) * dstep, ok[u]);
           }
       }
     } else if (nsplit == 1) {
@@ -636,7 +519,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         float4 acc[U][CPL], acc2[U][CPL], ext[U][CPL];
         bool ok[U];
         TOut* dst[U];
-        int mrow_idx[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           int rc, mc;
@@ -648,18 +530,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             acc2[u][i] = zero4;
             ext[u][i] = zero4;
             if (EPI == EPI_GATE) acc2[u][i] = *reinterpret_cast<const float4*>(stage + rc * BN + (((ck + 16) ^ (rc & 7)) << 2));
-            if (EPI == EPI_RESID || EPI == EPI_RESID_LN)
+            if (EPI == EPI_RESID)
               ext[u][i] = *reinterpret_cast<const float4*>(args.resid + static_cast<size_t>(mc) * args.ldr + n0 + ck * 4);
+            if (EPI == EPI_MUL) ext[u][i] = load_mul(mul_src + static_cast<size_t>(mc) * args.ldr + n0 + ck * 4);
             if (EPI == EPI_PIXSHUF) ext[u][i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dst[u]) + i * LPR * 4);
           }
-          mrow_idx[u] = mc;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
           for (int i = 0; i < CPL; ++i) {
-            const float4 r = finish(acc[u][i], acc2[u][i], ext[u][i], i, dst[u], ok[u]);
-            if (EPI == EPI_RESID_LN) layer_norm_row(r, mrow_idx[u], ok[u]);
+            finish(acc[u][i], acc2[u][i], ext[u][i], i, dst[u], ok[u]);
           }
       }
     } else {
@@ -687,6 +568,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
           if (EPI == EPI_RESID)
             e = *reinterpret_cast<const float4*>(args.resid + static_cast<size_t>(mc) * args.ldr + n0 + ck * 4);
+          if (EPI == EPI_MUL) e = load_mul(mul_src + static_cast<size_t>(mc) * args.ldr + n0 + ck * 4);
           if (EPI == EPI_PIXSHUF) e = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d) + i * LPR * 4);
           float4 v = zero4, g = zero4;
 #pragma unroll

@@ -15,13 +15,9 @@
 #include "elem_kernels.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
-#include "chain.cuh"
-#include "level_chain.cuh"
 #include "face_block.cuh"
 #include "pair_block.cuh"
-#include "quad_block.cuh"
 #include "idc_kernels.cuh"
-#include "sca_kernel.cuh"
 #include "cr_kernels.cuh"
 
 using namespace hd;
@@ -62,43 +58,32 @@ constexpr float kBnEps = 1e-5f;
 
 inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
-bool g_use_pdl = true;  // HD_PDL=0 disables programmatic dependent launch
-bool g_bn256 = true;    // HD_BN256=0: 128x128 tiles for the dense 3x3 convs too
-int g_two_cta = 1;      // HD_TWO_CTA=0: never use cta_group::2 pairs; 2: wherever the shape allows (tests)
-bool g_face = true;     // HD_FACE=0: per-op kernels at the 16x16 level instead of the fused per-face block kernel
-bool g_fuse_scale = false;  // HD_FUSE_SCALE=1: rescale the gated rows in the SCA GEMM epilogue (measured +83 us/step: too few CTAs)
-bool g_quad = false;    // HD_QUAD=1: 4-CTA-cluster block kernel at the 4x4 level (parity green; measured 35 us/step slower)
-bool g_pair = true;     // HD_PAIR=0: per-op kernels at the 8x8 level instead of the fused face-pair block kernel
-bool g_chain = false;   // HD_CHAIN=1: run the 1x1-level blocks as one persistent cooperative kernel (measured slower)
-// HD_SPLIT=n: the 4x4 / 2x2 / 1x1 levels (latency-bound: ~120 GEMMs of 7-10 us that cannot fill the chip) run as n
-// independent face-range chains on n streams, forked and joined inside the step's CUDA graph, each GEMM sized
-// for 1/n of the SMs so the chains' kernels co-reside.  1 = off (default).  Measured on B200 at B=256: 2.21 ms/step
-// with 2 chains, 2.41 with 3, 2.37 with 4, against 2.16 unsplit — these kernels are latency-bound, so a
-// half-size kernel takes as long as a full-size one and concurrency buys nothing.
-int g_split = 1;
-// HD_SCA_FUSED=1: SCA GEMM + rescale as one mma.sync kernel (sca_kernel.cuh).  Parity-green, measured slower at
-// B=256 (9.4 / 10.1 / 17.4 us at the 4x4 / 2x2 / 1x1 levels against 8.0 / 10.3 / 10.7 for the split-K tcgen05 GEMM
-// + rescale): 64x32 tiles without split-K make every CTA ingest its whole A and W panels at ~60 B/clk/SM.
-bool g_sca_fused = false;
-bool g_cr_stn_cs = true;  // HD_CR_STN_CS=0: one thread per (pixel, 2 output channels) in the first STN localisation conv
-bool g_cr_tc = true;     // HD_CR_TC=0: every CoarseRestoration GEMM on the FFMA kernel (no split-precision tcgen05 path)
-bool g_dw_small = true;  // HD_DW_SMALL=0: the generic tiled depthwise kernel at the 2x2 / 4x4 levels too
-int g_cta_target = 120;  // HD_CTA_TARGET: split-K until a GEMM's grid has at least this many CTAs
-int g_sca_target = 120;  // HD_SCA_TARGET: the same for the SCA GEMMs (M = faces)
-constexpr int kMaxSplit = 4;
-int g_max_stages = 6;   // HD_MAX_STAGES=3: no 6-stage / 16-epilogue-warp variant (one CTA per SM)
-// HD_FUSE_LN=1 computes LayerNorm + modulation in the residual GEMM's epilogue where the tile holds the whole
-// row (c = 128).  Measured on B200 at B=256: the fused epilogue costs 31.6 us against 14.2 us (GEMM) + 10.2 us
-// (standalone LN): these GEMMs are epilogue-bound, so the standalone bandwidth-bound kernel stays the default.
-bool g_fuse_ln = false;
-// HD_FUSE_DW=1 runs depthwise 3x3 + gate + pool in conv1's epilogue at the 2x2..8x8 levels (EPI_DWGATE).
-// Measured on B200 at B=256: parity-equal but slower (2.75 vs 2.62 ms/step: the 9-tap stencil is
-// latency-bound on the 8 epilogue warps), so the standalone sliding-window kernel stays the default.
-// HD_LV: bit mask of UNet levels (bit l = level l) whose NAF-block runs execute as ONE persistent level-chain kernel
-// (level_chain.cuh) instead of nine launches per block.  HD_LV_COOP=0 launches it without the cooperative attribute.
-int g_lv = 1 << 4;
-bool g_lv_coop = true;
-int g_fuse_dw = 0;       // HD_FUSE_DW: bit mask of spatial sizes (2 | 4 | 8) whose depthwise 3x3 runs in conv1's epilogue
+// Tuning switches, read from the environment once per handle at hd_create (a handle keeps its own copy: two handles
+// created under different environments do not see each other's settings).
+struct Tunables {
+  bool pdl = true;        // HD_PDL=0 disables programmatic dependent launch
+  bool bn256 = true;      // HD_BN256=0: 128x128 tiles for the dense 3x3 convs too
+  int two_cta = 1;        // HD_TWO_CTA=0: never use cta_group::2 pairs; 2: wherever the shape allows (tests)
+  bool face = true;       // HD_FACE=0: per-op kernels at the 16x16 level instead of the fused per-face block kernel
+  bool pair = true;       // HD_PAIR=0: per-op kernels at the 8x8 level instead of the fused face-pair block kernel
+  bool sca_mul = true;    // HD_SCA_MUL=0: separate scale_rows kernel at the 1x1 level too
+  bool cr_stn_cs = true;  // HD_CR_STN_CS=0: one thread per (pixel, 2 output channels) in the first STN localisation conv
+  bool cr_tc = true;      // HD_CR_TC=0: every CoarseRestoration GEMM on the FFMA kernel (no split-precision tcgen05 path)
+  bool dw_small = true;   // HD_DW_SMALL=0: the generic tiled depthwise kernel at the 2x2 / 4x4 levels too
+  int cta_target = 120;   // HD_CTA_TARGET: split-K until a GEMM's grid has at least this many CTAs
+  int sca_target = 120;   // HD_SCA_TARGET: the same for the SCA GEMMs (M = faces)
+  void read_env() {
+    auto flag = [](const char* name, bool& v) { if (const char* e = getenv(name)) v = atoi(e) != 0; };
+    flag("HD_PDL", pdl); flag("HD_BN256", bn256); flag("HD_FACE", face); flag("HD_PAIR", pair); flag("HD_SCA_MUL", sca_mul);
+    flag("HD_CR_STN_CS", cr_stn_cs); flag("HD_CR_TC", cr_tc); flag("HD_DW_SMALL", dw_small);
+    if (const char* e = getenv("HD_TWO_CTA")) two_cta = atoi(e);
+    if (const char* e = getenv("HD_CTA_TARGET")) cta_target = std::max(atoi(e), 1);
+    if (const char* e = getenv("HD_SCA_TARGET")) sca_target = std::max(atoi(e), 1);
+  }
+};
+// PDL attribute of the launches issued by the calling thread: set from the handle's Tunables by every entry point
+// that launches kernels (set_launch_tunables), so the launch helpers need no handle argument.
+thread_local bool t_use_pdl = true;
 
 // Per-step kernel launch: programmatic stream serialization lets kernel N+1 be scheduled (and run its
 // prologue / weight prefetch) while kernel N drains; every such kernel executes pdl_wait() first.
@@ -114,7 +99,7 @@ void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaSt
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cfg.numAttrs = t_use_pdl ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
@@ -165,7 +150,6 @@ struct BlockW {
   std::vector<float> b3_h, b5_h;  // host copies of the folded conv3 / conv5 biases (cumulative residual bias)
   bool dw_folded = false;  // 1x1 level: depthwise 3x3 == per-channel scale, folded into conv1 (gate-packed)
   bool has_mod = true;     // false: unconditional NAFBlock of the FPG encoder (models/fpg/naf.py:105-126)
-  bool dw_fused = false;   // 2x2..8x8 levels, bf16: depthwise 3x3 + gate + pool run in conv1's epilogue (gate-packed)
 };
 
 // FacialPriorGuidance (models/fpg/model.py:7-64): NAFNet encoder over the CR latent, run once per face batch
@@ -252,16 +236,6 @@ struct Op {
   std::string tap;
   TapInfo info;
   std::string label;  // kernel kind + shape, for hd_profile_step
-  int chain = 0;      // stream the op is issued on: 0 = the handle's stream, j > 0 = side stream j - 1
-  bool fork = false;  // before this op: side streams wait for everything issued so far
-  bool join = false;  // after this op: the handle's stream waits for the side streams
-};
-
-// Face range an op builder works on.  Default: the whole batch in the shared workspace.  Inside a split
-// region each chain owns faces [f0, f0 + nf) of the per-level tensors and slab `id` of every scratch buffer.
-struct ChainCx {
-  int id = 0, f0 = 0, nf = -1, nslab = 1;
-  int cta_target = 120;  // split-K until a GEMM's grid has at least this many CTAs
 };
 
 thread_local std::string g_label;  // label picked up by the next add_op
@@ -274,8 +248,6 @@ struct Plan {
   int64_t graph_first = 0;
   const float* graph_noise = nullptr;
   double flops_per_face = 0;
-  ChainCx cx;        // context the op builders are working in (reset to the whole batch once the plan is built)
-  int n_chains = 1;  // > 1: the plan has a split region (fork / join ops)
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -293,6 +265,7 @@ struct SrcTensor {
 
 struct hd_handle {
   hd_config cfg{};
+  Tunables tun;
   std::string err;
   bool fused = false, bf16 = true, weights_loaded = false, condition_set = false;
   int S = 16, Bcap = 0, max_steps = 0, sm_count = 0, sm_major = 0, sm_minor = 0;
@@ -300,10 +273,7 @@ struct hd_handle {
   int mod_stride = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-  cudaStream_t side[kMaxSplit - 1] = {};
-  cudaEvent_t ev_fork = nullptr, ev_join[kMaxSplit - 1] = {};
   size_t act_bytes = 0, pooled_rows = 0;
-  int split = 1;  // HD_SPLIT at hd_create
   EncodeTiledFn encode = nullptr;
   Arena arena;
   DeviceStatus* d_status = nullptr;
@@ -421,7 +391,7 @@ void launch_tc_inst2(const TcLaunch& L, cudaStream_t st) {
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_use_pdl ? 2 : 1;
+  cfg.numAttrs = t_use_pdl ? 2 : 1;
   cudaLaunchKernelEx(&cfg, kern, L.mapA, L.mapB, L.args);
 }
 
@@ -456,7 +426,7 @@ void launch_tc2_inst(const TcLaunch& L, cudaStream_t st) {
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_use_pdl ? 2 : 1;
+  cfg.numAttrs = t_use_pdl ? 2 : 1;
   cudaLaunchKernelEx(&cfg, kern, L.mapA, L.mapB, L.args);
 }
 
@@ -496,11 +466,9 @@ void launch_tc(const TcLaunch& L, cudaStream_t st) {
       break;
     case EPI_RELU: launch_tc_inst<EPI_RELU, A_PLAIN, bf16>(L, st); break;
     case EPI_RESID: launch_tc_inst<EPI_RESID, A_PLAIN, float>(L, st); break;
-    case EPI_RESID_LN: launch_tc_inst<EPI_RESID_LN, A_PLAIN, float>(L, st); break;
     case EPI_GATE: launch_tc_inst<EPI_GATE, A_PLAIN, bf16>(L, st); break;
-    case EPI_DWGATE: launch_tc_inst<EPI_DWGATE, A_PLAIN, bf16>(L, st); break;
     case EPI_PIXSHUF: launch_tc_inst<EPI_PIXSHUF, A_PLAIN, float>(L, st); break;
-    case EPI_SCALE: launch_tc_inst<EPI_SCALE, A_PLAIN, float>(L, st); break;
+    case EPI_MUL: launch_tc_inst<EPI_MUL, A_PLAIN, bf16>(L, st); break;
     default: break;
   }
 }
@@ -524,11 +492,6 @@ TcLaunch build_tc(hd_handle* h, const GemmDesc& d, long long a_rows_alloc) {
   a.bias = d.bias; a.out = d.out; a.ldo = d.ldo; a.resid = d.resid; a.ldr = d.ldr;
   a.sp = d.sp; a.kb_per_tap = 1; a.conv_bh = 1; a.conv_bb = 1;
   a.status = h->d_status;
-  a.ln_w = d.ln_w; a.ln_b = d.ln_b; a.mod_table = d.mod_table; a.mod_row_idx = d.mod_row_idx;
-  a.mod_stride = d.mod_stride; a.ln_shift_off = d.ln_shift_off; a.ln_scale_off = d.ln_scale_off;
-  a.rows_per_face = d.rows_per_face; a.ln_out = static_cast<bf16*>(d.ln_out);
-  a.dw_w = d.dw_w; a.dw_b = d.dw_b; a.pooled = static_cast<bf16*>(d.pooled);
-  a.scale_src = static_cast<const bf16*>(d.scale_src); a.scale_dst = static_cast<bf16*>(d.scale_dst); a.scale_ld = d.scale_ld;
   a.trace = nullptr;
   if (d.a_mode == A_CONV3) {
     const int n = d.sp, C = d.C;
@@ -555,8 +518,8 @@ TcLaunch build_tc(hd_handle* h, const GemmDesc& d, long long a_rows_alloc) {
                     (d.epi == EPI_RELU && d.out_dtype == DT_BF16);
   const bool conv_ok = d.a_mode != A_CONV3 || (d.epi == EPI_RELU && d.out_dtype == DT_BF16);
   const long long pair_ctas = static_cast<long long>((m_tiles + 1) / 2) * 2 * (d.N / 256);
-  L.two_cta = g_two_cta != 0 && epi2 && conv_ok && d.N % 256 == 0 && a_rows_alloc % 256 == 0 &&
-              (g_two_cta == 2 || (a.num_kb >= 18 && pair_ctas >= 128));  // measured: wins from K >= 1152 (tools/gemm_bench.py)
+  L.two_cta = h->tun.two_cta != 0 && epi2 && conv_ok && d.N % 256 == 0 && a_rows_alloc % 256 == 0 &&
+              (h->tun.two_cta == 2 || (a.num_kb >= 18 && pair_ctas >= 128));  // measured: wins from K >= 1152 (tools/gemm_bench.py)
   if (L.two_cta) {
     L.bn = 256;
     cuuint64_t dims[2] = {(cuuint64_t)d.K, (cuuint64_t)d.N};
@@ -567,7 +530,7 @@ TcLaunch build_tc(hd_handle* h, const GemmDesc& d, long long a_rows_alloc) {
     L.stages = 4;
     return L;
   }
-  const int bn = (g_bn256 && d.a_mode == A_CONV3 && d.epi == EPI_RELU && d.out_dtype == DT_BF16 && d.N % 256 == 0) ? 256 : 128;
+  const int bn = (h->tun.bn256 && d.a_mode == A_CONV3 && d.epi == EPI_RELU && d.out_dtype == DT_BF16 && d.N % 256 == 0) ? 256 : 128;
   L.bn = bn;
   {
     cuuint64_t dims[2] = {(cuuint64_t)d.K, (cuuint64_t)d.N};
@@ -579,11 +542,9 @@ TcLaunch build_tc(hd_handle* h, const GemmDesc& d, long long a_rows_alloc) {
   const int tiles = cdiv(d.M, 128) * (d.N / bn);
   int split = 1;
   while (tiles * split < d.cta_target && split < 8 && a.num_kb % (2 * split) == 0 && a.num_kb / (2 * split) >= 2) split *= 2;
-  if (d.epi == EPI_RESID_LN || d.epi == EPI_DWGATE) split = 1;  // these epilogues need the finished tile in one CTA
   L.grid = dim3(cdiv(d.M, 128), d.N / bn, split);
   const int local_kb = a.num_kb / split;
   L.stages = local_kb <= 2 ? 2 : (tiles * split <= 160 ? 6 : 3);
-  if (g_max_stages < 6 && L.stages == 6) L.stages = 3;  // experiment: leave room for the PDL dependent to co-reside
   return L;
 }
 
@@ -715,33 +676,12 @@ void load_block(hd_handle* h, BlockW& bw, int wdt) {
     bw.w1 = pack_matrix(h, need(h, p + "conv1.weight", {2 * c, c}), 2 * c, c, 1, &perm, &rs, wdt);
     bw.b1 = upload_f32(h, bp);
     bw.dw_folded = true;
-  } else if ((g_fuse_dw & h->sp[bw.level]) != 0 && wdt == DT_BF16 && h->sp[bw.level] <= 8) {
-    // conv1 rows (and its bias, the depthwise taps and bias) in the gate-packed column order, so that the
-    // depthwise 3x3 + SimpleGate + pool can run over conv1's staged accumulator tile (EPI_DWGATE)
-    auto dw = host_vec(h, need(h, p + "conv2.weight", {2 * c, 9}));
-    auto dwb = host_vec(h, need(h, p + "conv2.bias", {2 * c}));
-    auto b1 = host_vec(h, need(h, p + "conv1.bias", {2 * c}));
-    std::vector<int> perm(2 * c);
-    std::vector<float> b1p(2 * c), dwbp(2 * c), dwp(static_cast<size_t>(18) * c);
-    for (int n = 0; n < 2 * c; ++n) {
-      const int g = n / 128, r = n % 128;
-      const int ch = r < 64 ? g * 64 + r : c + g * 64 + (r - 64);
-      perm[n] = ch;
-      b1p[n] = b1[ch];
-      dwbp[n] = dwb[ch];
-      for (int t = 0; t < 9; ++t) dwp[static_cast<size_t>(t) * 2 * c + n] = dw[static_cast<size_t>(ch) * 9 + t];
-    }
-    bw.w1 = pack_matrix(h, need(h, p + "conv1.weight", {2 * c, c}), 2 * c, c, 1, &perm, nullptr, wdt);
-    bw.b1 = upload_f32(h, b1p);
-    bw.dw_w = upload_f32(h, dwp);
-    bw.dw_b = upload_f32(h, dwbp);
-    bw.dw_fused = true;
   } else {
     bw.w1 = pack_matrix(h, need(h, p + "conv1.weight", {2 * c, c}), 2 * c, c, 1, nullptr, nullptr, wdt);
     bw.b1 = upload_f32(h, host_vec(h, need(h, p + "conv1.bias", {2 * c})));
   }
 
-  if (!bw.dw_fused) {  // depthwise 3x3: [2c,1,3,3] -> [9][2c]
+  {  // depthwise 3x3: [2c,1,3,3] -> [9][2c]
     auto w = host_vec(h, need(h, p + "conv2.weight", {2 * c, 9}));
     std::vector<float> t(static_cast<size_t>(18) * c);
     for (int ch = 0; ch < 2 * c; ++ch)
@@ -758,7 +698,7 @@ void load_block(hd_handle* h, BlockW& bw, int wdt) {
       for (int k = 0; k < c; ++k) t[static_cast<size_t>(k) * c + n] = w[static_cast<size_t>(n) * c + k];
     bw.wsca_t = upload_f32(h, t);
   }
-  if ((c == pb::C && h->sp[bw.level] == pb::SP) || (c == qb::C && h->sp[bw.level] == qb::SP)) {
+  if (c == pb::C && h->sp[bw.level] == pb::SP) {
     auto w = host_vec(h, need(h, p + "sca.1.weight", {c, c}));
     std::vector<uint16_t> t(w.size());
     for (int n = 0; n < c; ++n)
@@ -899,7 +839,6 @@ void add_op(Plan& P, std::function<void(cudaStream_t)> fn, const std::string& ta
   op.tap = tap;
   op.info = info;
   op.label = g_label;
-  op.chain = P.cx.id;
   P.ops.push_back(std::move(op));
 }
 
@@ -908,8 +847,8 @@ void add_gemm(hd_handle* h, Plan& P, GemmDesc d, long long a_rows_alloc, const s
   const long long taps_exec = d.a_mode == A_CONV3 ? 1 : 1;
   (void)taps_exec;
   P.flops_per_face += 2.0 * d.M * static_cast<double>(d.N) * d.K / P.batch;
-  if (d.cta_target == 120) d.cta_target = P.cx.nslab > 1 ? P.cx.cta_target : g_cta_target;
-  static const char* epi_names[] = {"bias", "relu", "sigmoid", "resid", "gate", "pixshuf", "resid+ln", "dw3x3+gate+pool", "bias+scale_rows"};
+  if (d.cta_target == 120) d.cta_target = h->tun.cta_target;
+  static const char* epi_names[] = {"bias", "relu", "sigmoid", "resid", "gate", "pixshuf", "bias*mul"};
   const std::string what = g_label;
   if (tc_eligible(h, d)) {
     TcLaunch L = build_tc(h, d, a_rows_alloc);
@@ -919,6 +858,7 @@ void add_gemm(hd_handle* h, Plan& P, GemmDesc d, long long a_rows_alloc, const s
     add_op(P, [L](cudaStream_t st) { launch_tc(L, st); }, tap, info);
     return;
   }
+  if (d.epi == EPI_MUL) HD_THROW(HD_ERR_INVALID, "EPI_MUL exists on the tcgen05 path only (M=%d N=%d K=%d)", d.M, d.N, d.K);
   if (d.epi == EPI_GATE) {
     // fp32 mode: bias epilogue into a packed fp32 buffer, then the SimpleGate kernel
     GemmDesc g = d;
@@ -964,40 +904,22 @@ void launch_ln(int c, const float* x, const float* lw, const float* lb, T* out, 
   }
 }
 
-// Chain context helpers: batch / first face of the current chain, its slab of a scratch buffer, and the row
-// capacity a GEMM A operand living in that slab may claim (a multiple of 128 >= the rows actually used).
-int cx_batch(const Plan& P) { return P.cx.nf >= 0 ? P.cx.nf : P.batch; }
-void* cx_slab(const Plan& P, void* base, size_t bytes) {
-  if (P.cx.nslab <= 1) return base;
-  return static_cast<char*>(base) + static_cast<size_t>(P.cx.id) * ((bytes / P.cx.nslab) & ~static_cast<size_t>(1023));
-}
-long long cx_rows_alloc(const hd_handle* h, const Plan& P, int rpf) {
-  if (P.cx.nslab <= 1) return static_cast<long long>(h->Bcap) * rpf;
-  return static_cast<long long>(cdiv(static_cast<long long>(cx_batch(P)) * rpf, 128LL)) * 128;
-}
+// rows a GEMM A operand in the shared workspace may claim (a multiple of 128 >= the rows actually used)
+long long rows_cap(const hd_handle* h, int rpf) { return static_cast<long long>(h->Bcap) * rpf; }
 
-// next_ln1: the block that follows at the same level (its norm1 can be fused into this block's conv5
-// epilogue); skip_ln1: this block's norm1 output was already produced by its predecessor.
-void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapname, const BlockW* next_ln1 = nullptr,
-               bool skip_ln1 = false) {
-  const int B = cx_batch(P), f0 = P.cx.f0, l = bw.level, c = bw.c, sp = h->sp[l];
+// One ConditionalNAFBlock / NAFBlock as one kernel per op (conditional_naf.py:108-136): the plan of the 4x4, 2x2 and
+// 1x1 levels, of the FPG encoder, and of every level in the debug (per-layer tap) plan.
+void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapname) {
+  const int B = P.batch, l = bw.level, c = bw.c, sp = h->sp[l];
   const int rows = B * sp * sp, rpf = sp * sp;
-  const long long rows_alloc = cx_rows_alloc(h, P, rpf);
+  const long long rows_alloc = rows_cap(h, rpf);
   const int adt = h->bf16 ? DT_BF16 : DT_F32;
-  const size_t as = esize(adt);
-  float* resid = h->resid[l] + static_cast<size_t>(f0) * rpf * c;
-  const int* row_idx = h->row_idx + f0;
-  ModRef mod{h->mod_table, row_idx, h->mod_stride};
+  float* resid = h->resid[l];
+  ModRef mod{h->mod_table, h->row_idx, h->mod_stride};
   const bool bf = h->bf16;
-  void *act_a = cx_slab(P, h->act_a, h->act_bytes), *act_h = cx_slab(P, h->act_h, 2 * h->act_bytes),
-       *act_g = cx_slab(P, h->act_g, h->act_bytes);
-  // per-face vectors: slab stride = the chain's face capacity rounded up to whole 128-row tiles
-  const size_t pool_off = P.cx.nslab <= 1 ? 0 : static_cast<size_t>(P.cx.id) * cx_rows_alloc(h, P, 1) * 2048;
-  void* pooled = static_cast<char*>(h->pooled) + pool_off * as;
-  float* sca_s = h->sca_s + pool_off;
-
+  void *act_a = h->act_a, *act_h = h->act_h, *act_g = h->act_g, *pooled = h->pooled;
+  float* sca_s = h->sca_s;
   const int has_mod = bw.has_mod ? 1 : 0;
-  const bool fuse_scale = g_fuse_scale && bf && rpf <= 16;
   auto ln = [=](const float* lw, const float* lb, int shift_off, int scale_off) {
     return [=](cudaStream_t st) {
       if (bf) launch_ln<bf16>(c, resid, lw, lb, static_cast<bf16*>(act_a), rows, rpf, mod, shift_off, scale_off, has_mod, st);
@@ -1006,26 +928,10 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
   };
   const std::string L0 = fmt("L%d c=%d ", l, c);
   // norm1 + modulation (shift_att = chunk 0, scale_att = chunk 1)
-  // c == 128: one GEMM tile holds the whole channel row, so LayerNorm + modulation ride in the residual epilogue
-  const bool fuse_ln = g_fuse_ln && bf && c == 128 && bw.has_mod;
-  auto fused_ln = [&](GemmDesc& d, const float* lw, const float* lb, int shift_off, int scale_off) {
-    d.epi = EPI_RESID_LN;
-    d.ln_w = lw; d.ln_b = lb; d.mod_table = h->mod_table; d.mod_row_idx = row_idx; d.mod_stride = h->mod_stride;
-    d.ln_shift_off = shift_off; d.ln_scale_off = scale_off; d.rows_per_face = rpf; d.ln_out = act_a;
-  };
-  if (!(fuse_ln && skip_ln1)) {
-    g_label = L0 + "ln1";
-    add_op(P, ln(bw.ln1_w, bw.ln1_b, bw.mod_off, bw.mod_off + c));
-  }
+  g_label = L0 + "ln1";
+  add_op(P, ln(bw.ln1_w, bw.ln1_b, bw.mod_off, bw.mod_off + c));
   g_label = L0 + "conv1";
-  if (bw.dw_fused) {  // conv1 with depthwise 3x3 + SimpleGate + per-face mean in the epilogue
-    GemmDesc d;
-    d.M = rows; d.N = 2 * c; d.K = c; d.A = act_a; d.lda = c; d.a_dtype = adt;
-    d.W = bw.w1; d.ldw = c; d.w_dtype = adt; d.bias = bw.b1; d.epi = EPI_DWGATE; d.sp = sp;
-    d.out = act_g; d.ldo = c; d.out_dtype = adt; d.dw_w = bw.dw_w; d.dw_b = bw.dw_b; d.pooled = pooled;
-    add_gemm(h, P, d, rows_alloc);
-    P.flops_per_face += 2.0 * 9 * 2 * c * rpf;
-  } else if (bw.dw_folded) {  // conv1 + (folded) depthwise + SimpleGate; the pooled mean over 1 pixel is g itself
+  if (bw.dw_folded) {  // conv1 + (folded) depthwise + SimpleGate; the pooled mean over 1 pixel is g itself
     GemmDesc d;
     d.M = rows; d.N = 2 * c; d.K = c; d.A = act_a; d.lda = c; d.a_dtype = adt;
     d.W = bw.w1; d.ldw = c; d.w_dtype = adt; d.bias = bw.b1; d.epi = EPI_GATE;
@@ -1039,9 +945,9 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
     add_gemm(h, P, d, rows_alloc);
   }
   g_label = L0 + "dwconv_gate_pool";
-  if (!bw.dw_folded && !bw.dw_fused) {  // depthwise 3x3 + SimpleGate + pool
+  if (!bw.dw_folded) {  // depthwise 3x3 + SimpleGate + pool
     const float *dw_w = bw.dw_w, *dw_b = bw.dw_b;
-    if (g_dw_small && (sp == 2 || sp == 4) && c % 4 == 0) {  // register-resident faces (dwconv_small_kernel)
+    if (h->tun.dw_small && (sp == 2 || sp == 4) && c % 4 == 0) {  // register-resident faces (dwconv_small_kernel)
       add_op(P, [=](cudaStream_t st) {
         const dim3 grid(cdiv(static_cast<size_t>(B) * (c / 4), 256));
         if (bf && sp == 2) launch_k(dwconv_small_kernel<bf16, 2>, grid, dim3(256), 0, st, static_cast<const bf16*>(act_h), dw_w, dw_b, static_cast<bf16*>(act_g), static_cast<bf16*>(pooled), c, B);
@@ -1060,58 +966,39 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
     });
     P.flops_per_face += 2.0 * 9 * 2 * c * rpf;
   }
-  const bool sca_fused = bf && g_sca_fused && !fuse_scale && c % sca::BK == 0 && rpf <= 16;  // 4x4, 2x2, 1x1 levels
-  if (sca_fused) {  // SCA GEMM + rescale of the face's rows in one mma.sync kernel, out of place into act_h
-    const bf16* a_src = static_cast<const bf16*>(bw.dw_folded ? act_g : pooled);
-    const bf16* wsca = static_cast<const bf16*>(bw.wsca);
-    const float* bsca = bw.bsca;
-    static bool configured = false;
-    if (!configured) {
-      CUDA_CHECK(cudaFuncSetAttribute(sca::sca_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sca::SMEM_BYTES));
-      configured = true;
-    }
-    g_label = L0 + fmt("sca+scale mma.sync M=%d N=%d K=%d grid=(%d,%d)", B, c, c, c / sca::BN, cdiv(B, sca::BM));
+  // SCA (conditional_naf.py:119  x * sca(x)).  At 1x1 spatial on the tensor-core path the pooled mean is the gated
+  // tensor itself and one face is one row, so the rescale rides in the SCA GEMM's epilogue (EPI_MUL, out of place
+  // into act_h); elsewhere: SCA GEMM on the pooled vectors, then the per-face rescale of the gated rows.
+  const bool sca_mul = bw.dw_folded && bf && h->tun.sca_mul;
+  g_label = L0 + "sca";
+  {
+    GemmDesc d;
+    d.M = B; d.N = c; d.K = c; d.A = bw.dw_folded ? act_g : pooled; d.lda = c; d.a_dtype = adt;
+    d.W = bw.wsca; d.ldw = c; d.w_dtype = adt; d.bias = bw.bsca; d.epi = EPI_BIAS;
+    d.out = sca_s; d.ldo = c; d.out_dtype = DT_F32;
+    d.cta_target = h->tun.sca_target;
+    if (sca_mul) { d.epi = EPI_MUL; d.resid = static_cast<const float*>(act_g); d.ldr = c; d.out = act_h; d.out_dtype = adt; }
+    add_gemm(h, P, d, rows_cap(h, 1));
+  }
+  if (!sca_mul) {
+    g_label = L0 + "scale_rows";
     add_op(P, [=](cudaStream_t st) {
-      launch_k(sca::sca_scale_kernel, dim3(c / sca::BN, cdiv(B, sca::BM)), dim3(sca::THREADS), sca::SMEM_BYTES, st, a_src, wsca, bsca,
-               static_cast<const bf16*>(act_g), static_cast<bf16*>(act_h), sca_s, B, c, rpf);
+      const size_t total8 = static_cast<size_t>(rows) * c / 8;
+      if (bf) launch_k(scale_rows_kernel<bf16>, dim3(cdiv(total8, 256)), dim3(256), 0, st, static_cast<bf16*>(act_g), sca_s, total8, c, rpf);
+      else launch_k(scale_rows_kernel<float>, dim3(cdiv(total8, 256)), dim3(256), 0, st, static_cast<float*>(act_g), sca_s, total8, c, rpf);
     });
-    P.flops_per_face += 2.0 * c * static_cast<double>(c);
-  } else {
-    g_label = L0 + "sca";
-    {  // SCA 1x1 on the pooled vector
-      GemmDesc d;
-      d.M = B; d.N = c; d.K = c; d.A = bw.dw_folded ? act_g : pooled; d.lda = c; d.a_dtype = adt;
-      d.W = bw.wsca; d.ldw = c; d.w_dtype = adt; d.bias = bw.bsca; d.epi = EPI_BIAS;
-      d.out = sca_s; d.ldo = c; d.out_dtype = DT_F32;
-      if (P.cx.nslab <= 1) d.cta_target = g_sca_target;
-      if (fuse_scale) {  // the face's rows are rescaled by the SCA GEMM's own epilogue, out of place into act_h
-        d.epi = EPI_SCALE; d.scale_src = act_g; d.scale_dst = act_h; d.scale_ld = c; d.rows_per_face = rpf;
-      }
-      add_gemm(h, P, d, cx_rows_alloc(h, P, 1));
-    }
-    if (!fuse_scale) {
-      g_label = L0 + "scale_rows";
-      add_op(P, [=](cudaStream_t st) {
-        const size_t total8 = static_cast<size_t>(rows) * c / 8;
-        if (bf) launch_k(scale_rows_kernel<bf16>, dim3(cdiv(total8, 256)), dim3(256), 0, st, static_cast<bf16*>(act_g), sca_s, total8, c, rpf);
-        else launch_k(scale_rows_kernel<float>, dim3(cdiv(total8, 256)), dim3(256), 0, st, static_cast<float*>(act_g), sca_s, total8, c, rpf);
-      });
-    }
   }
   g_label = L0 + "conv3";
   {  // conv3 (+beta) + residual
     GemmDesc d;
-    d.M = rows; d.N = c; d.K = c; d.A = (fuse_scale || sca_fused) ? act_h : act_g; d.lda = c; d.a_dtype = adt;
+    d.M = rows; d.N = c; d.K = c; d.A = sca_mul ? act_h : act_g; d.lda = c; d.a_dtype = adt;
     d.W = bw.w3; d.ldw = c; d.w_dtype = adt; d.bias = bw.b3; d.epi = EPI_RESID;
     d.out = resid; d.ldo = c; d.out_dtype = DT_F32; d.resid = resid; d.ldr = c;
-    if (fuse_ln) fused_ln(d, bw.ln2_w, bw.ln2_b, bw.mod_off + 2 * c, bw.mod_off + 3 * c);
     add_gemm(h, P, d, rows_alloc);
   }
   // norm2 + modulation (shift_ffn = chunk 2, scale_ffn = chunk 3)
-  if (!fuse_ln) {
-    g_label = L0 + "ln2";
-    add_op(P, ln(bw.ln2_w, bw.ln2_b, bw.mod_off + 2 * c, bw.mod_off + 3 * c));
-  }
+  g_label = L0 + "ln2";
+  add_op(P, ln(bw.ln2_w, bw.ln2_b, bw.mod_off + 2 * c, bw.mod_off + 3 * c));
   g_label = L0 + "conv4";
   {  // conv4 + SimpleGate
     GemmDesc d;
@@ -1126,8 +1013,6 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
     d.M = rows; d.N = c; d.K = c; d.A = act_g; d.lda = c; d.a_dtype = adt;
     d.W = bw.w5; d.ldw = c; d.w_dtype = adt; d.bias = bw.b5; d.epi = EPI_RESID;
     d.out = resid; d.ldo = c; d.out_dtype = DT_F32; d.resid = resid; d.ldr = c;
-    if (fuse_ln && next_ln1 != nullptr)
-      fused_ln(d, next_ln1->ln1_w, next_ln1->ln1_b, next_ln1->mod_off, next_ln1->mod_off + c);
     TapInfo ti;
     ti.ptr = resid; ti.dtype = DT_F32; ti.C = c; ti.HW = rpf; ti.ld = c;
     add_gemm(h, P, d, rows_alloc, tapname, ti);
@@ -1136,15 +1021,15 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
 
 void add_hca(hd_handle* h, Plan& P, int j, int level) {
   const HcaW& w = h->hca[j];
-  const int B = cx_batch(P), f0 = P.cx.f0, d = w.d, sp = w.sp, rpf = sp * sp, rows = B * rpf;
-  const long long rows_alloc = cx_rows_alloc(h, P, rpf);
+  const int B = P.batch, d = w.d, sp = w.sp, rpf = sp * sp, rows = B * rpf;
+  const long long rows_alloc = rows_cap(h, rpf);
   const int adt = h->bf16 ? DT_BF16 : DT_F32;
   const bool bf = h->bf16;
-  const float* fd = h->resid[level] + static_cast<size_t>(f0) * rpf * d;
-  const float *wc = w.wc + static_cast<size_t>(f0) * d, *ws = w.ws + static_cast<size_t>(f0) * rpf;
-  const float* idc = j == 0 ? h->idc_add + static_cast<size_t>(f0) * d : nullptr;
-  void* act_a = cx_slab(P, h->act_a, h->act_bytes);
-  void* hca_out = cx_slab(P, h->hca_out, h->act_bytes);
+  const float* fd = h->resid[level];
+  const float *wc = w.wc, *ws = w.ws;
+  const float* idc = j == 0 ? h->idc_add : nullptr;
+  void* act_a = h->act_a;
+  void* hca_out = h->hca_out;
   g_label = fmt("hca%d apply", j);
   add_op(P, [=](cudaStream_t st) {
     const size_t total8 = static_cast<size_t>(rows) * d / 8;
@@ -1169,10 +1054,10 @@ void add_hca(hd_handle* h, Plan& P, int j, int level) {
 // Fused per-face kernel (face_block.cuh) over the blocks [first, first + count) of the 16x16 level:
 // reads and writes the level's fp32 residual stream in place.
 bool face_blocks_ok(hd_handle* h, size_t first, int count, bool debug) {
-  if (!g_face || debug || !h->bf16 || count > fb::MAX_BLOCKS) return false;
+  if (!h->tun.face || debug || !h->bf16 || count > fb::MAX_BLOCKS) return false;
   for (int i = 0; i < count; ++i) {
     const BlockW& bw = h->blocks[first + i];
-    if (bw.c != fb::C || h->sp[bw.level] != fb::SP || !bw.has_mod || bw.dw_fused || bw.dw_folded || bw.wsca_t == nullptr) return false;
+    if (bw.c != fb::C || h->sp[bw.level] != fb::SP || !bw.has_mod || bw.dw_folded || bw.wsca_t == nullptr) return false;
   }
   return true;
 }
@@ -1259,10 +1144,10 @@ void add_face_blocks(hd_handle* h, Plan& P, size_t first, int count) {
 
 // Fused face-pair kernel (pair_block.cuh) over the blocks [first, first + count) of the 8x8 level.
 bool pair_blocks_ok(hd_handle* h, size_t first, int count, bool debug) {
-  if (!g_pair || debug || !h->bf16 || count > pb::MAX_BLOCKS) return false;
+  if (!h->tun.pair || debug || !h->bf16 || count > pb::MAX_BLOCKS) return false;
   for (int i = 0; i < count; ++i) {
     const BlockW& bw = h->blocks[first + i];
-    if (bw.c != pb::C || h->sp[bw.level] != pb::SP || !bw.has_mod || bw.dw_fused || bw.dw_folded || bw.wsca_tb == nullptr) return false;
+    if (bw.c != pb::C || h->sp[bw.level] != pb::SP || !bw.has_mod || bw.dw_folded || bw.wsca_tb == nullptr) return false;
   }
   return true;
 }
@@ -1348,431 +1233,6 @@ void add_pair_blocks(hd_handle* h, Plan& P, size_t first, int count) {
   add_op(P, [=](cudaStream_t st) { launch_k(pb::pair_block_kernel, dim3((B + 1) / 2), dim3(pb::THREADS), pb::SMEM_BYTES, st, a); }, tap, ti);
 }
 
-// 4-CTA-cluster kernel (quad_block.cuh) over the blocks [first, first + count) of the 4x4 level.
-bool quad_blocks_ok(hd_handle* h, size_t first, int count, bool debug) {
-  if (!g_quad || debug || !h->bf16 || count > qb::MAX_BLOCKS) return false;
-  for (int i = 0; i < count; ++i) {
-    const BlockW& bw = h->blocks[first + i];
-    if (bw.c != qb::C || h->sp[bw.level] != qb::SP || !bw.has_mod || bw.dw_fused || bw.dw_folded || bw.wsca_tb == nullptr) return false;
-  }
-  return true;
-}
-
-void add_quad_blocks(hd_handle* h, Plan& P, size_t first, int count) {
-  const int B = P.batch;
-  const int c = qb::C, rpf = qb::FPX;
-  const int n_mtiles = cdiv(B, qb::FACES);
-  std::vector<CUtensorMap> maps;
-  std::vector<qb::BlockParams> bps;
-  auto add_map = [&](const void* base, int N) {
-    CUtensorMap m;
-    cuuint64_t dims[2] = {(cuuint64_t)c, (cuuint64_t)N};
-    cuuint64_t strides[1] = {(cuuint64_t)c * 2};
-    cuuint32_t box[2] = {64, 128};
-    encode_map(h, &m, base, 2, dims, strides, box);
-    maps.push_back(m);
-  };
-  std::vector<float> cum(c, 0.f);
-  for (int i = 0; i < count; ++i) {
-    const BlockW& bw = h->blocks[first + i];
-    add_map(bw.w1, 2 * c);
-    add_map(bw.w3, c);
-    add_map(bw.w4, 2 * c);
-    add_map(bw.w5, c);
-    qb::BlockParams bp;
-    memset(&bp, 0, sizeof(bp));
-    bp.ln1_w = bw.ln1_w; bp.ln1_b = bw.ln1_b; bp.ln2_w = bw.ln2_w; bp.ln2_b = bw.ln2_b;
-    bp.b1 = bw.b1; bp.dw_w = bw.dw_w; bp.dw_b = bw.dw_b; bp.wsca_t = static_cast<const bf16*>(bw.wsca_tb); bp.bsca = bw.bsca;
-    bp.b4 = bw.b4; bp.mod_off = bw.mod_off;
-    for (int k = 0; k < c; ++k) cum[k] += bw.b3_h[k];
-    bp.cb3 = upload_f32(h, cum);
-    for (int k = 0; k < c; ++k) cum[k] += bw.b5_h[k];
-    bp.cb5 = upload_f32(h, cum);
-    bps.push_back(bp);
-    P.flops_per_face += 2.0 * rpf * 6.0 * c * c + 2.0 * c * c + 2.0 * 9 * 2 * c * rpf;
-  }
-  qb::Args a;
-  memset(&a, 0, sizeof(a));
-  CUtensorMap* d_maps = static_cast<CUtensorMap*>(h->arena.alloc(maps.size() * sizeof(CUtensorMap)));
-  qb::BlockParams* d_bps = static_cast<qb::BlockParams*>(h->arena.alloc(bps.size() * sizeof(qb::BlockParams)));
-  CUDA_CHECK(cudaMemcpy(d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-  CUDA_CHECK(cudaMemcpy(d_bps, bps.data(), bps.size() * sizeof(qb::BlockParams), cudaMemcpyHostToDevice));
-  a.maps = d_maps;
-  a.blocks = d_bps;
-  a.n_blocks = count;
-  a.n_faces = B;
-  a.n_mtiles = n_mtiles;
-  a.x = h->resid[h->blocks[first].level];
-  a.xa = static_cast<bf16*>(h->arena.alloc(static_cast<size_t>(2) * n_mtiles * 128 * c * 2));
-  a.stats = static_cast<float2*>(h->arena.alloc(static_cast<size_t>(n_mtiles) * qb::CL * 2 * 128 * sizeof(float2)));
-  a.means = h->arena.get<float>(static_cast<size_t>(n_mtiles) * qb::FACES * c);
-  a.zero_bias = upload_f32(h, std::vector<float>(c, 0.f));
-  a.mod_table = h->mod_table;
-  a.mod_row_idx = h->row_idx;
-  a.mod_stride = h->mod_stride;
-  a.status = h->d_status;
-  static bool configured = false;
-  if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(qb::quad_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, qb::SMEM_BYTES));
-    configured = true;
-  }
-  g_label = fmt("L%d c=%d quad_block x%d (%s)", h->blocks[first].level, c, count, h->blocks[first].prefix.c_str());
-  TapInfo ti;
-  ti.ptr = a.x; ti.dtype = DT_F32; ti.C = c; ti.HW = rpf; ti.ld = c;
-  std::string tap = h->blocks[first + count - 1].prefix;
-  if (!tap.empty() && tap.back() == '.') tap.pop_back();
-  const bool tracing = getenv("HD_QUAD_TRACE") != nullptr;
-  long long* tr = nullptr;
-  if (tracing) {
-    tr = h->arena.get<long long>(64);
-    a.trace = tr;
-    a.trace_cta = atoi(getenv("HD_QUAD_TRACE"));
-  }
-  const int n_st = 3 + 11 * count;
-  add_op(P, [=](cudaStream_t st) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(qb::CL * n_mtiles);
-    cfg.blockDim = dim3(qb::THREADS);
-    cfg.dynamicSmemBytes = qb::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = qb::CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = g_use_pdl ? 2 : 1;
-    cudaLaunchKernelEx(&cfg, qb::quad_block_kernel, a);
-    if (tracing) {
-      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-      cudaStreamIsCapturing(st, &cs);
-      if (cs != cudaStreamCaptureStatusNone) return;
-      long long hst[64];
-      cudaStreamSynchronize(st);
-      cudaMemcpy(hst, tr, sizeof(hst), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[quad_block trace, clocks since start]");
-      for (int i = 1; i < n_st && i < 64; ++i) fprintf(stderr, " %lld", hst[i] - hst[0]);
-      fprintf(stderr, "\n");
-    }
-  }, tap, ti);
-}
-
-// Persistent chain over the blocks [first, first + count) of one 1x1-spatial level (see chain.cuh).
-// Expects blocks[first]'s norm1 output in act_a; leaves the level's residual stream finished in resid[level].
-void add_chain_1x1(hd_handle* h, Plan& P, size_t first, int count) {
-  const int B = P.batch;
-  const BlockW& b0 = h->blocks[first];
-  const int c = b0.c, level = b0.level;
-  const int m_tiles = cdiv(B, 128);
-  const long long rows_alloc = h->Bcap;
-  const int grid_target = std::min(h->sm_count, 128);
-  std::vector<chain::Phase> phases;
-  std::vector<CUtensorMap> maps;
-  auto add_map = [&](const void* base, int K, long long rows, int ld) {
-    CUtensorMap m;
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {64, 128};
-    encode_map(h, &m, base, 2, dims, strides, box);
-    maps.push_back(m);
-    return static_cast<int>(maps.size()) - 1;
-  };
-  const int map_a = add_map(h->act_a, c, rows_alloc, c);
-  const int map_g = add_map(h->act_g, c, rows_alloc, c);
-  int max_units = 0;
-  auto gemm = [&](int mapA, const void* W, int N, int K) {
-    chain::Phase ph;
-    memset(&ph, 0, sizeof(ph));
-    ph.kind = chain::PH_GEMM;
-    ph.map_a = mapA;
-    ph.map_w = add_map(W, K, N, K);
-    ph.n_tiles = N / 128;
-    ph.num_kb = K / 64;
-    int split = 1;
-    while (m_tiles * ph.n_tiles * split * 2 <= grid_target && split < 8 && ph.num_kb % (2 * split) == 0 &&
-           ph.num_kb / (2 * split) >= 2)
-      split *= 2;
-    ph.split = split;
-    max_units = std::max(max_units, m_tiles * ph.n_tiles * split);
-    phases.push_back(ph);
-    P.flops_per_face += 2.0 * B * static_cast<double>(N) * K / P.batch;
-    return ph;
-  };
-  auto fix = [&](int kind, const chain::Phase& g, int N, const float* bias) {
-    chain::Phase ph;
-    memset(&ph, 0, sizeof(ph));
-    ph.kind = kind;
-    ph.N = N;
-    ph.src_n_tiles = g.n_tiles;
-    ph.src_split = g.split;
-    ph.bias = bias;
-    return ph;
-  };
-  bf16* act_a = static_cast<bf16*>(h->act_a);
-  bf16* act_g = static_cast<bf16*>(h->act_g);
-  float* x = h->resid[level];
-  for (int i = 0; i < count; ++i) {
-    const BlockW& bw = h->blocks[first + i];
-    const BlockW* nx = i + 1 < count ? &h->blocks[first + i + 1] : nullptr;
-    {  // conv1 (+ folded depthwise) -> SimpleGate -> g
-      auto g = gemm(map_a, bw.w1, 2 * c, c);
-      auto f = fix(chain::PH_FIX_GATE, g, 2 * c, bw.b1);
-      f.out = act_g;
-      phases.push_back(f);
-    }
-    {  // SCA: g *= Wsca g + b   (mean over one pixel is g itself)
-      auto g = gemm(map_g, bw.wsca, c, c);
-      auto f = fix(chain::PH_FIX_SCALE, g, c, bw.bsca);
-      f.in = act_g; f.out = act_g;
-      phases.push_back(f);
-    }
-    {  // conv3 (+beta) + residual, then norm2 + modulation
-      auto g = gemm(map_g, bw.w3, c, c);
-      auto f = fix(chain::PH_FIX_RESID, g, c, bw.b3);
-      f.x = x; f.out = act_a; f.ln_w = bw.ln2_w; f.ln_b = bw.ln2_b;
-      f.shift_off = bw.mod_off + 2 * c; f.scale_off = bw.mod_off + 3 * c;
-      phases.push_back(f);
-    }
-    {  // conv4 -> SimpleGate
-      auto g = gemm(map_a, bw.w4, 2 * c, c);
-      auto f = fix(chain::PH_FIX_GATE, g, 2 * c, bw.b4);
-      f.out = act_g;
-      phases.push_back(f);
-    }
-    {  // conv5 (+gamma) + residual, then the next block's norm1 + modulation
-      auto g = gemm(map_g, bw.w5, c, c);
-      auto f = fix(chain::PH_FIX_RESID, g, c, bw.b5);
-      f.x = x; f.out = act_a;
-      if (nx != nullptr) {
-        f.ln_w = nx->ln1_w; f.ln_b = nx->ln1_b; f.shift_off = nx->mod_off; f.scale_off = nx->mod_off + c;
-      }
-      phases.push_back(f);
-    }
-  }
-  // device copies
-  chain::Phase* d_ph = static_cast<chain::Phase*>(h->arena.alloc(phases.size() * sizeof(chain::Phase)));
-  CUtensorMap* d_maps = static_cast<CUtensorMap*>(h->arena.alloc(maps.size() * sizeof(CUtensorMap)));
-  CUDA_CHECK(cudaMemcpy(d_ph, phases.data(), phases.size() * sizeof(chain::Phase), cudaMemcpyHostToDevice));
-  CUDA_CHECK(cudaMemcpy(d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-  chain::ChainArgs ca;
-  memset(&ca, 0, sizeof(ca));
-  ca.phases = d_ph;
-  ca.n_phases = static_cast<int>(phases.size());
-  ca.maps = d_maps;
-  ca.partial = h->arena.get<float>(static_cast<size_t>(max_units) * 128 * 128);
-  ca.barrier = h->arena.get<unsigned int>(64);
-  ca.rows = B;
-  ca.m_tiles = m_tiles;
-  ca.mod_table = h->mod_table;
-  ca.mod_row_idx = h->row_idx;
-  ca.mod_stride = h->mod_stride;
-  ca.rows_per_face = 1;
-  ca.status = h->d_status;
-  const int grid = std::min(h->sm_count, max_units);
-  static bool configured = false;
-  if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(chain::chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_BYTES));
-    configured = true;
-  }
-  g_label = fmt("L%d c=%d chain of %d blocks: %zu phases, grid %d", level, c, count, phases.size(), grid);
-  add_op(P, [=](cudaStream_t st) {
-    cudaMemsetAsync(ca.barrier, 0, sizeof(unsigned int), st);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(chain::THREADS);
-    cfg.dynamicSmemBytes = chain::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the grid barrier cannot deadlock
-    attr[0].val.cooperative = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, chain::chain_kernel, ca);
-  });
-}
-
-
-// Persistent level chain (level_chain.cuh) over the blocks [first, first + count) of one small-spatial level.
-// Expects blocks[first]'s norm1 output in act_a; leaves the finished residual stream in resid[level].
-bool level_chain_ok(hd_handle* h, size_t first, int count, bool debug) {
-  if (debug || !h->bf16 || count < 1) return false;
-  const BlockW& b0 = h->blocks[first];
-  if (((g_lv >> b0.level) & 1) == 0) return false;
-  if (h->sp[b0.level] != 1) return false;  // 1x1 spatial: depthwise folded into conv1, pooled mean == the tensor
-  for (int i = 0; i < count; ++i) {
-    const BlockW& bw = h->blocks[first + i];
-    if (bw.level != b0.level || !bw.dw_folded || !bw.has_mod || bw.c % 128 != 0 || bw.c / 128 > 32) return false;
-  }
-  return true;
-}
-
-void add_level_chain(hd_handle* h, Plan& P, size_t first, int count) {
-  const int B = P.batch;
-  const BlockW& b0 = h->blocks[first];
-  const int c = b0.c, level = b0.level, rpf = h->sp[level] * h->sp[level];
-  const int rows = B * rpf;
-  const int m_tiles = cdiv(rows, 128);
-  const long long rows_alloc = static_cast<long long>(h->Bcap) * rpf;
-  std::vector<lv::Phase> phases;
-  std::vector<CUtensorMap> maps;
-  auto add_map = [&](const void* base, int K, long long nrows, int ld) {
-    CUtensorMap m;
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)nrows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {64, 128};
-    encode_map(h, &m, base, 2, dims, strides, box);
-    maps.push_back(m);
-    return static_cast<int>(maps.size()) - 1;
-  };
-  bf16* act_a = static_cast<bf16*>(h->act_a);
-  bf16* act_g = static_cast<bf16*>(h->act_g);
-  bf16* act_h = static_cast<bf16*>(h->act_h);
-  float* x = h->resid[level];
-  const int map_a = add_map(act_a, c, rows_alloc, c);
-  const int map_g = add_map(act_g, c, rows_alloc, c);
-  const int map_h = add_map(act_h, c, rows_alloc, c);
-  auto gemm = [&](int kind, int mapA, const void* W, int N, int K, const float* bias) {
-    lv::Phase ph;
-    memset(&ph, 0, sizeof(ph));
-    ph.kind = kind;
-    ph.map_a = mapA;
-    ph.map_w = add_map(W, K, N, K);
-    ph.m_tiles = m_tiles;
-    ph.n_tiles = N / 128;
-    ph.num_kb = K / 64;
-    ph.N = N;
-    ph.bias = bias;
-    int split = 1;
-    while (split < lv::CL && m_tiles * ph.n_tiles * split * 2 <= lv::GRID && ph.num_kb % (2 * split) == 0 &&
-           ph.num_kb / (2 * split) >= 2)
-      split *= 2;
-    ph.split = split;
-    P.flops_per_face += 2.0 * rows * static_cast<double>(N) * K / P.batch;
-    return ph;
-  };
-  for (int i = 0; i < count; ++i) {
-    const BlockW& bw = h->blocks[first + i];
-    const BlockW* nx = i + 1 < count ? &h->blocks[first + i + 1] : nullptr;
-    {  // conv1 (+ folded depthwise) -> SimpleGate -> g            conditional_naf.py:116-118
-      lv::Phase ph = gemm(lv::LV_GATE, map_a, bw.w1, 2 * c, c, bw.b1);
-      ph.out = act_g;
-      phases.push_back(ph);
-    }
-    {  // SCA: g2 = g * (Wsca g + b)                                conditional_naf.py:119
-      lv::Phase ph = gemm(lv::LV_MUL, map_g, bw.wsca, c, c, bw.bsca);
-      ph.mul = act_g; ph.out = act_h;
-      phases.push_back(ph);
-    }
-    {  // conv3 (+beta) + residual, then norm2 + modulation          conditional_naf.py:120-127
-      lv::Phase ph = gemm(lv::LV_RESID, map_h, bw.w3, c, c, bw.b3);
-      ph.x = x; ph.ln = 1; ph.out = act_a; ph.ln_w = bw.ln2_w; ph.ln_b = bw.ln2_b;
-      ph.shift_off = bw.mod_off + 2 * c; ph.scale_off = bw.mod_off + 3 * c;
-      phases.push_back(ph);
-    }
-    {  // conv4 -> SimpleGate                                       conditional_naf.py:128-129
-      lv::Phase ph = gemm(lv::LV_GATE, map_a, bw.w4, 2 * c, c, bw.b4);
-      ph.out = act_g;
-      phases.push_back(ph);
-    }
-    {  // conv5 (+gamma) + residual, then the next block's norm1     conditional_naf.py:130-134,114-115
-      lv::Phase ph = gemm(lv::LV_RESID, map_g, bw.w5, c, c, bw.b5);
-      ph.x = x;
-      if (nx != nullptr) {
-        ph.ln = 1; ph.out = act_a; ph.ln_w = nx->ln1_w; ph.ln_b = nx->ln1_b;
-        ph.shift_off = nx->mod_off; ph.scale_off = nx->mod_off + c;
-      }
-      phases.push_back(ph);
-    }
-  }
-  lv::Phase* d_ph = static_cast<lv::Phase*>(h->arena.alloc(phases.size() * sizeof(lv::Phase)));
-  CUtensorMap* d_maps = static_cast<CUtensorMap*>(h->arena.alloc(maps.size() * sizeof(CUtensorMap)));
-  CUDA_CHECK(cudaMemcpy(d_ph, phases.data(), phases.size() * sizeof(lv::Phase), cudaMemcpyHostToDevice));
-  CUDA_CHECK(cudaMemcpy(d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-  lv::Args a;
-  memset(&a, 0, sizeof(a));
-  a.phases = d_ph;
-  a.n_phases = static_cast<int>(phases.size());
-  a.maps = d_maps;
-  a.rows = rows;
-  a.rows_per_face = rpf;
-  a.stats = static_cast<float2*>(h->arena.alloc(static_cast<size_t>(m_tiles) * 128 * 32 * sizeof(float2)));
-  a.sync = h->arena.get<unsigned int>(64);
-  a.mod_table = h->mod_table;
-  a.mod_row_idx = h->row_idx;
-  a.mod_stride = h->mod_stride;
-  a.status = h->d_status;
-  const int n_ph = a.n_phases;
-  const bool tracing = getenv("HD_LV_TRACE") != nullptr;
-  if (tracing) a.trace = h->arena.get<long long>(static_cast<size_t>(lv::GRID) * n_ph * 8);
-  static bool configured = false;
-  if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(lv::level_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lv::SMEM_BYTES));
-    configured = true;
-  }
-  g_label = fmt("L%d c=%d level_chain x%d blocks: %d phases, grid %d x cluster %d", level, c, count, n_ph, lv::GRID, lv::CL);
-  TapInfo ti;
-  ti.ptr = x; ti.dtype = DT_F32; ti.C = c; ti.HW = rpf; ti.ld = c;
-  std::string tap = h->blocks[first + count - 1].prefix;
-  if (!tap.empty() && tap.back() == '.') tap.pop_back();
-  const bool coop = g_lv_coop;
-  add_op(P, [=](cudaStream_t st) {
-    cudaMemsetAsync(a.sync, 0, 64 * sizeof(unsigned int), st);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(lv::GRID);
-    cfg.blockDim = dim3(lv::THREADS);
-    cfg.dynamicSmemBytes = lv::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the grid barriers cannot deadlock
-    attr[0].val.cooperative = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = coop ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, lv::level_chain_kernel, a);
-    if (tracing) {
-      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-      cudaStreamIsCapturing(st, &cs);
-      if (cs != cudaStreamCaptureStatusNone) return;
-      cudaStreamSynchronize(st);
-      std::vector<long long> tr(static_cast<size_t>(lv::GRID) * n_ph * 8);
-      cudaMemcpy(tr.data(), a.trace, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-      // medians over CTAs of the per-phase intervals (clocks): barrier pass -> accumulator ready -> staged+handshake ->
-      // reduce/epilogue done -> (LN barrier) -> phase arrive; and phase-to-phase period
-      static const char* names[] = {"gemm_gate", "gemm_mul", "gemm_resid"};
-      fprintf(stderr, "[level_chain trace] phase kind split: bar->acc acc->drained drained->handshake handshake->epi epi->lnbar epi|lnbar->arrive | period (median clocks over %d CTAs)\n", lv::GRID);
-      for (int p = 0; p < n_ph && p < 12; ++p) {
-        auto med = [&](int from, int to) {
-          std::vector<long long> v;
-          for (int cta = 0; cta < lv::GRID; ++cta) {
-            const long long* t = tr.data() + (static_cast<size_t>(cta) * n_ph + p) * 8;
-            if (t[from] != 0 && t[to] != 0) v.push_back(t[to] - t[from]);
-          }
-          if (v.empty()) return -1ll;
-          std::sort(v.begin(), v.end());
-          return v[v.size() / 2];
-        };
-        long long period = -1;
-        if (p + 1 < n_ph) {
-          std::vector<long long> v;
-          for (int cta = 0; cta < lv::GRID; ++cta) {
-            const long long* t0 = tr.data() + (static_cast<size_t>(cta) * n_ph + p) * 8;
-            const long long* t1 = tr.data() + (static_cast<size_t>(cta) * n_ph + p + 1) * 8;
-            if (t0[5] != 0 && t1[5] != 0) v.push_back(t1[5] - t0[5]);
-          }
-          if (!v.empty()) { std::sort(v.begin(), v.end()); period = v[v.size() / 2]; }
-        }
-        const bool has_ln = phases[p].kind == lv::LV_RESID && phases[p].ln;
-        fprintf(stderr, "  %2d %-10s S=%d: %6lld %6lld %6lld %6lld %6lld %6lld | %6lld\n", p, names[phases[p].kind], phases[p].split,
-                med(0, 1), med(1, 6), med(6, 2), med(2, 3), has_ln ? med(3, 4) : -1ll, has_ln ? med(4, 5) : med(3, 5), period);
-      }
-    }
-  }, tap, ti);
-}
-
 Plan* get_plan(hd_handle* h, int B, bool debug = false) {
   auto& cache = debug ? h->plans_dbg : h->plans;
   auto it = cache.find(B);
@@ -1795,27 +1255,24 @@ Plan* get_plan(hd_handle* h, int B, bool debug = false) {
     }, "intro", ti);
     P.flops_per_face += 2.0 * 36 * 128 * S * S;
   }
-  // ---- builders for one UNet stage; each works on the current chain context (P.cx) ----
+  // ---- builders for one UNet stage ----
   auto emit_blocks = [&](size_t first, int count, const std::string& prefix) {
-    const bool whole = P.cx.nslab <= 1;  // the fused kernels address the whole batch
-    if (whole && face_blocks_ok(h, first, count, debug)) { add_face_blocks(h, P, first, count); return; }
-    if (whole && pair_blocks_ok(h, first, count, debug)) { add_pair_blocks(h, P, first, count); return; }
-    if (whole && quad_blocks_ok(h, first, count, debug)) { add_quad_blocks(h, P, first, count); return; }
-    for (int i = 0; i < count; ++i)
-      add_block(h, P, h->blocks[first + i], prefix + std::to_string(i), i + 1 < count ? &h->blocks[first + i + 1] : nullptr, i > 0);
+    if (face_blocks_ok(h, first, count, debug)) { add_face_blocks(h, P, first, count); return; }
+    if (pair_blocks_ok(h, first, count, debug)) { add_pair_blocks(h, P, first, count); return; }
+    for (int i = 0; i < count; ++i) add_block(h, P, h->blocks[first + i], prefix + std::to_string(i));
   };
   auto emit_down = [&](int l) {  // 2x2 stride-2 conv as space-to-depth + GEMM: resid[l] -> resid[l + 1]
-    const int Bq = cx_batch(P), f0 = P.cx.f0;
+    const int Bq = P.batch;
     const int c = h->c[l], n = h->sp[l], rows_out = Bq * (n / 2) * (n / 2);
-    const float* src = h->resid[l] + static_cast<size_t>(f0) * n * n * c;
-    void* act_a = cx_slab(P, h->act_a, h->act_bytes);
+    const float* src = h->resid[l];
+    void* act_a = h->act_a;
     g_label = fmt("down%d s2d", l);
     add_op(P, [=](cudaStream_t st) {
       const size_t total8 = static_cast<size_t>(rows_out) * 4 * c / 8;
       if (bf) launch_k(s2d_kernel<bf16>, dim3(cdiv(total8, 256)), dim3(256), 0, st, src, static_cast<bf16*>(act_a), Bq, n, c);
       else launch_k(s2d_kernel<float>, dim3(cdiv(total8, 256)), dim3(256), 0, st, src, static_cast<float*>(act_a), Bq, n, c);
     });
-    float* out = h->resid[l + 1] + static_cast<size_t>(f0) * (n / 2) * (n / 2) * 2 * c;
+    float* out = h->resid[l + 1];
     GemmDesc d;
     d.M = rows_out; d.N = 2 * c; d.K = 4 * c; d.A = act_a; d.lda = 4 * c; d.a_dtype = adt;
     d.W = h->down_w[l]; d.ldw = 4 * c; d.w_dtype = adt; d.bias = h->down_b[l]; d.epi = EPI_BIAS;
@@ -1823,18 +1280,18 @@ Plan* get_plan(hd_handle* h, int B, bool debug = false) {
     TapInfo ti;
     ti.ptr = out; ti.dtype = DT_F32; ti.C = 2 * c; ti.HW = (n / 2) * (n / 2); ti.ld = 2 * c;
     g_label = fmt("down%d", l);
-    add_gemm(h, P, d, cx_rows_alloc(h, P, (n / 2) * (n / 2)), "downs." + std::to_string(l), ti);
+    add_gemm(h, P, d, rows_cap(h, (n / 2) * (n / 2)), "downs." + std::to_string(l), ti);
   };
   auto emit_up = [&](int L) {  // 1x1 conv + PixelShuffle(2) + skip add: level 4 - L -> resid[3 - L] (in place on the skip)
-    const int Bq = cx_batch(P), f0 = P.cx.f0;
+    const int Bq = P.batch;
     const int lin = 4 - L, lout = 3 - L;
     const int cin = h->c[lin], n = h->sp[lin], rows_in = Bq * n * n;
     const void* a_ptr;
     if (h->fused) {
-      a_ptr = cx_slab(P, h->hca_out, h->act_bytes);
+      a_ptr = h->hca_out;
     } else {
-      const float* src = h->resid[lin] + static_cast<size_t>(f0) * n * n * cin;
-      void* act_a = cx_slab(P, h->act_a, h->act_bytes);
+      const float* src = h->resid[lin];
+      void* act_a = h->act_a;
       a_ptr = act_a;
       g_label = fmt("up%d cast", L);
       add_op(P, [=](cudaStream_t st) {
@@ -1843,7 +1300,7 @@ Plan* get_plan(hd_handle* h, int B, bool debug = false) {
         else launch_k(cast_kernel<float>, dim3(cdiv(total8, 256)), dim3(256), 0, st, src, static_cast<float*>(act_a), total8);
       });
     }
-    float* out = h->resid[lout] + static_cast<size_t>(f0) * 4 * n * n * (cin / 2);
+    float* out = h->resid[lout];
     GemmDesc d;
     d.M = rows_in; d.N = 2 * cin; d.K = cin; d.A = a_ptr; d.lda = cin; d.a_dtype = adt;
     d.W = h->up_w[L]; d.ldw = cin; d.w_dtype = adt; d.bias = nullptr; d.epi = EPI_PIXSHUF; d.sp = n;
@@ -1851,36 +1308,7 @@ Plan* get_plan(hd_handle* h, int B, bool debug = false) {
     TapInfo ti;
     ti.ptr = out; ti.dtype = DT_F32; ti.C = cin / 2; ti.HW = 4 * n * n; ti.ld = cin / 2;
     g_label = fmt("up%d", L);
-    add_gemm(h, P, d, cx_rows_alloc(h, P, n * n), "ups." + std::to_string(L), ti);
-  };
-  auto emit_mid = [&](size_t first) {
-    if (P.cx.nslab <= 1 && level_chain_ok(h, first, kMidBlocks, debug)) {
-      // the 8 bottleneck blocks as one persistent level-chain kernel (level_chain.cuh); norm1 of the first block first
-      const BlockW& b0 = h->blocks[first];
-      const int c = b0.c, rows = B;
-      const float* resid = h->resid[4];
-      void* act_a = h->act_a;
-      ModRef mod{h->mod_table, h->row_idx, h->mod_stride};
-      const float *lw = b0.ln1_w, *lb = b0.ln1_b;
-      const int so = b0.mod_off, co = b0.mod_off + c;
-      g_label = "L4 level_chain ln1";
-      add_op(P, [=](cudaStream_t st) { launch_ln<bf16>(c, resid, lw, lb, static_cast<bf16*>(act_a), rows, 1, mod, so, co, 1, st); });
-      add_level_chain(h, P, first, kMidBlocks);
-    } else if (P.cx.nslab <= 1 && g_chain && !debug && bf && h->sp[4] == 1 && h->blocks[first].dw_folded) {
-      // the 8 bottleneck blocks as one persistent cooperative kernel (chain.cuh); norm1 of the first block first
-      const BlockW& b0 = h->blocks[first];
-      const int c = b0.c, rows = B;
-      const float* resid = h->resid[4];
-      void* act_a = h->act_a;
-      ModRef mod{h->mod_table, h->row_idx, h->mod_stride};
-      const float *lw = b0.ln1_w, *lb = b0.ln1_b;
-      const int so = b0.mod_off, co = b0.mod_off + c;
-      g_label = "L4 chain ln1";
-      add_op(P, [=](cudaStream_t st) { launch_ln<bf16>(c, resid, lw, lb, static_cast<bf16*>(act_a), rows, 1, mod, so, co, 1, st); });
-      add_chain_1x1(h, P, first, kMidBlocks);
-    } else {
-      emit_blocks(first, kMidBlocks, "middle_blks.");
-    }
+    add_gemm(h, P, d, rows_cap(h, n * n), "ups." + std::to_string(L), ti);
   };
   // block index of the first block of each stage, in execution order
   size_t enc_first[4], dec_first[4], mid_first;
@@ -1890,57 +1318,23 @@ Plan* get_plan(hd_handle* h, int B, bool debug = false) {
     mid_first = bi; bi += kMidBlocks;
     for (int L = 0; L < 4; ++L) { dec_first[L] = bi; bi += kDecBlocks[L]; }
   }
-  // Split region (HD_SPLIT): everything from down1 to up2 — the 4x4, 2x2 and 1x1 levels — built once per
-  // face-range chain.  Chains touch disjoint faces of the per-level tensors and private slabs of the scratch
-  // buffers, so they are independent between the fork (after the 8x8 encoder) and the join (before the 8x8
-  // decoder); the ops are interleaved round-robin so plain launches alternate streams too.
-  const int n_chains = (!debug && bf && h->split > 1 && B >= 16 * h->split) ? h->split : 1;
-  P.n_chains = n_chains;
-  auto emit_inner = [&]() {
-    emit_down(1);
-    emit_blocks(enc_first[2], kEncBlocks[2], "encoders.2.");
-    emit_down(2);
-    emit_blocks(enc_first[3], kEncBlocks[3], "encoders.3.");
-    emit_down(3);
-    emit_mid(mid_first);
-    if (h->fused) add_hca(h, P, 0, 4);
-    emit_up(0);
-    emit_blocks(dec_first[0], kDecBlocks[0], "decoders.0.");
-    if (h->fused) add_hca(h, P, 1, 3);
-    emit_up(1);
-    emit_blocks(dec_first[1], kDecBlocks[1], "decoders.1.");
-    if (h->fused) add_hca(h, P, 2, 2);
-    emit_up(2);
-  };
   emit_blocks(enc_first[0], kEncBlocks[0], "encoders.0.");
   emit_down(0);
   emit_blocks(enc_first[1], kEncBlocks[1], "encoders.1.");
-  if (n_chains == 1) {
-    emit_inner();
-  } else {
-    const size_t region_begin = P.ops.size();
-    std::vector<std::vector<Op>> per_chain(n_chains);
-    const int per = cdiv(B, n_chains);
-    const double flops_before = P.flops_per_face;
-    for (int j = 0; j < n_chains; ++j) {
-      P.cx.id = j; P.cx.nslab = n_chains; P.cx.f0 = j * per; P.cx.nf = std::min(per, B - j * per);
-      P.cx.cta_target = std::max(120 / n_chains, 24);
-      emit_inner();
-      per_chain[j].assign(std::make_move_iterator(P.ops.begin() + region_begin), std::make_move_iterator(P.ops.end()));
-      P.ops.resize(region_begin);
-      for (auto& op : per_chain[j]) op.tap.clear();  // a chain sees only its faces: taps come from the per-op plan
-    }
-    P.cx = ChainCx();
-    // add_gemm divides by the whole batch, so the chains' shares already add up to one face
-    (void)flops_before;
-    size_t longest = 0;
-    for (auto& v : per_chain) longest = std::max(longest, v.size());
-    for (size_t i = 0; i < longest; ++i)
-      for (int j = 0; j < n_chains; ++j)
-        if (i < per_chain[j].size()) P.ops.push_back(std::move(per_chain[j][i]));
-    P.ops[region_begin].fork = true;
-    P.ops.back().join = true;
-  }
+  emit_down(1);
+  emit_blocks(enc_first[2], kEncBlocks[2], "encoders.2.");
+  emit_down(2);
+  emit_blocks(enc_first[3], kEncBlocks[3], "encoders.3.");
+  emit_down(3);
+  emit_blocks(mid_first, kMidBlocks, "middle_blks.");
+  if (h->fused) add_hca(h, P, 0, 4);
+  emit_up(0);
+  emit_blocks(dec_first[0], kDecBlocks[0], "decoders.0.");
+  if (h->fused) add_hca(h, P, 1, 3);
+  emit_up(1);
+  emit_blocks(dec_first[1], kDecBlocks[1], "decoders.1.");
+  if (h->fused) add_hca(h, P, 2, 2);
+  emit_up(2);
   emit_blocks(dec_first[2], kDecBlocks[2], "decoders.2.");
   if (h->fused) add_hca(h, P, 3, 1);
   emit_up(3);
@@ -2326,7 +1720,7 @@ void load_cr_block(hd_handle* h, CrBlockW& b, const std::string& p, int c) {
   b.b4 = cr_vec(h, p + "conv4.bias", 2 * c);
   b.w5 = cr_mat(h, p + "conv5.weight", c, c, 1, nullptr, &gamma);
   b.b5 = upload_f32(h, b5);
-  if (c >= 128 && h->bf16 && g_cr_tc) {
+  if (c >= 128 && h->bf16 && h->tun.cr_tc) {
     auto split = [&](const float* w, int N, int K) {
       bf16* out = h->arena.get<bf16>(static_cast<size_t>(N) * 3 * K);
       const size_t total = static_cast<size_t>(N) * (K / 8);
@@ -2428,7 +1822,7 @@ void load_cr_impl(hd_handle* h) {
   R.loc2 = h->arena.get<float>(cap * 27 * 27 * 10);
   R.theta = h->arena.get<float>(cap * 6);
   R.stage = h->arena.get<float>(cap * 3 * R.H * R.H);
-  R.use_tc = h->bf16 && g_cr_tc;
+  R.use_tc = h->bf16 && h->tun.cr_tc;
   if (R.use_tc) R.a3 = h->arena.get<bf16>(cap * 3 * e[2]);  // levels with c >= 128: rows x c <= e[2]
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   for (void* p : h->temp_dev) cudaFree(p);
@@ -2516,7 +1910,7 @@ Plan* get_cr_plan(hd_handle* h, int B) {
     const int k1 = s.k1, k2 = s.k2, n1 = s.n1, n2 = s.n2, fc = s.fc, hid = s.hid;
     g_label = L0 + fmt("stn conv%dx%d+pool+relu", k1, k1);
     add_op(P, [=](cudaStream_t st) {
-      if (g_cr_stn_cs) launch_k(cr_stn_conv_pool_cs_kernel<8>, ew(static_cast<size_t>(B) * n1 * n1 * 4, 128), dim3(128), 0, st, x, w1, b1, loc1, B, n, c, k1, n1);
+      if (h->tun.cr_stn_cs) launch_k(cr_stn_conv_pool_cs_kernel<8>, ew(static_cast<size_t>(B) * n1 * n1 * 4, 128), dim3(128), 0, st, x, w1, b1, loc1, B, n, c, k1, n1);
       else launch_k(cr_stn_conv_pool_kernel<8, 2>, ew(static_cast<size_t>(B) * n1 * n1 * 4, 128), dim3(128), 0, st, x, w1, b1, loc1, B, n, c, k1, n1);
     });
     g_label = L0 + fmt("stn conv%dx%d+pool+relu", k2, k2);
@@ -2662,6 +2056,7 @@ void poll_status(hd_handle* h) {
 
 void join_in(hd_handle* h, void* user_stream) {
   poll_status(h);
+  t_use_pdl = h->tun.pdl;
   cudaStream_t us = static_cast<cudaStream_t>(user_stream);
   CUDA_CHECK(cudaEventRecord(h->ev_in, us));
   CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_in, 0));
@@ -2673,26 +2068,10 @@ void join_out(hd_handle* h, void* user_stream) {
   CUDA_CHECK(cudaStreamWaitEvent(us, h->ev_out, 0));
 }
 
-// Issues one op of a plan: ops of a split region go to their chain's stream; the fork / join edges are event
-// waits, which stream capture turns into parallel branches of the step's CUDA graph.
-void exec_op(hd_handle* h, const Op& op, cudaStream_t st, int n_chains) {
-  if (op.fork) {
-    cudaEventRecord(h->ev_fork, st);
-    for (int j = 0; j + 1 < n_chains; ++j) cudaStreamWaitEvent(h->side[j], h->ev_fork, 0);
-  }
-  op.fn(op.chain == 0 ? st : h->side[op.chain - 1]);
-  if (op.join) {
-    for (int j = 0; j + 1 < n_chains; ++j) {
-      cudaEventRecord(h->ev_join[j], h->side[j]);
-      cudaStreamWaitEvent(st, h->ev_join[j], 0);
-    }
-  }
-}
-
 void run_plan(hd_handle* h, Plan* P, cudaStream_t st, const char* const* tap_names, float* const* tap_out, int n_taps,
               int B) {
   for (auto& op : P->ops) {
-    exec_op(h, op, st, P->n_chains);
+    op.fn(st);
     if (n_taps > 0 && !op.tap.empty()) {
       for (int i = 0; i < n_taps; ++i) {
         if (op.tap != tap_names[i]) continue;
@@ -2800,13 +2179,8 @@ void hd_destroy(hd_handle* h) {
   h->arena.release();
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   if (h->ev_out) cudaEventDestroy(h->ev_out);
-  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_status) cudaEventDestroy(h->ev_status);
   if (h->status_host) cudaFreeHost(h->status_host);
-  for (int j = 0; j < kMaxSplit - 1; ++j) {
-    if (h->ev_join[j]) cudaEventDestroy(h->ev_join[j]);
-    if (h->side[j]) cudaStreamDestroy(h->side[j]);
-  }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -2830,30 +2204,11 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   cudaDeviceProp prop;
   CUDA_CHECK(cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10) HD_THROW(HD_ERR_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
-  if (const char* e = getenv("HD_PDL")) g_use_pdl = atoi(e) != 0;
-  if (const char* e = getenv("HD_SCA_FUSED")) g_sca_fused = atoi(e) != 0;
-  if (const char* e = getenv("HD_CR_STN_CS")) g_cr_stn_cs = atoi(e) != 0;
-  if (const char* e = getenv("HD_CR_TC")) g_cr_tc = atoi(e) != 0;
-  if (const char* e = getenv("HD_DW_SMALL")) g_dw_small = atoi(e) != 0;
-  if (const char* e = getenv("HD_CTA_TARGET")) g_cta_target = std::max(atoi(e), 1);
-  if (const char* e = getenv("HD_SCA_TARGET")) g_sca_target = std::max(atoi(e), 1);
-  if (const char* e = getenv("HD_SPLIT")) g_split = std::min(std::max(atoi(e), 1), kMaxSplit);
-  if (const char* e = getenv("HD_FUSE_DW")) g_fuse_dw = atoi(e) == 1 ? 14 : atoi(e);
-  if (const char* e = getenv("HD_BN256")) g_bn256 = atoi(e) != 0;
-  if (const char* e = getenv("HD_TWO_CTA")) g_two_cta = atoi(e);
-  if (const char* e = getenv("HD_CHAIN")) g_chain = atoi(e) != 0;
-  if (const char* e = getenv("HD_FACE")) g_face = atoi(e) != 0;
-  if (const char* e = getenv("HD_PAIR")) g_pair = atoi(e) != 0;
-  if (const char* e = getenv("HD_QUAD")) g_quad = atoi(e) != 0;
-  if (const char* e = getenv("HD_FUSE_SCALE")) g_fuse_scale = atoi(e) != 0;
-  if (const char* e = getenv("HD_MAX_STAGES")) g_max_stages = atoi(e);
-  if (const char* e = getenv("HD_FUSE_LN")) g_fuse_ln = atoi(e) != 0;
-  if (const char* e = getenv("HD_LV")) g_lv = atoi(e);
-  if (const char* e = getenv("HD_LV_COOP")) g_lv_coop = atoi(e) != 0;
   h = new hd_handle();
   struct Guard { hd_handle*& p; bool armed = true; ~Guard() { if (armed && p) { hd_destroy(p); p = nullptr; } } } guard{h};
   h->cfg = *cfg;
-  h->split = g_split;
+  h->tun.read_env();
+  t_use_pdl = h->tun.pdl;
   h->fused = cfg->model == HD_MODEL_FUSED;
   h->bf16 = cfg->precision == HD_PRECISION_BF16;
   h->S = cfg->latent_size;
@@ -2864,11 +2219,6 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
-  CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-  for (int j = 0; j < kMaxSplit - 1; ++j) {
-    CUDA_CHECK(cudaStreamCreateWithFlags(&h->side[j], cudaStreamNonBlocking));
-    CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_join[j], cudaEventDisableTiming));
-  }
   {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -2916,7 +2266,7 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   h->act_h = A.alloc(2 * max_pc * as);
   h->act_g = A.alloc(max_pc * as);
   h->hca_out = A.alloc(max_pc * as);
-  h->pooled_rows = Bc + 128 * kMaxSplit;  // split chains round their face capacity up to whole 128-row tiles
+  h->pooled_rows = Bc;
   h->pooled = A.alloc(h->pooled_rows * 2048 * as);
   h->sca_s = A.get<float>(h->pooled_rows * 2048);
   if (!h->bf16) h->gate_tmp = A.get<float>(2 * max_pc);
@@ -3135,7 +2485,7 @@ int32_t hd_sample(hd_handle* h, float* x_inout, const hd_step_coef* coef, int32_
   int* ridx = h->row_idx;
   const int Bcap = h->Bcap;
   auto one_step = [&](cudaStream_t s) {
-    for (auto& op : P->ops) exec_op(h, op, s, P->n_chains);
+    for (auto& op : P->ops) op.fn(s);
     launch_k(sampler_update_kernel, dim3(cdiv(threads, 256)), dim3(256), 0, s, xs, eb, cf, ss, 0, noise, seed, first_face, B, epf);
     launch_k(advance_rows_kernel, dim3(1), dim3(256), 0, s, ss, ridx, Bcap);
   };
@@ -3473,10 +2823,10 @@ int32_t hd_debug_gemm(hd_handle* h, const float* a, const float* w, const float*
     launch_k(cast_kernel<bf16>, dim3(cdiv(ta, 256)), dim3(256), 0, st, a, static_cast<bf16*>(da), ta);
     launch_k(cast_kernel<bf16>, dim3(cdiv(tw, 256)), dim3(256), 0, st, w, static_cast<bf16*>(dw), tw);
     d.A = da; d.W = dw; d.a_dtype = DT_BF16; d.w_dtype = DT_BF16;
-    const int saved = g_two_cta;
-    g_two_cta = use_tc == 2 ? 2 : (use_tc == 3 ? 0 : saved);  // 2: force cta_group::2 pairs, 3: force single-CTA tiles
+    const int saved = h->tun.two_cta;
+    h->tun.two_cta = use_tc == 2 ? 2 : (use_tc == 3 ? 0 : saved);  // 2: force cta_group::2 pairs, 3: force single-CTA tiles
     TcLaunch L = build_tc(h, d, m_alloc);
-    g_two_cta = saved;
+    h->tun.two_cta = saved;
     if (use_tc == 2 && !L.two_cta) HD_THROW(HD_ERR_INVALID, "shape not eligible for the 2-CTA kernel (N %% 256)");
     launch_tc(L, st);  // warm-up (also warms L2 with the operands)
     launch_tc(L, st);

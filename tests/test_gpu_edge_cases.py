@@ -86,36 +86,3 @@ def test_sampler_ragged_and_repeatable(fused16):
     assert not torch.equal(a, x)                                                    # input untouched, output new
     c = H.ddim_sample(m, x, sched, 8, facial_priors=pc, identity_embedding=ic)      # different schedule -> new table
     assert not torch.equal(a, c)
-
-
-@pytest.fixture(scope="module")
-def fused16_split():
-    import os
-    os.environ["HD_SPLIT"] = "2"
-    try:
-        m, sd = build(H.FusedDenoiser, seed=2, precision="bf16", max_batch=80)
-        m.engine(80)
-    finally:
-        os.environ["HD_SPLIT"] = "1"
-    yield m, sd
-    m.invalidate()
-
-
-@pytest.mark.parametrize("batch", [33, 70])
-def test_split_chains_per_face_timesteps(fused16_split, batch):
-    """HD_SPLIT=2 (off by default, measured slower): from 32 faces up the 4x4 / 2x2 / 1x1 levels run as two
-    face-range chains on two streams: an odd split point, per-face timesteps (the chain's row index offset) and
-    every face checked on its own."""
-    m, sd = fused16_split
-    x = inputs("latents", batch, seed=300 + batch)
-    priors, ident = testing.synthetic_condition(batch, 16, seed=300 + batch)
-    t = (torch.arange(batch) * 13 + 5) % 1000
-    out = m(x.cuda(), t.cuda(), [p.cuda() for p in priors], ident.cuda()).sample
-    again = m(x.cuda(), t.cuda(), [p.cuda() for p in priors], ident.cuda()).sample
-    m.engine().synchronize()
-    with torch.no_grad():
-        ref = denoiser_ref.fused_denoiser_forward(sd, x, t, priors, ident)
-    worst = max(rel_l2(out[i], ref[i]) for i in range(batch))
-    print(f"split chains B={batch}: rel-L2 {rel_l2(out, ref):.3e}, worst face {worst:.3e}")
-    assert worst <= 1.2e-2 and rel_l2(out, ref) <= 1e-2
-    assert torch.equal(out, again)
