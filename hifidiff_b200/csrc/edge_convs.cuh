@@ -1,0 +1,286 @@
+// The two 3x3 convolutions at the ends of the UNet (models/denoiser/model.py:159-176,235,261-262) on the tensor cores,
+// one CTA per face (latent 16x16 = 256 pixels), and the x_{t-1} update fused behind the last one:
+//
+//   intro   4 -> 128 channels, K = 36.  im2col of the fp32 latent built in shared memory as bf16 hi + lo, weights as
+//           bf16 hi + lo; a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with fp32 accumulation (everything but the lo*lo term:
+//           ~2^-16 relative, i.e. fp32-grade — the bf16 mode keeps its fp32 stem).  Output: the fp32 residual stream.
+//   ending  128 -> 4 channels, K = 1152.  The bf16 NHWC input tile of the face is staged once (XOR-swizzled 16-byte
+//           chunks); each tap's A fragments are ldmatrix gathers of shifted pixel rows (zero row for the padding),
+//           weights as bf16 hi + lo (exact against the fp32 weights to ~2^-17).  N is padded 4 -> 8.
+//           FUSE: epsilon goes to shared memory instead of HBM and the same CTA applies the scheduler step
+//           (train_refiner.py:120; sampler_update_group below, the body of sampler_update_kernel) to its face's 1024
+//           latent values; the last CTA to finish advances the step counter and the per-face table rows.  That is
+//           ending + sampler_update + advance_rows in one launch.
+//
+// These are N = 4 / K = 36 edge cases, bandwidth-bound once the arithmetic is off the CUDA cores (they were LDS-bound
+// FFMA kernels at 30 us each): warp-level mma.sync.m16n8k16 is enough here, the dense contractions of the network
+// (gemm_tc.cuh, face_block.cuh, pair_block.cuh) are tcgen05.
+#pragma once
+
+#include "common.cuh"
+#include "elem_kernels.cuh"
+
+namespace hd {
+namespace edge {
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2(uint32_t addr, uint32_t (&r)[2]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+constexpr int S = 16, NPIX = S * S;
+
+// ------------------------------------------------------------------------------------------------------------------
+// ending
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int END_KSTEPS = 9 * 8;                              // 9 taps x 8 chunks of 16 channels
+constexpr int END_W_BYTES = END_KSTEPS * 8 * 16 * 2;           // [kstep][n = 8][k = 16] bf16
+constexpr int END_TILE_BYTES = NPIX * 128 * 2;
+constexpr int END_SMEM = END_TILE_BYTES + 256 + 2 * END_W_BYTES + 4 * NPIX * 4;
+
+struct EndArgs {
+  const bf16* x;          // [B, 16, 16, 128] NHWC
+  const bf16* w_hi;       // [72][8][16]
+  const bf16* w_lo;
+  const float* bias;      // [4]
+  float* eps;             // [B, 4, 16, 16] NCHW (written when !fuse)
+  // fused scheduler step
+  float* x_state;         // [B, 4, 16, 16], updated in place
+  const StepCoef* coefs;
+  StepState* state;
+  const float* noise;     // explicit z, [steps][B][1024], or nullptr (Philox)
+  unsigned long long seed;
+  long long first_face;
+  int batch;
+  int* row_idx;           // [n_rows] per-face table rows, advanced with the step
+  int n_rows;
+  unsigned int* ticket;   // CTA completion counter, left at zero
+};
+
+template <bool FUSE>
+__global__ void __launch_bounds__(256, 2) ending_mma_kernel(const EndArgs a) {
+  extern __shared__ __align__(128) uint8_t s_raw[];
+  bf16* tile = reinterpret_cast<bf16*>(s_raw);
+  uint8_t* zero_row = s_raw + END_TILE_BYTES;
+  bf16* s_whi = reinterpret_cast<bf16*>(s_raw + END_TILE_BYTES + 256);
+  bf16* s_wlo = reinterpret_cast<bf16*>(s_raw + END_TILE_BYTES + 256 + END_W_BYTES);
+  float* s_eps = reinterpret_cast<float*>(s_raw + END_TILE_BYTES + 256 + 2 * END_W_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int face = blockIdx.x;
+  pdl_trigger();
+  // weights (constants): before the dependency wait
+  for (int i = tid; i < END_W_BYTES / 16; i += 256) {
+    reinterpret_cast<uint4*>(s_whi)[i] = __ldg(reinterpret_cast<const uint4*>(a.w_hi) + i);
+    reinterpret_cast<uint4*>(s_wlo)[i] = __ldg(reinterpret_cast<const uint4*>(a.w_lo) + i);
+  }
+  if (tid < 16) reinterpret_cast<uint4*>(zero_row)[tid] = make_uint4(0u, 0u, 0u, 0u);
+  pdl_wait();
+  {  // the face's input tile: 4096 16-byte chunks, 16 per thread, all loads of a batch in flight
+    const uint4* src = reinterpret_cast<const uint4*>(a.x + static_cast<size_t>(face) * NPIX * 128);
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = src[(b * 8 + u) * 256 + tid];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = (b * 8 + u) * 256 + tid;
+        const int r = i >> 4, ck = i & 15;
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(tile) + r * 256 + ((ck ^ (r & 7)) << 4)) = v[u];
+      }
+    }
+  }
+  __syncthreads();
+  // warp w owns image rows 2w and 2w+1 (two 16-pixel M tiles); lane l supplies the address of pixel x = l % 16,
+  // channel half l / 16 of every A fragment
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  const int lx = lane & 15, khalf = lane >> 4;
+  const uint32_t tile_u32 = smem_addr(tile), zero_u32 = smem_addr(zero_row);
+  const uint32_t whi_u32 = smem_addr(s_whi) + (lane & 7) * 32 + ((lane >> 3) & 1) * 16;
+  const uint32_t wlo_u32 = smem_addr(s_wlo) + (lane & 7) * 32 + ((lane >> 3) & 1) * 16;
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+    uint32_t row_addr[2];
+    int row_sw[2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int yy = 2 * warp + mt + dy, xx = lx + dx;
+      const bool inside = yy >= 0 && yy < S && xx >= 0 && xx < S;
+      const int r = yy * S + xx;
+      row_addr[mt] = inside ? tile_u32 + r * 256 : zero_u32;
+      row_sw[mt] = inside ? (r & 7) : -1;
+    }
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      const int ks = tap * 8 + cc;
+      uint32_t bh[2], bl[2];
+      ldmatrix_x2(whi_u32 + ks * 256, bh);
+      ldmatrix_x2(wlo_u32 + ks * 256, bl);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        uint32_t af[4];
+        const int ck = cc * 2 + khalf;
+        ldmatrix_x4(row_sw[mt] >= 0 ? row_addr[mt] + ((ck ^ row_sw[mt]) << 4) : row_addr[mt], af);
+        mma_16816(acc[mt], af, bh);
+        mma_16816(acc[mt], af, bl);
+      }
+    }
+  }
+  // C fragment: rows g = lane / 4 and g + 8 (pixel x), columns 2 * (lane % 4) + {0, 1} (output channel; 0..3 are real)
+  const int g = lane >> 2, q = lane & 3;
+  if (q < 2) {
+    const float b0 = __ldg(a.bias + 2 * q), b1 = __ldg(a.bias + 2 * q + 1);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int y = 2 * warp + mt;
+      const float v[4] = {acc[mt][0] + b0, acc[mt][1] + b1, acc[mt][2] + b0, acc[mt][3] + b1};
+      if (FUSE) {
+        s_eps[(2 * q) * NPIX + y * S + g] = v[0];
+        s_eps[(2 * q + 1) * NPIX + y * S + g] = v[1];
+        s_eps[(2 * q) * NPIX + y * S + g + 8] = v[2];
+        s_eps[(2 * q + 1) * NPIX + y * S + g + 8] = v[3];
+      } else {
+        float* e = a.eps + static_cast<size_t>(face) * 4 * NPIX + y * S;
+        e[(2 * q) * NPIX + g] = v[0];
+        e[(2 * q + 1) * NPIX + g] = v[1];
+        e[(2 * q) * NPIX + g + 8] = v[2];
+        e[(2 * q + 1) * NPIX + g + 8] = v[3];
+      }
+    }
+  }
+  if (FUSE) {
+    __syncthreads();
+    // scheduler step on this face's 1024 latent values: thread t = group t of four consecutive elements, exactly the
+    // work item (and the Philox counter) of sampler_update_kernel
+    const int step = a.state->step;
+    const float4 ev = reinterpret_cast<const float4*>(s_eps)[tid];
+    sampler_update_group(a.x_state, ev, a.coefs[step], step, face, tid, static_cast<size_t>(face) * 256 + tid, a.noise, a.seed,
+                         a.first_face, a.batch, 256);
+    // the last CTA to finish ends the step: step += 1, every face points at the next table row
+    __shared__ unsigned int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last != 0u) {
+      const int next = step + 1;
+      for (int i = tid; i < a.n_rows; i += 256) a.row_idx[i] = next;
+      if (tid == 0) { a.state->step = next; *a.ticket = 0u; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// intro
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int IN_K = 48;                                   // 36 (channel-major: k = ci * 9 + tap) padded to 3 k-steps
+constexpr int IN_ASTRIDE = 56;                             // bf16 per A row: 112 bytes, conflict-free ldmatrix rows
+constexpr int IN_A_BYTES = NPIX * IN_ASTRIDE * 2;
+constexpr int IN_W_BYTES = 3 * 16 * 8 * 16 * 2;            // [kstep 3][n tile 16][n 8][k 16] bf16
+constexpr int IN_X_BYTES = 4 * (S + 2) * (S + 2) * 4;
+constexpr int IN_SMEM = 2 * IN_A_BYTES + 2 * IN_W_BYTES + IN_X_BYTES;
+
+__global__ void __launch_bounds__(256, 2) intro_mma_kernel(const float* __restrict__ x, const bf16* __restrict__ w_hi,
+                                                           const bf16* __restrict__ w_lo, const float* __restrict__ bias,
+                                                           float* __restrict__ out) {
+  extern __shared__ __align__(128) uint8_t s_raw[];
+  bf16* a_hi = reinterpret_cast<bf16*>(s_raw);
+  bf16* a_lo = reinterpret_cast<bf16*>(s_raw + IN_A_BYTES);
+  bf16* s_whi = reinterpret_cast<bf16*>(s_raw + 2 * IN_A_BYTES);
+  bf16* s_wlo = reinterpret_cast<bf16*>(s_raw + 2 * IN_A_BYTES + IN_W_BYTES);
+  float* s_x = reinterpret_cast<float*>(s_raw + 2 * IN_A_BYTES + 2 * IN_W_BYTES);   // [4][18][18], zero border
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int face = blockIdx.x;
+  pdl_trigger();
+  for (int i = tid; i < IN_W_BYTES / 16; i += 256) {
+    reinterpret_cast<uint4*>(s_whi)[i] = __ldg(reinterpret_cast<const uint4*>(w_hi) + i);
+    reinterpret_cast<uint4*>(s_wlo)[i] = __ldg(reinterpret_cast<const uint4*>(w_lo) + i);
+  }
+  for (int i = tid; i < 4 * (S + 2) * (S + 2); i += 256) s_x[i] = 0.f;
+  pdl_wait();
+  __syncthreads();
+  {
+    const float4 v = *reinterpret_cast<const float4*>(x + static_cast<size_t>(face) * 4 * NPIX + tid * 4);
+    const int ci = tid >> 6, rem = (tid & 63) * 4, py = rem >> 4, px = rem & 15;
+    float* d = s_x + (ci * (S + 2) + py + 1) * (S + 2) + px + 1;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  {  // im2col row of pixel tid, split into bf16 hi + lo
+    const int py = tid >> 4, px = tid & 15;
+    bf16* rh = a_hi + tid * IN_ASTRIDE;
+    bf16* rl = a_lo + tid * IN_ASTRIDE;
+#pragma unroll
+    for (int k = 0; k < IN_K; k += 2) {
+      float v[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int kk = k + j;
+        v[j] = 0.f;
+        if (kk < 36) {
+          const int ci = kk / 9, tap = kk % 9;
+          v[j] = s_x[(ci * (S + 2) + py + tap / 3) * (S + 2) + px + tap % 3];
+        }
+      }
+      const bf16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]);
+      *reinterpret_cast<__nv_bfloat162*>(rh + k) = __nv_bfloat162(h0, h1);
+      *reinterpret_cast<__nv_bfloat162*>(rl + k) = __floats2bfloat162_rn(v[0] - __bfloat162float(h0), v[1] - __bfloat162float(h1));
+    }
+  }
+  __syncthreads();
+  // A fragments of the warp's two image rows, hi and lo, for the three k-steps: kept in registers for all 16 N tiles
+  uint32_t ah[2][3][4], al[2][3][4];
+  {
+    const int lx = lane & 15, khalf = lane >> 4;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int r = (2 * warp + mt) * S + lx;
+#pragma unroll
+      for (int ks = 0; ks < 3; ++ks) {
+        const uint32_t off = static_cast<uint32_t>(r * IN_ASTRIDE + ks * 16 + khalf * 8) * 2u;
+        ldmatrix_x4(smem_addr(a_hi) + off, ah[mt][ks]);
+        ldmatrix_x4(smem_addr(a_lo) + off, al[mt][ks]);
+      }
+    }
+  }
+  const uint32_t whi_u32 = smem_addr(s_whi) + (lane & 7) * 32 + ((lane >> 3) & 1) * 16;
+  const uint32_t wlo_u32 = smem_addr(s_wlo) + (lane & 7) * 32 + ((lane >> 3) & 1) * 16;
+  const int g = lane >> 2, q = lane & 3;
+  float* obase = out + static_cast<size_t>(face) * NPIX * 128;
+#pragma unroll 2
+  for (int nt = 0; nt < 16; ++nt) {
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks) {
+      uint32_t bh[2], bl[2];
+      ldmatrix_x2(whi_u32 + (ks * 16 + nt) * 256, bh);
+      ldmatrix_x2(wlo_u32 + (ks * 16 + nt) * 256, bl);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_16816(acc[mt], ah[mt][ks], bh);
+        mma_16816(acc[mt], al[mt][ks], bh);
+        mma_16816(acc[mt], ah[mt][ks], bl);
+      }
+    }
+    const float2 b = __ldg(reinterpret_cast<const float2*>(bias + nt * 8 + 2 * q));
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int r = (2 * warp + mt) * S;
+      *reinterpret_cast<float2*>(obase + static_cast<size_t>(r + g) * 128 + nt * 8 + 2 * q) = make_float2(acc[mt][0] + b.x, acc[mt][1] + b.y);
+      *reinterpret_cast<float2*>(obase + static_cast<size_t>(r + g + 8) * 128 + nt * 8 + 2 * q) = make_float2(acc[mt][2] + b.x, acc[mt][3] + b.y);
+    }
+  }
+}
+
+}  // namespace edge
+}  // namespace hd

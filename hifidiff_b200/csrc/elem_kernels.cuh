@@ -713,22 +713,13 @@ __device__ __forceinline__ float philox_unit(uint32_t r) {
   return (static_cast<float>(r >> 9) + 0.5f) * 1.1920928955078125e-07f;  // 2^-23
 }
 
-__global__ void __launch_bounds__(256) sampler_update_kernel(float* __restrict__ x, const float* __restrict__ eps,
-                                                             const StepCoef* __restrict__ coefs,
-                                                             const StepState* __restrict__ state, int fixed_step,
-                                                             const float* __restrict__ noise, unsigned long long seed,
-                                                             long long first_face, int batch, int elems_per_face) {
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int groups = elems_per_face >> 2;
-  pdl_trigger();
-  pdl_wait();
-  if (i >= static_cast<size_t>(batch) * groups) return;
-  const int step = state != nullptr ? state->step : fixed_step;
-  const StepCoef cf = coefs[step];
-  const int face = static_cast<int>(i / groups);
-  const int grp = static_cast<int>(i - static_cast<size_t>(face) * groups);
+// The scheduler step (DDIM / DDPM, coefficients from schedulers.py::step_coefficients) on one group of four
+// consecutive latent values: i = face * groups + grp indexes float4s of x; Philox counter = (grp, global face, step).
+// Shared by sampler_update_kernel and by the fused ending kernel (edge_convs.cuh) so both produce the same bits.
+__device__ __forceinline__ void sampler_update_group(float* __restrict__ x, float4 ev, const StepCoef cf, int step, int face,
+                                                     int grp, size_t i, const float* __restrict__ noise,
+                                                     unsigned long long seed, long long first_face, int batch, int groups) {
   const float4 xv = *reinterpret_cast<const float4*>(x + i * 4);
-  const float4 ev = *reinterpret_cast<const float4*>(eps + i * 4);
   float xs[4] = {xv.x, xv.y, xv.z, xv.w};
   const float es[4] = {ev.x, ev.y, ev.z, ev.w};
   float z[4] = {0.f, 0.f, 0.f, 0.f};
@@ -759,6 +750,23 @@ __global__ void __launch_bounds__(256) sampler_update_kernel(float* __restrict__
     xs[j] = r;
   }
   *reinterpret_cast<float4*>(x + i * 4) = make_float4(xs[0], xs[1], xs[2], xs[3]);
+}
+
+__global__ void __launch_bounds__(256) sampler_update_kernel(float* __restrict__ x, const float* __restrict__ eps,
+                                                             const StepCoef* __restrict__ coefs,
+                                                             const StepState* __restrict__ state, int fixed_step,
+                                                             const float* __restrict__ noise, unsigned long long seed,
+                                                             long long first_face, int batch, int elems_per_face) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int groups = elems_per_face >> 2;
+  pdl_trigger();
+  pdl_wait();
+  if (i >= static_cast<size_t>(batch) * groups) return;
+  const int step = state != nullptr ? state->step : fixed_step;
+  const int face = static_cast<int>(i / groups);
+  const int grp = static_cast<int>(i - static_cast<size_t>(face) * groups);
+  const float4 ev = *reinterpret_cast<const float4*>(eps + i * 4);
+  sampler_update_group(x, ev, coefs[step], step, face, grp, i, noise, seed, first_face, batch, groups);
 }
 
 // end of a sampler step: step += 1 and point every face at the next table row (single block)

@@ -15,6 +15,7 @@
 #include "elem_kernels.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "edge_convs.cuh"
 #include "face_block.cuh"
 #include "pair_block.cuh"
 #include "idc_kernels.cuh"
@@ -67,6 +68,7 @@ struct Tunables {
   bool face = true;       // HD_FACE=0: per-op kernels at the 16x16 level instead of the fused per-face block kernel
   bool pair = true;       // HD_PAIR=0: per-op kernels at the 8x8 level instead of the fused face-pair block kernel
   bool sca_mul = true;    // HD_SCA_MUL=0: separate scale_rows kernel at the 1x1 level too
+  bool edge_mma = true;   // HD_EDGE_MMA=0: CUDA-core intro / ending convs and separate sampler-update / advance launches
   bool cr_stn_cs = true;  // HD_CR_STN_CS=0: one thread per (pixel, 2 output channels) in the first STN localisation conv
   bool cr_tc = true;      // HD_CR_TC=0: every CoarseRestoration GEMM on the FFMA kernel (no split-precision tcgen05 path)
   bool dw_small = true;   // HD_DW_SMALL=0: the generic tiled depthwise kernel at the 2x2 / 4x4 levels too
@@ -74,7 +76,7 @@ struct Tunables {
   int sca_target = 120;   // HD_SCA_TARGET: the same for the SCA GEMMs (M = faces)
   void read_env() {
     auto flag = [](const char* name, bool& v) { if (const char* e = getenv(name)) v = atoi(e) != 0; };
-    flag("HD_PDL", pdl); flag("HD_BN256", bn256); flag("HD_FACE", face); flag("HD_PAIR", pair); flag("HD_SCA_MUL", sca_mul);
+    flag("HD_PDL", pdl); flag("HD_BN256", bn256); flag("HD_FACE", face); flag("HD_PAIR", pair); flag("HD_SCA_MUL", sca_mul); flag("HD_EDGE_MMA", edge_mma);
     flag("HD_CR_STN_CS", cr_stn_cs); flag("HD_CR_TC", cr_tc); flag("HD_DW_SMALL", dw_small);
     if (const char* e = getenv("HD_TWO_CTA")) two_cta = atoi(e);
     if (const char* e = getenv("HD_CTA_TARGET")) cta_target = std::max(atoi(e), 1);
@@ -248,6 +250,7 @@ struct Plan {
   int64_t graph_first = 0;
   const float* graph_noise = nullptr;
   double flops_per_face = 0;
+  int ending_idx = -1;  // index of the ending-conv op when hd_sample may replace it by the fused ending + scheduler-step kernel
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -287,6 +290,8 @@ struct hd_handle {
   void *down_w[4] = {}, *up_w[4] = {};
   float* down_b[4] = {};
   float *intro_w = nullptr, *intro_b = nullptr, *end_w = nullptr, *end_b = nullptr;
+  hd::bf16 *intro_mma_hi = nullptr, *intro_mma_lo = nullptr, *end_mma_hi = nullptr, *end_mma_lo = nullptr;  // edge_convs.cuh fragment order
+  unsigned int* end_ticket = nullptr;
   float *tm1_w = nullptr, *tm1_b = nullptr, *tm3_w = nullptr, *tm3_b = nullptr, *mlp_w = nullptr, *mlp_b = nullptr;
   float *idc_w = nullptr, *idc_b = nullptr, *freqs = nullptr;
   int64_t weight_elems_step = 0;
@@ -765,6 +770,55 @@ void load_weights_impl(hd_handle* h) {
                                              nullptr, DT_F32));
   h->end_b = upload_f32(h, host_vec(h, need(h, "ending.bias", {4})));
   h->weight_elems_step += 128 * 36 + 4 * 9 * 128;
+  if (h->bf16 && h->S == edge::S) {
+    // intro / ending weights as bf16 hi + lo in mma.sync B-fragment order [k-step][n][16 k] (edge_convs.cuh)
+    auto split = [&](const std::vector<float>& v, hd::bf16** hi, hd::bf16** lo) {
+      std::vector<uint16_t> vh(v.size()), vl(v.size());
+      auto to_bf16 = [](float f) {
+        uint32_t u;
+        memcpy(&u, &f, 4);
+        u += 0x7FFFu + ((u >> 16) & 1u);
+        return static_cast<uint16_t>(u >> 16);
+      };
+      for (size_t i = 0; i < v.size(); ++i) {
+        vh[i] = to_bf16(v[i]);
+        const uint32_t hb = static_cast<uint32_t>(vh[i]) << 16;
+        float hf;
+        memcpy(&hf, &hb, 4);
+        vl[i] = to_bf16(v[i] - hf);
+      }
+      *hi = static_cast<hd::bf16*>(h->arena.alloc(v.size() * 2));
+      *lo = static_cast<hd::bf16*>(h->arena.alloc(v.size() * 2));
+      CUDA_CHECK(cudaMemcpy(*hi, vh.data(), v.size() * 2, cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMemcpy(*lo, vl.data(), v.size() * 2, cudaMemcpyHostToDevice));
+    };
+    {
+      auto w = host_vec(h, need(h, "ending.weight", {4, kWidth, 9}));  // [o][c][tap]
+      std::vector<float> f(static_cast<size_t>(edge::END_KSTEPS) * 8 * 16, 0.f);
+      for (int tap = 0; tap < 9; ++tap)
+        for (int cc = 0; cc < 8; ++cc)
+          for (int n = 0; n < 4; ++n)
+            for (int k = 0; k < 16; ++k)
+              f[((static_cast<size_t>(tap) * 8 + cc) * 8 + n) * 16 + k] = w[(static_cast<size_t>(n) * kWidth + cc * 16 + k) * 9 + tap];
+      split(f, &h->end_mma_hi, &h->end_mma_lo);
+    }
+    {
+      auto w = host_vec(h, need(h, "intro.weight", {kWidth, 36}));  // [o][ci * 9 + tap]
+      std::vector<float> f(static_cast<size_t>(3) * 16 * 8 * 16, 0.f);
+      for (int ks = 0; ks < 3; ++ks)
+        for (int nt = 0; nt < 16; ++nt)
+          for (int n = 0; n < 8; ++n)
+            for (int k = 0; k < 16; ++k) {
+              const int kk = ks * 16 + k;
+              if (kk < 36) f[((static_cast<size_t>(ks) * 16 + nt) * 8 + n) * 16 + k] = w[static_cast<size_t>(nt * 8 + n) * 36 + kk];
+            }
+      split(f, &h->intro_mma_hi, &h->intro_mma_lo);
+    }
+    h->end_ticket = h->arena.get<unsigned int>(64);
+    CUDA_CHECK(cudaFuncSetAttribute(edge::ending_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, edge::END_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(edge::ending_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, edge::END_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(edge::intro_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, edge::IN_SMEM));
+  }
 
   for (int l = 0; l < 4; ++l) {
     const int c = h->c[l];
@@ -1249,10 +1303,17 @@ Plan* get_plan(hd_handle* h, int B, bool debug = false) {
     const float *w = h->intro_w, *b = h->intro_b;
     TapInfo ti;
     ti.ptr = out; ti.dtype = DT_F32; ti.C = kWidth; ti.HW = S * S; ti.ld = kWidth;
-    g_label = "intro conv3x3";
-    add_op(P, [=](cudaStream_t st) {
-      launch_k(intro_conv_kernel, dim3(B), dim3(256), (36 * 128 + 4 * (S + 2) * (S + 2)) * sizeof(float), st, h->cur_x, w, b, out, S);
-    }, "intro", ti);
+    if (h->tun.edge_mma && h->intro_mma_hi != nullptr) {
+      const bf16 *whi = h->intro_mma_hi, *wlo = h->intro_mma_lo;
+      g_label = "intro conv3x3 mma.sync (3 x bf16 split)";
+      add_op(P, [=](cudaStream_t st) { launch_k(edge::intro_mma_kernel, dim3(B), dim3(256), edge::IN_SMEM, st, h->cur_x, whi, wlo, b, out); },
+             "intro", ti);
+    } else {
+      g_label = "intro conv3x3";
+      add_op(P, [=](cudaStream_t st) {
+        launch_k(intro_conv_kernel, dim3(B), dim3(256), (36 * 128 + 4 * (S + 2) * (S + 2)) * sizeof(float), st, h->cur_x, w, b, out, S);
+      }, "intro", ti);
+    }
     P.flops_per_face += 2.0 * 36 * 128 * S * S;
   }
   // ---- builders for one UNet stage ----
@@ -1344,12 +1405,25 @@ Plan* get_plan(hd_handle* h, int B, bool debug = false) {
     const float *w = h->end_w, *b = h->end_b;
     const void* in = h->fused ? h->hca_out : static_cast<const void*>(h->resid[0]);
     const bool in_bf = h->fused && bf;
+    if (in_bf && h->tun.edge_mma && h->end_mma_hi != nullptr) {
+      edge::EndArgs ea;
+      memset(&ea, 0, sizeof(ea));
+      ea.x = static_cast<const bf16*>(in); ea.w_hi = h->end_mma_hi; ea.w_lo = h->end_mma_lo; ea.bias = b;
+      g_label = "ending conv3x3 mma.sync";
+      add_op(P, [=](cudaStream_t st) {
+        edge::EndArgs e2 = ea;
+        e2.eps = h->cur_eps;
+        launch_k(edge::ending_mma_kernel<false>, dim3(B), dim3(256), edge::END_SMEM, st, e2);
+      });
+      P.ending_idx = static_cast<int>(P.ops.size()) - 1;
+    } else {
     g_label = "ending conv3x3";
     add_op(P, [=](cudaStream_t st) {
       const size_t wbytes = 4 * 9 * 128 * sizeof(float);
       if (in_bf) launch_k(ending_conv_kernel<bf16>, dim3(B), dim3(256), S * S * 128 * 2 + wbytes, st, static_cast<const bf16*>(in), w, b, h->cur_eps, B, S);
       else launch_k(ending_conv_kernel<float>, dim3(B), dim3(256), S * S * 128 * 4 + wbytes, st, static_cast<const float*>(in), w, b, h->cur_eps, B, S);
     });
+    }
     P.flops_per_face += 2.0 * 9 * 128 * 4 * S * S;
   }
   Plan* raw = up.get();
@@ -2323,7 +2397,8 @@ int32_t hd_get_info(hd_handle* h, hd_info* info) {
   info->weight_elems_per_step = h->weight_elems_step;
   if (!h->plans.empty()) {
     const Plan& P = *h->plans.rbegin()->second;
-    info->launches_per_step = static_cast<int32_t>(P.ops.size());
+    // launches of one SAMPLER step: the plan, plus the scheduler-step and advance kernels unless they are fused
+    info->launches_per_step = static_cast<int32_t>(P.ops.size()) + (P.ending_idx >= 0 ? 0 : 2);
     info->flops_per_face_step = P.flops_per_face;
   }
   HD_API_END(h)
@@ -2484,7 +2559,23 @@ int32_t hd_sample(hd_handle* h, float* x_inout, const hd_step_coef* coef, int32_
   StepState* ss = h->state;
   int* ridx = h->row_idx;
   const int Bcap = h->Bcap;
+  const bool fused_end = P->ending_idx >= 0;
+  edge::EndArgs ea;
+  memset(&ea, 0, sizeof(ea));
+  if (fused_end) {
+    ea.x = static_cast<const bf16*>(h->hca_out); ea.w_hi = h->end_mma_hi; ea.w_lo = h->end_mma_lo; ea.bias = h->end_b;
+    ea.x_state = xs; ea.coefs = cf; ea.state = ss; ea.noise = noise; ea.seed = seed; ea.first_face = first_face; ea.batch = B;
+    ea.row_idx = ridx; ea.n_rows = Bcap; ea.ticket = h->end_ticket;
+    CUDA_CHECK(cudaMemsetAsync(h->end_ticket, 0, sizeof(unsigned int), st));
+  }
   auto one_step = [&](cudaStream_t s) {
+    if (fused_end) {
+      // ending conv + scheduler step + step advance in one launch (edge_convs.cuh)
+      for (int i = 0; i < static_cast<int>(P->ops.size()); ++i)
+        if (i != P->ending_idx) P->ops[i].fn(s);
+      launch_k(edge::ending_mma_kernel<true>, dim3(B), dim3(256), edge::END_SMEM, s, ea);
+      return;
+    }
     for (auto& op : P->ops) op.fn(s);
     launch_k(sampler_update_kernel, dim3(cdiv(threads, 256)), dim3(256), 0, s, xs, eb, cf, ss, 0, noise, seed, first_face, B, epf);
     launch_k(advance_rows_kernel, dim3(1), dim3(256), 0, s, ss, ridx, Bcap);

@@ -86,3 +86,60 @@ def test_sampler_ragged_and_repeatable(fused16):
     assert not torch.equal(a, x)                                                    # input untouched, output new
     c = H.ddim_sample(m, x, sched, 8, facial_priors=pc, identity_embedding=ic)      # different schedule -> new table
     assert not torch.equal(a, c)
+
+
+def test_edge_convs_on_tensor_cores_and_fused_scheduler_step():
+    """intro / ending 3x3 on mma.sync with split-precision operands (edge_convs.cuh) and the scheduler step fused
+    behind the ending conv.  (1) The intro tap stays fp32-grade against the oracle and eps within the bf16 bar.
+    (2) hd_sample's fused launch (ending conv + x_{t-1} update + step advance) is BIT-IDENTICAL to the unfused
+    sequence driven from the host — module forward (same conv kernel, eps to HBM) then hd_sampler_update per step —
+    over 6 DDPM steps with Philox noise on a ragged batch.  (3) Against the CUDA-core kernels with separate launches
+    (HD_EDGE_MMA=0): 2 launches fewer per step.  (Two bf16 runs whose stems differ by 1e-6 decorrelate their
+    rounding noise, so eps of the two variants agree to the bf16 noise floor only, not bit for bit.)"""
+    import ctypes as C
+    import os
+    from hifidiff_b200.sampler import _coef_array
+    batch, steps, seed, first = 5, 6, 5, 17
+    x = inputs("latents", batch, seed=41)
+    priors, ident = testing.synthetic_condition(batch, 16, seed=41)
+    cond = ([p.cuda() for p in priors], ident.cuda())
+    sched = H.DDPMScheduler(num_train_timesteps=1000, beta_schedule="scaled_linear", prediction_type="epsilon",
+                            clip_sample=False)
+    m, sd = build(H.FusedDenoiser, seed=2, precision="bf16", eps_gain=0.15, max_batch=8, max_steps=steps)
+    out, taps = m.forward_with_taps(x.cuda(), 321, ["intro"], *cond)
+    x0 = H.ddpm_sample(m, x.cuda(), sched, steps, facial_priors=cond[0], identity_embedding=cond[1], seed=seed, first_face=first)
+    m.engine().synchronize()
+    launches_fused = m.engine().info().launches_per_step
+    # the same steps one by one from the host
+    sched.set_timesteps(steps)
+    coefs = sched.step_coefficients()
+    eng = m.engine()
+    xs = x.cuda().clone()
+    for i, t in enumerate(sched.timesteps.tolist()):
+        eps = m(xs, t, *cond).sample
+        arr = _coef_array([coefs[i]])
+        eng.check(eng.lib.hd_sampler_update(eng.handle, xs.data_ptr(), eps.data_ptr(), arr, i, C.c_uint64(seed), C.c_int64(first),
+                                            batch, None, None), "hd_sampler_update")
+    eng.synchronize()
+    ref_taps = {}
+    with torch.no_grad():
+        ref = denoiser_ref.fused_denoiser_forward(sd, x, 321, priors, ident, ref_taps)
+    e_intro, e_eps = rel_l2(taps["intro"], ref_taps["intro"]), rel_l2(out.sample, ref)
+    m.invalidate()
+    os.environ["HD_EDGE_MMA"] = "0"
+    try:
+        m0, _ = build(H.FusedDenoiser, seed=2, precision="bf16", eps_gain=0.15, max_batch=8, max_steps=steps)
+        out0 = m0(x.cuda(), 321, *cond).sample
+        x00 = H.ddpm_sample(m0, x.cuda(), sched, steps, facial_priors=cond[0], identity_embedding=cond[1], seed=seed, first_face=first)
+        m0.engine().synchronize()
+        launches_plain = m0.engine().info().launches_per_step
+        m0.invalidate()
+    finally:
+        del os.environ["HD_EDGE_MMA"]
+    print(f"edge convs: intro vs oracle {e_intro:.2e}, eps vs oracle {e_eps:.2e} (CUDA-core variant {rel_l2(out0, ref):.2e}); "
+          f"DDPM-{steps} x0 fused == host-driven: {torch.equal(x0, xs)}; vs CUDA-core variant {rel_l2(x0, x00):.2e}; "
+          f"launches {launches_fused} vs {launches_plain}")
+    assert e_intro <= 2e-5 and e_eps <= 1e-2 and rel_l2(out0, ref) <= 1e-2
+    assert torch.equal(x0, xs)
+    assert rel_l2(x0, x00) <= 1e-2
+    assert launches_plain - launches_fused == 2
