@@ -419,6 +419,71 @@ __global__ void __launch_bounds__(256, 2) dwconv_gate_pool_kernel(const T* __res
   }
 }
 
+// Faces too large to stage whole (latent 32: 32x32 at the first level): depthwise 3x3 + SimpleGate with the taps read
+// from global memory (L1/L2-resident neighbours), thread = (pixel, 2 gate channels); the pool is its own kernel.
+// Correctness path for `image_res` 256 (train_refiner.py:27): not tuned.
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv_gate_any_kernel(const T* __restrict__ h, const float* __restrict__ w9,
+                                                              const float* __restrict__ bias, T* __restrict__ g, int sp,
+                                                              int c, size_t total) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int half_c = c >> 1;
+  const size_t pix = i / half_c;
+  const int j = static_cast<int>(i - pix * half_c) * 2;
+  const int npix = sp * sp;
+  const int pf = static_cast<int>(pix % npix);
+  const int py = pf / sp, px = pf - py * sp;
+  const int C2 = 2 * c;
+  float a1[2] = {bias[j], bias[j + 1]}, a2[2] = {bias[c + j], bias[c + j + 1]};
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+    if (yy < 0 || yy >= sp || xx < 0 || xx >= sp) continue;
+    const T* src = h + (pix + static_cast<size_t>((t / 3 - 1) * sp + (t % 3 - 1))) * C2;
+    const float2 x1 = ld_pair(src + j), x2 = ld_pair(src + c + j);
+    a1[0] = fmaf(x1.x, w9[t * C2 + j], a1[0]);
+    a1[1] = fmaf(x1.y, w9[t * C2 + j + 1], a1[1]);
+    a2[0] = fmaf(x2.x, w9[t * C2 + c + j], a2[0]);
+    a2[1] = fmaf(x2.y, w9[t * C2 + c + j + 1], a2[1]);
+  }
+  st_pair(g + pix * c + j, a1[0] * a2[0], a1[1] * a2[1]);
+}
+
+// pooled[face, ch] = mean over the face's pixels of g[face, p, ch]; thread = (face, channel), pixels in order
+template <typename T>
+__global__ void __launch_bounds__(256) pool_faces_kernel(const T* __restrict__ g, T* __restrict__ pooled, int npix, int c,
+                                                         int faces) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(faces) * c) return;
+  const size_t face = i / c;
+  const int ch = static_cast<int>(i - face * c);
+  const T* src = g + face * npix * c + ch;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (int p = 0; p < npix; p += 4) {
+    s0 += to_f32(src[static_cast<size_t>(p) * c]);
+    s1 += to_f32(src[static_cast<size_t>(p + 1) * c]);
+    s2 += to_f32(src[static_cast<size_t>(p + 2) * c]);
+    s3 += to_f32(src[static_cast<size_t>(p + 3) * c]);
+  }
+  pooled[i] = from_f32<T>(((s0 + s1) + (s2 + s3)) / static_cast<float>(npix));
+}
+
+// nchw_rows[b, p, ch] = src[b, ch * hw + p]: idc_conv(identity).reshape(B, 2048, n, n) as NHWC rows (model.py:245-246)
+__global__ void chw_to_hwc_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int hw) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * C * hw) return;
+  const int ch = static_cast<int>(i % C);
+  const size_t bp = i / C;
+  const int p = static_cast<int>(bp % hw);
+  const size_t b = bp / hw;
+  dst[i] = src[(b * C + ch) * hw + p];
+}
+
 // The same op at the 2x2 and 4x4 levels, where a face is 4 / 16 pixels: one thread owns 4 gate channels of one
 // face, holds all of the face's pixels in registers (x1 pass, then x2 pass multiplied in), and needs no shared
 // memory, no halo and no cross-thread reduction for the pool.  A warp reads 128 consecutive channels per pixel
@@ -601,7 +666,7 @@ __global__ void __launch_bounds__(256) hca_apply_kernel(const float* __restrict_
   load8(wc + static_cast<size_t>(face) * c + k, g);
   if (idc != nullptr) {
     float a[8];
-    load8(idc + static_cast<size_t>(face) * c + k, a);
+    load8(idc + row * c + k, a);   // idc_conv(identity) in NHWC rows (model.py:245-246 reshape(B, 2048, n, n))
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] += a[j];
   }
@@ -709,6 +774,69 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
     c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
   }
 }
+// ending for faces too large for one tile (latent 32): one block = `band` image rows of one face plus a one-row halo,
+// thread = pixel.  grid (B, S / band); dynamic smem (band + 2) * S * 128 * sizeof(TIn) + 4*9*128*4.  Correctness path
+// for `image_res` 256: same arithmetic as ending_conv_kernel, not tuned.
+template <typename TIn>
+__global__ void __launch_bounds__(256) ending_conv_band_kernel(const TIn* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, float* __restrict__ eps,
+                                                               int S, int band) {
+  extern __shared__ __align__(16) uint8_t s_endb_raw[];
+  constexpr int EPC = 16 / sizeof(TIn);
+  constexpr int CPR = 128 / EPC;
+  const int rows_t = band + 2;
+  TIn* tile = reinterpret_cast<TIn*>(s_endb_raw);
+  float* s_w = reinterpret_cast<float*>(s_endb_raw + static_cast<size_t>(rows_t) * S * 128 * sizeof(TIn));
+  const int face = blockIdx.x, y0 = blockIdx.y * band;
+  pdl_trigger();
+  for (int i = threadIdx.x; i < 1152; i += blockDim.x) reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+  pdl_wait();
+  const TIn* xf = x + static_cast<size_t>(face) * S * S * 128;
+  for (int i = threadIdx.x; i < rows_t * S * CPR; i += blockDim.x) {
+    const int r = i / CPR, ck = i % CPR;           // r = tile pixel: (ty, xx)
+    const int ty = r / S, xx = r - ty * S;
+    const int yy = y0 - 1 + ty;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (yy >= 0 && yy < S) v = *reinterpret_cast<const uint4*>(xf + static_cast<size_t>(yy * S + xx) * 128 + ck * EPC);
+    *reinterpret_cast<uint4*>(tile + r * 128 + ((ck ^ (r % CPR)) * EPC)) = v;
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < band * S; p += blockDim.x) {
+    const int ly = p / S, px = p - ly * S;
+    const int py = y0 + ly;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int xx = px + tap % 3 - 1;
+      if (xx < 0 || xx >= S) continue;              // rows outside the face are zero rows of the tile
+      const int r = (ly + tap / 3) * S + xx;
+      const TIn* row = tile + r * 128;
+      const float* wt = s_w + tap * 128;
+#pragma unroll 4
+      for (int ck = 0; ck < CPR; ++ck) {
+        float v[EPC];
+        if (sizeof(TIn) == 2) {
+          float t8[8];
+          load8(reinterpret_cast<const bf16*>(row) + ((ck ^ (r % CPR)) * EPC), t8);
+#pragma unroll
+          for (int k = 0; k < EPC; ++k) v[k] = t8[k];
+        } else {
+          const float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(row) + ((ck ^ (r % CPR)) * EPC));
+          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const float* wr = wt + o * 9 * 128 + ck * EPC;
+#pragma unroll
+          for (int k = 0; k < EPC; ++k) acc[o] = fmaf(v[k], wr[k], acc[o]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) eps[((static_cast<size_t>(face) * 4 + o) * S + py) * S + px] = acc[o] + bias[o];
+  }
+}
+
 __device__ __forceinline__ float philox_unit(uint32_t r) {
   return (static_cast<float>(r >> 9) + 0.5f) * 1.1920928955078125e-07f;  // 2^-23
 }

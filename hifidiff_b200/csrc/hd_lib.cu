@@ -1009,6 +1009,18 @@ void add_block(hd_handle* h, Plan& P, const BlockW& bw, const std::string& tapna
         else if (sp == 2) launch_k(dwconv_small_kernel<float, 2>, grid, dim3(256), 0, st, static_cast<const float*>(act_h), dw_w, dw_b, static_cast<float*>(act_g), static_cast<float*>(pooled), c, B);
         else launch_k(dwconv_small_kernel<float, 4>, grid, dim3(256), 0, st, static_cast<const float*>(act_h), dw_w, dw_b, static_cast<float*>(act_g), static_cast<float*>(pooled), c, B);
       });
+    } else if (sp > 16) {  // faces too large to stage whole (latent 32): taps from global memory, pool as its own kernel
+      add_op(P, [=](cudaStream_t st) {
+        const size_t total = static_cast<size_t>(rows) * c / 2;
+        if (bf) launch_k(dwconv_gate_any_kernel<bf16>, dim3(cdiv(total, 256)), dim3(256), 0, st, static_cast<const bf16*>(act_h), dw_w, dw_b, static_cast<bf16*>(act_g), sp, c, total);
+        else launch_k(dwconv_gate_any_kernel<float>, dim3(cdiv(total, 256)), dim3(256), 0, st, static_cast<const float*>(act_h), dw_w, dw_b, static_cast<float*>(act_g), sp, c, total);
+      });
+      g_label = L0 + "pool_faces";
+      add_op(P, [=](cudaStream_t st) {
+        const size_t total = static_cast<size_t>(B) * c;
+        if (bf) launch_k(pool_faces_kernel<bf16>, dim3(cdiv(total, 256)), dim3(256), 0, st, static_cast<const bf16*>(act_g), static_cast<bf16*>(pooled), rpf, c, B);
+        else launch_k(pool_faces_kernel<float>, dim3(cdiv(total, 256)), dim3(256), 0, st, static_cast<const float*>(act_g), static_cast<float*>(pooled), rpf, c, B);
+      });
     } else
     add_op(P, [=](cudaStream_t st) {
       const int tile_px = sp >= 16 ? sp * sp : 64;   // whole faces per tile; small tiles below 16x16 for parallelism
@@ -1416,6 +1428,14 @@ Plan* get_plan(hd_handle* h, int B, bool debug = false) {
         launch_k(edge::ending_mma_kernel<false>, dim3(B), dim3(256), edge::END_SMEM, st, e2);
       });
       P.ending_idx = static_cast<int>(P.ops.size()) - 1;
+    } else if (S > 16) {
+      const int band = in_bf ? 16 : 8;   // image rows per block: (band + 2) * S * 128 elements of shared memory
+      g_label = "ending conv3x3 (row bands)";
+      add_op(P, [=](cudaStream_t st) {
+        const size_t wbytes = 4 * 9 * 128 * sizeof(float);
+        if (in_bf) launch_k(ending_conv_band_kernel<bf16>, dim3(B, S / band), dim3(256), static_cast<size_t>(band + 2) * S * 128 * 2 + wbytes, st, static_cast<const bf16*>(in), w, b, h->cur_eps, S, band);
+        else launch_k(ending_conv_band_kernel<float>, dim3(B, S / band), dim3(256), static_cast<size_t>(band + 2) * S * 128 * 4 + wbytes, st, static_cast<const float*>(in), w, b, h->cur_eps, S, band);
+      });
     } else {
     g_label = "ending conv3x3";
     add_op(P, [=](cudaStream_t st) {
@@ -2266,7 +2286,10 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   HD_API_BEGIN
   if (!out || !cfg) HD_THROW(HD_ERR_INVALID, "null argument");
   if (cfg->struct_size != (int32_t)sizeof(hd_config)) HD_THROW(HD_ERR_INVALID, "hd_config size mismatch");
-  if (cfg->latent_size != 16) HD_THROW(HD_ERR_UNSUPPORTED, "latent_size %d: only 16 (image_res 128) is supported", cfg->latent_size);
+  // model.py:198-200: the latent size must be a multiple of 16 (four stride-2 levels); 16 (image_res 128, the default,
+  // train_refiner.py:27) runs the tuned kernels, 32 (image_res 256) the general ones
+  if (cfg->latent_size != 16 && cfg->latent_size != 32)
+    HD_THROW(HD_ERR_UNSUPPORTED, "latent_size %d: 16 (image_res 128) and 32 (image_res 256) are supported", cfg->latent_size);
   if (cfg->max_batch < 1) HD_THROW(HD_ERR_INVALID, "max_batch must be >= 1");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -2304,6 +2327,8 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
   CUDA_CHECK(cudaFuncSetAttribute(dwconv_gate_pool_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 128 * 4));
   CUDA_CHECK(cudaFuncSetAttribute(ending_conv_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 128 * 2 + 4 * 9 * 128 * 4));
   CUDA_CHECK(cudaFuncSetAttribute(ending_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 128 * 4 + 4 * 9 * 128 * 4));
+  CUDA_CHECK(cudaFuncSetAttribute(ending_conv_band_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 18 * 32 * 128 * 2 + 4 * 9 * 128 * 4));
+  CUDA_CHECK(cudaFuncSetAttribute(ending_conv_band_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 10 * 32 * 128 * 4 + 4 * 9 * 128 * 4));
   // block table in execution order with table offsets
   int off = 0;
   auto push = [&](const std::string& prefix, int level) {
@@ -2368,7 +2393,7 @@ int32_t hd_create(hd_handle** out, const hd_config* cfg) {
     CUDA_CHECK(cudaMemcpy(h->freqs, f, sizeof(f), cudaMemcpyHostToDevice));
   }
   if (h->fused) {
-    h->idc_add = A.get<float>(Bc * 2048);
+    h->idc_add = A.get<float>(Bc * 2048 * (h->S / 16) * (h->S / 16));
     h->cond_nhwc = A.get<float>(max_pc);
     h->cond_stage = A.get<float>(max_pc);
     h->cond_pool = A.get<float>(Bc * 2048);
@@ -2473,7 +2498,13 @@ int32_t hd_set_condition(hd_handle* h, const float* const priors[5], const float
       src = h->cond_stage;
       staged = true;
     }
-    simt_f32(B, 2048, 2048, src, h->idc_w, h->idc_b, h->idc_add, EPI_BIAS, st);
+    const int hw = (h->S / 16) * (h->S / 16);   // bottleneck pixels per face; idc_conv has 2048 * hw output channels (model.py:198-200)
+    if (hw == 1) {
+      simt_f32(B, 2048, 2048, src, h->idc_w, h->idc_b, h->idc_add, EPI_BIAS, st);
+    } else {  // (B, 2048 * hw) -> reshape(B, 2048, n, n) -> NHWC rows [B * hw][2048]
+      simt_f32(B, 2048 * hw, 2048, src, h->idc_w, h->idc_b, h->cond_nhwc, EPI_BIAS, st);
+      chw_to_hwc_rows_kernel<<<cdiv(static_cast<size_t>(B) * 2048 * hw, 256), 256, 0, st>>>(h->cond_nhwc, h->idc_add, B, 2048, hw);
+    }
   }
   CUDA_CHECK(cudaGetLastError());
   // Device-pointer inputs: fully asynchronous (every buffer written above is consumed in stream order).  Host-pointer

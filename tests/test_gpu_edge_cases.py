@@ -92,8 +92,8 @@ def test_edge_convs_on_tensor_cores_and_fused_scheduler_step():
     """intro / ending 3x3 on mma.sync with split-precision operands (edge_convs.cuh) and the scheduler step fused
     behind the ending conv.  (1) The intro tap stays fp32-grade against the oracle and eps within the bf16 bar.
     (2) hd_sample's fused launch (ending conv + x_{t-1} update + step advance) is BIT-IDENTICAL to the unfused
-    sequence driven from the host — module forward (same conv kernel, eps to HBM) then hd_sampler_update per step —
-    over 6 DDPM steps with Philox noise on a ragged batch.  (3) Against the CUDA-core kernels with separate launches
+    sequence driven from the host — module forward (same conv kernel, eps to HBM) then hd_sampler_update — step by
+    step over 6 DDPM steps with explicit noise on a ragged batch.  (3) Against the CUDA-core kernels with separate launches
     (HD_EDGE_MMA=0): 2 launches fewer per step.  (Two bf16 runs whose stems differ by 1e-6 decorrelate their
     rounding noise, so eps of the two variants agree to the bf16 noise floor only, not bit for bit.)"""
     import ctypes as C
@@ -110,17 +110,25 @@ def test_edge_convs_on_tensor_cores_and_fused_scheduler_step():
     x0 = H.ddpm_sample(m, x.cuda(), sched, steps, facial_priors=cond[0], identity_embedding=cond[1], seed=seed, first_face=first)
     m.engine().synchronize()
     launches_fused = m.engine().info().launches_per_step
-    # the same steps one by one from the host
+    # the same scheduler steps one at a time, with explicit noise, two ways: (a) hd_sample(n_steps = 1) = the fused
+    # launch, (b) module forward (eps to HBM) + hd_sampler_update.  Both see a one-row time table, so every input
+    # of the step is the same bit pattern.
     sched.set_timesteps(steps)
     coefs = sched.step_coefficients()
     eng = m.engine()
-    xs = x.cuda().clone()
+    z = torch.randn((steps, batch, 1024), generator=torch.Generator().manual_seed(43)).cuda()
+    xa, xb = x.cuda().clone(), x.cuda().clone()
     for i, t in enumerate(sched.timesteps.tolist()):
-        eps = m(xs, t, *cond).sample
         arr = _coef_array([coefs[i]])
-        eng.check(eng.lib.hd_sampler_update(eng.handle, xs.data_ptr(), eps.data_ptr(), arr, i, C.c_uint64(seed), C.c_int64(first),
-                                            batch, None, None), "hd_sampler_update")
+        zi = z[i].contiguous()
+        eng.check(eng.lib.hd_sample(eng.handle, xa.data_ptr(), arr, 1, C.c_uint64(seed), C.c_int64(first), batch, zi.data_ptr(),
+                                    None), "hd_sample")
+        eps = m(xb, t, *cond).sample
+        eng.check(eng.lib.hd_sampler_update(eng.handle, xb.data_ptr(), eps.data_ptr(), arr, 0, C.c_uint64(seed), C.c_int64(first),
+                                            batch, zi.data_ptr(), None), "hd_sampler_update")
     eng.synchronize()
+    xs = xb
+    x0_steps = xa
     ref_taps = {}
     with torch.no_grad():
         ref = denoiser_ref.fused_denoiser_forward(sd, x, 321, priors, ident, ref_taps)
@@ -137,9 +145,9 @@ def test_edge_convs_on_tensor_cores_and_fused_scheduler_step():
     finally:
         del os.environ["HD_EDGE_MMA"]
     print(f"edge convs: intro vs oracle {e_intro:.2e}, eps vs oracle {e_eps:.2e} (CUDA-core variant {rel_l2(out0, ref):.2e}); "
-          f"DDPM-{steps} x0 fused == host-driven: {torch.equal(x0, xs)}; vs CUDA-core variant {rel_l2(x0, x00):.2e}; "
+          f"DDPM-{steps} fused launch == forward + hd_sampler_update: {torch.equal(x0_steps, xs)}; x0 vs CUDA-core variant {rel_l2(x0, x00):.2e}; "
           f"launches {launches_fused} vs {launches_plain}")
     assert e_intro <= 2e-5 and e_eps <= 1e-2 and rel_l2(out0, ref) <= 1e-2
-    assert torch.equal(x0, xs)
+    assert torch.equal(x0_steps, xs)
     assert rel_l2(x0, x00) <= 1e-2
     assert launches_plain - launches_fused == 2

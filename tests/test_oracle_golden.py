@@ -136,3 +136,31 @@ def test_oracle_against_live_reference_block():
     x, temb = torch.randn(3, 256, 8, 8, generator=gen(1)), torch.randn(3, 512, generator=gen(2))
     with torch.no_grad():
         assert rel_l2(denoiser_ref.cond_naf_block(sd, "", x, temb), blk([x, temb])[0]) < TOL
+
+
+def test_fused_step_latent32():
+    """Latent size 32 (`--image_res 256`): the oracle reproduces the reference's eps, the small-spatial taps and the
+    FPG priors stored by tests/golden/make_golden_s32.py (idc_conv reshape to (B, 2048, 2, 2), model.py:198-200,245-246)."""
+    g = golden("fused_step_s32.npz")
+    with torch.device("meta"):
+        m = H.FusedDenoiser(32)
+    sd = state_for(m, seed=2)
+    assert tuple(sd["idc_conv.weight"].shape) == (8192, 2048, 1, 1)
+    x = torch.randn((2, 4, 32, 32), generator=torch.Generator().manual_seed(701))
+    priors, ident = testing.synthetic_condition(2, 32, seed=0)
+    taps = {}
+    with torch.no_grad():
+        y = denoiser_ref.fused_denoiser_forward(sd, x, torch.from_numpy(g["t"]), priors, ident, taps)
+    assert rel_l2(y, g["eps"]) < TOL
+    for k in ("downs.3", "middle_blks.7", "hcas.0", "ups.0", "decoders.0.1", "hcas.1"):
+        assert rel_l2(taps[k], g["tap_" + k.replace(".", "_")]) < TOL, k
+    with torch.device("meta"):
+        fpg = H.FacialPriorGuidance()
+    sdf = state_for(fpg, seed=7)
+    lat = torch.randn((2, 4, 32, 32), generator=torch.Generator().manual_seed(731))
+    with torch.no_grad():
+        pri = cond_ref.fpg_forward(sdf, lat, "")
+    for j in range(3):
+        assert rel_l2(pri[j], g[f"fpg_prior{j}"]) < TOL, j
+    for j in range(5):
+        assert abs(float(pri[j].mean()) - g["fpg_prior_stats"][j][0]) < 1e-5 and abs(float(pri[j].std()) - g["fpg_prior_stats"][j][1]) < 1e-5
