@@ -868,13 +868,15 @@ __device__ __forceinline__ void sampler_update_group(float* __restrict__ x, floa
     }
   }
 #pragma unroll
+  // every product and sum rounded on its own (no FMA contraction): that is how the torch ops of diffusers' step()
+  // evaluate it, and it keeps the two kernels that inline this function bit-identical
   for (int j = 0; j < 4; ++j) {
-    float x0 = (xs[j] - cf.sqrt_beta_prod * es[j]) / cf.sqrt_alpha_prod;
+    float x0 = __fdiv_rn(__fsub_rn(xs[j], __fmul_rn(cf.sqrt_beta_prod, es[j])), cf.sqrt_alpha_prod);
     if (cf.clip > 0.f) x0 = fminf(fmaxf(x0, -cf.clip), cf.clip);
-    float r = cf.k_x0 * x0;
-    if (cf.k_eps != 0.f) r += cf.k_eps * es[j];
-    if (cf.k_x != 0.f) r += cf.k_x * xs[j];
-    if (cf.k_noise != 0.f) r += cf.k_noise * z[j];
+    float r = __fmul_rn(cf.k_x0, x0);
+    if (cf.k_eps != 0.f) r = __fadd_rn(r, __fmul_rn(cf.k_eps, es[j]));
+    if (cf.k_x != 0.f) r = __fadd_rn(r, __fmul_rn(cf.k_x, xs[j]));
+    if (cf.k_noise != 0.f) r = __fadd_rn(r, __fmul_rn(cf.k_noise, z[j]));
     xs[j] = r;
   }
   *reinterpret_cast<float4*>(x + i * 4) = make_float4(xs[0], xs[1], xs[2], xs[3]);

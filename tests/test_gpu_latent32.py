@@ -84,3 +84,25 @@ def test_ddim_trajectory_latent32():
     print(f"latent 32 DDIM-10 bf16: PSNR vs oracle loop {q:.2f} dB")
     assert q >= 50.0
     m.invalidate()
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("bf16", 1.5e-2)])
+def test_refiner_forward_latent32(prec, tol):
+    """FacialRefiner(latent_res=32).forward(latents, t, cr_face 256x256, cr_latent 32x32) with IDC ResNet-50 and FPG
+    native, against the oracle's refiner (models/refiner.py:32-38)."""
+    m, sd = build(H.FacialRefiner, seed=3, precision=prec, max_batch=2, args=(32,))
+    x = _inputs(1, seed=2)
+    cr_face = torch.rand((1, 3, 256, 256), generator=torch.Generator().manual_seed(741))
+    cr_latent = torch.randn((1, 4, 32, 32), generator=torch.Generator().manual_seed(742))
+    with torch.no_grad():
+        out = m(x.cuda(), torch.tensor([640]), cr_face.cuda(), cr_latent.cuda()).sample
+        priors, ident = m.condition(cr_face.cuda(), cr_latent.cuda()) if False else m._cond
+        m.denoiser.engine().synchronize()
+        taps = {}
+        want = cond_ref.refiner_forward(sd, x, torch.tensor([640]), cr_face, cr_latent, taps)
+    e_id = rel_l2(ident, taps["identity"])
+    e_pr = max(rel_l2(priors[j], taps[f"prior{j}"]) for j in range(5))
+    print(f"refiner latent 32 {prec}: identity {e_id:.3e}, worst prior {e_pr:.3e}, eps {rel_l2(out, want):.3e}")
+    assert e_id <= min(tol, 1e-2) and e_pr <= min(tol, 1e-2)
+    assert rel_l2(out, want) <= tol
+    m.denoiser.invalidate()
