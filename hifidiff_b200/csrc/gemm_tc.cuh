@@ -262,6 +262,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   pdl_trigger();
   const int nsplit = static_cast<int>(cluster_nctaid_z());
   const int zrank = blockIdx.z;  // == rank in the (1,1,S) cluster
+  // Epilogue operands fetched BEFORE the accumulator is complete (their L2 / DRAM latency then hides under the
+  // mainloop instead of sitting in the epilogue of these latency-bound one-wave GEMMs): the bias chunks of every
+  // variant, and — for the 16-epilogue-warp variants with a per-element second operand — the residual rows
+  // (EPI_RESID) or the bf16 multiplicand (EPI_MUL) of the rows this warp will finish.
+  constexpr int E_CH = (EPI == EPI_GATE) ? BN / 8 : BN / 4;
+  constexpr int E_LPR = E_CH < 32 ? E_CH : 32;
+  constexpr int E_CPL = E_CH / E_LPR;
+  constexpr bool PRE = (EPI == EPI_RESID || EPI == EPI_MUL) && EW == 16 && BN == 128;
+  float4 bias_pre[E_CPL], bias2_pre[E_CPL];
+  float4 ext_pre[PRE ? 8 : 1];
   const int kb_count = args.num_kb / nsplit;
   const int kb_begin = zrank * kb_count;
 
@@ -359,7 +369,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else {
     // ---------------- epilogue phase A (warps 2..5): TMEM -> swizzled fp32 staging tile ----------------
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    {
+      const int sl = lane % E_LPR;
+#pragma unroll
+      for (int i = 0; i < E_CPL; ++i) {
+        const int ck = i * E_LPR + sl;
+        bias_pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        bias2_pre[i] = bias_pre[i];
+        if (EPI != EPI_PIXSHUF) bias_pre[i] = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + ck * 4));
+        if (EPI == EPI_GATE) bias2_pre[i] = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + 64 + ck * 4));
+      }
+    }
     pdl_wait();                 // phase B reads the residual / overwrites buffers the predecessor may still use
+    if (PRE) {
+      // pass p of this warp finishes row (zrank * BM / nsplit) + p * 16 + (warp - 2) of the tile, lanes along the columns
+      const int rows_here = BM / nsplit, row_base = zrank * rows_here, ew = warp - 2;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const int rl = p * NUM_EPI_WARPS + ew;
+        const int m = m0 + row_base + rl;
+        ext_pre[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rl < rows_here && m < args.M) {
+          if (EPI == EPI_RESID) {
+            ext_pre[p] = *reinterpret_cast<const float4*>(args.resid + static_cast<size_t>(m) * args.ldr + n0 + lane * 4);
+          } else {
+            const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(args.resid) + static_cast<size_t>(m) * args.ldr + n0 + lane * 4);
+            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+            ext_pre[p] = make_float4(a.x, a.y, b.x, b.y);
+          }
+        }
+      }
+    }
     mbar_wait(smem_u32(tmem_full_bar), 0u, args.status, 0x300u);
     tc_fence_after_sync();
     if (trace != nullptr && threadIdx.x == 64) trace[4] = clock64();
@@ -410,15 +450,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     if (EPI == EPI_GATE) out_col0 = n0 >> 1;
 
-    float4 bias_r[CPL], bias2_r[CPL];
-#pragma unroll
-    for (int i = 0; i < CPL; ++i) {
-      const int ck = i * LPR + sl;
-      bias_r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      bias2_r[i] = bias_r[i];
-      if (EPI != EPI_PIXSHUF) bias_r[i] = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + ck * 4));
-      if (EPI == EPI_GATE) bias2_r[i] = __ldg(reinterpret_cast<const float4*>(args.bias + n0 + 64 + ck * 4));
-    }
+    static_assert(CPL == E_CPL && LPR == E_LPR, "bias preload uses the phase B lane mapping");
+    float4 (&bias_r)[CPL] = bias_pre;
+    float4 (&bias2_r)[CPL] = bias2_pre;
 
     const int passes = (rows_here + NUM_EPI_WARPS * RPI - 1) / (NUM_EPI_WARPS * RPI);
 
@@ -487,6 +521,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         soff[i] = ((i * LPR + sl) ^ swz) << 2;
         soff2[i] = ((i * LPR + sl + 16) ^ swz) << 2;
       }
+      if (PRE) {
+        // second operand already in registers (ext_pre, fetched under the mainloop): PASSES == 8, CPL == 1
+#pragma unroll
+        for (int it0 = 0; it0 < PASSES; it0 += U) {
+          float4 acc[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) acc[u] = *reinterpret_cast<const float4*>(sbase + (it0 + u) * (STEP * BN) + soff[0]);
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            finish(acc[u], zero4, ext_pre[(it0 + u) & 7], 0, dbase + (it0 + u) * dstep, m0 + r0 + (it0 + u) * STEP < args.M);
+        }
+      } else
 #pragma unroll 1
       for (int it0 = 0; it0 < PASSES; it0 += U) {
         float4 acc[U][CPL], acc2[U][CPL], ext[U][CPL];
@@ -548,8 +594,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       // and would otherwise serialise), then summed in fixed split order -> deterministic
       constexpr int MAXS = 8;
       constexpr int NP = (EPI == EPI_GATE) ? 2 : 1;
-#pragma unroll 1
-      for (int pass = 0; pass < passes; ++pass) {
+      auto do_pass = [&](int pass, float4 e_pre) {
         bool okay;
         int rc, mc;
         TOut* d;
@@ -558,7 +603,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int i = 0; i < CPL; ++i) {
           const int ck = i * LPR + sl;
           float4 part[NP][MAXS];
-          float4 e = zero4;
+          float4 e = e_pre;
 #pragma unroll
           for (int pi = 0; pi < NP; ++pi) {
             const uint32_t a = stage_u32 + static_cast<uint32_t>((rc * BN + (((ck + 16 * pi) ^ (rc & 7)) << 2)) * 4);
@@ -566,9 +611,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int sidx = 0; sidx < MAXS; ++sidx)
               if (sidx < nsplit) part[pi][sidx] = ld_dsmem_f4(a, static_cast<uint32_t>(sidx));
           }
-          if (EPI == EPI_RESID)
-            e = *reinterpret_cast<const float4*>(args.resid + static_cast<size_t>(mc) * args.ldr + n0 + ck * 4);
-          if (EPI == EPI_MUL) e = load_mul(mul_src + static_cast<size_t>(mc) * args.ldr + n0 + ck * 4);
+          if (!PRE) {
+            if (EPI == EPI_RESID)
+              e = *reinterpret_cast<const float4*>(args.resid + static_cast<size_t>(mc) * args.ldr + n0 + ck * 4);
+            if (EPI == EPI_MUL) e = load_mul(mul_src + static_cast<size_t>(mc) * args.ldr + n0 + ck * 4);
+          }
           if (EPI == EPI_PIXSHUF) e = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(d) + i * LPR * 4);
           float4 v = zero4, g = zero4;
 #pragma unroll
@@ -582,6 +629,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
           finish(v, g, e, i, d, okay);
         }
+      };
+      if (PRE) {  // at most 128 / 2 / 16 = 4 passes; the second operand comes from ext_pre
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass)
+          if (pass < passes) do_pass(pass, ext_pre[pass & 7]);
+      } else {
+#pragma unroll 1
+        for (int pass = 0; pass < passes; ++pass) do_pass(pass, zero4);
       }
     }
   }
