@@ -37,6 +37,8 @@ struct TcArgs {
   int kb_per_tap;             // A_CONV3: C / 64
   int conv_bh, conv_bb;       // A_CONV3: box rows in h and in batch (conv_bh * sp * conv_bb == 128)
   DeviceStatus* status;
+  const void* pf_ptr;         // weights of the NEXT tensor-core GEMM of the plan: each CTA prefetches its share into L2
+  unsigned int pf_bytes;      // (0 = none) so that GEMM's weight stream starts from L2 instead of HBM
   long long* trace;           // optional per-CTA timeline (16 slots per CTA), nullptr in production
 };
 
@@ -121,6 +123,26 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// L2 prefetch of `bytes` (multiple of 16) at a 16-byte-aligned global address
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(p)), "r"(bytes) : "memory");
+}
+// This CTA's share of the next GEMM's weight matrix, 2 KB per instruction, issued by the lanes of one warp.  The
+// ~0.8 GB of weights are streamed from HBM once per denoise step whatever happens; fetching GEMM i+1's matrix while
+// GEMM i runs turns the DRAM latency at the head of every weight stream into an L2 hit.
+__device__ __forceinline__ void prefetch_next_weights(const void* ptr, uint32_t bytes, int lane) {
+  if (bytes == 0u) return;
+  const uint32_t ncta = gridDim.x * gridDim.y * gridDim.z;
+  const uint32_t cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const uint32_t per = ((bytes / ncta) + 15u) & ~15u;
+  const uint32_t begin = cta * per;
+  if (begin >= bytes) return;
+  const uint32_t end = begin + per < bytes ? begin + per : bytes;
+  for (uint32_t off = begin + static_cast<uint32_t>(lane) * 2048u; off < end; off += 32u * 2048u) {
+    const uint32_t n = end - off < 2048u ? end - off : 2048u;
+    prefetch_l2_bulk(static_cast<const char*>(ptr) + off, n & ~15u);
+  }
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
@@ -369,6 +391,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else {
     // ---------------- epilogue phase A (warps 2..5): TMEM -> swizzled fp32 staging tile ----------------
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    if (warp == 2) prefetch_next_weights(args.pf_ptr, args.pf_bytes, lane);
     {
       const int sl = lane % E_LPR;
 #pragma unroll
@@ -819,6 +842,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   } else {
     // ---------------- epilogue phase A: this CTA's 128 accumulator rows -> staging ----------------
     const int quad = warp & 3;
+    if (warp == 2) prefetch_next_weights(args.pf_ptr, args.pf_bytes, lane);
     pdl_wait();
     mbar_wait(smem_u32(tmem_full_bar), 0u, args.status, 0x700u);
     tc_fence_after_sync();

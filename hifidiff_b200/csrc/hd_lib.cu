@@ -68,6 +68,7 @@ struct Tunables {
   bool face = true;       // HD_FACE=0: per-op kernels at the 16x16 level instead of the fused per-face block kernel
   bool pair = true;       // HD_PAIR=0: per-op kernels at the 8x8 level instead of the fused face-pair block kernel
   bool sca_mul = true;    // HD_SCA_MUL=0: separate scale_rows kernel at the 1x1 level too
+  bool w_prefetch = true; // HD_W_PREFETCH=0: GEMMs do not prefetch the next GEMM's weights into L2
   bool edge_mma = true;   // HD_EDGE_MMA=0: CUDA-core intro / ending convs and separate sampler-update / advance launches
   bool cr_stn_cs = true;  // HD_CR_STN_CS=0: one thread per (pixel, 2 output channels) in the first STN localisation conv
   bool cr_tc = true;      // HD_CR_TC=0: every CoarseRestoration GEMM on the FFMA kernel (no split-precision tcgen05 path)
@@ -76,7 +77,7 @@ struct Tunables {
   int sca_target = 120;   // HD_SCA_TARGET: the same for the SCA GEMMs (M = faces)
   void read_env() {
     auto flag = [](const char* name, bool& v) { if (const char* e = getenv(name)) v = atoi(e) != 0; };
-    flag("HD_PDL", pdl); flag("HD_BN256", bn256); flag("HD_FACE", face); flag("HD_PAIR", pair); flag("HD_SCA_MUL", sca_mul); flag("HD_EDGE_MMA", edge_mma);
+    flag("HD_PDL", pdl); flag("HD_BN256", bn256); flag("HD_FACE", face); flag("HD_PAIR", pair); flag("HD_SCA_MUL", sca_mul); flag("HD_EDGE_MMA", edge_mma); flag("HD_W_PREFETCH", w_prefetch);
     flag("HD_CR_STN_CS", cr_stn_cs); flag("HD_CR_TC", cr_tc); flag("HD_DW_SMALL", dw_small);
     if (const char* e = getenv("HD_TWO_CTA")) two_cta = atoi(e);
     if (const char* e = getenv("HD_CTA_TARGET")) cta_target = std::max(atoi(e), 1);
@@ -242,6 +243,8 @@ struct Op {
 
 thread_local std::string g_label;  // label picked up by the next add_op
 
+struct TcLaunch;
+
 struct Plan {
   int batch = 0;
   std::vector<Op> ops;
@@ -250,6 +253,9 @@ struct Plan {
   int64_t graph_first = 0;
   const float* graph_noise = nullptr;
   double flops_per_face = 0;
+  std::shared_ptr<TcLaunch> last_tc;   // the previous tensor-core GEMM of the plan: it prefetches the next one's weights
+  const void* first_w = nullptr;       // weights of the first such GEMM (prefetched by the last one: the plan repeats every step)
+  unsigned int first_w_bytes = 0;
   int ending_idx = -1;  // index of the ending-conv op when hd_sample may replace it by the fused ending + scheduler-step kernel
 };
 
@@ -905,11 +911,20 @@ void add_gemm(hd_handle* h, Plan& P, GemmDesc d, long long a_rows_alloc, const s
   static const char* epi_names[] = {"bias", "relu", "sigmoid", "resid", "gate", "pixshuf", "bias*mul"};
   const std::string what = g_label;
   if (tc_eligible(h, d)) {
-    TcLaunch L = build_tc(h, d, a_rows_alloc);
+    std::shared_ptr<TcLaunch> Lp = std::make_shared<TcLaunch>(build_tc(h, d, a_rows_alloc));
+    TcLaunch& L = *Lp;
+    if (h->tun.w_prefetch && d.ldw == d.K && (d.a_mode != A_CONV3)) {
+      // this GEMM's weights are what the previous GEMM of the plan prefetches into L2 (the first one of the step is
+      // prefetched by the last: the same plan runs again for the next timestep)
+      const unsigned int wbytes = static_cast<unsigned int>(static_cast<size_t>(d.N) * d.K * 2);
+      if (P.last_tc) { P.last_tc->args.pf_ptr = d.W; P.last_tc->args.pf_bytes = wbytes; }
+      if (P.first_w == nullptr) { P.first_w = d.W; P.first_w_bytes = wbytes; }
+    }
+    if (h->tun.w_prefetch) P.last_tc = Lp;
     g_label = fmt("%s gemm_tc %s%s M=%d N=%d K=%d grid=(%d,%d,%d) stages=%d", what.c_str(), epi_names[d.epi],
                   L.two_cta ? (d.a_mode == A_CONV3 ? "+conv3 2CTA" : " 2CTA") : d.a_mode == A_CONV3 ? (L.bn == 256 ? "+conv3 BN=256" : "+conv3") : "",
                   d.M, d.N, d.K, L.grid.x, L.grid.y, L.grid.z, L.stages);
-    add_op(P, [L](cudaStream_t st) { launch_tc(L, st); }, tap, info);
+    add_op(P, [Lp](cudaStream_t st) { launch_tc(*Lp, st); }, tap, info);
     return;
   }
   if (d.epi == EPI_MUL) HD_THROW(HD_ERR_INVALID, "EPI_MUL exists on the tcgen05 path only (M=%d N=%d K=%d)", d.M, d.N, d.K);
@@ -1446,6 +1461,7 @@ Plan* get_plan(hd_handle* h, int B, bool debug = false) {
     }
     P.flops_per_face += 2.0 * 9 * 128 * 4 * S * S;
   }
+  if (P.last_tc && P.first_w != nullptr) { P.last_tc->args.pf_ptr = P.first_w; P.last_tc->args.pf_bytes = P.first_w_bytes; }
   Plan* raw = up.get();
   cache[B] = std::move(up);
   return raw;
