@@ -108,19 +108,21 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, pw = [], None, set(), []
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
+                pw.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
             except (ValueError, IndexError):
                 continue
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        pw.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None, "sm_max_mhz": mx,
+                "power_w": pw[len(pw) // 2] if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def cpu_baseline(args, n_threads=None):
@@ -506,7 +508,11 @@ def main():
     ms_denoise = e0.elapsed_time(e1) / T
 
     step_e2e()
+    clocks_e2e = ClockSampler(local_rank)
+    if rank == 0:
+        clocks_e2e.start()
     ms_e2e, _ = timed(step_e2e, args.steps)
+    clock_info_e2e = clocks_e2e.stop() if rank == 0 else None
     model.engine().synchronize()
 
     # the condition networks of the refiner cascade (FPG over the CR latent, IDC ResNet-50 over the CR face), native,
@@ -613,6 +619,7 @@ def main():
                 "executed_gflop_per_face_step": info.flops_per_face_step / 1e9,
             },
             "clocks": clock_info,
+            "clocks_e2e": clock_info_e2e,
             "finite": finite,
             "condition_nets": cond_nets,
         }
