@@ -61,13 +61,15 @@ def parse():
 
 
 def load_traffic():
-    """DRAM bytes per denoise step from the committed ncu pass (profiles/r1_traffic.json), or None."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    try:
-        with open(path) as f:
-            return json.load(f)["per_step_bytes"]
-    except Exception:
-        return None
+    """DRAM bytes per denoise step: a CONSTANT read from the committed ncu pass of the same kernels
+    (profiles/r2_traffic.json, else the round-1 file) — not measured in this run — or None."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return json.load(f)["per_step_bytes"], name
+        except Exception:
+            continue
+    return None, None
 
 
 def load_peaks():
@@ -609,8 +611,9 @@ def main():
             "launches_per_denoise_step": launches_headline,
             "roofline": {
                 "bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved_tf / peaks["bf16_tflops_sustained"], "traffic": load_traffic() if B == 256 else None,
-                "traffic_note": "ncu cold-cache sum over the step's launches (upper bound), see profiles/r1_traffic.json",
+                "frac": achieved_tf / peaks["bf16_tflops_sustained"], "traffic": load_traffic()[0] if B == 256 else None,
+                "traffic_note": f"constant from profiles/{load_traffic()[1]}: ncu cold-cache sum over one step's launches (upper bound), "
+                                "not measured in this run",
                 "kernel": "one denoise step = one CUDA-graph launch (tcgen05 GEMM family dominates)",
                 "algorithmic": f"{GFLOP_PER_FACE_STEP} GFLOP/face/step x {B} faces",
                 "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)",
