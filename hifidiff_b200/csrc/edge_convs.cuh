@@ -282,5 +282,97 @@ __global__ void __launch_bounds__(256, 2) intro_mma_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// STN localisation conv of the CoarseRestoration stages with few channels and large images (models/cr/stn.py:13-22):
+//   Conv2d(Cin, 8, k, valid) -> MaxPool2d(2) -> ReLU,  Cin = 32 (128x128, k = 9) / 64 (64x64, k = 9)
+// as an implicit GEMM on mma.sync.m16n8k16 — N = 8 IS the layer's channel count.  One CTA = a 16x16 tile of conv
+// outputs (8x8 pooled): the (16+k-1)^2 input patch is staged once in shared memory as bf16 hi + lo (fp32 input, three
+// products: fp32-grade), pixel stride padded by 16 bytes so ldmatrix rows are conflict-free; warp w owns conv rows
+// 2w, 2w+1, so the 2x2 max-pool is an in-register max plus one shuffle.  Weights hi + lo in B-fragment order
+// [tap * Cin/16 + chunk][8][16] come from global memory (256 bytes per k-step, identical for all warps: L1 hits).
+// in [B, n, n, Cin] fp32 NHWC -> out [B, no, no, 8] fp32.  dynamic smem: 2 * (16+k-1)^2 * (Cin*2 + 16) bytes.
+// (Was cr_stn_conv_pool_cs_kernel on CUDA cores: 30 % of the CoarseRestoration pass.)
+// ------------------------------------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void __launch_bounds__(256) stn_conv_mma_kernel(const float* __restrict__ in, const bf16* __restrict__ w_hi,
+                                                           const bf16* __restrict__ w_lo, const float* __restrict__ bias,
+                                                           float* __restrict__ out, int n, int k, int no) {
+  extern __shared__ __align__(128) uint8_t s_raw[];
+  constexpr int PSTRIDE = CIN * 2 + 16;       // bytes per staged pixel
+  constexpr int CCH = CIN / 16;               // 16-channel chunks (k-steps per tap)
+  const int pw = 16 + k - 1;                  // patch width / height
+  uint8_t* a_hi = s_raw;
+  uint8_t* a_lo = s_raw + static_cast<size_t>(pw) * pw * PSTRIDE;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int face = blockIdx.z, ty0 = blockIdx.y * 16, tx0 = blockIdx.x * 16;
+  pdl_trigger();
+  pdl_wait();
+  {  // stage the patch: pixels beyond the image are zero (their conv outputs are never stored)
+    constexpr int V = CIN / 4;                // float4 per pixel
+    const float* src = in + static_cast<size_t>(face) * n * n * CIN;
+    for (int i = tid; i < pw * pw * V; i += 256) {
+      const int pix = i / V, v = i - pix * V;
+      const int py = pix / pw, px = pix - py * pw;
+      const int gy = ty0 + py, gx = tx0 + px;
+      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy < n && gx < n) f = *reinterpret_cast<const float4*>(src + (static_cast<size_t>(gy) * n + gx) * CIN + v * 4);
+      const bf16 h0 = __float2bfloat16_rn(f.x), h1 = __float2bfloat16_rn(f.y), h2 = __float2bfloat16_rn(f.z), h3 = __float2bfloat16_rn(f.w);
+      const uint32_t off = static_cast<uint32_t>(pix) * PSTRIDE + v * 8;
+      *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(pack_bf16x2(f.x, f.y), pack_bf16x2(f.z, f.w));
+      *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(pack_bf16x2(f.x - __bfloat162float(h0), f.y - __bfloat162float(h1)),
+                                                        pack_bf16x2(f.z - __bfloat162float(h2), f.w - __bfloat162float(h3)));
+    }
+  }
+  __syncthreads();
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  const int lx = lane & 15, khalf = lane >> 4;
+  const int g = lane >> 2, q = lane & 3;
+  const uint32_t hi_u32 = smem_addr(a_hi), lo_u32 = smem_addr(a_lo);
+  const uint32_t* whi = reinterpret_cast<const uint32_t*>(w_hi) + g * 8 + q;   // B fragment: n = g, k = 2q (+8)
+  const uint32_t* wlo = reinterpret_cast<const uint32_t*>(w_lo) + g * 8 + q;
+#pragma unroll 1
+  for (int ky = 0; ky < k; ++ky) {
+#pragma unroll 1
+    for (int kx = 0; kx < k; ++kx) {
+      const int ks0 = (ky * k + kx) * CCH;
+      // lane's pixel of conv rows 2w and 2w+1 for this tap
+      const uint32_t p0 = static_cast<uint32_t>((2 * warp + ky) * pw + lx + kx) * PSTRIDE + khalf * 16;
+      const uint32_t p1 = p0 + static_cast<uint32_t>(pw) * PSTRIDE;
+#pragma unroll
+      for (int cc = 0; cc < CCH; ++cc) {
+        uint32_t bh[2], bl[2];
+        bh[0] = __ldg(whi + (ks0 + cc) * 64); bh[1] = __ldg(whi + (ks0 + cc) * 64 + 4);
+        bl[0] = __ldg(wlo + (ks0 + cc) * 64); bl[1] = __ldg(wlo + (ks0 + cc) * 64 + 4);
+        uint32_t ah0[4], al0[4], ah1[4], al1[4];
+        ldmatrix_x4(hi_u32 + p0 + cc * 32, ah0);
+        ldmatrix_x4(lo_u32 + p0 + cc * 32, al0);
+        ldmatrix_x4(hi_u32 + p1 + cc * 32, ah1);
+        ldmatrix_x4(lo_u32 + p1 + cc * 32, al1);
+        mma_16816(acc[0], ah0, bh); mma_16816(acc[0], al0, bh); mma_16816(acc[0], ah0, bl);
+        mma_16816(acc[1], ah1, bh); mma_16816(acc[1], al1, bh); mma_16816(acc[1], ah1, bl);
+      }
+    }
+  }
+  // 2x2 max-pool: vertical = the two conv rows of this warp; horizontal = pixel g with pixel g + 1 (lane + 4)
+  float m[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float v = fmaxf(acc[0][i], acc[1][i]);
+    m[i] = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+  }
+  if ((g & 1) == 0) {
+    const int oy = (ty0 >> 1) + warp;
+    const float b0 = __ldg(bias + 2 * q), b1 = __ldg(bias + 2 * q + 1);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {   // pixels g (m[0], m[1]) and g + 8 (m[2], m[3])
+      const int ox = (tx0 >> 1) + (g >> 1) + half * 4;
+      if (oy < no && ox < no) {
+        float* o = out + ((static_cast<size_t>(face) * no + oy) * no + ox) * 8 + 2 * q;
+        *reinterpret_cast<float2*>(o) = make_float2(fmaxf(m[2 * half] + b0, 0.f), fmaxf(m[2 * half + 1] + b1, 0.f));   // bias commutes with max
+      }
+    }
+  }
+}
+
 }  // namespace edge
 }  // namespace hd

@@ -201,6 +201,7 @@ struct CrStnW {
   int k1 = 0, k2 = 0, n1 = 0, n2 = 0, fc = 0, hid = 0;
   float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;      // localisation convs, [Cout][k][k][Cin]
   float *f1 = nullptr, *fb1 = nullptr, *f2 = nullptr, *fb2 = nullptr;    // regressor, f1 columns in NHWC order
+  hd::bf16 *w1_mma_hi = nullptr, *w1_mma_lo = nullptr;                   // first conv as bf16 hi / lo in mma.sync B-fragment order (Cin <= 64)
 };
 struct CrStageW {
   int c = 0, res = 0, sampling = 0;  // 0 none, 1 down (2x2 s2 conv), 2 up (1x1 conv + PixelShuffle)
@@ -1861,6 +1862,34 @@ void load_cr_stn(hd_handle* h, CrStnW& s, const std::string& p, int c, int res) 
   s.hid = static_cast<int>(std::sqrt(static_cast<double>(s.fc)));
   if (s.hid > 96) HD_THROW(HD_ERR_UNSUPPORTED, "STN regressor width %d", s.hid);
   s.w1 = cr_conv_ohwi(h, p + "localization.0.weight", 8, c, s.k1);
+  if (c <= 64 && c % 16 == 0 && h->bf16 && h->tun.cr_tc) {
+    // [tap * c/16 + chunk][n = 8][16 k] bf16 hi + lo for edge::stn_conv_mma_kernel
+    auto w = host_vec(h, need(h, p + "localization.0.weight", {8, c, s.k1 * s.k1}));  // [o][i][tap]
+    const int cch = c / 16, taps = s.k1 * s.k1;
+    std::vector<uint16_t> vh(static_cast<size_t>(taps) * cch * 128), vl(vh.size());
+    auto to_bf16 = [](float f) {
+      uint32_t u;
+      memcpy(&u, &f, 4);
+      u += 0x7FFFu + ((u >> 16) & 1u);
+      return static_cast<uint16_t>(u >> 16);
+    };
+    for (int tap = 0; tap < taps; ++tap)
+      for (int cc = 0; cc < cch; ++cc)
+        for (int o = 0; o < 8; ++o)
+          for (int kk = 0; kk < 16; ++kk) {
+            const float f = w[(static_cast<size_t>(o) * c + cc * 16 + kk) * taps + tap];
+            const size_t idx = ((static_cast<size_t>(tap) * cch + cc) * 8 + o) * 16 + kk;
+            vh[idx] = to_bf16(f);
+            const uint32_t hb = static_cast<uint32_t>(vh[idx]) << 16;
+            float hf;
+            memcpy(&hf, &hb, 4);
+            vl[idx] = to_bf16(f - hf);
+          }
+    s.w1_mma_hi = static_cast<hd::bf16*>(h->arena.alloc(vh.size() * 2));
+    s.w1_mma_lo = static_cast<hd::bf16*>(h->arena.alloc(vl.size() * 2));
+    CUDA_CHECK(cudaMemcpy(s.w1_mma_hi, vh.data(), vh.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(s.w1_mma_lo, vl.data(), vl.size() * 2, cudaMemcpyHostToDevice));
+  }
   s.b1 = cr_vec(h, p + "localization.0.bias", 8);
   s.w2 = cr_conv_ohwi(h, p + "localization.3.weight", 10, 8, s.k2);
   s.b2 = cr_vec(h, p + "localization.3.bias", 10);
@@ -2018,11 +2047,29 @@ Plan* get_cr_plan(hd_handle* h, int B) {
     float *loc1 = R.loc1, *loc2 = R.loc2, *theta = R.theta;
     const float *w1 = s.w1, *b1 = s.b1, *w2 = s.w2, *b2 = s.b2, *f1 = s.f1, *fb1 = s.fb1, *f2 = s.f2, *fb2 = s.fb2;
     const int k1 = s.k1, k2 = s.k2, n1 = s.n1, n2 = s.n2, fc = s.fc, hid = s.hid;
+    const bf16 *w1h = s.w1_mma_hi, *w1l = s.w1_mma_lo;
+    if (R.use_tc && w1h != nullptr && (c == 32 || c == 64)) {
+      // the two large-image levels: implicit GEMM on mma.sync with split-precision operands (edge_convs.cuh)
+      const int conv_n = n - k1 + 1, tiles = cdiv(conv_n, 16), pw = 16 + k1 - 1;
+      const size_t smem = static_cast<size_t>(2) * pw * pw * (c * 2 + 16);
+      static bool configured = false;
+      if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(edge::stn_conv_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 24 * 24 * (32 * 2 + 16)));
+        CUDA_CHECK(cudaFuncSetAttribute(edge::stn_conv_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 24 * 24 * (64 * 2 + 16)));
+        configured = true;
+      }
+      g_label = L0 + fmt("stn conv%dx%d+pool+relu mma.sync (3 x bf16 split)", k1, k1);
+      add_op(P, [=](cudaStream_t st) {
+        if (c == 32) launch_k(edge::stn_conv_mma_kernel<32>, dim3(tiles, tiles, B), dim3(256), smem, st, x, w1h, w1l, b1, loc1, n, k1, n1);
+        else launch_k(edge::stn_conv_mma_kernel<64>, dim3(tiles, tiles, B), dim3(256), smem, st, x, w1h, w1l, b1, loc1, n, k1, n1);
+      });
+    } else {
     g_label = L0 + fmt("stn conv%dx%d+pool+relu", k1, k1);
     add_op(P, [=](cudaStream_t st) {
       if (h->tun.cr_stn_cs) launch_k(cr_stn_conv_pool_cs_kernel<8>, ew(static_cast<size_t>(B) * n1 * n1 * 4, 128), dim3(128), 0, st, x, w1, b1, loc1, B, n, c, k1, n1);
       else launch_k(cr_stn_conv_pool_kernel<8, 2>, ew(static_cast<size_t>(B) * n1 * n1 * 4, 128), dim3(128), 0, st, x, w1, b1, loc1, B, n, c, k1, n1);
     });
+    }
     g_label = L0 + fmt("stn conv%dx%d+pool+relu", k2, k2);
     add_op(P, [=](cudaStream_t st) {
       launch_k(cr_stn_conv_pool_kernel<10, 5>, ew(static_cast<size_t>(B) * n2 * n2 * 2, 128), dim3(128), 0, st, static_cast<const float*>(loc1), w2, b2, loc2, B, n1, 8, k2, n2);
