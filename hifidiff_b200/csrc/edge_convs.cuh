@@ -283,77 +283,110 @@ __global__ void __launch_bounds__(256, 2) intro_mma_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// STN localisation conv of the CoarseRestoration stages with few channels and large images (models/cr/stn.py:13-22):
-//   Conv2d(Cin, 8, k, valid) -> MaxPool2d(2) -> ReLU,  Cin = 32 (128x128, k = 9) / 64 (64x64, k = 9)
+// First STN localisation conv of every CoarseRestoration stage (models/cr/stn.py:13-22):
+//   Conv2d(Cin, 8, k, valid) -> MaxPool2d(2) -> ReLU,  (Cin, image, k) = (32, 128, 9) (64, 64, 9) (128, 32, 7)
+//   (256, 16, 5) (512, 8, 3)
 // as an implicit GEMM on mma.sync.m16n8k16 — N = 8 IS the layer's channel count.  One CTA = a 16x16 tile of conv
-// outputs (8x8 pooled): the (16+k-1)^2 input patch is staged once in shared memory as bf16 hi + lo (fp32 input, three
-// products: fp32-grade), pixel stride padded by 16 bytes so ldmatrix rows are conflict-free; warp w owns conv rows
-// 2w, 2w+1, so the 2x2 max-pool is an in-register max plus one shuffle.  Weights hi + lo in B-fragment order
-// [tap * Cin/16 + chunk][8][16] come from global memory (256 bytes per k-step, identical for all warps: L1 hits).
-// in [B, n, n, Cin] fp32 NHWC -> out [B, no, no, 8] fp32.  dynamic smem: 2 * (16+k-1)^2 * (Cin*2 + 16) bytes.
-// (Was cr_stn_conv_pool_cs_kernel on CUDA cores: 30 % of the CoarseRestoration pass.)
+// outputs (8x8 pooled) of one face.  Channels go through in passes of CH: the (16+k-1)^2 input patch of the pass is
+// staged in shared memory as bf16 hi + lo (fp32 input, three products: fp32-grade), pixel stride padded by 16 bytes so
+// the ldmatrix rows are conflict-free; warp w owns conv rows 2w, 2w+1, so the 2x2 max-pool is an in-register max plus
+// one shuffle.  Weights (hi + lo, one 512-byte block of four 8x8 B matrices per k-step, rows ordered
+// [pass][ky][kx][chunk]) stream through a two-deep cp.async ring, one filter row ahead of the MMAs.
+// in [B, n, n, Cin] fp32 NHWC -> out [B, no, no, 8] fp32.
+// dynamic smem: 2 * (16+k-1)^2 * (CH*2 + 16) + 2 * k * (CH/16) * 512 bytes.
+// (Was cr_stn_conv_pool_cs_kernel on CUDA cores, latency-bound at 270-470 us per launch: 30 % of the CR pass.)
 // ------------------------------------------------------------------------------------------------------------------
-template <int CIN>
-__global__ void __launch_bounds__(256) stn_conv_mma_kernel(const float* __restrict__ in, const bf16* __restrict__ w_hi,
-                                                           const bf16* __restrict__ w_lo, const float* __restrict__ bias,
-                                                           float* __restrict__ out, int n, int k, int no) {
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+inline size_t stn_conv_smem(int ch, int k) {
+  const int pw = 16 + k - 1;
+  return static_cast<size_t>(2) * pw * pw * (ch * 2 + 16) + static_cast<size_t>(2) * k * (ch / 16) * 512;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) stn_conv_mma_kernel(const float* __restrict__ in, const bf16* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ out,
+                                                           int n, int cin, int k, int no) {
   extern __shared__ __align__(128) uint8_t s_raw[];
-  constexpr int PSTRIDE = CIN * 2 + 16;       // bytes per staged pixel
-  constexpr int CCH = CIN / 16;               // 16-channel chunks (k-steps per tap)
+  constexpr int PSTRIDE = CH * 2 + 16;        // bytes per staged pixel
+  constexpr int CCH = CH / 16;                // k-steps per tap and pass
   const int pw = 16 + k - 1;                  // patch width / height
+  const uint32_t patch_bytes = static_cast<uint32_t>(pw) * pw * PSTRIDE;
+  const uint32_t row_bytes = static_cast<uint32_t>(k) * CCH * 512;
   uint8_t* a_hi = s_raw;
-  uint8_t* a_lo = s_raw + static_cast<size_t>(pw) * pw * PSTRIDE;
+  uint8_t* a_lo = s_raw + patch_bytes;
+  const uint32_t hi_u32 = smem_addr(a_hi), lo_u32 = hi_u32 + patch_bytes, w_u32 = hi_u32 + 2 * patch_bytes;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int face = blockIdx.z, ty0 = blockIdx.y * 16, tx0 = blockIdx.x * 16;
+  const int n_rows = (cin / CH) * k;          // filter rows over all passes
+  const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(w);
+  auto load_row = [&](int r) {
+    const uint8_t* src = wsrc + static_cast<size_t>(r) * row_bytes;
+    const uint32_t dst = w_u32 + (r & 1) * row_bytes;
+    for (uint32_t i = tid * 16; i < row_bytes; i += 256 * 16) cp_async_16(dst + i, src + i);
+    cp_async_commit();
+  };
   pdl_trigger();
+  load_row(0);                                // constants: before the dependency wait
   pdl_wait();
-  {  // stage the patch: pixels beyond the image are zero (their conv outputs are never stored)
-    constexpr int V = CIN / 4;                // float4 per pixel
-    const float* src = in + static_cast<size_t>(face) * n * n * CIN;
-    for (int i = tid; i < pw * pw * V; i += 256) {
-      const int pix = i / V, v = i - pix * V;
-      const int py = pix / pw, px = pix - py * pw;
-      const int gy = ty0 + py, gx = tx0 + px;
-      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gy < n && gx < n) f = *reinterpret_cast<const float4*>(src + (static_cast<size_t>(gy) * n + gx) * CIN + v * 4);
-      const bf16 h0 = __float2bfloat16_rn(f.x), h1 = __float2bfloat16_rn(f.y), h2 = __float2bfloat16_rn(f.z), h3 = __float2bfloat16_rn(f.w);
-      const uint32_t off = static_cast<uint32_t>(pix) * PSTRIDE + v * 8;
-      *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(pack_bf16x2(f.x, f.y), pack_bf16x2(f.z, f.w));
-      *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(pack_bf16x2(f.x - __bfloat162float(h0), f.y - __bfloat162float(h1)),
-                                                        pack_bf16x2(f.z - __bfloat162float(h2), f.w - __bfloat162float(h3)));
-    }
-  }
-  __syncthreads();
+  const bool active = ty0 + 2 * warp < n - k + 1;   // warps whose conv rows exist
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   const int lx = lane & 15, khalf = lane >> 4;
-  const int g = lane >> 2, q = lane & 3;
-  const uint32_t hi_u32 = smem_addr(a_hi), lo_u32 = smem_addr(a_lo);
-  const uint32_t* whi = reinterpret_cast<const uint32_t*>(w_hi) + g * 8 + q;   // B fragment: n = g, k = 2q (+8)
-  const uint32_t* wlo = reinterpret_cast<const uint32_t*>(w_lo) + g * 8 + q;
+  const uint32_t b_lane = (lane >> 3) * 128 + (lane & 7) * 16;
+  const float* src_face = in + static_cast<size_t>(face) * n * n * cin;
 #pragma unroll 1
-  for (int ky = 0; ky < k; ++ky) {
+  for (int r = 0; r < n_rows; ++r) {
+    const int pass = r / k, ky = r - pass * k;
+    if (ky == 0) {
+      if (r > 0) __syncthreads();             // the previous pass's patch is no longer read
+      // stage this pass's patch; pixels beyond the image only feed conv outputs that are never stored
+      constexpr int V = CH / 4;               // float4 per pixel
+      const float* src = src_face + pass * CH;
+      for (int i = tid; i < pw * pw * V; i += 256) {
+        const int pix = i / V, v = i - pix * V;
+        const int py = pix / pw, px = pix - py * pw;
+        const int gy = ty0 + py, gx = tx0 + px;
+        if (gy < n && gx < n) {
+          const float4 f = *reinterpret_cast<const float4*>(src + (static_cast<size_t>(gy) * n + gx) * cin + v * 4);
+          const float r0 = __bfloat162float(__float2bfloat16_rn(f.x)), r1 = __bfloat162float(__float2bfloat16_rn(f.y));
+          const float r2 = __bfloat162float(__float2bfloat16_rn(f.z)), r3 = __bfloat162float(__float2bfloat16_rn(f.w));
+          const uint32_t off = static_cast<uint32_t>(pix) * PSTRIDE + v * 8;
+          *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(pack_bf16x2(f.x, f.y), pack_bf16x2(f.z, f.w));
+          *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(pack_bf16x2(f.x - r0, f.y - r1), pack_bf16x2(f.z - r2, f.w - r3));
+        }
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();                          // row r (and the patch) visible; everyone is done with row r-1
+    if (r + 1 < n_rows) load_row(r + 1);
+    if (active) {
+      const uint32_t wrow = w_u32 + (r & 1) * row_bytes + b_lane;
+      const uint32_t p0 = static_cast<uint32_t>((2 * warp + ky) * pw + lx) * PSTRIDE + khalf * 16;
 #pragma unroll 1
-    for (int kx = 0; kx < k; ++kx) {
-      const int ks0 = (ky * k + kx) * CCH;
-      // lane's pixel of conv rows 2w and 2w+1 for this tap
-      const uint32_t p0 = static_cast<uint32_t>((2 * warp + ky) * pw + lx + kx) * PSTRIDE + khalf * 16;
-      const uint32_t p1 = p0 + static_cast<uint32_t>(pw) * PSTRIDE;
+      for (int kx = 0; kx < k; ++kx) {
+        const uint32_t q0 = p0 + kx * PSTRIDE, q1 = q0 + pw * PSTRIDE;
 #pragma unroll
-      for (int cc = 0; cc < CCH; ++cc) {
-        uint32_t bh[2], bl[2];
-        bh[0] = __ldg(whi + (ks0 + cc) * 64); bh[1] = __ldg(whi + (ks0 + cc) * 64 + 4);
-        bl[0] = __ldg(wlo + (ks0 + cc) * 64); bl[1] = __ldg(wlo + (ks0 + cc) * 64 + 4);
-        uint32_t ah0[4], al0[4], ah1[4], al1[4];
-        ldmatrix_x4(hi_u32 + p0 + cc * 32, ah0);
-        ldmatrix_x4(lo_u32 + p0 + cc * 32, al0);
-        ldmatrix_x4(hi_u32 + p1 + cc * 32, ah1);
-        ldmatrix_x4(lo_u32 + p1 + cc * 32, al1);
-        mma_16816(acc[0], ah0, bh); mma_16816(acc[0], al0, bh); mma_16816(acc[0], ah0, bl);
-        mma_16816(acc[1], ah1, bh); mma_16816(acc[1], al1, bh); mma_16816(acc[1], ah1, bl);
+        for (int cc = 0; cc < CCH; ++cc) {
+          uint32_t b[4], ah0[4], al0[4], ah1[4], al1[4];
+          ldmatrix_x4(wrow + (kx * CCH + cc) * 512, b);    // b[0..1] = hi fragment, b[2..3] = lo fragment
+          ldmatrix_x4(hi_u32 + q0 + cc * 32, ah0);
+          ldmatrix_x4(lo_u32 + q0 + cc * 32, al0);
+          ldmatrix_x4(hi_u32 + q1 + cc * 32, ah1);
+          ldmatrix_x4(lo_u32 + q1 + cc * 32, al1);
+          const uint32_t bh[2] = {b[0], b[1]}, bl[2] = {b[2], b[3]};
+          mma_16816(acc[0], ah0, bh); mma_16816(acc[1], ah1, bh);
+          mma_16816(acc[0], al0, bh); mma_16816(acc[1], al1, bh);
+          mma_16816(acc[0], ah0, bl); mma_16816(acc[1], ah1, bl);
+        }
       }
     }
   }
-  // 2x2 max-pool: vertical = the two conv rows of this warp; horizontal = pixel g with pixel g + 1 (lane + 4)
+  // 2x2 max-pool: vertical = the two conv rows of this warp; horizontal = pixel g with pixel g ^ 1 (lane ^ 4)
+  const int g = lane >> 2, q = lane & 3;
   float m[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

@@ -1,0 +1,179 @@
+// Small-K fp32-grade GEMM for the wide, shallow stages of CoarseRestoration (models/cr/model.py:8-88: the 1x1 convs
+// of the NAF blocks at c = 32 / 64, the 2x2 stride-2 down convs and the 1x1 up convs + PixelShuffle):
+//   out[M, N] = epilogue(A[M, K] W[N, K]^T),   M = faces x pixels (10^5 .. 10^6 rows), K = 32 .. 512, N = 32 .. 1024
+// These are HBM-bound by shape (a few hundred flops per row against 128 .. 768 bytes of fp32 traffic), but on CUDA
+// cores the FFMA issue rate was the limit (18 TFLOP/s, 4-8x off the memory floor).  Here the arithmetic is
+// mma.sync.m16n8k16 with split operands — A and W as bf16 hi + lo, a_hi w_hi + a_lo w_hi + a_hi w_lo accumulated in
+// fp32 (everything but the lo x lo term: ~2^-16 relative, the same contract as the split tcgen05 GEMM of the deeper
+// stages) — so that the kernel waits on memory, not on the FMA pipe.  K is too small here for a TMA / tcgen05
+// pipeline to amortise its set-up, and A needs the fp32 -> hi / lo conversion on the way into shared memory anyway.
+//
+// CTA = 256 threads = 8 warps, tile 128 rows x BN columns, warp w owns rows 16w .. 16w+15 and all BN columns.
+// K goes through in chunks of 32: global -> registers (the next chunk's loads are in flight during the MMAs) ->
+// hi / lo split -> shared memory rows of 64 + 16 bytes (conflict-free ldmatrix).
+#pragma once
+
+#include "common.cuh"
+#include "edge_convs.cuh"
+
+namespace hd {
+namespace mma3 {
+
+struct Args {
+  const float* A;      // [M, lda] fp32
+  const bf16* w_hi;    // [N, K]
+  const bf16* w_lo;    // [N, K]
+  const float* bias;   // [N] or nullptr
+  float* out;          // [M, ldo] fp32 (EPI_PIXSHUF: the up-sampled skip buffer, accumulated in place)
+  const float* resid;  // EPI_RESID: [M, ldr]
+  int lda, ldo, ldr;
+  int M, N, K;
+  int sp;              // EPI_PIXSHUF: spatial size of the GEMM rows
+};
+
+constexpr int BM = 128, KC = 32, ROWB = KC * 2 + 16;
+
+// W fp32 [N, K] -> hi, lo bf16 [N, K] (once, at load)
+__global__ void split_hl_kernel(const float* __restrict__ w, bf16* __restrict__ hi, bf16* __restrict__ lo, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float f = w[i];
+  const bf16 h = __float2bfloat16_rn(f);
+  hi[i] = h;
+  lo[i] = __float2bfloat16_rn(f - __bfloat162float(h));
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(256, 2) gemm_mma3_kernel(const Args g) {
+  constexpr int NT = BN / 8;
+  __shared__ __align__(128) uint8_t s_a[2][BM * ROWB];   // hi, lo
+  __shared__ __align__(128) uint8_t s_w[2][BN * ROWB];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  constexpr int WJ = (BN * 4 + 255) / 256;     // 16-byte weight chunks per thread and matrix
+  float4 areg[4];
+  uint4 whreg[WJ], wlreg[WJ];
+  auto load_w = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < WJ; ++j) {
+      const int i = tid + 256 * j;
+      if (i < BN * 4) {
+        const size_t off = static_cast<size_t>(n0 + (i >> 2)) * g.K + k0 + (i & 3) * 8;
+        whreg[j] = __ldg(reinterpret_cast<const uint4*>(g.w_hi + off));
+        wlreg[j] = __ldg(reinterpret_cast<const uint4*>(g.w_lo + off));
+      }
+    }
+  };
+  auto load_a = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = tid + 256 * j, row = m0 + (i >> 3);
+      areg[j] = row < g.M ? *reinterpret_cast<const float4*>(g.A + static_cast<size_t>(row) * g.lda + k0 + (i & 7) * 4)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto stage = [&]() {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = tid + 256 * j;
+      const float4 f = areg[j];
+      const float r0 = __bfloat162float(__float2bfloat16_rn(f.x)), r1 = __bfloat162float(__float2bfloat16_rn(f.y));
+      const float r2 = __bfloat162float(__float2bfloat16_rn(f.z)), r3 = __bfloat162float(__float2bfloat16_rn(f.w));
+      const uint32_t off = (i >> 3) * ROWB + (i & 7) * 8;
+      *reinterpret_cast<uint2*>(s_a[0] + off) = make_uint2(pack_bf16x2(f.x, f.y), pack_bf16x2(f.z, f.w));
+      *reinterpret_cast<uint2*>(s_a[1] + off) = make_uint2(pack_bf16x2(f.x - r0, f.y - r1), pack_bf16x2(f.z - r2, f.w - r3));
+    }
+#pragma unroll
+    for (int j = 0; j < WJ; ++j) {
+      const int i = tid + 256 * j;
+      if (i < BN * 4) {
+        const uint32_t off = (i >> 2) * ROWB + (i & 3) * 16;
+        *reinterpret_cast<uint4*>(s_w[0] + off) = whreg[j];
+        *reinterpret_cast<uint4*>(s_w[1] + off) = wlreg[j];
+      }
+    }
+  };
+  pdl_trigger();
+  load_w(0);                                   // constants: before the dependency wait
+  pdl_wait();
+  load_a(0);
+  float acc[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  const uint32_t a_lane = (warp * 16 + (lane & 15)) * ROWB + (lane >> 4) * 16;
+  const uint32_t w_lane = ((lane >> 4) * 8 + (lane & 7)) * ROWB + ((lane >> 3) & 1) * 16;
+  const uint32_t ah_u32 = edge::smem_addr(s_a[0]) + a_lane, al_u32 = edge::smem_addr(s_a[1]) + a_lane;
+  const uint32_t wh_u32 = edge::smem_addr(s_w[0]) + w_lane, wl_u32 = edge::smem_addr(s_w[1]) + w_lane;
+#pragma unroll 1
+  for (int k0 = 0; k0 < g.K; k0 += KC) {
+    if (k0 > 0) __syncthreads();               // the previous chunk is no longer read
+    stage();
+    __syncthreads();
+    if (k0 + KC < g.K) { load_w(k0 + KC); load_a(k0 + KC); }
+#pragma unroll
+    for (int s = 0; s < KC / 16; ++s) {
+      uint32_t ah[4], al[4];
+      edge::ldmatrix_x4(ah_u32 + s * 32, ah);
+      edge::ldmatrix_x4(al_u32 + s * 32, al);
+#pragma unroll
+      for (int jp = 0; jp < NT / 2; ++jp) {
+        uint32_t bh[4], bl[4];
+        edge::ldmatrix_x4(wh_u32 + jp * 16 * ROWB + s * 32, bh);   // n-tiles 2jp (bh[0..1]) and 2jp+1 (bh[2..3])
+        edge::ldmatrix_x4(wl_u32 + jp * 16 * ROWB + s * 32, bl);
+        const uint32_t bh0[2] = {bh[0], bh[1]}, bh1[2] = {bh[2], bh[3]}, bl0[2] = {bl[0], bl[1]}, bl1[2] = {bl[2], bl[3]};
+        edge::mma_16816(acc[2 * jp], ah, bh0);     edge::mma_16816(acc[2 * jp + 1], ah, bh1);
+        edge::mma_16816(acc[2 * jp], al, bh0);     edge::mma_16816(acc[2 * jp + 1], al, bh1);
+        edge::mma_16816(acc[2 * jp], ah, bl0);     edge::mma_16816(acc[2 * jp + 1], ah, bl1);
+      }
+    }
+  }
+  // C fragment: rows g and g + 8 of the warp's 16, columns 8j + 2q + {0, 1}
+  const int gq = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int m = m0 + warp * 16 + gq + half * 8;
+    if (m >= g.M) continue;
+    if (EPI == EPI_PIXSHUF) {
+      // column n = quarter * (N/4) + channel: quarter (dy, dx) of the 2x2 up-sampled pixel (PixelShuffle(2))
+      const int quarter = g.N >> 2, sp = g.sp;
+      const int face = m / (sp * sp), rem = m - face * sp * sp;
+      const int py = rem / sp, px = rem - py * sp;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int n = n0 + j * 8 + 2 * q;
+        const int qd = n / quarter, kch = n - qd * quarter;
+        const size_t orow = (static_cast<size_t>(face) * (2 * sp) + (2 * py + (qd >> 1))) * (2 * sp) + (2 * px + (qd & 1));
+        float2* o = reinterpret_cast<float2*>(g.out + orow * g.ldo + kch);
+        float2 v = *o;
+        v.x += acc[j][2 * half];
+        v.y += acc[j][2 * half + 1];
+        *o = v;
+      }
+    } else {
+      float* orow = g.out + static_cast<size_t>(m) * g.ldo + n0 + 2 * q;
+      const float* rrow = EPI == EPI_RESID ? g.resid + static_cast<size_t>(m) * g.ldr + n0 + 2 * q : nullptr;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        float2 v = make_float2(acc[j][2 * half], acc[j][2 * half + 1]);
+        if (g.bias != nullptr) {
+          const float2 b = __ldg(reinterpret_cast<const float2*>(g.bias + n0 + j * 8 + 2 * q));
+          v.x += b.x;
+          v.y += b.y;
+        }
+        if (EPI == EPI_RESID) {
+          const float2 r = *reinterpret_cast<const float2*>(rrow + j * 8);
+          v.x += r.x;
+          v.y += r.y;
+        }
+        *reinterpret_cast<float2*>(orow + j * 8) = v;
+      }
+    }
+  }
+}
+
+inline bool eligible(int M, int N, int K, int epi) {
+  return M >= 1024 && K % KC == 0 && N % 32 == 0 && (epi == EPI_BIAS || epi == EPI_RESID || (epi == EPI_PIXSHUF && (N / 4) % 2 == 0));
+}
+
+}  // namespace mma3
+}  // namespace hd

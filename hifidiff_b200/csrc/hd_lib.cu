@@ -10,12 +10,15 @@
 #include <string>
 #include <vector>
 
+#include <unordered_map>
+
 #include "../../include/hifidiff_b200.h"
 #include "common.cuh"
 #include "elem_kernels.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "edge_convs.cuh"
+#include "gemm_mma3.cuh"
 #include "face_block.cuh"
 #include "pair_block.cuh"
 #include "idc_kernels.cuh"
@@ -72,13 +75,14 @@ struct Tunables {
   bool edge_mma = true;   // HD_EDGE_MMA=0: CUDA-core intro / ending convs and separate sampler-update / advance launches
   bool cr_stn_cs = true;  // HD_CR_STN_CS=0: one thread per (pixel, 2 output channels) in the first STN localisation conv
   bool cr_tc = true;      // HD_CR_TC=0: every CoarseRestoration GEMM on the FFMA kernel (no split-precision tcgen05 path)
+  bool cr_mma3 = true;    // HD_CR_MMA3=0: the shallow CoarseRestoration stages (c = 32 / 64, down / up convs) stay on the FFMA GEMM
   bool dw_small = true;   // HD_DW_SMALL=0: the generic tiled depthwise kernel at the 2x2 / 4x4 levels too
   int cta_target = 120;   // HD_CTA_TARGET: split-K until a GEMM's grid has at least this many CTAs
   int sca_target = 120;   // HD_SCA_TARGET: the same for the SCA GEMMs (M = faces)
   void read_env() {
     auto flag = [](const char* name, bool& v) { if (const char* e = getenv(name)) v = atoi(e) != 0; };
     flag("HD_PDL", pdl); flag("HD_BN256", bn256); flag("HD_FACE", face); flag("HD_PAIR", pair); flag("HD_SCA_MUL", sca_mul); flag("HD_EDGE_MMA", edge_mma); flag("HD_W_PREFETCH", w_prefetch);
-    flag("HD_CR_STN_CS", cr_stn_cs); flag("HD_CR_TC", cr_tc); flag("HD_DW_SMALL", dw_small);
+    flag("HD_CR_STN_CS", cr_stn_cs); flag("HD_CR_TC", cr_tc); flag("HD_CR_MMA3", cr_mma3); flag("HD_DW_SMALL", dw_small);
     if (const char* e = getenv("HD_TWO_CTA")) two_cta = atoi(e);
     if (const char* e = getenv("HD_CTA_TARGET")) cta_target = std::max(atoi(e), 1);
     if (const char* e = getenv("HD_SCA_TARGET")) sca_target = std::max(atoi(e), 1);
@@ -201,7 +205,7 @@ struct CrStnW {
   int k1 = 0, k2 = 0, n1 = 0, n2 = 0, fc = 0, hid = 0;
   float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;      // localisation convs, [Cout][k][k][Cin]
   float *f1 = nullptr, *fb1 = nullptr, *f2 = nullptr, *fb2 = nullptr;    // regressor, f1 columns in NHWC order
-  hd::bf16 *w1_mma_hi = nullptr, *w1_mma_lo = nullptr;                   // first conv as bf16 hi / lo in mma.sync B-fragment order (Cin <= 64)
+  hd::bf16* w1_mma = nullptr;                                            // first conv as bf16 hi + lo 8x8 B matrices for edge::stn_conv_mma_kernel
 };
 struct CrStageW {
   int c = 0, res = 0, sampling = 0;  // 0 none, 1 down (2x2 s2 conv), 2 up (1x1 conv + PixelShuffle)
@@ -219,6 +223,7 @@ struct CrW {
   float *pooled = nullptr, *sca_s = nullptr, *loc1 = nullptr, *loc2 = nullptr, *theta = nullptr, *stage = nullptr;
   bf16* a3 = nullptr;  // split-precision A operand [rows][3K]
   bool use_tc = true;
+  std::unordered_map<const float*, std::pair<bf16*, bf16*>> split_hl;  // fp32 weight -> bf16 hi / lo for gemm_mma3
 };
 
 struct HcaW {
@@ -371,6 +376,22 @@ void launch_simt(const GemmDesc& d, cudaStream_t st) {
   else if (!abf && !wbf && obf) launch_simt_typed<float, float, bf16>(d, st);
   else launch_simt_typed<float, float, float>(d, st);  // unreachable by construction (checked in add_gemm)
 }
+
+// split-precision mma.sync GEMM for the shallow CoarseRestoration stages (gemm_mma3.cuh)
+template <int BN>
+void launch_mma3_bn(const mma3::Args& a, int epi, cudaStream_t st) {
+  const dim3 grid(static_cast<unsigned>((a.M + mma3::BM - 1) / mma3::BM), static_cast<unsigned>(a.N / BN));
+  if (epi == EPI_BIAS) launch_k(mma3::gemm_mma3_kernel<BN, EPI_BIAS>, grid, dim3(256), 0, st, a);
+  else if (epi == EPI_RESID) launch_k(mma3::gemm_mma3_kernel<BN, EPI_RESID>, grid, dim3(256), 0, st, a);
+  else launch_k(mma3::gemm_mma3_kernel<BN, EPI_PIXSHUF>, grid, dim3(256), 0, st, a);
+}
+
+void launch_mma3(const mma3::Args& a, int epi, cudaStream_t st) {
+  if (a.N % 128 == 0) launch_mma3_bn<128>(a, epi, st);
+  else if (a.N % 64 == 0) launch_mma3_bn<64>(a, epi, st);
+  else launch_mma3_bn<32>(a, epi, st);
+}
+
 
 struct TcLaunch {
   CUtensorMap mapA, mapB;
@@ -1862,33 +1883,36 @@ void load_cr_stn(hd_handle* h, CrStnW& s, const std::string& p, int c, int res) 
   s.hid = static_cast<int>(std::sqrt(static_cast<double>(s.fc)));
   if (s.hid > 96) HD_THROW(HD_ERR_UNSUPPORTED, "STN regressor width %d", s.hid);
   s.w1 = cr_conv_ohwi(h, p + "localization.0.weight", 8, c, s.k1);
-  if (c <= 64 && c % 16 == 0 && h->bf16 && h->tun.cr_tc) {
-    // [tap * c/16 + chunk][n = 8][16 k] bf16 hi + lo for edge::stn_conv_mma_kernel
+  if ((c == 32 || c % 64 == 0) && h->bf16 && h->tun.cr_tc) {
+    // edge::stn_conv_mma_kernel's order: [pass][tap][chunk] k-steps of 512 bytes, each {hi, lo} x {k 0-7, k 8-15} 8x8
+    // matrices [n = 8][8 k]
     auto w = host_vec(h, need(h, p + "localization.0.weight", {8, c, s.k1 * s.k1}));  // [o][i][tap]
-    const int cch = c / 16, taps = s.k1 * s.k1;
-    std::vector<uint16_t> vh(static_cast<size_t>(taps) * cch * 128), vl(vh.size());
+    const int ch = c == 32 ? 32 : 64, cch = ch / 16, taps = s.k1 * s.k1;
+    std::vector<uint16_t> v(static_cast<size_t>(c / 16) * taps * 256);
     auto to_bf16 = [](float f) {
       uint32_t u;
       memcpy(&u, &f, 4);
       u += 0x7FFFu + ((u >> 16) & 1u);
       return static_cast<uint16_t>(u >> 16);
     };
-    for (int tap = 0; tap < taps; ++tap)
-      for (int cc = 0; cc < cch; ++cc)
-        for (int o = 0; o < 8; ++o)
-          for (int kk = 0; kk < 16; ++kk) {
-            const float f = w[(static_cast<size_t>(o) * c + cc * 16 + kk) * taps + tap];
-            const size_t idx = ((static_cast<size_t>(tap) * cch + cc) * 8 + o) * 16 + kk;
-            vh[idx] = to_bf16(f);
-            const uint32_t hb = static_cast<uint32_t>(vh[idx]) << 16;
-            float hf;
-            memcpy(&hf, &hb, 4);
-            vl[idx] = to_bf16(f - hf);
-          }
-    s.w1_mma_hi = static_cast<hd::bf16*>(h->arena.alloc(vh.size() * 2));
-    s.w1_mma_lo = static_cast<hd::bf16*>(h->arena.alloc(vl.size() * 2));
-    CUDA_CHECK(cudaMemcpy(s.w1_mma_hi, vh.data(), vh.size() * 2, cudaMemcpyHostToDevice));
-    CUDA_CHECK(cudaMemcpy(s.w1_mma_lo, vl.data(), vl.size() * 2, cudaMemcpyHostToDevice));
+    for (int pass = 0; pass < c / ch; ++pass)
+      for (int tap = 0; tap < taps; ++tap)
+        for (int cc = 0; cc < cch; ++cc) {
+          uint16_t* blk = v.data() + ((static_cast<size_t>(pass) * taps + tap) * cch + cc) * 256;
+          for (int o = 0; o < 8; ++o)
+            for (int kk = 0; kk < 16; ++kk) {
+              const float f = w[(static_cast<size_t>(o) * c + pass * ch + cc * 16 + kk) * taps + tap];
+              const uint16_t hi = to_bf16(f);
+              const uint32_t hb = static_cast<uint32_t>(hi) << 16;
+              float hf;
+              memcpy(&hf, &hb, 4);
+              const int at = (kk >> 3) * 64 + o * 8 + (kk & 7);
+              blk[at] = hi;
+              blk[128 + at] = to_bf16(f - hf);
+            }
+        }
+    s.w1_mma = static_cast<hd::bf16*>(h->arena.alloc(v.size() * 2));
+    CUDA_CHECK(cudaMemcpy(s.w1_mma, v.data(), v.size() * 2, cudaMemcpyHostToDevice));
   }
   s.b1 = cr_vec(h, p + "localization.0.bias", 8);
   s.w2 = cr_conv_ohwi(h, p + "localization.3.weight", 10, 8, s.k2);
@@ -1984,6 +2008,25 @@ Plan* get_cr_plan(hd_handle* h, int B) {
     GemmDesc d;
     d.M = M; d.N = N; d.K = K; d.A = A; d.lda = lda; d.a_dtype = DT_F32; d.W = W; d.ldw = K; d.w_dtype = DT_F32;
     d.bias = bias; d.epi = epi; d.out = out; d.ldo = ldo; d.out_dtype = DT_F32; d.resid = resid; d.ldr = ldo; d.sp = sp;
+    if (R.use_tc && h->tun.cr_mma3 && lda % 4 == 0 && ldo % 2 == 0 && mma3::eligible(M, N, K, epi)) {
+      // shallow stages: FFMA-bound on CUDA cores, memory-bound on mma.sync with split operands
+      auto& cache = h->cr.split_hl;
+      auto it = cache.find(W);
+      if (it == cache.end()) {
+        const size_t nw = static_cast<size_t>(N) * K;
+        bf16 *hi = h->arena.get<bf16>(nw), *lo = h->arena.get<bf16>(nw);
+        mma3::split_hl_kernel<<<cdiv(nw, static_cast<size_t>(256)), 256, 0, h->stream>>>(W, hi, lo, nw);
+        CUDA_CHECK(cudaGetLastError());
+        it = cache.emplace(W, std::make_pair(hi, lo)).first;
+      }
+      mma3::Args a;
+      a.A = A; a.w_hi = it->second.first; a.w_lo = it->second.second; a.bias = bias; a.out = out; a.resid = resid;
+      a.lda = lda; a.ldo = ldo; a.ldr = ldo; a.M = M; a.N = N; a.K = K; a.sp = sp;
+      g_label = label + fmt(" gemm_mma3 M=%d N=%d K=%d (3 x bf16 split)", M, N, K);
+      add_op(P, [a, epi](cudaStream_t st) { launch_mma3(a, epi, st); });
+      P.flops_per_face += 2.0 * M * static_cast<double>(N) * K / P.batch;
+      return;
+    }
     g_label = label + fmt(" gemm_ffma M=%d N=%d K=%d", M, N, K);
     add_op(P, [d](cudaStream_t st) { launch_simt(d, st); });
     P.flops_per_face += 2.0 * M * static_cast<double>(N) * K / P.batch;
@@ -2047,21 +2090,21 @@ Plan* get_cr_plan(hd_handle* h, int B) {
     float *loc1 = R.loc1, *loc2 = R.loc2, *theta = R.theta;
     const float *w1 = s.w1, *b1 = s.b1, *w2 = s.w2, *b2 = s.b2, *f1 = s.f1, *fb1 = s.fb1, *f2 = s.f2, *fb2 = s.fb2;
     const int k1 = s.k1, k2 = s.k2, n1 = s.n1, n2 = s.n2, fc = s.fc, hid = s.hid;
-    const bf16 *w1h = s.w1_mma_hi, *w1l = s.w1_mma_lo;
-    if (R.use_tc && w1h != nullptr && (c == 32 || c == 64)) {
-      // the two large-image levels: implicit GEMM on mma.sync with split-precision operands (edge_convs.cuh)
-      const int conv_n = n - k1 + 1, tiles = cdiv(conv_n, 16), pw = 16 + k1 - 1;
-      const size_t smem = static_cast<size_t>(2) * pw * pw * (c * 2 + 16);
+    const bf16* w1m = s.w1_mma;
+    if (R.use_tc && w1m != nullptr) {
+      // implicit GEMM on mma.sync with split-precision operands (edge_convs.cuh)
+      const int conv_n = n - k1 + 1, tiles = cdiv(conv_n, 16), ch = c == 32 ? 32 : 64;
+      const size_t smem = edge::stn_conv_smem(ch, k1);
       static bool configured = false;
       if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(edge::stn_conv_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 24 * 24 * (32 * 2 + 16)));
-        CUDA_CHECK(cudaFuncSetAttribute(edge::stn_conv_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 24 * 24 * (64 * 2 + 16)));
+        CUDA_CHECK(cudaFuncSetAttribute(edge::stn_conv_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(edge::stn_conv_smem(32, 9))));
+        CUDA_CHECK(cudaFuncSetAttribute(edge::stn_conv_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(edge::stn_conv_smem(64, 9))));
         configured = true;
       }
       g_label = L0 + fmt("stn conv%dx%d+pool+relu mma.sync (3 x bf16 split)", k1, k1);
       add_op(P, [=](cudaStream_t st) {
-        if (c == 32) launch_k(edge::stn_conv_mma_kernel<32>, dim3(tiles, tiles, B), dim3(256), smem, st, x, w1h, w1l, b1, loc1, n, k1, n1);
-        else launch_k(edge::stn_conv_mma_kernel<64>, dim3(tiles, tiles, B), dim3(256), smem, st, x, w1h, w1l, b1, loc1, n, k1, n1);
+        if (ch == 32) launch_k(edge::stn_conv_mma_kernel<32>, dim3(tiles, tiles, B), dim3(256), smem, st, x, w1m, b1, loc1, n, c, k1, n1);
+        else launch_k(edge::stn_conv_mma_kernel<64>, dim3(tiles, tiles, B), dim3(256), smem, st, x, w1m, b1, loc1, n, c, k1, n1);
       });
     } else {
     g_label = L0 + fmt("stn conv%dx%d+pool+relu", k1, k1);
