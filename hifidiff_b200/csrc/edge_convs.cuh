@@ -17,6 +17,8 @@
 // (gemm_tc.cuh, face_block.cuh, pair_block.cuh) are tcgen05.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "elem_kernels.cuh"
 
@@ -288,10 +290,16 @@ __global__ void __launch_bounds__(256, 2) intro_mma_kernel(const float* __restri
 //   (256, 16, 5) (512, 8, 3)
 // as an implicit GEMM on mma.sync.m16n8k16 — N = 8 IS the layer's channel count.  One CTA = a 16x16 tile of conv
 // outputs (8x8 pooled) of one face.  Channels go through in passes of CH: the (16+k-1)^2 input patch of the pass is
-// staged in shared memory as bf16 hi + lo (fp32 input, three products: fp32-grade), pixel stride padded by 16 bytes so
-// the ldmatrix rows are conflict-free; warp w owns conv rows 2w, 2w+1, so the 2x2 max-pool is an in-register max plus
-// one shuffle.  Weights (hi + lo, one 512-byte block of four 8x8 B matrices per k-step, rows ordered
-// [pass][ky][kx][chunk]) stream through a two-deep cp.async ring, one filter row ahead of the MMAs.
+// staged in shared memory as fp16 hi + lo, pixel stride padded by 16 bytes so the ldmatrix rows are conflict-free;
+// warp w owns conv rows 2w, 2w+1, so the 2x2 max-pool is an in-register max plus one shuffle.  Weights (hi + lo, one
+// 512-byte block of four 8x8 B matrices per k-step, rows ordered [pass][ky][kx][chunk]) stream through a two-deep
+// cp.async ring, one filter row ahead of the MMAs.
+// Precision: the affine parameters regressed from this conv steer a bilinear resampling of the whole feature map, so
+// the operands keep 22 mantissa bits: x * s = hi + lo in fp16 (11 + 11 bits) with s the power of two that brings the
+// CTA's patch maximum into [2^14, 2^15) (so fp16's narrow exponent range never clips: anything lost to underflow is
+// below 2^-39 of the patch maximum), weights likewise with a per-layer scale at load; a_hi w_hi + a_lo w_hi +
+// a_hi w_lo accumulated in fp32 and unscaled once in the epilogue.  (A bf16 split, 16 bits, cost 9e-4 of the
+// network's output error against the reference; this one does not show next to the FFMA kernels' 3e-5.)
 // in [B, n, n, Cin] fp32 NHWC -> out [B, no, no, 8] fp32.
 // dynamic smem: 2 * (16+k-1)^2 * (CH*2 + 16) + 2 * k * (CH/16) * 512 bytes.
 // (Was cr_stn_conv_pool_cs_kernel on CUDA cores, latency-bound at 270-470 us per launch: 30 % of the CR pass.)
@@ -307,10 +315,20 @@ inline size_t stn_conv_smem(int ch, int k) {
   return static_cast<size_t>(2) * pw * pw * (ch * 2 + 16) + static_cast<size_t>(2) * k * (ch / 16) * 512;
 }
 
+__device__ __forceinline__ void mma_16816_f16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 template <int CH>
-__global__ void __launch_bounds__(256) stn_conv_mma_kernel(const float* __restrict__ in, const bf16* __restrict__ w,
+__global__ void __launch_bounds__(256) stn_conv_mma_kernel(const float* __restrict__ in, const __half* __restrict__ w,
                                                            const float* __restrict__ bias, float* __restrict__ out,
-                                                           int n, int cin, int k, int no) {
+                                                           int n, int cin, int k, int no, float w_unscale) {
   extern __shared__ __align__(128) uint8_t s_raw[];
   constexpr int PSTRIDE = CH * 2 + 16;        // bytes per staged pixel
   constexpr int CCH = CH / 16;                // k-steps per tap and pass
@@ -333,11 +351,34 @@ __global__ void __launch_bounds__(256) stn_conv_mma_kernel(const float* __restri
   pdl_trigger();
   load_row(0);                                // constants: before the dependency wait
   pdl_wait();
+  const int vh = min(pw, n - ty0), vw = min(pw, n - tx0);   // the part of the patch that lies inside the image
+  const float* src_face = in + static_cast<size_t>(face) * n * n * cin;
+  float a_scale;
+  {  // power-of-two scale of this CTA's patch (all channels): max |x| * s in [2^14, 2^15)
+    __shared__ float s_max[8];
+    const int v4 = cin / 4;
+    float mx = 0.f;
+#pragma unroll 4
+    for (int i = tid; i < vh * vw * v4; i += 256) {
+      const int pix = i / v4, v = i - pix * v4;
+      const int py = pix / vw, px = pix - py * vw;
+      const float4 f = *reinterpret_cast<const float4*>(src_face + (static_cast<size_t>(ty0 + py) * n + tx0 + px) * cin + v * 4);
+      mx = fmaxf(fmaxf(mx, fmaxf(fabsf(f.x), fabsf(f.y))), fmaxf(fabsf(f.z), fabsf(f.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_max[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(fmaxf(s_max[0], s_max[1]), fmaxf(s_max[2], s_max[3])), fmaxf(fmaxf(s_max[4], s_max[5]), fmaxf(s_max[6], s_max[7])));
+    a_scale = mx > 0.f ? ldexpf(1.f, 14 - ilogbf(mx)) : 1.f;
+  }
   const bool active = ty0 + 2 * warp < n - k + 1;   // warps whose conv rows exist
-  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  // The tensor core truncates when it adds into the fp32 accumulator; over the 3 * k * k * Cin / 16 MMAs of one
+  // output that bias reaches 1e-5.  Each filter row is therefore summed from zero and added to the total with
+  // round-to-nearest FADDs.
+  float tot[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   const int lx = lane & 15, khalf = lane >> 4;
   const uint32_t b_lane = (lane >> 3) * 128 + (lane & 7) * 16;
-  const float* src_face = in + static_cast<size_t>(face) * n * n * cin;
 #pragma unroll 1
   for (int r = 0; r < n_rows; ++r) {
     const int pass = r / k, ky = r - pass * k;
@@ -346,24 +387,24 @@ __global__ void __launch_bounds__(256) stn_conv_mma_kernel(const float* __restri
       // stage this pass's patch; pixels beyond the image only feed conv outputs that are never stored
       constexpr int V = CH / 4;               // float4 per pixel
       const float* src = src_face + pass * CH;
-      for (int i = tid; i < pw * pw * V; i += 256) {
+#pragma unroll 4
+      for (int i = tid; i < vh * vw * V; i += 256) {
         const int pix = i / V, v = i - pix * V;
-        const int py = pix / pw, px = pix - py * pw;
-        const int gy = ty0 + py, gx = tx0 + px;
-        if (gy < n && gx < n) {
-          const float4 f = *reinterpret_cast<const float4*>(src + (static_cast<size_t>(gy) * n + gx) * cin + v * 4);
-          const float r0 = __bfloat162float(__float2bfloat16_rn(f.x)), r1 = __bfloat162float(__float2bfloat16_rn(f.y));
-          const float r2 = __bfloat162float(__float2bfloat16_rn(f.z)), r3 = __bfloat162float(__float2bfloat16_rn(f.w));
-          const uint32_t off = static_cast<uint32_t>(pix) * PSTRIDE + v * 8;
-          *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(pack_bf16x2(f.x, f.y), pack_bf16x2(f.z, f.w));
-          *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(pack_bf16x2(f.x - r0, f.y - r1), pack_bf16x2(f.z - r2, f.w - r3));
-        }
+        const int py = pix / vw, px = pix - py * vw;
+        float4 f = *reinterpret_cast<const float4*>(src + (static_cast<size_t>(ty0 + py) * n + tx0 + px) * cin + v * 4);
+        f.x *= a_scale; f.y *= a_scale; f.z *= a_scale; f.w *= a_scale;
+        const float r0 = __half2float(__float2half_rn(f.x)), r1 = __half2float(__float2half_rn(f.y));
+        const float r2 = __half2float(__float2half_rn(f.z)), r3 = __half2float(__float2half_rn(f.w));
+        const uint32_t off = static_cast<uint32_t>(py * pw + px) * PSTRIDE + v * 8;
+        *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(pack_half2(f.x, f.y), pack_half2(f.z, f.w));
+        *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(pack_half2(f.x - r0, f.y - r1), pack_half2(f.z - r2, f.w - r3));
       }
     }
     cp_async_wait_all();
     __syncthreads();                          // row r (and the patch) visible; everyone is done with row r-1
     if (r + 1 < n_rows) load_row(r + 1);
     if (active) {
+      float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       const uint32_t wrow = w_u32 + (r & 1) * row_bytes + b_lane;
       const uint32_t p0 = static_cast<uint32_t>((2 * warp + ky) * pw + lx) * PSTRIDE + khalf * 16;
 #pragma unroll 1
@@ -378,20 +419,23 @@ __global__ void __launch_bounds__(256) stn_conv_mma_kernel(const float* __restri
           ldmatrix_x4(hi_u32 + q1 + cc * 32, ah1);
           ldmatrix_x4(lo_u32 + q1 + cc * 32, al1);
           const uint32_t bh[2] = {b[0], b[1]}, bl[2] = {b[2], b[3]};
-          mma_16816(acc[0], ah0, bh); mma_16816(acc[1], ah1, bh);
-          mma_16816(acc[0], al0, bh); mma_16816(acc[1], al1, bh);
-          mma_16816(acc[0], ah0, bl); mma_16816(acc[1], ah1, bl);
+          mma_16816_f16(acc[0], ah0, bh); mma_16816_f16(acc[1], ah1, bh);
+          mma_16816_f16(acc[0], al0, bh); mma_16816_f16(acc[1], al1, bh);
+          mma_16816_f16(acc[0], ah0, bl); mma_16816_f16(acc[1], ah1, bl);
         }
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { tot[0][i] += acc[0][i]; tot[1][i] += acc[1][i]; }
     }
   }
   // 2x2 max-pool: vertical = the two conv rows of this warp; horizontal = pixel g with pixel g ^ 1 (lane ^ 4)
   const int g = lane >> 2, q = lane & 3;
   float m[4];
+  const float unscale = w_unscale / a_scale;   // powers of two: exact
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float v = fmaxf(acc[0][i], acc[1][i]);
-    m[i] = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+    const float v = fmaxf(tot[0][i], tot[1][i]);
+    m[i] = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4)) * unscale;
   }
   if ((g & 1) == 0) {
     const int oy = (ty0 >> 1) + warp;

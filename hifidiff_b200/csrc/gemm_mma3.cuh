@@ -3,14 +3,16 @@
 //   out[M, N] = epilogue(A[M, K] W[N, K]^T),   M = faces x pixels (10^5 .. 10^6 rows), K = 32 .. 512, N = 32 .. 1024
 // These are HBM-bound by shape (a few hundred flops per row against 128 .. 768 bytes of fp32 traffic), but on CUDA
 // cores the FFMA issue rate was the limit (18 TFLOP/s, 4-8x off the memory floor).  Here the arithmetic is
-// mma.sync.m16n8k16 with split operands — A and W as bf16 hi + lo, a_hi w_hi + a_lo w_hi + a_hi w_lo accumulated in
-// fp32 (everything but the lo x lo term: ~2^-16 relative, the same contract as the split tcgen05 GEMM of the deeper
-// stages) — so that the kernel waits on memory, not on the FMA pipe.  K is too small here for a TMA / tcgen05
-// pipeline to amortise its set-up, and A needs the fp32 -> hi / lo conversion on the way into shared memory anyway.
+// mma.sync.m16n8k8 on TF32 with split operands ("3xTF32") — A and W as tf32 hi + lo (11 + 11 mantissa bits),
+// a_hi w_hi + a_lo w_hi + a_hi w_lo accumulated in fp32: everything but the lo x lo term, ~2^-21 relative, and the
+// fp32 exponent range — so that the kernel waits on memory, not on the FMA pipe, and the nine data-dependent
+// resamplings downstream see fp32-grade features (a bf16 split, 2^-17, cost 8e-4 of the network's output error).
+// K is too small here for a TMA / tcgen05 pipeline to amortise its set-up, and A needs the fp32 -> hi / lo
+// conversion on the way into shared memory anyway.
 //
 // CTA = 256 threads = 8 warps, tile 128 rows x BN columns, warp w owns rows 16w .. 16w+15 and all BN columns.
 // K goes through in chunks of 32: global -> registers (the next chunk's loads are in flight during the MMAs) ->
-// hi / lo split -> shared memory rows of 64 + 16 bytes (conflict-free ldmatrix).
+// hi / lo split -> shared memory rows of 128 + 16 bytes (conflict-free ldmatrix; a 32-bit element is a b16 pair).
 #pragma once
 
 #include "common.cuh"
@@ -21,8 +23,8 @@ namespace mma3 {
 
 struct Args {
   const float* A;      // [M, lda] fp32
-  const bf16* w_hi;    // [N, K]
-  const bf16* w_lo;    // [N, K]
+  const float* w_hi;   // [N, K] tf32
+  const float* w_lo;   // [N, K] tf32
   const float* bias;   // [N] or nullptr
   float* out;          // [M, ldo] fp32 (EPI_PIXSHUF: the up-sampled skip buffer, accumulated in place)
   const float* resid;  // EPI_RESID: [M, ldr]
@@ -31,37 +33,46 @@ struct Args {
   int sp;              // EPI_PIXSHUF: spatial size of the GEMM rows
 };
 
-constexpr int BM = 128, KC = 32, ROWB = KC * 2 + 16;
+constexpr int BM = 128, KC = 32, ROWB = KC * 4 + 16;
 
-// W fp32 [N, K] -> hi, lo bf16 [N, K] (once, at load)
-__global__ void split_hl_kernel(const float* __restrict__ w, bf16* __restrict__ hi, bf16* __restrict__ lo, size_t n) {
+__device__ __forceinline__ float to_tf32(float f) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(f));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ void mma_1688_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// W fp32 [N, K] -> hi, lo tf32 [N, K] (once, at load)
+__global__ void split_hl_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float f = w[i];
-  const bf16 h = __float2bfloat16_rn(f);
+  const float f = w[i], h = to_tf32(f);
   hi[i] = h;
-  lo[i] = __float2bfloat16_rn(f - __bfloat162float(h));
+  lo[i] = to_tf32(f - h);
 }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(256, 2) gemm_mma3_kernel(const Args g) {
   constexpr int NT = BN / 8;
-  __shared__ __align__(128) uint8_t s_a[2][BM * ROWB];   // hi, lo
-  __shared__ __align__(128) uint8_t s_w[2][BN * ROWB];
+  extern __shared__ __align__(128) uint8_t s_raw[];
+  uint8_t* s_a[2] = {s_raw, s_raw + BM * ROWB};                                  // hi, lo
+  uint8_t* s_w[2] = {s_raw + 2 * BM * ROWB, s_raw + 2 * BM * ROWB + BN * ROWB};
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  constexpr int WJ = (BN * 4 + 255) / 256;     // 16-byte weight chunks per thread and matrix
+  constexpr int WJ = BN * 8 / 256;             // 16-byte weight chunks per thread and matrix
   float4 areg[4];
   uint4 whreg[WJ], wlreg[WJ];
   auto load_w = [&](int k0) {
 #pragma unroll
     for (int j = 0; j < WJ; ++j) {
       const int i = tid + 256 * j;
-      if (i < BN * 4) {
-        const size_t off = static_cast<size_t>(n0 + (i >> 2)) * g.K + k0 + (i & 3) * 8;
-        whreg[j] = __ldg(reinterpret_cast<const uint4*>(g.w_hi + off));
-        wlreg[j] = __ldg(reinterpret_cast<const uint4*>(g.w_lo + off));
-      }
+      const size_t off = static_cast<size_t>(n0 + (i >> 3)) * g.K + k0 + (i & 7) * 4;
+      whreg[j] = __ldg(reinterpret_cast<const uint4*>(g.w_hi + off));
+      wlreg[j] = __ldg(reinterpret_cast<const uint4*>(g.w_lo + off));
     }
   };
   auto load_a = [&](int k0) {
@@ -77,20 +88,17 @@ __global__ void __launch_bounds__(256, 2) gemm_mma3_kernel(const Args g) {
     for (int j = 0; j < 4; ++j) {
       const int i = tid + 256 * j;
       const float4 f = areg[j];
-      const float r0 = __bfloat162float(__float2bfloat16_rn(f.x)), r1 = __bfloat162float(__float2bfloat16_rn(f.y));
-      const float r2 = __bfloat162float(__float2bfloat16_rn(f.z)), r3 = __bfloat162float(__float2bfloat16_rn(f.w));
-      const uint32_t off = (i >> 3) * ROWB + (i & 7) * 8;
-      *reinterpret_cast<uint2*>(s_a[0] + off) = make_uint2(pack_bf16x2(f.x, f.y), pack_bf16x2(f.z, f.w));
-      *reinterpret_cast<uint2*>(s_a[1] + off) = make_uint2(pack_bf16x2(f.x - r0, f.y - r1), pack_bf16x2(f.z - r2, f.w - r3));
+      const float4 hi = make_float4(to_tf32(f.x), to_tf32(f.y), to_tf32(f.z), to_tf32(f.w));
+      const uint32_t off = (i >> 3) * ROWB + (i & 7) * 16;
+      *reinterpret_cast<float4*>(s_a[0] + off) = hi;
+      *reinterpret_cast<float4*>(s_a[1] + off) = make_float4(to_tf32(f.x - hi.x), to_tf32(f.y - hi.y), to_tf32(f.z - hi.z), to_tf32(f.w - hi.w));
     }
 #pragma unroll
     for (int j = 0; j < WJ; ++j) {
       const int i = tid + 256 * j;
-      if (i < BN * 4) {
-        const uint32_t off = (i >> 2) * ROWB + (i & 3) * 16;
-        *reinterpret_cast<uint4*>(s_w[0] + off) = whreg[j];
-        *reinterpret_cast<uint4*>(s_w[1] + off) = wlreg[j];
-      }
+      const uint32_t off = (i >> 3) * ROWB + (i & 7) * 16;
+      *reinterpret_cast<uint4*>(s_w[0] + off) = whreg[j];
+      *reinterpret_cast<uint4*>(s_w[1] + off) = wlreg[j];
     }
   };
   pdl_trigger();
@@ -111,7 +119,7 @@ __global__ void __launch_bounds__(256, 2) gemm_mma3_kernel(const Args g) {
     __syncthreads();
     if (k0 + KC < g.K) { load_w(k0 + KC); load_a(k0 + KC); }
 #pragma unroll
-    for (int s = 0; s < KC / 16; ++s) {
+    for (int s = 0; s < KC / 8; ++s) {
       uint32_t ah[4], al[4];
       edge::ldmatrix_x4(ah_u32 + s * 32, ah);
       edge::ldmatrix_x4(al_u32 + s * 32, al);
@@ -121,9 +129,9 @@ __global__ void __launch_bounds__(256, 2) gemm_mma3_kernel(const Args g) {
         edge::ldmatrix_x4(wh_u32 + jp * 16 * ROWB + s * 32, bh);   // n-tiles 2jp (bh[0..1]) and 2jp+1 (bh[2..3])
         edge::ldmatrix_x4(wl_u32 + jp * 16 * ROWB + s * 32, bl);
         const uint32_t bh0[2] = {bh[0], bh[1]}, bh1[2] = {bh[2], bh[3]}, bl0[2] = {bl[0], bl[1]}, bl1[2] = {bl[2], bl[3]};
-        edge::mma_16816(acc[2 * jp], ah, bh0);     edge::mma_16816(acc[2 * jp + 1], ah, bh1);
-        edge::mma_16816(acc[2 * jp], al, bh0);     edge::mma_16816(acc[2 * jp + 1], al, bh1);
-        edge::mma_16816(acc[2 * jp], ah, bl0);     edge::mma_16816(acc[2 * jp + 1], ah, bl1);
+        mma_1688_tf32(acc[2 * jp], ah, bh0);     mma_1688_tf32(acc[2 * jp + 1], ah, bh1);
+        mma_1688_tf32(acc[2 * jp], al, bh0);     mma_1688_tf32(acc[2 * jp + 1], al, bh1);
+        mma_1688_tf32(acc[2 * jp], ah, bl0);     mma_1688_tf32(acc[2 * jp + 1], ah, bl1);
       }
     }
   }
@@ -170,6 +178,8 @@ __global__ void __launch_bounds__(256, 2) gemm_mma3_kernel(const Args g) {
     }
   }
 }
+
+template <int BN> constexpr int smem_bytes() { return 2 * (BM + BN) * ROWB; }
 
 inline bool eligible(int M, int N, int K, int epi) {
   return M >= 1024 && K % KC == 0 && N % 32 == 0 && (epi == EPI_BIAS || epi == EPI_RESID || (epi == EPI_PIXSHUF && (N / 4) % 2 == 0));

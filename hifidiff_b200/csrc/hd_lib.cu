@@ -76,16 +76,19 @@ struct Tunables {
   bool cr_stn_cs = true;  // HD_CR_STN_CS=0: one thread per (pixel, 2 output channels) in the first STN localisation conv
   bool cr_tc = true;      // HD_CR_TC=0: every CoarseRestoration GEMM on the FFMA kernel (no split-precision tcgen05 path)
   bool cr_mma3 = true;    // HD_CR_MMA3=0: the shallow CoarseRestoration stages (c = 32 / 64, down / up convs) stay on the FFMA GEMM
+  bool cr_stn_mma = true; // HD_CR_STN_MMA=0: the first STN localisation conv stays on CUDA cores
   bool dw_small = true;   // HD_DW_SMALL=0: the generic tiled depthwise kernel at the 2x2 / 4x4 levels too
   int cta_target = 120;   // HD_CTA_TARGET: split-K until a GEMM's grid has at least this many CTAs
   int sca_target = 120;   // HD_SCA_TARGET: the same for the SCA GEMMs (M = faces)
+  int cr_chunk = 128;     // HD_CR_CHUNK: faces per CoarseRestoration pass (~14 MB of fp32 workspace per face; 32: 66 ms, 64: 53 ms, 128: 48 ms, 256: 46 ms per 256 faces)
   void read_env() {
     auto flag = [](const char* name, bool& v) { if (const char* e = getenv(name)) v = atoi(e) != 0; };
     flag("HD_PDL", pdl); flag("HD_BN256", bn256); flag("HD_FACE", face); flag("HD_PAIR", pair); flag("HD_SCA_MUL", sca_mul); flag("HD_EDGE_MMA", edge_mma); flag("HD_W_PREFETCH", w_prefetch);
-    flag("HD_CR_STN_CS", cr_stn_cs); flag("HD_CR_TC", cr_tc); flag("HD_CR_MMA3", cr_mma3); flag("HD_DW_SMALL", dw_small);
+    flag("HD_CR_STN_CS", cr_stn_cs); flag("HD_CR_TC", cr_tc); flag("HD_CR_MMA3", cr_mma3); flag("HD_CR_STN_MMA", cr_stn_mma); flag("HD_DW_SMALL", dw_small);
     if (const char* e = getenv("HD_TWO_CTA")) two_cta = atoi(e);
     if (const char* e = getenv("HD_CTA_TARGET")) cta_target = std::max(atoi(e), 1);
     if (const char* e = getenv("HD_SCA_TARGET")) sca_target = std::max(atoi(e), 1);
+    if (const char* e = getenv("HD_CR_CHUNK")) cr_chunk = std::min(std::max(atoi(e), 1), 256);
   }
 };
 // PDL attribute of the launches issued by the calling thread: set from the handle's Tunables by every entry point
@@ -205,7 +208,8 @@ struct CrStnW {
   int k1 = 0, k2 = 0, n1 = 0, n2 = 0, fc = 0, hid = 0;
   float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;      // localisation convs, [Cout][k][k][Cin]
   float *f1 = nullptr, *fb1 = nullptr, *f2 = nullptr, *fb2 = nullptr;    // regressor, f1 columns in NHWC order
-  hd::bf16* w1_mma = nullptr;                                            // first conv as bf16 hi + lo 8x8 B matrices for edge::stn_conv_mma_kernel
+  __half* w1_mma = nullptr;                                              // first conv as scaled fp16 hi + lo 8x8 B matrices for edge::stn_conv_mma_kernel
+  float w1_unscale = 1.f;                                                // 2^-e of that scale
 };
 struct CrStageW {
   int c = 0, res = 0, sampling = 0;  // 0 none, 1 down (2x2 s2 conv), 2 up (1x1 conv + PixelShuffle)
@@ -223,7 +227,7 @@ struct CrW {
   float *pooled = nullptr, *sca_s = nullptr, *loc1 = nullptr, *loc2 = nullptr, *theta = nullptr, *stage = nullptr;
   bf16* a3 = nullptr;  // split-precision A operand [rows][3K]
   bool use_tc = true;
-  std::unordered_map<const float*, std::pair<bf16*, bf16*>> split_hl;  // fp32 weight -> bf16 hi / lo for gemm_mma3
+  std::unordered_map<const float*, std::pair<float*, float*>> split_hl;  // fp32 weight -> tf32 hi / lo for gemm_mma3
 };
 
 struct HcaW {
@@ -381,9 +385,17 @@ void launch_simt(const GemmDesc& d, cudaStream_t st) {
 template <int BN>
 void launch_mma3_bn(const mma3::Args& a, int epi, cudaStream_t st) {
   const dim3 grid(static_cast<unsigned>((a.M + mma3::BM - 1) / mma3::BM), static_cast<unsigned>(a.N / BN));
-  if (epi == EPI_BIAS) launch_k(mma3::gemm_mma3_kernel<BN, EPI_BIAS>, grid, dim3(256), 0, st, a);
-  else if (epi == EPI_RESID) launch_k(mma3::gemm_mma3_kernel<BN, EPI_RESID>, grid, dim3(256), 0, st, a);
-  else launch_k(mma3::gemm_mma3_kernel<BN, EPI_PIXSHUF>, grid, dim3(256), 0, st, a);
+  constexpr int smem = mma3::smem_bytes<BN>();
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(mma3::gemm_mma3_kernel<BN, EPI_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(mma3::gemm_mma3_kernel<BN, EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(mma3::gemm_mma3_kernel<BN, EPI_PIXSHUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  if (epi == EPI_BIAS) launch_k(mma3::gemm_mma3_kernel<BN, EPI_BIAS>, grid, dim3(256), smem, st, a);
+  else if (epi == EPI_RESID) launch_k(mma3::gemm_mma3_kernel<BN, EPI_RESID>, grid, dim3(256), smem, st, a);
+  else launch_k(mma3::gemm_mma3_kernel<BN, EPI_PIXSHUF>, grid, dim3(256), smem, st, a);
 }
 
 void launch_mma3(const mma3::Args& a, int epi, cudaStream_t st) {
@@ -1815,7 +1827,6 @@ Plan* get_idc_plan(hd_handle* h, int B) {
 // CoarseRestoration: NAFNet U-Net with a spatial transformer after every stage
 // (models/cr/model.py:8-88, models/cr/stn.py:9-52), once per face before the sampling loop, fp32 throughout.
 // ------------------------------------------------------------------------------------------------
-constexpr int kCrChunk = 32;  // faces per pass (~14 MB of fp32 workspace per face)
 constexpr int kCrC[5] = {32, 64, 128, 256, 512};
 constexpr int kCrRes[5] = {128, 64, 32, 16, 8};
 
@@ -1883,17 +1894,24 @@ void load_cr_stn(hd_handle* h, CrStnW& s, const std::string& p, int c, int res) 
   s.hid = static_cast<int>(std::sqrt(static_cast<double>(s.fc)));
   if (s.hid > 96) HD_THROW(HD_ERR_UNSUPPORTED, "STN regressor width %d", s.hid);
   s.w1 = cr_conv_ohwi(h, p + "localization.0.weight", 8, c, s.k1);
-  if ((c == 32 || c % 64 == 0) && h->bf16 && h->tun.cr_tc) {
+  if ((c == 32 || c % 64 == 0) && h->bf16 && h->tun.cr_tc && h->tun.cr_stn_mma) {
     // edge::stn_conv_mma_kernel's order: [pass][tap][chunk] k-steps of 512 bytes, each {hi, lo} x {k 0-7, k 8-15} 8x8
-    // matrices [n = 8][8 k]
+    // matrices [n = 8][8 k]; fp16 hi + lo of w * 2^e with max |w| * 2^e in [2^14, 2^15)
     auto w = host_vec(h, need(h, p + "localization.0.weight", {8, c, s.k1 * s.k1}));  // [o][i][tap]
     const int ch = c == 32 ? 32 : 64, cch = ch / 16, taps = s.k1 * s.k1;
+    float wmax = 0.f;
+    for (float f : w) wmax = std::max(wmax, std::fabs(f));
+    const float wscale = wmax > 0.f ? std::ldexp(1.f, 14 - std::ilogb(wmax)) : 1.f;
+    s.w1_unscale = 1.f / wscale;
     std::vector<uint16_t> v(static_cast<size_t>(c / 16) * taps * 256);
-    auto to_bf16 = [](float f) {
-      uint32_t u;
-      memcpy(&u, &f, 4);
-      u += 0x7FFFu + ((u >> 16) & 1u);
-      return static_cast<uint16_t>(u >> 16);
+    auto to_half = [](float f) {
+      const __half_raw r = static_cast<__half_raw>(__float2half_rn(f));
+      return r.x;
+    };
+    auto from_half = [](uint16_t x) {
+      __half_raw r;
+      r.x = x;
+      return __half2float(__half(r));
     };
     for (int pass = 0; pass < c / ch; ++pass)
       for (int tap = 0; tap < taps; ++tap)
@@ -1901,17 +1919,14 @@ void load_cr_stn(hd_handle* h, CrStnW& s, const std::string& p, int c, int res) 
           uint16_t* blk = v.data() + ((static_cast<size_t>(pass) * taps + tap) * cch + cc) * 256;
           for (int o = 0; o < 8; ++o)
             for (int kk = 0; kk < 16; ++kk) {
-              const float f = w[(static_cast<size_t>(o) * c + pass * ch + cc * 16 + kk) * taps + tap];
-              const uint16_t hi = to_bf16(f);
-              const uint32_t hb = static_cast<uint32_t>(hi) << 16;
-              float hf;
-              memcpy(&hf, &hb, 4);
+              const float f = w[(static_cast<size_t>(o) * c + pass * ch + cc * 16 + kk) * taps + tap] * wscale;
+              const uint16_t hi = to_half(f);
               const int at = (kk >> 3) * 64 + o * 8 + (kk & 7);
               blk[at] = hi;
-              blk[128 + at] = to_bf16(f - hf);
+              blk[128 + at] = to_half(f - from_half(hi));
             }
         }
-    s.w1_mma = static_cast<hd::bf16*>(h->arena.alloc(v.size() * 2));
+    s.w1_mma = static_cast<__half*>(h->arena.alloc(v.size() * 2));
     CUDA_CHECK(cudaMemcpy(s.w1_mma, v.data(), v.size() * 2, cudaMemcpyHostToDevice));
   }
   s.b1 = cr_vec(h, p + "localization.0.bias", 8);
@@ -1935,7 +1950,7 @@ void load_cr_impl(hd_handle* h) {
   CrW& R = h->cr;
   R.H = 8 * h->S;
   if (R.H != 128) HD_THROW(HD_ERR_UNSUPPORTED, "CoarseRestoration is built for 128x128 faces (latent size 16)");
-  R.cap = kCrChunk;
+  R.cap = h->tun.cr_chunk;
   {  // intro (32,3,3,3) -> [27][32]; outro (3,32,3,3) -> [3][9][32]
     auto w = host_vec(h, need(h, "intro.weight", {32, 27}));
     std::vector<float> t(27 * 32);
@@ -2014,7 +2029,7 @@ Plan* get_cr_plan(hd_handle* h, int B) {
       auto it = cache.find(W);
       if (it == cache.end()) {
         const size_t nw = static_cast<size_t>(N) * K;
-        bf16 *hi = h->arena.get<bf16>(nw), *lo = h->arena.get<bf16>(nw);
+        float *hi = h->arena.get<float>(nw), *lo = h->arena.get<float>(nw);
         mma3::split_hl_kernel<<<cdiv(nw, static_cast<size_t>(256)), 256, 0, h->stream>>>(W, hi, lo, nw);
         CUDA_CHECK(cudaGetLastError());
         it = cache.emplace(W, std::make_pair(hi, lo)).first;
@@ -2022,7 +2037,7 @@ Plan* get_cr_plan(hd_handle* h, int B) {
       mma3::Args a;
       a.A = A; a.w_hi = it->second.first; a.w_lo = it->second.second; a.bias = bias; a.out = out; a.resid = resid;
       a.lda = lda; a.ldo = ldo; a.ldr = ldo; a.M = M; a.N = N; a.K = K; a.sp = sp;
-      g_label = label + fmt(" gemm_mma3 M=%d N=%d K=%d (3 x bf16 split)", M, N, K);
+      g_label = label + fmt(" gemm_mma3 M=%d N=%d K=%d (3 x tf32 split)", M, N, K);
       add_op(P, [a, epi](cudaStream_t st) { launch_mma3(a, epi, st); });
       P.flops_per_face += 2.0 * M * static_cast<double>(N) * K / P.batch;
       return;
@@ -2090,7 +2105,8 @@ Plan* get_cr_plan(hd_handle* h, int B) {
     float *loc1 = R.loc1, *loc2 = R.loc2, *theta = R.theta;
     const float *w1 = s.w1, *b1 = s.b1, *w2 = s.w2, *b2 = s.b2, *f1 = s.f1, *fb1 = s.fb1, *f2 = s.f2, *fb2 = s.fb2;
     const int k1 = s.k1, k2 = s.k2, n1 = s.n1, n2 = s.n2, fc = s.fc, hid = s.hid;
-    const bf16* w1m = s.w1_mma;
+    const __half* w1m = s.w1_mma;
+    const float w1u = s.w1_unscale;
     if (R.use_tc && w1m != nullptr) {
       // implicit GEMM on mma.sync with split-precision operands (edge_convs.cuh)
       const int conv_n = n - k1 + 1, tiles = cdiv(conv_n, 16), ch = c == 32 ? 32 : 64;
@@ -2101,10 +2117,10 @@ Plan* get_cr_plan(hd_handle* h, int B) {
         CUDA_CHECK(cudaFuncSetAttribute(edge::stn_conv_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(edge::stn_conv_smem(64, 9))));
         configured = true;
       }
-      g_label = L0 + fmt("stn conv%dx%d+pool+relu mma.sync (3 x bf16 split)", k1, k1);
+      g_label = L0 + fmt("stn conv%dx%d+pool+relu mma.sync (3 x fp16 split, scaled)", k1, k1);
       add_op(P, [=](cudaStream_t st) {
-        if (ch == 32) launch_k(edge::stn_conv_mma_kernel<32>, dim3(tiles, tiles, B), dim3(256), smem, st, x, w1m, b1, loc1, n, c, k1, n1);
-        else launch_k(edge::stn_conv_mma_kernel<64>, dim3(tiles, tiles, B), dim3(256), smem, st, x, w1m, b1, loc1, n, c, k1, n1);
+        if (ch == 32) launch_k(edge::stn_conv_mma_kernel<32>, dim3(tiles, tiles, B), dim3(256), smem, st, x, w1m, b1, loc1, n, c, k1, n1, w1u);
+        else launch_k(edge::stn_conv_mma_kernel<64>, dim3(tiles, tiles, B), dim3(256), smem, st, x, w1m, b1, loc1, n, c, k1, n1, w1u);
       });
     } else {
     g_label = L0 + fmt("stn conv%dx%d+pool+relu", k1, k1);

@@ -79,7 +79,7 @@ class CoarseRestoration(nn.Module):
         self.decoders = nn.Sequential(_NAFSTNBlock(16 * w, 8, 2, "up"), _NAFSTNBlock(8 * w, 16, 2, "up"),
                                       _NAFSTNBlock(4 * w, 32, 2, "up"), _NAFSTNBlock(2 * w, 64, 2, "up"))
         self.native = True      # CUDA inputs run on the library's kernels (False: PyTorch ops)
-        self.tensor_cores = True  # 1x1 convs at c >= 128 as split-precision (3 x bf16) tcgen05 GEMMs; False: FFMA everywhere
+        self.tensor_cores = True  # 1x1 / down / up convs and the STN localisation conv as split-precision (3 x bf16) tensor-core GEMMs; False: FFMA everywhere
         self._engine = None
         self._engine_dev = None
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())

@@ -15,7 +15,7 @@ sd = testing.random_state({k: v.shape for k, v in s0.items()}, {k: v.dtype for k
 m = m.to_empty(device="cuda")
 m.load_state_dict(sd)
 m.eval()
-x = torch.rand(32, 3, 128, 128, device="cuda")
+x = torch.rand(int(sys.argv[1]) if len(sys.argv) > 1 else 32, 3, 128, 128, device="cuda")
 with torch.no_grad():
     m(x)
     torch.cuda.synchronize()
