@@ -108,6 +108,76 @@ __global__ void __launch_bounds__(256) cr_dwconv_gate_kernel(const float* __rest
       make_float4(a1.x * a2.x, a1.y * a2.y, a1.z * a2.z, a1.w * a2.w);
 }
 
+// The same, one thread per (column, 4 gate channels) walking down a strip of R rows: every input row is loaded once
+// (3 columns x 2 halves) and scattered into the accumulators of the three output rows it touches, the 18 weight
+// vectors stay in registers — 6 loads per output instead of 36 (the per-pixel kernel above was L1-bound at a quarter
+// of the HBM rate on the 128x128 and 64x64 stages).  The taps reach each accumulator in the same order as above
+// (bias, then ky-major, kx-minor), so the results are bit-identical.
+template <int R>
+__global__ void __launch_bounds__(128, 3) cr_dwconv_gate_strip_kernel(const float* __restrict__ h, const float* __restrict__ w9,
+                                                                   const float* __restrict__ bias, float* __restrict__ g,
+                                                                   int B, int n, int c) {
+  pdl_trigger();
+  const int c4 = c / 4, C2 = 2 * c, strips = n / R;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(B) * strips * n * c4) return;
+  const int j = static_cast<int>(i % c4) * 4;
+  size_t r = i / c4;
+  const int px = static_cast<int>(r % n); r /= n;
+  const int y0 = static_cast<int>(r % strips) * R;
+  const int face = static_cast<int>(r / strips);
+  float4 w[9][2];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    w[t][0] = __ldg(reinterpret_cast<const float4*>(w9 + t * C2 + j));
+    w[t][1] = __ldg(reinterpret_cast<const float4*>(w9 + t * C2 + c + j));
+  }
+  const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + j)), b2 = __ldg(reinterpret_cast<const float4*>(bias + c + j));
+  pdl_wait();
+  const float* base = h + static_cast<size_t>(face) * n * n * C2 + j;
+  float* out = g + static_cast<size_t>(face) * n * n * c + j;
+  const bool has_l = px > 0, has_r = px + 1 < n;
+  float4 acc[3][2];   // output rows y - 1, y, y + 1 of the input row being scattered, at slots (y - 1) % 3 ...
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { acc[k][0] = b1; acc[k][1] = b2; }
+  auto fma4 = [](float4& a, const float4& x, const float4& ww) {
+    a.x = fmaf(x.x, ww.x, a.x); a.y = fmaf(x.y, ww.y, a.y); a.z = fmaf(x.z, ww.z, a.z); a.w = fmaf(x.w, ww.w, a.w);
+  };
+#pragma unroll
+  for (int s = 0; s < R + 2; ++s) {          // input row y = y0 - 1 + s
+    const int y = y0 - 1 + s;
+    if (y >= 0 && y < n) {
+      const float* row = base + (static_cast<size_t>(y) * n + px) * C2;
+      float4 x[3][2];
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const bool ok = kx == 0 ? has_l : (kx == 2 ? has_r : true);
+        if (ok) {
+          x[kx][0] = *reinterpret_cast<const float4*>(row + (kx - 1) * C2);
+          x[kx][1] = *reinterpret_cast<const float4*>(row + (kx - 1) * C2 + c);
+        }
+      }
+      // input row y is tap row ky of output row Y = y0 + s - ky, whose accumulators live in slot (s - ky) % 3
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        if (s - ky < 0 || s - ky >= R) continue;   // static after unrolling
+        const int slot = (s - ky + 3) % 3;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const bool ok = kx == 0 ? has_l : (kx == 2 ? has_r : true);
+          if (ok) { fma4(acc[slot][0], x[kx][0], w[ky * 3 + kx][0]); fma4(acc[slot][1], x[kx][1], w[ky * 3 + kx][1]); }
+        }
+      }
+    }
+    if (s >= 2) {                              // output row y0 + s - 2 has received its three tap rows
+      const int slot = (s + 1) % 3;
+      const float4 a1 = acc[slot][0], a2 = acc[slot][1];
+      *reinterpret_cast<float4*>(out + (static_cast<size_t>(y0 + s - 2) * n + px) * c) = make_float4(a1.x * a2.x, a1.y * a2.y, a1.z * a2.z, a1.w * a2.w);
+      acc[slot][0] = b1; acc[slot][1] = b2;
+    }
+  }
+}
+
 // per-face channel mean (AdaptiveAvgPool2d(1), cr/naf.py:57): g [B][HW][c] -> pooled [B][c].
 // grid (c/32, B), block 1024: lane = channel, 32 row lanes, fixed-order reduction.
 constexpr int kCrPoolLanes = 32;

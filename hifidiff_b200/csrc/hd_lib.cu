@@ -77,6 +77,7 @@ struct Tunables {
   bool cr_tc = true;      // HD_CR_TC=0: every CoarseRestoration GEMM on the FFMA kernel (no split-precision tcgen05 path)
   bool cr_mma3 = true;    // HD_CR_MMA3=0: the shallow CoarseRestoration stages (c = 32 / 64, down / up convs) stay on the FFMA GEMM
   bool cr_stn_mma = true; // HD_CR_STN_MMA=0: the first STN localisation conv stays on CUDA cores
+  bool cr_dw_strip = true; // HD_CR_DW_STRIP=0: CoarseRestoration depthwise conv one thread per pixel instead of per column strip
   bool dw_small = true;   // HD_DW_SMALL=0: the generic tiled depthwise kernel at the 2x2 / 4x4 levels too
   int cta_target = 120;   // HD_CTA_TARGET: split-K until a GEMM's grid has at least this many CTAs
   int sca_target = 120;   // HD_SCA_TARGET: the same for the SCA GEMMs (M = faces)
@@ -84,7 +85,7 @@ struct Tunables {
   void read_env() {
     auto flag = [](const char* name, bool& v) { if (const char* e = getenv(name)) v = atoi(e) != 0; };
     flag("HD_PDL", pdl); flag("HD_BN256", bn256); flag("HD_FACE", face); flag("HD_PAIR", pair); flag("HD_SCA_MUL", sca_mul); flag("HD_EDGE_MMA", edge_mma); flag("HD_W_PREFETCH", w_prefetch);
-    flag("HD_CR_STN_CS", cr_stn_cs); flag("HD_CR_TC", cr_tc); flag("HD_CR_MMA3", cr_mma3); flag("HD_CR_STN_MMA", cr_stn_mma); flag("HD_DW_SMALL", dw_small);
+    flag("HD_CR_STN_CS", cr_stn_cs); flag("HD_CR_TC", cr_tc); flag("HD_CR_MMA3", cr_mma3); flag("HD_CR_STN_MMA", cr_stn_mma); flag("HD_CR_DW_STRIP", cr_dw_strip); flag("HD_DW_SMALL", dw_small);
     if (const char* e = getenv("HD_TWO_CTA")) two_cta = atoi(e);
     if (const char* e = getenv("HD_CTA_TARGET")) cta_target = std::max(atoi(e), 1);
     if (const char* e = getenv("HD_SCA_TARGET")) sca_target = std::max(atoi(e), 1);
@@ -2075,7 +2076,9 @@ Plan* get_cr_plan(hd_handle* h, int B) {
     const float *dw_w = b.dw_w, *dw_b = b.dw_b;
     g_label = L0 + "dwconv+gate";
     add_op(P, [=](cudaStream_t st) {
-      launch_k(cr_dwconv_gate_kernel, ew(static_cast<size_t>(rows) * (c / 4)), dim3(256), 0, st, static_cast<const float*>(act_h), dw_w, dw_b, act_g, B, n, c);
+      if (!h->tun.cr_dw_strip) launch_k(cr_dwconv_gate_kernel, ew(static_cast<size_t>(rows) * (c / 4)), dim3(256), 0, st, static_cast<const float*>(act_h), dw_w, dw_b, act_g, B, n, c);
+      else if (n >= 16) launch_k(cr_dwconv_gate_strip_kernel<16>, ew(static_cast<size_t>(rows / 16) * (c / 4), 128), dim3(128), 0, st, static_cast<const float*>(act_h), dw_w, dw_b, act_g, B, n, c);
+      else launch_k(cr_dwconv_gate_strip_kernel<8>, ew(static_cast<size_t>(rows / 8) * (c / 4), 128), dim3(128), 0, st, static_cast<const float*>(act_h), dw_w, dw_b, act_g, B, n, c);
     });
     g_label = L0 + "pool";
     add_op(P, [=](cudaStream_t st) {
