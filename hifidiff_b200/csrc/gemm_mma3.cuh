@@ -179,6 +179,132 @@ __global__ void __launch_bounds__(256, 2) gemm_mma3_kernel(const Args g) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// K = 32 / 64 (the 1x1 convs of the NAF blocks at c = 32 / 64: most of the pixels of the network): the 3xTF32 kernel
+// above is bound by the MMA issue rate there (130 TFLOP/s of k8 instructions).  With the whole K extent of a row in
+// one shared-memory stage the split can be fp16 instead — x * s = hi + lo, 11 + 11 mantissa bits, s the power of two
+// that brings the ROW's maximum into [2^14, 2^15) so that fp16's exponent range never clips (anything lost to
+// underflow is below 2^-39 of the row maximum); weights likewise with one scale per layer — and the MMAs are k16:
+// half the instructions and half the ldmatrix traffic for the same 22 bits.  The accumulator is unscaled per row in
+// the epilogue (powers of two: exact).
+// ------------------------------------------------------------------------------------------------------------------
+struct ArgsH {
+  const float* A;       // [M, lda] fp32
+  const __half* w_hi;   // [N, K] fp16 of w * 2^e
+  const __half* w_lo;
+  const float* bias;
+  float* out;
+  const float* resid;
+  int lda, ldo, ldr;
+  int M, N;
+  float w_unscale;      // 2^-e
+};
+
+template <int BN, int K> constexpr int smem_bytes_h() { return 2 * (BM + BN) * (K * 2 + 16) + BM * 4; }
+
+template <int BN, int K, int EPI>
+__global__ void __launch_bounds__(256, 2) gemm_mma3h_kernel(const ArgsH g) {
+  constexpr int NT = BN / 8, RB = K * 2 + 16;
+  constexpr int LPR = K / 4;                    // lanes (float4) per row
+  constexpr int AJ = BM * LPR / 256;            // float4 per thread
+  constexpr int WCH = BN * K / 8;               // 16-byte chunks per weight matrix
+  constexpr int WJ = (WCH + 255) / 256;
+  extern __shared__ __align__(128) uint8_t s_raw[];
+  uint8_t* s_a[2] = {s_raw, s_raw + BM * RB};
+  uint8_t* s_w[2] = {s_raw + 2 * BM * RB, s_raw + 2 * BM * RB + BN * RB};
+  float* s_inv = reinterpret_cast<float*>(s_raw + 2 * (BM + BN) * RB);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  pdl_trigger();
+#pragma unroll
+  for (int j = 0; j < WJ; ++j) {                // weights: constants, before the dependency wait
+    const int i = tid + 256 * j;
+    if (i < WCH) {
+      const size_t off = static_cast<size_t>(n0 + i / (K / 8)) * K + (i % (K / 8)) * 8;
+      const uint32_t dst = (i / (K / 8)) * RB + (i % (K / 8)) * 16;
+      *reinterpret_cast<uint4*>(s_w[0] + dst) = __ldg(reinterpret_cast<const uint4*>(g.w_hi + off));
+      *reinterpret_cast<uint4*>(s_w[1] + dst) = __ldg(reinterpret_cast<const uint4*>(g.w_lo + off));
+    }
+  }
+  pdl_wait();
+  float4 areg[AJ];
+#pragma unroll
+  for (int j = 0; j < AJ; ++j) {
+    const int i = tid + 256 * j, row = m0 + i / LPR;
+    areg[j] = row < g.M ? *reinterpret_cast<const float4*>(g.A + static_cast<size_t>(row) * g.lda + (i % LPR) * 4)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int j = 0; j < AJ; ++j) {
+    const int i = tid + 256 * j;
+    float4 f = areg[j];
+    float mx = fmaxf(fmaxf(fabsf(f.x), fabsf(f.y)), fmaxf(fabsf(f.z), fabsf(f.w)));
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));   // the row's LPR lanes are adjacent
+    const uint32_t e = (__float_as_uint(mx) >> 23) & 0xFFu;
+    const float sc = e >= 15u ? __uint_as_float((268u - e) << 23) : 1.f;
+    if (i % LPR == 0) s_inv[i / LPR] = e >= 15u ? __uint_as_float((e - 14u) << 23) : 1.f;
+    f.x *= sc; f.y *= sc; f.z *= sc; f.w *= sc;
+    const float r0 = __half2float(__float2half_rn(f.x)), r1 = __half2float(__float2half_rn(f.y));
+    const float r2 = __half2float(__float2half_rn(f.z)), r3 = __half2float(__float2half_rn(f.w));
+    const uint32_t off = (i / LPR) * RB + (i % LPR) * 8;
+    *reinterpret_cast<uint2*>(s_a[0] + off) = make_uint2(edge::pack_half2(f.x, f.y), edge::pack_half2(f.z, f.w));
+    *reinterpret_cast<uint2*>(s_a[1] + off) = make_uint2(edge::pack_half2(f.x - r0, f.y - r1), edge::pack_half2(f.z - r2, f.w - r3));
+  }
+  __syncthreads();
+  float acc[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  const uint32_t a_lane = (warp * 16 + (lane & 15)) * RB + (lane >> 4) * 16;
+  const uint32_t w_lane = ((lane >> 4) * 8 + (lane & 7)) * RB + ((lane >> 3) & 1) * 16;
+  const uint32_t ah_u32 = edge::smem_addr(s_a[0]) + a_lane, al_u32 = edge::smem_addr(s_a[1]) + a_lane;
+  const uint32_t wh_u32 = edge::smem_addr(s_w[0]) + w_lane, wl_u32 = edge::smem_addr(s_w[1]) + w_lane;
+#pragma unroll
+  for (int s = 0; s < K / 16; ++s) {
+    uint32_t ah[4], al[4];
+    edge::ldmatrix_x4(ah_u32 + s * 32, ah);
+    edge::ldmatrix_x4(al_u32 + s * 32, al);
+#pragma unroll
+    for (int jp = 0; jp < NT / 2; ++jp) {
+      uint32_t bh[4], bl[4];
+      edge::ldmatrix_x4(wh_u32 + jp * 16 * RB + s * 32, bh);
+      edge::ldmatrix_x4(wl_u32 + jp * 16 * RB + s * 32, bl);
+      const uint32_t bh0[2] = {bh[0], bh[1]}, bh1[2] = {bh[2], bh[3]}, bl0[2] = {bl[0], bl[1]}, bl1[2] = {bl[2], bl[3]};
+      edge::mma_16816_f16(acc[2 * jp], ah, bh0);     edge::mma_16816_f16(acc[2 * jp + 1], ah, bh1);
+      edge::mma_16816_f16(acc[2 * jp], al, bh0);     edge::mma_16816_f16(acc[2 * jp + 1], al, bh1);
+      edge::mma_16816_f16(acc[2 * jp], ah, bl0);     edge::mma_16816_f16(acc[2 * jp + 1], ah, bl1);
+    }
+  }
+  const int gq = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int rl = warp * 16 + gq + half * 8, m = m0 + rl;
+    if (m >= g.M) continue;
+    const float us = s_inv[rl] * g.w_unscale;
+    float* orow = g.out + static_cast<size_t>(m) * g.ldo + n0 + 2 * q;
+    const float* rrow = EPI == EPI_RESID ? g.resid + static_cast<size_t>(m) * g.ldr + n0 + 2 * q : nullptr;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      float2 v = make_float2(acc[j][2 * half] * us, acc[j][2 * half + 1] * us);
+      if (g.bias != nullptr) {
+        const float2 b = __ldg(reinterpret_cast<const float2*>(g.bias + n0 + j * 8 + 2 * q));
+        v.x += b.x;
+        v.y += b.y;
+      }
+      if (EPI == EPI_RESID) {
+        const float2 r = *reinterpret_cast<const float2*>(rrow + j * 8);
+        v.x += r.x;
+        v.y += r.y;
+      }
+      *reinterpret_cast<float2*>(orow + j * 8) = v;
+    }
+  }
+}
+
+inline bool eligible_h(int M, int N, int K, int epi) {
+  return M >= 1024 && (K == 32 || K == 64) && N % 32 == 0 && (epi == EPI_BIAS || epi == EPI_RESID);
+}
+
 template <int BN> constexpr int smem_bytes() { return 2 * (BM + BN) * ROWB; }
 
 inline bool eligible(int M, int N, int K, int epi) {

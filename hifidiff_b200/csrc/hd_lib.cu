@@ -76,6 +76,7 @@ struct Tunables {
   bool cr_stn_cs = true;  // HD_CR_STN_CS=0: one thread per (pixel, 2 output channels) in the first STN localisation conv
   bool cr_tc = true;      // HD_CR_TC=0: every CoarseRestoration GEMM on the FFMA kernel (no split-precision tcgen05 path)
   bool cr_mma3 = true;    // HD_CR_MMA3=0: the shallow CoarseRestoration stages (c = 32 / 64, down / up convs) stay on the FFMA GEMM
+  bool cr_mma3h = true;   // HD_CR_MMA3H=0: K = 32 / 64 GEMMs of CoarseRestoration on the 3xTF32 kernel instead of the row-scaled fp16 split
   bool cr_stn_mma = true; // HD_CR_STN_MMA=0: the first STN localisation conv stays on CUDA cores
   bool cr_dw_strip = true; // HD_CR_DW_STRIP=0: CoarseRestoration depthwise conv one thread per pixel instead of per column strip
   bool dw_small = true;   // HD_DW_SMALL=0: the generic tiled depthwise kernel at the 2x2 / 4x4 levels too
@@ -85,7 +86,7 @@ struct Tunables {
   void read_env() {
     auto flag = [](const char* name, bool& v) { if (const char* e = getenv(name)) v = atoi(e) != 0; };
     flag("HD_PDL", pdl); flag("HD_BN256", bn256); flag("HD_FACE", face); flag("HD_PAIR", pair); flag("HD_SCA_MUL", sca_mul); flag("HD_EDGE_MMA", edge_mma); flag("HD_W_PREFETCH", w_prefetch);
-    flag("HD_CR_STN_CS", cr_stn_cs); flag("HD_CR_TC", cr_tc); flag("HD_CR_MMA3", cr_mma3); flag("HD_CR_STN_MMA", cr_stn_mma); flag("HD_CR_DW_STRIP", cr_dw_strip); flag("HD_DW_SMALL", dw_small);
+    flag("HD_CR_STN_CS", cr_stn_cs); flag("HD_CR_TC", cr_tc); flag("HD_CR_MMA3", cr_mma3); flag("HD_CR_STN_MMA", cr_stn_mma); flag("HD_CR_MMA3H", cr_mma3h); flag("HD_CR_DW_STRIP", cr_dw_strip); flag("HD_DW_SMALL", dw_small);
     if (const char* e = getenv("HD_TWO_CTA")) two_cta = atoi(e);
     if (const char* e = getenv("HD_CTA_TARGET")) cta_target = std::max(atoi(e), 1);
     if (const char* e = getenv("HD_SCA_TARGET")) sca_target = std::max(atoi(e), 1);
@@ -229,6 +230,8 @@ struct CrW {
   bf16* a3 = nullptr;  // split-precision A operand [rows][3K]
   bool use_tc = true;
   std::unordered_map<const float*, std::pair<float*, float*>> split_hl;  // fp32 weight -> tf32 hi / lo for gemm_mma3
+  struct SplitH { __half *hi, *lo; float unscale; };
+  std::unordered_map<const float*, SplitH> split_h;                      // fp32 weight -> scaled fp16 hi / lo for gemm_mma3h
 };
 
 struct HcaW {
@@ -403,6 +406,30 @@ void launch_mma3(const mma3::Args& a, int epi, cudaStream_t st) {
   if (a.N % 128 == 0) launch_mma3_bn<128>(a, epi, st);
   else if (a.N % 64 == 0) launch_mma3_bn<64>(a, epi, st);
   else launch_mma3_bn<32>(a, epi, st);
+}
+
+template <int BN, int K>
+void launch_mma3h_bnk(const mma3::ArgsH& a, int epi, cudaStream_t st) {
+  const dim3 grid(static_cast<unsigned>((a.M + mma3::BM - 1) / mma3::BM), static_cast<unsigned>(a.N / BN));
+  constexpr int smem = mma3::smem_bytes_h<BN, K>();
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(mma3::gemm_mma3h_kernel<BN, K, EPI_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_CHECK(cudaFuncSetAttribute(mma3::gemm_mma3h_kernel<BN, K, EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  if (epi == EPI_BIAS) launch_k(mma3::gemm_mma3h_kernel<BN, K, EPI_BIAS>, grid, dim3(256), smem, st, a);
+  else launch_k(mma3::gemm_mma3h_kernel<BN, K, EPI_RESID>, grid, dim3(256), smem, st, a);
+}
+template <int K>
+void launch_mma3h_k(const mma3::ArgsH& a, int epi, cudaStream_t st) {
+  if (a.N % 128 == 0) launch_mma3h_bnk<128, K>(a, epi, st);
+  else if (a.N % 64 == 0) launch_mma3h_bnk<64, K>(a, epi, st);
+  else launch_mma3h_bnk<32, K>(a, epi, st);
+}
+void launch_mma3h(const mma3::ArgsH& a, int K, int epi, cudaStream_t st) {
+  if (K == 32) launch_mma3h_k<32>(a, epi, st);
+  else launch_mma3h_k<64>(a, epi, st);
 }
 
 
@@ -2024,6 +2051,41 @@ Plan* get_cr_plan(hd_handle* h, int B) {
     GemmDesc d;
     d.M = M; d.N = N; d.K = K; d.A = A; d.lda = lda; d.a_dtype = DT_F32; d.W = W; d.ldw = K; d.w_dtype = DT_F32;
     d.bias = bias; d.epi = epi; d.out = out; d.ldo = ldo; d.out_dtype = DT_F32; d.resid = resid; d.ldr = ldo; d.sp = sp;
+    if (R.use_tc && h->tun.cr_mma3 && h->tun.cr_mma3h && lda % 4 == 0 && ldo % 2 == 0 && mma3::eligible_h(M, N, K, epi)) {
+      // K = 32 / 64: the whole K extent in one stage, row-scaled fp16 split (k16 MMAs)
+      auto& cache = h->cr.split_h;
+      auto it = cache.find(W);
+      if (it == cache.end()) {
+        const size_t nw = static_cast<size_t>(N) * K;
+        std::vector<float> wf(nw);
+        CUDA_CHECK(cudaMemcpyAsync(wf.data(), W, nw * 4, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_CHECK(cudaStreamSynchronize(h->stream));
+        float wmax = 0.f;
+        for (float f : wf) wmax = std::max(wmax, std::fabs(f));
+        const float wscale = wmax > 0.f && std::isfinite(wmax) ? std::ldexp(1.f, 14 - std::ilogb(wmax)) : 1.f;
+        std::vector<uint16_t> vh(nw), vl(nw);
+        for (size_t i = 0; i < nw; ++i) {
+          const float f = wf[i] * wscale;
+          const __half hh = __float2half_rn(f);
+          vh[i] = static_cast<__half_raw>(hh).x;
+          vl[i] = static_cast<__half_raw>(__float2half_rn(f - __half2float(hh))).x;
+        }
+        CrW::SplitH sp;
+        sp.hi = static_cast<__half*>(h->arena.alloc(nw * 2));
+        sp.lo = static_cast<__half*>(h->arena.alloc(nw * 2));
+        sp.unscale = 1.f / wscale;
+        CUDA_CHECK(cudaMemcpy(sp.hi, vh.data(), nw * 2, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(sp.lo, vl.data(), nw * 2, cudaMemcpyHostToDevice));
+        it = cache.emplace(W, sp).first;
+      }
+      mma3::ArgsH a;
+      a.A = A; a.w_hi = it->second.hi; a.w_lo = it->second.lo; a.bias = bias; a.out = out; a.resid = resid;
+      a.lda = lda; a.ldo = ldo; a.ldr = ldo; a.M = M; a.N = N; a.w_unscale = it->second.unscale;
+      g_label = label + fmt(" gemm_mma3h M=%d N=%d K=%d (3 x fp16 split, row-scaled)", M, N, K);
+      add_op(P, [a, K, epi](cudaStream_t st) { launch_mma3h(a, K, epi, st); });
+      P.flops_per_face += 2.0 * M * static_cast<double>(N) * K / P.batch;
+      return;
+    }
     if (R.use_tc && h->tun.cr_mma3 && lda % 4 == 0 && ldo % 2 == 0 && mma3::eligible(M, N, K, epi)) {
       // shallow stages: FFMA-bound on CUDA cores, memory-bound on mma.sync with split operands
       auto& cache = h->cr.split_hl;
