@@ -8,72 +8,103 @@
 namespace hd {
 
 // intro: 3x3 conv 3 -> 32, pad 1 (cr/model.py:41-49,78).  x NCHW [B][3][H][H] -> out NHWC [B][H][H][32].
-// w [27][32] (k = (c*3 + ky)*3 + kx), thread = one pixel x 8 output channels.
+// w [27][32] (k = (c*3 + ky)*3 + kx), thread = four pixels of a row x 8 output channels: every weight vector read
+// from shared memory serves four pixels (the one-pixel version issued 81 loads for 216 FMAs and was LSU-bound at
+// 3x the time of writing its output).  Taps are added in (c, ky, kx) order after the bias.
 __global__ void __launch_bounds__(256) cr_intro_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ b, float* __restrict__ out, int B, int H) {
+  __shared__ __align__(16) float sw[27 * 32];
   pdl_trigger();
+  for (int i = threadIdx.x; i < 27 * 32; i += 256) sw[i] = w[i];
+  __syncthreads();
   pdl_wait();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= static_cast<size_t>(B) * H * H * 4) return;
+  if (i >= static_cast<size_t>(B) * H * (H / 4) * 4) return;
   const int cg = static_cast<int>(i & 3);
   size_t r = i >> 2;
-  const int px = static_cast<int>(r % H); r /= H;
+  const int px0 = static_cast<int>(r % (H / 4)) * 4; r /= (H / 4);
   const int py = static_cast<int>(r % H);
   const int face = static_cast<int>(r / H);
-  float acc[8];
+  float acc[4][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = b[cg * 8 + j];
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = acc[2][j] = acc[3][j] = b[cg * 8 + j];
+#pragma unroll
   for (int c = 0; c < 3; ++c)
+#pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int yy = py + ky - 1;
       if (yy < 0 || yy >= H) continue;
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = px + kx - 1;
-        if (xx < 0 || xx >= H) continue;
-        const float v = x[((static_cast<size_t>(face) * 3 + c) * H + yy) * H + xx];
-        const float* wr = w + ((c * 3 + ky) * 3 + kx) * 32 + cg * 8;
+      const float* row = x + ((static_cast<size_t>(face) * 3 + c) * H + yy) * H + px0;
+      float v[6];
+      v[0] = px0 > 0 ? row[-1] : 0.f;
+      const float4 mid = *reinterpret_cast<const float4*>(row);
+      v[1] = mid.x; v[2] = mid.y; v[3] = mid.z; v[4] = mid.w;
+      v[5] = px0 + 4 < H ? row[4] : 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+      for (int kx = 0; kx < 3; ++kx) {
+        const float* wr = sw + ((c * 3 + ky) * 3 + kx) * 32 + cg * 8;
+        const float4 w0 = *reinterpret_cast<const float4*>(wr), w1 = *reinterpret_cast<const float4*>(wr + 4);
+        const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const int xx = px0 + p + kx - 1;
+          if (xx < 0 || xx >= H) continue;     // the reference's zero padding: the tap is skipped, not added as 0
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(v[p + kx], ww[j], acc[p][j]);
+        }
       }
     }
-  store8(out + ((static_cast<size_t>(face) * H + py) * H + px) * 32 + cg * 8, acc);
+#pragma unroll
+  for (int p = 0; p < 4; ++p) store8(out + ((static_cast<size_t>(face) * H + py) * H + px0 + p) * 32 + cg * 8, acc[p]);
 }
 
 // outro: 3x3 conv 32 -> 3, pad 1 (cr/model.py:50-58,86).  x NHWC [B][H][H][32] -> out NCHW [B][3][H][H].
-// w [3][9][32], thread = one pixel.
+// w [3][9][32] in shared memory.  Eight lanes per pixel, four input channels each: a tap of a pixel is one contiguous
+// 128-byte read (one thread per pixel made every load instruction touch 32 cache lines), then a three-step shuffle
+// reduction over the eight lanes.
 __global__ void __launch_bounds__(256) cr_outro_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ b, float* __restrict__ out, int B, int H) {
+  __shared__ __align__(16) float sw[3 * 9 * 32];
   pdl_trigger();
+  for (int i = threadIdx.x; i < 3 * 9 * 32; i += 256) sw[i] = w[i];
+  __syncthreads();
   pdl_wait();
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= static_cast<size_t>(B) * H * H) return;
-  size_t r = i;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // grid covers B*H*H*8 exactly (H % 4 == 0)
+  const int l = static_cast<int>(i & 7);
+  size_t r = i >> 3;
+  const bool valid = r < static_cast<size_t>(B) * H * H;
+  if (!valid) r = 0;
   const int px = static_cast<int>(r % H); r /= H;
   const int py = static_cast<int>(r % H);
   const int face = static_cast<int>(r / H);
-  float acc[3] = {b[0], b[1], b[2]};
+  float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int yy = py + ky - 1;
     if (yy < 0 || yy >= H) continue;
+#pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
       const int xx = px + kx - 1;
       if (xx < 0 || xx >= H) continue;
-      const float* src = x + ((static_cast<size_t>(face) * H + yy) * H + xx) * 32;
+      const float4 v = *reinterpret_cast<const float4*>(x + ((static_cast<size_t>(face) * H + yy) * H + xx) * 32 + l * 4);
       const int tap = ky * 3 + kx;
 #pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 v = *reinterpret_cast<const float4*>(src + c4 * 4);
-#pragma unroll
-        for (int o = 0; o < 3; ++o) {
-          const float4 ww = __ldg(reinterpret_cast<const float4*>(w + (o * 9 + tap) * 32 + c4 * 4));
-          acc[o] = fmaf(v.x, ww.x, acc[o]); acc[o] = fmaf(v.y, ww.y, acc[o]);
-          acc[o] = fmaf(v.z, ww.z, acc[o]); acc[o] = fmaf(v.w, ww.w, acc[o]);
-        }
+      for (int o = 0; o < 3; ++o) {
+        const float4 ww = *reinterpret_cast<const float4*>(sw + (o * 9 + tap) * 32 + l * 4);
+        acc[o] = fmaf(v.x, ww.x, acc[o]); acc[o] = fmaf(v.y, ww.y, acc[o]);
+        acc[o] = fmaf(v.z, ww.z, acc[o]); acc[o] = fmaf(v.w, ww.w, acc[o]);
       }
     }
   }
 #pragma unroll
-  for (int o = 0; o < 3; ++o) out[((static_cast<size_t>(face) * 3 + o) * H + py) * H + px] = acc[o];
+  for (int o = 0; o < 3; ++o) {
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], d);
+  }
+  if (valid && l < 3) {
+    const float v = l == 0 ? acc[0] : (l == 1 ? acc[1] : acc[2]);
+    out[((static_cast<size_t>(face) * 3 + l) * H + py) * H + px] = v + b[l];
+  }
 }
 
 // depthwise 3x3 (pad 1, bias) + SimpleGate at any spatial size (cr/naf.py:34-42,113-114): h [B][n][n][2c] ->
@@ -385,31 +416,46 @@ __global__ void __launch_bounds__(128) cr_stn_conv_pool_cs_kernel(const float* _
   }
 }
 
-// STN regressor (stn.py:29-33,45-47): theta = W2 relu(W1 xs + b1) + b2, one block per face.
+// STN regressor (stn.py:29-33,45-47): theta = W2 relu(W1 xs + b1) + b2.
 //   xs [fc] (NHWC order of the localisation output; W1's columns are permuted to match at load), W1 [hid][fc],
 //   W2 [6][hid] -> theta [B][6].  hid <= 96.
+// grid (ceil(hid / 8), B): one warp per hidden unit (fc is up to 7290 at the 128x128 stage: one block per face left
+// 85 serial dot products to 8 warps, 440 us); the hidden vector goes through global memory and the last block of a
+// face to finish (ticket, left at zero) applies W2.  Every sum keeps a fixed order.
 __global__ void __launch_bounds__(256) cr_stn_fc_kernel(const float* __restrict__ xs, const float* __restrict__ w1,
                                                         const float* __restrict__ b1, const float* __restrict__ w2,
-                                                        const float* __restrict__ b2, float* __restrict__ theta, int fc,
-                                                        int hid) {
+                                                        const float* __restrict__ b2, float* __restrict__ theta,
+                                                        float* __restrict__ hidden, unsigned int* __restrict__ ticket,
+                                                        int fc, int hid) {
   __shared__ float hbuf[96];
+  __shared__ bool last;
   pdl_trigger();
   pdl_wait();
-  const int face = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* x = xs + static_cast<size_t>(face) * fc;
-  for (int j = warp; j < hid; j += 8) {
+  const int face = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 8 + warp;
+  if (j < hid) {
+    const float* x = xs + static_cast<size_t>(face) * fc;
     const float* wr = w1 + static_cast<size_t>(j) * fc;
     float s = 0.f;
-    for (int k = lane; k < fc; k += 32) s = fmaf(x[k], wr[k], s);
+#pragma unroll 8
+    for (int k = lane; k < fc; k += 32) s = fmaf(x[k], __ldg(wr + k), s);
     s = warp_sum(s);
-    if (lane == 0) hbuf[j] = fmaxf(s + b1[j], 0.f);
+    if (lane == 0) hidden[face * 96 + j] = fmaxf(s + b1[j], 0.f);
   }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket + face, 1u) + 1u == gridDim.x;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x < hid) hbuf[threadIdx.x] = __ldcg(hidden + face * 96 + threadIdx.x);
   __syncthreads();
   if (threadIdx.x < 6) {
     float s = b2[threadIdx.x];
     for (int k = 0; k < hid; ++k) s = fmaf(hbuf[k], w2[threadIdx.x * hid + k], s);
     theta[face * 6 + threadIdx.x] = s;
   }
+  if (threadIdx.x == 0) ticket[face] = 0u;
 }
 
 // affine_grid + grid_sample (bilinear, zeros padding, align_corners=False; stn.py:49-50) on the NHWC stream.

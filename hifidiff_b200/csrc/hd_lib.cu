@@ -227,6 +227,8 @@ struct CrW {
   // workspace for one chunk of faces (all fp32)
   float *r[5] = {}, *sk[5] = {}, *ln_out = nullptr, *act_h = nullptr, *act_g = nullptr, *tmp = nullptr;
   float *pooled = nullptr, *sca_s = nullptr, *loc1 = nullptr, *loc2 = nullptr, *theta = nullptr, *stage = nullptr;
+  float* stn_hidden = nullptr;          // [cap][96] hidden layer of the STN regressor
+  unsigned int* stn_ticket = nullptr;   // [cap] block-completion counters of cr_stn_fc_kernel
   bf16* a3 = nullptr;  // split-precision A operand [rows][3K]
   bool use_tc = true;
   std::unordered_map<const float*, std::pair<float*, float*>> split_hl;  // fp32 weight -> tf32 hi / lo for gemm_mma3
@@ -2027,6 +2029,8 @@ void load_cr_impl(hd_handle* h) {
   R.loc1 = h->arena.get<float>(cap * 60 * 60 * 8);
   R.loc2 = h->arena.get<float>(cap * 27 * 27 * 10);
   R.theta = h->arena.get<float>(cap * 6);
+  R.stn_hidden = h->arena.get<float>(cap * 96);
+  R.stn_ticket = h->arena.get<unsigned int>(cap);   // zero (arena memory is cleared), and every kernel leaves it so
   R.stage = h->arena.get<float>(cap * 3 * R.H * R.H);
   R.use_tc = h->bf16 && h->tun.cr_tc;
   if (R.use_tc) R.a3 = h->arena.get<bf16>(cap * 3 * e[2]);  // levels with c >= 128: rows x c <= e[2]
@@ -2167,7 +2171,8 @@ Plan* get_cr_plan(hd_handle* h, int B) {
     P.flops_per_face += 2.0 * 9 * 2 * c * rpf;
   };
   auto stn = [&](const CrStnW& s, const float* x, float* out, int n, int c, const std::string& L0) {
-    float *loc1 = R.loc1, *loc2 = R.loc2, *theta = R.theta;
+    float *loc1 = R.loc1, *loc2 = R.loc2, *theta = R.theta, *stn_hidden = R.stn_hidden;
+    unsigned int* stn_ticket = R.stn_ticket;
     const float *w1 = s.w1, *b1 = s.b1, *w2 = s.w2, *b2 = s.b2, *f1 = s.f1, *fb1 = s.fb1, *f2 = s.f2, *fb2 = s.fb2;
     const int k1 = s.k1, k2 = s.k2, n1 = s.n1, n2 = s.n2, fc = s.fc, hid = s.hid;
     const __half* w1m = s.w1_mma;
@@ -2200,7 +2205,7 @@ Plan* get_cr_plan(hd_handle* h, int B) {
     });
     g_label = L0 + "stn fc";
     add_op(P, [=](cudaStream_t st) {
-      launch_k(cr_stn_fc_kernel, dim3(B), dim3(256), 0, st, static_cast<const float*>(loc2), f1, fb1, f2, fb2, theta, fc, hid);
+      launch_k(cr_stn_fc_kernel, dim3(cdiv(hid, 8), B), dim3(256), 0, st, static_cast<const float*>(loc2), f1, fb1, f2, fb2, theta, stn_hidden, stn_ticket, fc, hid);
     });
     g_label = L0 + "stn affine_grid+grid_sample";
     add_op(P, [=](cudaStream_t st) {
@@ -2216,7 +2221,7 @@ Plan* get_cr_plan(hd_handle* h, int B) {
     const float *w = R.intro_w, *b = R.intro_b;
     float* out = R.r[0];
     g_label = "cr intro conv3x3";
-    add_op(P, [=](cudaStream_t st) { launch_k(cr_intro_kernel, ew(static_cast<size_t>(B) * H * H * 4), dim3(256), 0, st, h->cr_in, w, b, out, B, H); });
+    add_op(P, [=](cudaStream_t st) { launch_k(cr_intro_kernel, ew(static_cast<size_t>(B) * H * H), dim3(256), 0, st, h->cr_in, w, b, out, B, H); });
   }
   float* tmp = R.tmp;
   for (int i = 0; i < 4; ++i) {  // encoders: NAF blocks, STN, 2x2 stride-2 conv; the result is also the skip (model.py:79-81)
@@ -2265,7 +2270,7 @@ Plan* get_cr_plan(hd_handle* h, int B) {
     const float *w = R.outro_w, *b = R.outro_b;
     const float* in = R.r[0];
     g_label = "cr outro conv3x3";
-    add_op(P, [=](cudaStream_t st) { launch_k(cr_outro_kernel, ew(static_cast<size_t>(B) * H * H), dim3(256), 0, st, in, w, b, h->cr_out, B, H); });
+    add_op(P, [=](cudaStream_t st) { launch_k(cr_outro_kernel, ew(static_cast<size_t>(B) * H * H * 8), dim3(256), 0, st, in, w, b, h->cr_out, B, H); });
   }
   Plan* raw = up.get();
   h->cr_plans[B] = std::move(up);
