@@ -290,6 +290,56 @@ __global__ void __launch_bounds__(256) cr_split3_kernel(const float* __restrict_
   store8(o + 2 * K, mode == 0 ? hi : lo);
 }
 
+// The two element-wise producers of a split GEMM operand, writing [hi | lo | hi] directly (no fp32 round trip):
+//   SCA channel scale in front of conv3 (cr/naf.py:116-117): out3 = split(g[m, k] * s[face(m), k])
+__global__ void __launch_bounds__(256) cr_scale_split3_kernel(const float* __restrict__ g, const float* __restrict__ s,
+                                                              bf16* __restrict__ out3, size_t total8, int c, int rows_per_face) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const size_t e = i * 8;
+  const size_t row = e / c;
+  const int k = static_cast<int>(e - row * c);
+  const int face = static_cast<int>(row / rows_per_face);
+  float v[8], sc[8], hi[8], lo[8];
+  load8(g + e, v);
+  load8(s + static_cast<size_t>(face) * c + k, sc);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[j] *= sc[j];
+    hi[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+    lo[j] = v[j] - hi[j];
+  }
+  bf16* o = out3 + row * 3 * c + k;
+  store8(o, hi);
+  store8(o + c, lo);
+  store8(o + 2 * c, hi);
+}
+//   SimpleGate in front of conv5 (cr/naf.py:122-123): out3 = split(in[m, k] * in[m, c + k])
+__global__ void __launch_bounds__(256) cr_gate_split3_kernel(const float* __restrict__ in, bf16* __restrict__ out3, size_t rows, int c) {
+  pdl_trigger();
+  pdl_wait();
+  const int c8 = c / 8;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * c8) return;
+  const size_t r = i / c8;
+  const int k = static_cast<int>(i - r * c8) * 8;
+  float a[8], b[8], hi[8], lo[8];
+  load8(in + r * 2 * c + k, a);
+  load8(in + r * 2 * c + c + k, b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float v = a[j] * b[j];
+    hi[j] = __bfloat162float(__float2bfloat16_rn(v));
+    lo[j] = v - hi[j];
+  }
+  bf16* o = out3 + r * 3 * c + k;
+  store8(o, hi);
+  store8(o + c, lo);
+  store8(o + 2 * c, hi);
+}
+
 // STN localisation stage (stn.py:20-27): valid k x k conv (Cin -> Cout <= 10) + MaxPool2d(2,2) + ReLU, fused.
 //   in NHWC [B][n][n][Cin], w [Cout][k][k][Cin], out NHWC [B][no][no][Cout], no = (n - k + 1) / 2.
 // Thread = one pooled pixel x OG output channels (COUT / OG groups): the 2x2 conv outputs under the pool window

@@ -111,7 +111,9 @@ __global__ void __launch_bounds__(256) intro_conv_kernel(const float* __restrict
 // LPR = min(32, C/16) lanes per pixel row (>= 4 independent float4 loads per lane), 32/LPR rows per
 // warp, 4 warps per block; fp32 residual in, T out.  C in {128,...,2048}
 // ------------------------------------------------------------------------------------------------
-template <int C, typename TOut>
+// SPLIT3 (TOut = bf16): the row goes out as [hi | lo | hi] bf16 column blocks of width C (row stride 3C), the A
+// operand of the split-precision tensor-core GEMM (cr_split3_kernel's mode 0 without the fp32 round trip).
+template <int C, typename TOut, bool SPLIT3 = false>
 __global__ void __launch_bounds__(128) ln_mod_kernel(const float* __restrict__ x, const float* __restrict__ lw,
                                                      const float* __restrict__ lb, TOut* __restrict__ out, int rows,
                                                      int rows_per_face, ModRef mod, int shift_off, int scale_off,
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(128) ln_mod_kernel(const float* __restrict__ x
   for (int o = LPR / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   if (!ok) return;
   const float denom = sqrtf(ss * (1.f / C) + 1e-6f);
-  TOut* orow = out + static_cast<size_t>(row) * C;
+  TOut* orow = out + static_cast<size_t>(row) * (SPLIT3 ? 3 * C : C);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c0 = (i * LPR + sl) * 4;
@@ -176,7 +178,17 @@ __global__ void __launch_bounds__(128) ln_mod_kernel(const float* __restrict__ x
       y[2] = y[2] * (sc[i].z + 1.f) + sh[i].z;
       y[3] = y[3] * (sc[i].w + 1.f) + sh[i].w;
     }
-    if (sizeof(TOut) == 4) {
+    if (SPLIT3) {
+      float lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) lo[e] = y[e] - __bfloat162float(__float2bfloat16_rn(y[e]));
+      const uint2 ph = make_uint2(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]));
+      const uint2 pl = make_uint2(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));
+      bf16* o = reinterpret_cast<bf16*>(orow) + c0;
+      *reinterpret_cast<uint2*>(o) = ph;
+      *reinterpret_cast<uint2*>(o + C) = pl;
+      *reinterpret_cast<uint2*>(o + 2 * C) = ph;
+    } else if (sizeof(TOut) == 4) {
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(orow) + c0) = make_float4(y[0], y[1], y[2], y[3]);
     } else {
       uint2 p;

@@ -77,6 +77,7 @@ struct Tunables {
   bool cr_tc = true;      // HD_CR_TC=0: every CoarseRestoration GEMM on the FFMA kernel (no split-precision tcgen05 path)
   bool cr_mma3 = true;    // HD_CR_MMA3=0: the shallow CoarseRestoration stages (c = 32 / 64, down / up convs) stay on the FFMA GEMM
   bool cr_mma3h = true;   // HD_CR_MMA3H=0: K = 32 / 64 GEMMs of CoarseRestoration on the 3xTF32 kernel instead of the row-scaled fp16 split
+  bool cr_fuse_split = true; // HD_CR_FUSE_SPLIT=0: separate fp32 -> [hi|lo|hi] kernels in front of the split tcgen05 GEMMs
   bool cr_stn_mma = true; // HD_CR_STN_MMA=0: the first STN localisation conv stays on CUDA cores
   bool cr_dw_strip = true; // HD_CR_DW_STRIP=0: CoarseRestoration depthwise conv one thread per pixel instead of per column strip
   bool dw_small = true;   // HD_DW_SMALL=0: the generic tiled depthwise kernel at the 2x2 / 4x4 levels too
@@ -86,7 +87,7 @@ struct Tunables {
   void read_env() {
     auto flag = [](const char* name, bool& v) { if (const char* e = getenv(name)) v = atoi(e) != 0; };
     flag("HD_PDL", pdl); flag("HD_BN256", bn256); flag("HD_FACE", face); flag("HD_PAIR", pair); flag("HD_SCA_MUL", sca_mul); flag("HD_EDGE_MMA", edge_mma); flag("HD_W_PREFETCH", w_prefetch);
-    flag("HD_CR_STN_CS", cr_stn_cs); flag("HD_CR_TC", cr_tc); flag("HD_CR_MMA3", cr_mma3); flag("HD_CR_STN_MMA", cr_stn_mma); flag("HD_CR_MMA3H", cr_mma3h); flag("HD_CR_DW_STRIP", cr_dw_strip); flag("HD_DW_SMALL", dw_small);
+    flag("HD_CR_STN_CS", cr_stn_cs); flag("HD_CR_TC", cr_tc); flag("HD_CR_MMA3", cr_mma3); flag("HD_CR_STN_MMA", cr_stn_mma); flag("HD_CR_FUSE_SPLIT", cr_fuse_split); flag("HD_CR_MMA3H", cr_mma3h); flag("HD_CR_DW_STRIP", cr_dw_strip); flag("HD_DW_SMALL", dw_small);
     if (const char* e = getenv("HD_TWO_CTA")) two_cta = atoi(e);
     if (const char* e = getenv("HD_CTA_TARGET")) cta_target = std::max(atoi(e), 1);
     if (const char* e = getenv("HD_SCA_TARGET")) sca_target = std::max(atoi(e), 1);
@@ -1034,6 +1035,19 @@ void launch_ln(int c, const float* x, const float* lw, const float* lb, T* out, 
     case 1024: launch_k(ln_mod_wide_kernel<1024, T>, dim3(rows), dim3(256), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
     case 2048: launch_k(ln_mod_wide_kernel<2048, T>, dim3(rows), dim3(256), 0, st, x, lw, lb, out, rows, rpf, mod, shift_off, scale_off, has_mod); break;
     default: break;
+  }
+}
+
+// LayerNorm straight into the [hi | lo | hi] bf16 operand of the split-precision GEMM (CoarseRestoration, c >= 128)
+void launch_ln_split3(int c, const float* x, const float* lw, const float* lb, bf16* out3, int rows, int rpf, cudaStream_t st) {
+  const int lpr = std::min(32, c / 16);
+  const int grid = cdiv(rows, 4 * (32 / lpr));
+  ModRef nomod{nullptr, nullptr, 0};
+  switch (c) {
+    case 128: launch_k(ln_mod_kernel<128, bf16, true>, dim3(grid), dim3(128), 0, st, x, lw, lb, out3, rows, rpf, nomod, 0, 0, 0); break;
+    case 256: launch_k(ln_mod_kernel<256, bf16, true>, dim3(grid), dim3(128), 0, st, x, lw, lb, out3, rows, rpf, nomod, 0, 0, 0); break;
+    case 512: launch_k(ln_mod_kernel<512, bf16, true>, dim3(grid), dim3(128), 0, st, x, lw, lb, out3, rows, rpf, nomod, 0, 0, 0); break;
+    default: HD_THROW(HD_ERR_UNSUPPORTED, "split LayerNorm for c = %d", c);
   }
 }
 
@@ -2116,12 +2130,15 @@ Plan* get_cr_plan(hd_handle* h, int B) {
   auto ew = [&](size_t total, int per_block = 256) { return dim3(static_cast<unsigned>(cdiv(total, static_cast<size_t>(per_block)))); };
   // split-precision tensor-core GEMM (c >= 128): A fp32 -> [hi | lo | hi] bf16, W pre-split [hi | hi | lo], K' = 3K,
   // fp32 accumulate in TMEM: a_hi w_hi + a_lo w_hi + a_hi w_lo
+  // A == nullptr: the producer (LayerNorm, SCA scale, SimpleGate) has already written the split operand into R.a3
   auto gemm_tc3 = [&](int M, int N, int K, const float* A, const bf16* Ws, const float* bias, int epi, float* out, int ldo,
                       const float* resid, long long rows_alloc, const std::string& label) {
     bf16* a3 = R.a3;
     const size_t total = static_cast<size_t>(M) * (K / 8);
-    g_label = label + " split3";
-    add_op(P, [=](cudaStream_t st) { launch_k(cr_split3_kernel, ew(total), dim3(256), 0, st, A, a3, static_cast<size_t>(M), K, 0); });
+    if (A != nullptr) {
+      g_label = label + " split3";
+      add_op(P, [=](cudaStream_t st) { launch_k(cr_split3_kernel, ew(total), dim3(256), 0, st, A, a3, static_cast<size_t>(M), K, 0); });
+    }
     GemmDesc d;
     d.M = M; d.N = N; d.K = 3 * K; d.A = a3; d.lda = 3 * K; d.a_dtype = DT_BF16; d.W = Ws; d.ldw = 3 * K; d.w_dtype = DT_BF16;
     d.bias = bias; d.epi = epi; d.out = out; d.ldo = ldo; d.out_dtype = DT_F32; d.resid = resid; d.ldr = ldo;
@@ -2136,8 +2153,11 @@ Plan* get_cr_plan(hd_handle* h, int B) {
     ModRef nomod{nullptr, nullptr, 0};
     const float *l1w = b.ln1_w, *l1b = b.ln1_b, *l2w = b.ln2_w, *l2b = b.ln2_b;
     g_label = L0 + "ln1";
-    add_op(P, [=](cudaStream_t st) { launch_ln<float>(c, x, l1w, l1b, ln_out, rows, rpf, nomod, 0, 0, 0, st); });
-    if (tc) gemm_tc3(rows, 2 * c, c, ln_out, b.w1s, b.b1, EPI_BIAS, act_h, 2 * c, nullptr, rows_alloc, L0 + "conv1");
+    const bool fs = tc && h->tun.cr_fuse_split;   // producers write the split GEMM operand themselves
+    bf16* a3 = R.a3;
+    if (fs) add_op(P, [=](cudaStream_t st) { launch_ln_split3(c, x, l1w, l1b, a3, rows, rpf, st); });
+    else add_op(P, [=](cudaStream_t st) { launch_ln<float>(c, x, l1w, l1b, ln_out, rows, rpf, nomod, 0, 0, 0, st); });
+    if (tc) gemm_tc3(rows, 2 * c, c, fs ? nullptr : ln_out, b.w1s, b.b1, EPI_BIAS, act_h, 2 * c, nullptr, rows_alloc, L0 + "conv1");
     else gemm(rows, 2 * c, c, ln_out, c, b.w1, b.b1, EPI_BIAS, act_h, 2 * c, nullptr, 0, L0 + "conv1");
     const float *dw_w = b.dw_w, *dw_b = b.dw_b;
     g_label = L0 + "dwconv+gate";
@@ -2151,22 +2171,25 @@ Plan* get_cr_plan(hd_handle* h, int B) {
       launch_k(cr_pool_kernel, dim3(c / 32, B), dim3(1024), 0, st, static_cast<const float*>(act_g), pooled, rpf, c);
     });
     gemm(B, c, c, pooled, c, b.wsca, b.bsca, EPI_BIAS, sca_s, c, nullptr, 0, L0 + "sca");
-    g_label = L0 + "scale_rows";
+    g_label = L0 + (fs ? "scale_rows -> split3" : "scale_rows");
     add_op(P, [=](cudaStream_t st) {
       const size_t total8 = static_cast<size_t>(rows) * c / 8;
-      launch_k(scale_rows_kernel<float>, ew(total8), dim3(256), 0, st, act_g, static_cast<const float*>(sca_s), total8, c, rpf);
+      if (fs) launch_k(cr_scale_split3_kernel, ew(total8), dim3(256), 0, st, static_cast<const float*>(act_g), static_cast<const float*>(sca_s), a3, total8, c, rpf);
+      else launch_k(scale_rows_kernel<float>, ew(total8), dim3(256), 0, st, act_g, static_cast<const float*>(sca_s), total8, c, rpf);
     });
-    if (tc) gemm_tc3(rows, c, c, act_g, b.w3s, b.b3, EPI_RESID, x, c, x, rows_alloc, L0 + "conv3");
+    if (tc) gemm_tc3(rows, c, c, fs ? nullptr : act_g, b.w3s, b.b3, EPI_RESID, x, c, x, rows_alloc, L0 + "conv3");
     else gemm(rows, c, c, act_g, c, b.w3, b.b3, EPI_RESID, x, c, x, 0, L0 + "conv3");
     g_label = L0 + "ln2";
-    add_op(P, [=](cudaStream_t st) { launch_ln<float>(c, x, l2w, l2b, ln_out, rows, rpf, nomod, 0, 0, 0, st); });
-    if (tc) gemm_tc3(rows, 2 * c, c, ln_out, b.w4s, b.b4, EPI_BIAS, act_h, 2 * c, nullptr, rows_alloc, L0 + "conv4");
+    if (fs) add_op(P, [=](cudaStream_t st) { launch_ln_split3(c, x, l2w, l2b, a3, rows, rpf, st); });
+    else add_op(P, [=](cudaStream_t st) { launch_ln<float>(c, x, l2w, l2b, ln_out, rows, rpf, nomod, 0, 0, 0, st); });
+    if (tc) gemm_tc3(rows, 2 * c, c, fs ? nullptr : ln_out, b.w4s, b.b4, EPI_BIAS, act_h, 2 * c, nullptr, rows_alloc, L0 + "conv4");
     else gemm(rows, 2 * c, c, ln_out, c, b.w4, b.b4, EPI_BIAS, act_h, 2 * c, nullptr, 0, L0 + "conv4");
     g_label = L0 + "gate";
     add_op(P, [=](cudaStream_t st) {
-      launch_k(cr_gate_kernel, ew(static_cast<size_t>(rows) * (c / 4)), dim3(256), 0, st, static_cast<const float*>(act_h), act_g, static_cast<size_t>(rows), c);
+      if (fs) launch_k(cr_gate_split3_kernel, ew(static_cast<size_t>(rows) * (c / 8)), dim3(256), 0, st, static_cast<const float*>(act_h), a3, static_cast<size_t>(rows), c);
+      else launch_k(cr_gate_kernel, ew(static_cast<size_t>(rows) * (c / 4)), dim3(256), 0, st, static_cast<const float*>(act_h), act_g, static_cast<size_t>(rows), c);
     });
-    if (tc) gemm_tc3(rows, c, c, act_g, b.w5s, b.b5, EPI_RESID, x, c, x, rows_alloc, L0 + "conv5");
+    if (tc) gemm_tc3(rows, c, c, fs ? nullptr : act_g, b.w5s, b.b5, EPI_RESID, x, c, x, rows_alloc, L0 + "conv5");
     else gemm(rows, c, c, act_g, c, b.w5, b.b5, EPI_RESID, x, c, x, 0, L0 + "conv5");
     P.flops_per_face += 2.0 * 9 * 2 * c * rpf;
   };
