@@ -337,6 +337,7 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
                __float_as_uint(t[i].w));
       }
     }
+    stamp();
     block_sync();
     {
       const uint32_t srow = stage_row(R);
@@ -353,6 +354,7 @@ __global__ void __launch_bounds__(THREADS, 1) face_block_kernel(const Args args)
       tmem_wait_st();
     }
     block_sync();  // every row has left the staging area before the A operand is written over it
+    stamp();
     residual_ln(t_x, R, nullptr, eff, sA);
   }
 

@@ -1283,7 +1283,7 @@ void add_face_blocks(hd_handle* h, Plan& P, size_t first, int count) {
     long long* tr = h->arena.get<long long>(64);
     a.trace = tr;
     a.trace_cta = atoi(getenv("HD_FACE_TRACE"));
-    const int n_st = 3 + 6 * count;
+    const int n_st = 5 + 6 * count;
     add_op(P, [=](cudaStream_t st) {
       launch_k(fb::face_block_kernel, dim3(B), dim3(fb::THREADS), fb::SMEM_BYTES, st, a);
       cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
