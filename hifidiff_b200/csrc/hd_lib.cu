@@ -80,6 +80,7 @@ struct Tunables {
   bool cr_fuse_split = true; // HD_CR_FUSE_SPLIT=0: separate fp32 -> [hi|lo|hi] kernels in front of the split tcgen05 GEMMs
   bool cr_stn_mma = true; // HD_CR_STN_MMA=0: the first STN localisation conv stays on CUDA cores
   bool cr_dw_strip = true; // HD_CR_DW_STRIP=0: CoarseRestoration depthwise conv one thread per pixel instead of per column strip
+  bool face_warm = true;  // HD_FACE_WARM=0: no instruction-cache warm-up / first-wave-only prefetch in the fused face kernel
   bool dw_small = true;   // HD_DW_SMALL=0: the generic tiled depthwise kernel at the 2x2 / 4x4 levels too
   int cta_target = 120;   // HD_CTA_TARGET: split-K until a GEMM's grid has at least this many CTAs
   int sca_target = 120;   // HD_SCA_TARGET: the same for the SCA GEMMs (M = faces)
@@ -87,7 +88,7 @@ struct Tunables {
   void read_env() {
     auto flag = [](const char* name, bool& v) { if (const char* e = getenv(name)) v = atoi(e) != 0; };
     flag("HD_PDL", pdl); flag("HD_BN256", bn256); flag("HD_FACE", face); flag("HD_PAIR", pair); flag("HD_SCA_MUL", sca_mul); flag("HD_EDGE_MMA", edge_mma); flag("HD_W_PREFETCH", w_prefetch);
-    flag("HD_CR_STN_CS", cr_stn_cs); flag("HD_CR_TC", cr_tc); flag("HD_CR_MMA3", cr_mma3); flag("HD_CR_STN_MMA", cr_stn_mma); flag("HD_CR_FUSE_SPLIT", cr_fuse_split); flag("HD_CR_MMA3H", cr_mma3h); flag("HD_CR_DW_STRIP", cr_dw_strip); flag("HD_DW_SMALL", dw_small);
+    flag("HD_CR_STN_CS", cr_stn_cs); flag("HD_CR_TC", cr_tc); flag("HD_CR_MMA3", cr_mma3); flag("HD_CR_STN_MMA", cr_stn_mma); flag("HD_CR_FUSE_SPLIT", cr_fuse_split); flag("HD_CR_MMA3H", cr_mma3h); flag("HD_CR_DW_STRIP", cr_dw_strip); flag("HD_DW_SMALL", dw_small); flag("HD_FACE_WARM", face_warm);
     if (const char* e = getenv("HD_TWO_CTA")) two_cta = atoi(e);
     if (const char* e = getenv("HD_CTA_TARGET")) cta_target = std::max(atoi(e), 1);
     if (const char* e = getenv("HD_SCA_TARGET")) sca_target = std::max(atoi(e), 1);
@@ -1279,6 +1280,7 @@ void add_face_blocks(hd_handle* h, Plan& P, size_t first, int count) {
   ti.ptr = a.x; ti.dtype = DT_F32; ti.C = c; ti.HW = rpf; ti.ld = c;
   std::string tap = h->blocks[first + count - 1].prefix;
   if (!tap.empty() && tap.back() == '.') tap.pop_back();
+  a.first_wave = h->tun.face_warm ? h->sm_count : 0;
   if (getenv("HD_FACE_TRACE") != nullptr) {  // diagnostics: phase timeline of CTA 0, printed after every eager launch
     long long* tr = h->arena.get<long long>(64);
     a.trace = tr;
@@ -1360,6 +1362,7 @@ void add_pair_blocks(hd_handle* h, Plan& P, size_t first, int count) {
   a.mod_row_idx = h->row_idx;
   a.mod_stride = h->mod_stride;
   a.status = h->d_status;
+  a.warm = h->tun.face_warm ? 1 : 0;
   static bool configured = false;
   if (!configured) {
     CUDA_CHECK(cudaFuncSetAttribute(pb::pair_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::SMEM_BYTES));
