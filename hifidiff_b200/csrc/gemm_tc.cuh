@@ -39,6 +39,7 @@ struct TcArgs {
   DeviceStatus* status;
   const void* pf_ptr;         // weights of the NEXT tensor-core GEMM of the plan: each CTA prefetches its share into L2
   unsigned int pf_bytes;      // (0 = none) so that GEMM's weight stream starts from L2 instead of HBM
+  unsigned long long w_policy; // L2 eviction priority of the weight tiles (kL2EvictNormal / kL2EvictFirst)
   long long* trace;           // optional per-CTA timeline (16 slots per CTA), nullptr in production
 };
 
@@ -112,6 +113,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+// the same with an L2 eviction-priority hint (policy = one of the kL2* encodings below)
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull, kL2EvictNormal = 0x1000000000000000ull;
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
@@ -314,7 +323,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int i = 0; i < pre0; ++i) {
       const uint32_t fb = smem_u32(&full_bar[i]);
       mbar_expect_tx(fb, Cfg::STAGE_BYTES);
-      tma_load_2d(smem_u32(smem + i * Cfg::STAGE_BYTES) + Cfg::A_BYTES, &mapB, (kb_begin + i) * BK, n0, fb);
+      tma_load_2d_hint(smem_u32(smem + i * Cfg::STAGE_BYTES) + Cfg::A_BYTES, &mapB, (kb_begin + i) * BK, n0, fb, args.w_policy);
     }
   }
   if (warp == 1) {
@@ -362,7 +371,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         } else {
           tma_load_2d(sa, &mapA, kb * BK, m0, fb);
         }
-        if (i >= pre) tma_load_2d(sb, &mapB, kb * BK, n0, fb);
+        if (i >= pre) tma_load_2d_hint(sb, &mapB, kb * BK, n0, fb, args.w_policy);
       }
     }
   } else if (warp == 1) {
@@ -700,6 +709,12 @@ __device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* ma
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(leader_bar)
       : "memory");
 }
+__device__ __forceinline__ void tma2_load_2d_hint(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(leader_bar), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
                                              uint32_t leader_bar) {
   asm volatile(
@@ -818,7 +833,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         } else {
           tma2_load_2d(sa, &mapA, i * BK, m0, fb_leader);
         }
-        tma2_load_2d(sb, &mapB, i * BK, n0 + static_cast<int>(rank) * (BN / 2), fb_leader);
+        tma2_load_2d_hint(sb, &mapB, i * BK, n0 + static_cast<int>(rank) * (BN / 2), fb_leader, args.w_policy);
       }
     }
   } else if (warp == 1) {
