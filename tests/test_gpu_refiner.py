@@ -5,6 +5,7 @@ import pytest
 import torch
 
 import hifidiff_b200 as H
+from oracle import cond_ref
 
 from gpu_util import build
 from util import golden, inputs, rel_l2
@@ -39,8 +40,9 @@ def test_refiner_step(prec, native, tol_prior, tol_id, tol_eps):
 
 @pytest.mark.parametrize("prec,batch,tol", [("fp32", 3, 1e-5), ("bf16", 5, 1e-2), ("bf16", 70, 1e-2)])
 def test_idc_native_vs_module(prec, batch, tol):
-    """hd_idc_forward against the PyTorch ResNet-50 with the same state_dict (fp32 cuDNN, TF32 off): ragged batch
-    and a batch that spans two 64-face chunks; host input through the staging path gives the same bits."""
+    """hd_idc_forward against the CPU oracle (the restatement pinned to the reference's output) and against the
+    PyTorch ResNet-50 with the same state_dict (fp32 cuDNN, TF32 off): ragged batch and a batch that spans two 64-face
+    chunks; host input through the staging path gives the same bits."""
     with torch.no_grad():
         m, sd = build(H.FacialRefiner, seed=5, precision=prec, max_batch=4, args=())
         g = torch.Generator().manual_seed(11)
@@ -55,11 +57,16 @@ def test_idc_native_vs_module(prec, batch, tol):
         eng.check(eng.lib.hd_idc_forward(eng.handle, face.contiguous().data_ptr(), 128, out_h.data_ptr(), batch, None),
                   "hd_idc_forward")
         eng.synchronize()
+        n_or = min(batch, 6)                  # the oracle arm: the first faces and, for two chunks, the last ones
+        pick = list(range(n_or)) + ([batch - 2, batch - 1] if batch > 64 else [])
+        want = cond_ref.idc_forward({k: v.float().cpu() for k, v in sd.items()}, face[pick], "idc.")
     e = rel_l2(got, ref)
     worst = max(rel_l2(got[i], ref[i]) for i in range(batch))
-    print(f"idc {prec} B={batch}: rel-L2 {e:.3e} (worst face {worst:.3e})")
+    worst_or = max(rel_l2(got[i].cpu(), want[k]) for k, i in enumerate(pick))
+    print(f"idc {prec} B={batch}: rel-L2 {e:.3e} (worst face {worst:.3e}); vs the CPU oracle on faces {pick}: worst {worst_or:.3e}")
     assert torch.isfinite(got).all()
     assert worst <= tol
+    assert worst_or <= tol
     assert torch.equal(out_h, got)
     with pytest.raises(RuntimeError):
         eng.idc_forward(torch.rand((1, 3, 64, 64)).cuda())   # image size must be 8 x latent size
