@@ -84,6 +84,7 @@ struct Tunables {
   bool face_warm = true;  // HD_FACE_WARM=0: no instruction-cache warm-up / first-wave-only prefetch in the fused face kernel
   bool dw_small = true;   // HD_DW_SMALL=0: the generic tiled depthwise kernel at the 2x2 / 4x4 levels too
   int cta_target = 120;   // HD_CTA_TARGET: split-K until a GEMM's grid has at least this many CTAs
+  int max_split = 4;      // HD_MAX_SPLIT: deepest split-K (cluster size along z); 8-way DSMEM reductions measured slower at every batch (1 .. 256 faces: -1 .. -12 % per step with 4)
   int sca_target = 120;   // HD_SCA_TARGET: the same for the SCA GEMMs (M = faces)
   int cr_chunk = 128;     // HD_CR_CHUNK: faces per CoarseRestoration pass (~14 MB of fp32 workspace per face; 32: 66 ms, 64: 53 ms, 128: 48 ms, 256: 46 ms per 256 faces)
   void read_env() {
@@ -92,6 +93,7 @@ struct Tunables {
     flag("HD_CR_STN_CS", cr_stn_cs); flag("HD_CR_TC", cr_tc); flag("HD_CR_MMA3", cr_mma3); flag("HD_CR_STN_MMA", cr_stn_mma); flag("HD_CR_FUSE_SPLIT", cr_fuse_split); flag("HD_CR_MMA3H", cr_mma3h); flag("HD_CR_DW_STRIP", cr_dw_strip); flag("HD_DW_SMALL", dw_small); flag("HD_FACE_WARM", face_warm); flag("HD_W_EVICT_FIRST", w_evict_first);
     if (const char* e = getenv("HD_TWO_CTA")) two_cta = atoi(e);
     if (const char* e = getenv("HD_CTA_TARGET")) cta_target = std::max(atoi(e), 1);
+    if (const char* e = getenv("HD_MAX_SPLIT")) max_split = std::min(std::max(atoi(e), 1), 8);
     if (const char* e = getenv("HD_SCA_TARGET")) sca_target = std::max(atoi(e), 1);
     if (const char* e = getenv("HD_CR_CHUNK")) cr_chunk = std::min(std::max(atoi(e), 1), 256);
   }
@@ -620,7 +622,7 @@ TcLaunch build_tc(hd_handle* h, const GemmDesc& d, long long a_rows_alloc) {
   // split-K over a (1,1,S) cluster until the grid can cover the chip (>= 120 CTAs)
   const int tiles = cdiv(d.M, 128) * (d.N / bn);
   int split = 1;
-  while (tiles * split < d.cta_target && split < 8 && a.num_kb % (2 * split) == 0 && a.num_kb / (2 * split) >= 2) split *= 2;
+  while (tiles * split < d.cta_target && split < h->tun.max_split && a.num_kb % (2 * split) == 0 && a.num_kb / (2 * split) >= 2) split *= 2;
   L.grid = dim3(cdiv(d.M, 128), d.N / bn, split);
   const int local_kb = a.num_kb / split;
   L.stages = local_kb <= 2 ? 2 : (tiles * split <= 160 ? 6 : 3);
