@@ -67,7 +67,7 @@ inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) 
 struct Tunables {
   bool pdl = true;        // HD_PDL=0 disables programmatic dependent launch
   bool bn256 = true;      // HD_BN256=0: 128x128 tiles for the dense 3x3 convs too
-  int two_cta = 1;        // HD_TWO_CTA=0: never use cta_group::2 pairs; 2: wherever the shape allows (tests)
+  int two_cta = 1;        // HD_TWO_CTA=0: never use cta_group::2 pairs; 2 (set by hd_debug_gemm only): wherever the shape allows
   bool face = true;       // HD_FACE=0: per-op kernels at the 16x16 level instead of the fused per-face block kernel
   bool pair = true;       // HD_PAIR=0: per-op kernels at the 8x8 level instead of the fused face-pair block kernel
   bool sca_mul = true;    // HD_SCA_MUL=0: separate scale_rows kernel at the 1x1 level too
@@ -91,7 +91,7 @@ struct Tunables {
     auto flag = [](const char* name, bool& v) { if (const char* e = getenv(name)) v = atoi(e) != 0; };
     flag("HD_PDL", pdl); flag("HD_BN256", bn256); flag("HD_FACE", face); flag("HD_PAIR", pair); flag("HD_SCA_MUL", sca_mul); flag("HD_EDGE_MMA", edge_mma); flag("HD_W_PREFETCH", w_prefetch);
     flag("HD_CR_STN_CS", cr_stn_cs); flag("HD_CR_TC", cr_tc); flag("HD_CR_MMA3", cr_mma3); flag("HD_CR_STN_MMA", cr_stn_mma); flag("HD_CR_FUSE_SPLIT", cr_fuse_split); flag("HD_CR_MMA3H", cr_mma3h); flag("HD_CR_DW_STRIP", cr_dw_strip); flag("HD_DW_SMALL", dw_small); flag("HD_FACE_WARM", face_warm); flag("HD_W_EVICT_FIRST", w_evict_first);
-    if (const char* e = getenv("HD_TWO_CTA")) two_cta = atoi(e);
+    if (const char* e = getenv("HD_TWO_CTA")) two_cta = atoi(e) != 0 ? 1 : 0;  // 2 (pairs wherever the shape allows) only through hd_debug_gemm: a whole plan forced onto pairs hung in round 2
     if (const char* e = getenv("HD_CTA_TARGET")) cta_target = std::max(atoi(e), 1);
     if (const char* e = getenv("HD_MAX_SPLIT")) max_split = std::min(std::max(atoi(e), 1), 8);
     if (const char* e = getenv("HD_SCA_TARGET")) sca_target = std::max(atoi(e), 1);
