@@ -1997,6 +1997,46 @@ void load_cr_stn(hd_handle* h, CrStnW& s, const std::string& p, int c, int res) 
   s.fb2 = cr_vec(h, p + "fc_loc.2.bias", 6);
 }
 
+// Split copies of an fp32 weight matrix [N, K] for the mma.sync GEMMs of CoarseRestoration's shallow stages, made
+// once per matrix (at load for every matrix that can take the path; the look-up at plan time only builds one if a
+// shape was not foreseen): scaled fp16 hi + lo for gemm_mma3h (K = 32 / 64), tf32 hi + lo for gemm_mma3.
+const CrW::SplitH& cr_split_h(hd_handle* h, const float* W, int N, int K) {
+  auto& cache = h->cr.split_h;
+  auto it = cache.find(W);
+  if (it != cache.end()) return it->second;
+  const size_t nw = static_cast<size_t>(N) * K;
+  std::vector<float> wf(nw);
+  CUDA_CHECK(cudaMemcpyAsync(wf.data(), W, nw * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  float wmax = 0.f;
+  for (float f : wf) wmax = std::max(wmax, std::fabs(f));
+  const float wscale = wmax > 0.f && std::isfinite(wmax) ? std::ldexp(1.f, 14 - std::ilogb(wmax)) : 1.f;
+  std::vector<uint16_t> vh(nw), vl(nw);
+  for (size_t i = 0; i < nw; ++i) {
+    const float f = wf[i] * wscale;
+    const __half hh = __float2half_rn(f);
+    vh[i] = static_cast<__half_raw>(hh).x;
+    vl[i] = static_cast<__half_raw>(__float2half_rn(f - __half2float(hh))).x;
+  }
+  CrW::SplitH sp;
+  sp.hi = static_cast<__half*>(h->arena.alloc(nw * 2));
+  sp.lo = static_cast<__half*>(h->arena.alloc(nw * 2));
+  sp.unscale = 1.f / wscale;
+  CUDA_CHECK(cudaMemcpy(sp.hi, vh.data(), nw * 2, cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(sp.lo, vl.data(), nw * 2, cudaMemcpyHostToDevice));
+  return cache.emplace(W, sp).first->second;
+}
+const std::pair<float*, float*>& cr_split_tf32(hd_handle* h, const float* W, int N, int K) {
+  auto& cache = h->cr.split_hl;
+  auto it = cache.find(W);
+  if (it != cache.end()) return it->second;
+  const size_t nw = static_cast<size_t>(N) * K;
+  float *hi = h->arena.get<float>(nw), *lo = h->arena.get<float>(nw);
+  mma3::split_hl_kernel<<<cdiv(nw, static_cast<size_t>(256)), 256, 0, h->stream>>>(W, hi, lo, nw);
+  CUDA_CHECK(cudaGetLastError());
+  return cache.emplace(W, std::make_pair(hi, lo)).first->second;
+}
+
 void load_cr_impl(hd_handle* h) {
   CrW& R = h->cr;
   R.H = 8 * h->S;
@@ -2055,6 +2095,19 @@ void load_cr_impl(hd_handle* h) {
   R.stage = h->arena.get<float>(cap * 3 * R.H * R.H);
   R.use_tc = h->bf16 && h->tun.cr_tc;
   if (R.use_tc) R.a3 = h->arena.get<bf16>(cap * 3 * e[2]);  // levels with c >= 128: rows x c <= e[2]
+  R.split_h.clear();
+  R.split_hl.clear();
+  if (R.use_tc && h->tun.cr_mma3) {  // split weights of the mma.sync GEMMs: here, not at the first forward
+    for (const CrStageW& st : R.stages) {
+      const int c = st.c;
+      if (h->tun.cr_mma3h && (c == 32 || c == 64))
+        for (const CrBlockW& b : st.blocks) {
+          cr_split_h(h, b.w1, 2 * c, c); cr_split_h(h, b.w3, c, c); cr_split_h(h, b.w4, 2 * c, c); cr_split_h(h, b.w5, c, c);
+        }
+      if (st.sampling == 1) cr_split_tf32(h, st.samp_w, 2 * c, 4 * c);
+      if (st.sampling == 2) cr_split_tf32(h, st.samp_w, 2 * c, c);
+    }
+  }
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   for (void* p : h->temp_dev) cudaFree(p);
   h->temp_dev.clear();
@@ -2078,34 +2131,10 @@ Plan* get_cr_plan(hd_handle* h, int B) {
     d.bias = bias; d.epi = epi; d.out = out; d.ldo = ldo; d.out_dtype = DT_F32; d.resid = resid; d.ldr = ldo; d.sp = sp;
     if (R.use_tc && h->tun.cr_mma3 && h->tun.cr_mma3h && lda % 4 == 0 && ldo % 2 == 0 && mma3::eligible_h(M, N, K, epi)) {
       // K = 32 / 64: the whole K extent in one stage, row-scaled fp16 split (k16 MMAs)
-      auto& cache = h->cr.split_h;
-      auto it = cache.find(W);
-      if (it == cache.end()) {
-        const size_t nw = static_cast<size_t>(N) * K;
-        std::vector<float> wf(nw);
-        CUDA_CHECK(cudaMemcpyAsync(wf.data(), W, nw * 4, cudaMemcpyDeviceToHost, h->stream));
-        CUDA_CHECK(cudaStreamSynchronize(h->stream));
-        float wmax = 0.f;
-        for (float f : wf) wmax = std::max(wmax, std::fabs(f));
-        const float wscale = wmax > 0.f && std::isfinite(wmax) ? std::ldexp(1.f, 14 - std::ilogb(wmax)) : 1.f;
-        std::vector<uint16_t> vh(nw), vl(nw);
-        for (size_t i = 0; i < nw; ++i) {
-          const float f = wf[i] * wscale;
-          const __half hh = __float2half_rn(f);
-          vh[i] = static_cast<__half_raw>(hh).x;
-          vl[i] = static_cast<__half_raw>(__float2half_rn(f - __half2float(hh))).x;
-        }
-        CrW::SplitH sp;
-        sp.hi = static_cast<__half*>(h->arena.alloc(nw * 2));
-        sp.lo = static_cast<__half*>(h->arena.alloc(nw * 2));
-        sp.unscale = 1.f / wscale;
-        CUDA_CHECK(cudaMemcpy(sp.hi, vh.data(), nw * 2, cudaMemcpyHostToDevice));
-        CUDA_CHECK(cudaMemcpy(sp.lo, vl.data(), nw * 2, cudaMemcpyHostToDevice));
-        it = cache.emplace(W, sp).first;
-      }
+      const CrW::SplitH& sp = cr_split_h(h, W, N, K);
       mma3::ArgsH a;
-      a.A = A; a.w_hi = it->second.hi; a.w_lo = it->second.lo; a.bias = bias; a.out = out; a.resid = resid;
-      a.lda = lda; a.ldo = ldo; a.ldr = ldo; a.M = M; a.N = N; a.w_unscale = it->second.unscale;
+      a.A = A; a.w_hi = sp.hi; a.w_lo = sp.lo; a.bias = bias; a.out = out; a.resid = resid;
+      a.lda = lda; a.ldo = ldo; a.ldr = ldo; a.M = M; a.N = N; a.w_unscale = sp.unscale;
       g_label = label + fmt(" gemm_mma3h M=%d N=%d K=%d (3 x fp16 split, row-scaled)", M, N, K);
       add_op(P, [a, K, epi](cudaStream_t st) { launch_mma3h(a, K, epi, st); });
       P.flops_per_face += 2.0 * M * static_cast<double>(N) * K / P.batch;
@@ -2113,17 +2142,9 @@ Plan* get_cr_plan(hd_handle* h, int B) {
     }
     if (R.use_tc && h->tun.cr_mma3 && lda % 4 == 0 && ldo % 2 == 0 && mma3::eligible(M, N, K, epi)) {
       // shallow stages: FFMA-bound on CUDA cores, memory-bound on mma.sync with split operands
-      auto& cache = h->cr.split_hl;
-      auto it = cache.find(W);
-      if (it == cache.end()) {
-        const size_t nw = static_cast<size_t>(N) * K;
-        float *hi = h->arena.get<float>(nw), *lo = h->arena.get<float>(nw);
-        mma3::split_hl_kernel<<<cdiv(nw, static_cast<size_t>(256)), 256, 0, h->stream>>>(W, hi, lo, nw);
-        CUDA_CHECK(cudaGetLastError());
-        it = cache.emplace(W, std::make_pair(hi, lo)).first;
-      }
+      const std::pair<float*, float*>& wsp = cr_split_tf32(h, W, N, K);
       mma3::Args a;
-      a.A = A; a.w_hi = it->second.first; a.w_lo = it->second.second; a.bias = bias; a.out = out; a.resid = resid;
+      a.A = A; a.w_hi = wsp.first; a.w_lo = wsp.second; a.bias = bias; a.out = out; a.resid = resid;
       a.lda = lda; a.ldo = ldo; a.ldr = ldo; a.M = M; a.N = N; a.K = K; a.sp = sp;
       g_label = label + fmt(" gemm_mma3 M=%d N=%d K=%d (3 x tf32 split)", M, N, K);
       add_op(P, [a, epi](cudaStream_t st) { launch_mma3(a, epi, st); });
