@@ -164,10 +164,24 @@ class FacialRefiner(nn.Module):
         self.native_fpg = True   # run FPG on the sm_100a kernels (False: PyTorch eager)
         self.native_idc = True   # run the IDC ResNet-50 on the sm_100a kernels (False: PyTorch/cuDNN eager)
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._drop_condition())
+        # the engine keeps packed copies of the FPG / IDC weights: a load aimed directly at a sub-module
+        # (refiner.fpg.load_state_dict(...), refiner.idc.load_state_dict(...)) must drop them as well
+        for sub in (self.fpg, self.idc):
+            sub.register_load_state_dict_post_hook(lambda module, incompatible: self._weights_changed())
 
     def _drop_condition(self) -> None:
         self._cond_src = None
         self._cond = None
+
+    def _weights_changed(self) -> None:
+        """FPG / IDC parameters were replaced: forget the cached condition and the engine's packed copies."""
+        self._drop_condition()
+        self.denoiser.invalidate()
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)  # .to() / .cuda() / .float(): every cached tensor is stale
+        self._weights_changed()
+        return out
 
     @torch.no_grad()
     def condition(self, cr_face: torch.Tensor, cr_latent: torch.Tensor):

@@ -98,3 +98,31 @@ def test_refiner_constructor_matches_reference(ckpts):
     assert not res.missing_keys and not res.unexpected_keys
     for k, v in again.state_dict().items():
         assert torch.equal(v, sw[k]), k
+
+
+def test_submodule_loads_drop_the_packed_copies(ckpts):
+    """The engine keeps packed copies of the FPG / IDC weights and the refiner caches the hoisted condition: a load
+    aimed at a sub-module (`refiner.fpg.load_state_dict`, `refiner.idc.load_state_dict` — how refiner.py:17,24-25
+    themselves load) or a `.to()` must drop both, exactly as a load of the whole refiner does."""
+    _, _, _, sd_idc = ckpts
+    m = H.FacialRefiner(latent_res=16)
+    calls = []
+    orig = m.denoiser.invalidate
+    m.denoiser.invalidate = lambda: (calls.append(1), orig())[1]
+
+    def armed():
+        m._cond, m._cond_src = ("stale",), ("stale",)
+        calls.clear()
+
+    armed()
+    m.idc.load_state_dict(sd_idc)
+    assert calls and m._cond is None and m._cond_src is None
+    armed()
+    m.fpg.load_state_dict(m.fpg.state_dict())
+    assert calls and m._cond is None and m._cond_src is None
+    armed()
+    m.load_state_dict(m.state_dict())
+    assert m._cond is None and m._cond_src is None
+    armed()
+    m.to(torch.float32)
+    assert calls and m._cond is None and m._cond_src is None
