@@ -129,6 +129,10 @@ def ResNet50(channels: int = 3) -> ResNet:
     return ResNet((3, 4, 6, 3), channels)
 
 
+def _bump_epoch(module, incompatible) -> None:
+    module._hd_epoch = getattr(module, "_hd_epoch", 0) + 1
+
+
 def _tensor_key(tensors):
     """Strong references plus the version counters at the time the condition was computed."""
     return tuple((t, t._version) for t in tensors)
@@ -165,9 +169,12 @@ class FacialRefiner(nn.Module):
         self.native_idc = True   # run the IDC ResNet-50 on the sm_100a kernels (False: PyTorch/cuDNN eager)
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._drop_condition())
         # the engine keeps packed copies of the FPG / IDC weights: a load aimed directly at a sub-module
-        # (refiner.fpg.load_state_dict(...), refiner.idc.load_state_dict(...)) must drop them as well
+        # (refiner.fpg.load_state_dict(...), refiner.idc.load_state_dict(...)) must drop them as well.  The hooks only
+        # bump a counter on the sub-module itself (no reference to the parent: deepcopy-safe); `condition` compares.
         for sub in (self.fpg, self.idc):
-            sub.register_load_state_dict_post_hook(lambda module, incompatible: self._weights_changed())
+            sub._hd_epoch = 0
+            sub.register_load_state_dict_post_hook(_bump_epoch)
+        self._packed_epoch = (0, 0)
 
     def _drop_condition(self) -> None:
         self._cond_src = None
@@ -177,6 +184,12 @@ class FacialRefiner(nn.Module):
         """FPG / IDC parameters were replaced: forget the cached condition and the engine's packed copies."""
         self._drop_condition()
         self.denoiser.invalidate()
+
+    def _sync_weight_epoch(self) -> None:
+        epoch = (self.fpg._hd_epoch, self.idc._hd_epoch)
+        if epoch != self._packed_epoch:
+            self._weights_changed()
+            self._packed_epoch = epoch
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)  # .to() / .cuda() / .float(): every cached tensor is stale
@@ -196,6 +209,7 @@ class FacialRefiner(nn.Module):
         if (self.native_fpg and cr_latent.device.type != "cuda") or (self.native_idc and cr_face.device.type != "cuda"):
             # no silent detour through PyTorch eager: the native paths are the product; native_* = False is the opt-out
             raise RuntimeError("hifidiff_b200 has no CPU path: cr_face and cr_latent must be CUDA tensors")
+        self._sync_weight_epoch()
         if not _same_tensors(self._cond_src, (cr_face, cr_latent)):
             was_training = self.training
             self.eval()  # BatchNorm must use running statistics on the sampling path

@@ -5,8 +5,10 @@ This module reproduces the reference's constructor, `forward(x)` contract ((B,3,
 (B,3,128,128) coarse frontal face) and `state_dict()` layout exactly (checked against the unmodified reference by
 tests/golden/make_golden_cr.py: same keys, order, shapes, dtypes and seeded default init), so checkpoints load
 unchanged.  On a CUDA device `forward` runs on the library's own kernels (`hd_load_cr_weights` / `hd_cr_forward`:
-fp32 NHWC, NAF blocks on the FFMA GEMM, fused localisation conv + pool, affine-grid bilinear resampling) — a first,
-native version of this once-per-face stage.  There is no implicit fallback: a CPU tensor or a call that needs
+fp32 NHWC stream, every contraction on the tensor cores with split-precision operands and fp32 accumulation —
+tcgen05 3 x bf16 at c >= 128, row-scaled 3 x fp16 / 3xTF32 `mma.sync` GEMMs for the wide shallow stages, the STN
+localisation conv as a scaled fp16 implicit GEMM with fused pool + ReLU — and affine-grid bilinear resampling;
+DESIGN.md §1 row f.3).  There is no implicit fallback: a CPU tensor or a call that needs
 autograd raises; `native = False` is the explicit opt-out to the plain PyTorch arithmetic below (training, and the
 CPU tests that pin this module's layout and arithmetic against the reference).
 """
@@ -100,14 +102,14 @@ class CoarseRestoration(nn.Module):
         p = next(self.parameters())
         if p.device.type != "cuda":
             raise RuntimeError("the native CoarseRestoration path runs only on CUDA (sm_100a)")
-        if self._engine is None or self._engine_dev != p.device:
+        if self._engine is None or self._engine_dev != (p.device, bool(self.tensor_cores)):
             self.invalidate()
             with torch.cuda.device(p.device):
                 torch.cuda.synchronize()
                 eng = _Engine(_lib.HD_MODEL_DENOISER, 16, _lib.HD_PRECISION_BF16 if self.tensor_cores else _lib.HD_PRECISION_FP32,
                               p.device, 1, 1, False)
                 eng.load_cr_state(self.state_dict())
-            self._engine, self._engine_dev = eng, p.device
+            self._engine, self._engine_dev = eng, (p.device, bool(self.tensor_cores))
         return self._engine
 
     @torch.no_grad()

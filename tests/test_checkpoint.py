@@ -104,6 +104,7 @@ def test_submodule_loads_drop_the_packed_copies(ckpts):
     """The engine keeps packed copies of the FPG / IDC weights and the refiner caches the hoisted condition: a load
     aimed at a sub-module (`refiner.fpg.load_state_dict`, `refiner.idc.load_state_dict` — how refiner.py:17,24-25
     themselves load) or a `.to()` must drop both, exactly as a load of the whole refiner does."""
+    import copy
     _, _, _, sd_idc = ckpts
     m = H.FacialRefiner(latent_res=16)
     calls = []
@@ -111,14 +112,19 @@ def test_submodule_loads_drop_the_packed_copies(ckpts):
     m.denoiser.invalidate = lambda: (calls.append(1), orig())[1]
 
     def armed():
+        m._sync_weight_epoch()
         m._cond, m._cond_src = ("stale",), ("stale",)
         calls.clear()
 
     armed()
+    m._sync_weight_epoch()          # nothing loaded since: the cache survives
+    assert not calls and m._cond == ("stale",)
     m.idc.load_state_dict(sd_idc)
+    m._sync_weight_epoch()          # what `condition` does first
     assert calls and m._cond is None and m._cond_src is None
     armed()
     m.fpg.load_state_dict(m.fpg.state_dict())
+    m._sync_weight_epoch()
     assert calls and m._cond is None and m._cond_src is None
     armed()
     m.load_state_dict(m.state_dict())
@@ -126,3 +132,11 @@ def test_submodule_loads_drop_the_packed_copies(ckpts):
     armed()
     m.to(torch.float32)
     assert calls and m._cond is None and m._cond_src is None
+    # the hooks hold no reference to the parent: a deep copy tracks its own sub-modules
+    m.denoiser.invalidate = orig
+    armed()
+    m2 = copy.deepcopy(m)
+    m2.idc.load_state_dict(sd_idc)
+    m2._sync_weight_epoch()
+    m._sync_weight_epoch()
+    assert m2._cond is None and m._cond == ("stale",)
