@@ -11,7 +11,7 @@
 //   SCA                 per-face mean -> 128x128 GEMV on CUDA cores -> rescale of the gated operand
 //
 // Reference arithmetic: models/denoiser/conditional_naf.py:108-136 (block), utils.py:16-24 (LayerNorm2d),
-// utils.py:57-60 (SimpleGate); beta/gamma are folded into conv3/conv5, conv4 is gate-packed (hd_lib.cu).
+// utils.py:57-60 (SimpleGate); beta/gamma are folded into conv3/conv5, conv4 is gate-packed (hd_weights.inl).
 //
 // Shared memory (232000 B):  A 64 KB | T 128 KB (two planes; also parking space for W1 / W4) | W3/W5 32 KB | misc
 // Tensor memory (512 cols):  x m-tile 0 | x m-tile 1 | accumulator m-tile 0 | accumulator m-tile 1
