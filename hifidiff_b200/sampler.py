@@ -49,6 +49,8 @@ def sample(model, x_T: torch.Tensor, scheduler: _SchedulerBase, num_inference_st
     """
     if x_T.device.type != "cuda":
         raise RuntimeError("hifidiff_b200 has no CPU path: x_T must be a CUDA tensor")
+    if x_T.shape[0] == 0:  # an empty shard (fewer faces than ranks in `sample_sharded`): nothing to launch
+        return (model.denoiser if isinstance(model, FacialRefiner) else model)._check_latents(x_T).clone()
     if isinstance(model, FacialRefiner):
         facial_priors, identity_embedding = model.condition(cr_face, cr_latent)
         model = model.denoiser

@@ -46,7 +46,7 @@ def _worker(rank, world, port, n_faces, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_faces", [7, 8])
+@pytest.mark.parametrize("n_faces", [1, 7, 8])  # 1: the second rank owns an EMPTY shard
 def test_sample_sharded_world2_gloo(tmp_path, n_faces):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), n_faces, str(tmp_path)), nprocs=world, join=True)
