@@ -60,7 +60,7 @@ typedef struct hd_config {
   int32_t struct_size;  /* = sizeof(hd_config) */
   int32_t model;        /* hd_model_kind */
   int32_t precision;    /* hd_precision */
-  int32_t latent_size;  /* S: latents are (B,4,S,S); multiple of 16 (model.py:198-200), 16 supported */
+  int32_t latent_size;  /* S: latents are (B,4,S,S); 16 or 32 (model.py:198-200; --image_res 128 / 256) */
   int32_t device;       /* CUDA device ordinal */
   int32_t max_batch;    /* workspace is sized for this many faces per call */
   int32_t max_steps;    /* rows of the time-modulation table (>= sampler steps) */
@@ -162,7 +162,10 @@ int32_t hd_set_condition(hd_handle* h, const float* const priors[5], const float
                          int32_t batch, void* stream);
 
 /* One epsilon prediction.  Replaces Denoiser.forward (model.py:106-134) / FusedDenoiser.forward
- * (model.py:217-266).  t has t_len == 1 (shared) or t_len == batch entries.  */
+ * (model.py:217-266).  t has t_len == 1 (shared) or t_len == batch entries.
+ * The time-modulation table is keyed by the VALUES of t, so this entry point reads t on the host and
+ * waits for `stream` (the one exception to "calls do not synchronise" besides host buffers); the
+ * sampling loop proper is hd_sample, which runs every step from device-resident state. */
 int32_t hd_denoise_step(hd_handle* h, const float* x, const float* t, int32_t t_len,
                         float* eps_out, int32_t batch, void* stream);
 
