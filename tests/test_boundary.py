@@ -89,3 +89,45 @@ def test_no_oracle_import_in_product():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_built_library_is_blackwell_native():
+    """Static check on the shipped binary (no GPU needed): it holds sm_100a code only, and the hot kernels carry the
+    instructions their design claims — tcgen05.mma (UTCHMMA, incl. cta_group::2), tcgen05.ld (LDTM) and TMA tensor
+    loads (UTMALDG) in the GEMM family and in the fused face / pair block kernels, the bulk L2 prefetch (UBLKPF) in
+    the GEMMs, mma.sync (HMMA) + ldmatrix (LDSM) in the edge convs.  A rebuild that fell back to CUDA-core paths, or
+    for another architecture, fails here before it reaches a GPU box."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    elf = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"\.(sm_\d+a?)\.", elf))
+    assert archs == {"sm_100a"}, archs
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    per_kernel, cur = {}, None
+    for line in sass.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per_kernel[cur] = set()
+            continue
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        if m and cur:
+            per_kernel[cur].add(m.group(1))
+
+    def family(tag):
+        ks = [ops for name, ops in per_kernel.items() if tag in name]
+        assert ks, f"no kernel matching {tag}"
+        return ks
+
+    for ops in family("gemm_tc_kernel") + family("gemm_tc2_kernel"):
+        assert {"UTCHMMA", "LDTM", "UTMALDG"} <= ops, ops & {"UTCHMMA", "LDTM", "UTMALDG"}
+    assert any("UBLKPF" in ops for ops in family("gemm_tc_kernel"))
+    for tag in ("face_block_kernel", "pair_block_kernel"):
+        for ops in family(tag):
+            assert {"UTCHMMA", "LDTM", "UTMALDG"} <= ops, tag
+    for tag in ("intro_mma_kernel", "ending_mma_kernel", "stn_conv_mma_kernel", "gemm_mma3"):
+        for ops in family(tag):
+            assert "HMMA" in ops, tag
+    assert ".2CTA" in sass and "UTCBAR" in sass     # cta_group::2 pairs + tcgen05.commit
