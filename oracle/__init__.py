@@ -25,8 +25,11 @@ Parity pinning
   reference modules and this restatement on identical weights/inputs, asserts
   agreement, and commits the reference's outputs as fixtures under
   ``tests/golden/``.
-* Scheduler arithmetic (diffusers): PARITY UNPINNED by the reference — it holds
-  no test or golden vector at that boundary and diffusers is absent.  The
-  restatement follows the published 0.32.2 algorithm and is checked for
-  self-consistency (``tests/test_schedulers.py``).
+* Scheduler arithmetic (diffusers): the reference holds no test or golden vector
+  at that boundary and diffusers is absent, so the restatement of the published
+  0.32.2 algorithm is PINNED against the dependency's own known-answer tests
+  instead: ``tests/test_schedulers.py`` replays the full loops and variance
+  checks of diffusers' ``tests/schedulers/test_scheduler_ddim.py`` /
+  ``test_scheduler_ddpm.py`` and reproduces their asserted numbers (fixtures and
+  constants restated from the published suite; see ``schedulers_ref.py``).
 """

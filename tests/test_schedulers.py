@@ -1,5 +1,6 @@
-"""CPU: scheduler restatement (diffusers 0.32.2 semantics, PARITY UNPINNED by the reference) —
-self-consistency checks of SURVEY.md App. C, and the product's per-step coefficients against it."""
+"""CPU: scheduler restatement (diffusers 0.32.2 semantics; the reference itself holds no vector at this boundary) —
+the known-answer vectors of diffusers' own scheduler tests (bottom of this file), the self-consistency checks of
+SURVEY.md App. C, and the product's per-step coefficients against the oracle."""
 import numpy as np
 import pytest
 import torch
@@ -113,7 +114,7 @@ def test_unsupported_diffusers_kwargs_raise():
 
 
 def test_oracle_against_the_published_formulas_in_float64():
-    """Independent anchor for the (parity-unpinned) scheduler oracle: the closed forms of the papers, evaluated in
+    """Second, independent anchor for the scheduler oracle (next to diffusers' known answers below): the closed forms of the papers, evaluated in
     numpy float64 from the beta schedule alone — Ho et al. 2020 eq. 6-7 (posterior mean / beta-tilde), Song et al.
     2021 eq. 12 (DDIM) — against the fp32 op-by-op restatement of diffusers' step()."""
     T = 1000
@@ -143,3 +144,95 @@ def test_oracle_against_the_published_formulas_in_float64():
             got = ddpm.step(eps, t, x, variance_noise=z).double().numpy()
             # 1 - abar_t cancels in fp32 as t -> 0 (abar_1 = 0.99978): diffusers' op order carries ~6e-5 there
             assert np.abs(got - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), ("ddpm", n, t)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Known-answer vectors of diffusers' OWN test-suite (huggingface/diffusers, tests/schedulers/test_scheduler_ddim.py and
+# test_scheduler_ddpm.py, unchanged across the 0.2x / 0.3x releases incl. the pinned 0.32.2).  The package is not on
+# this box, so the fixtures below restate that suite's `dummy_sample_deter`, `dummy_model` and `get_scheduler_config`
+# (num_train_timesteps=1000, beta_start=1e-4, beta_end=0.02, beta_schedule="linear", clip_sample=True) and the numbers
+# its assertions hold.  These pin BOTH scheduler restatements (the oracle's step() and the product's coefficient table)
+# to the upstream implementation; upstream's tolerances are 1e-2 on the sum and 1e-3 on the mean, ours are tighter.
+# ------------------------------------------------------------------------------------------------------------------
+def _dummy_sample_deter():
+    b, c, h, w = 4, 3, 8, 8
+    n = b * c * h * w
+    return (torch.arange(n).reshape(c, h, w, b) / n).permute(3, 0, 1, 2)
+
+
+def _dummy_model(sample, t):
+    return sample * t / (t + 1)
+
+
+_KAT_CFG = dict(num_train_timesteps=1000, beta_start=1e-4, beta_end=0.02, beta_schedule="linear", clip_sample=True)
+# (config overrides, |x|.sum(), |x|.mean()) — DDIMSchedulerTest.test_full_loop_no_noise / ..._with_set_alpha_to_one
+_DDIM_KATS = [({}, 172.0067, 0.223967), ({"beta_start": 0.01}, 149.8295, 0.1951)]
+# DDPMSchedulerTest.test_full_loop_no_noise: 1000 ancestral steps, noise from torch.manual_seed(0)
+_DDPM_KAT = (258.9606, 0.3372)
+
+
+def _ddim_loop(step_fn, timesteps):
+    x = _dummy_sample_deter()
+    for i, t in enumerate(timesteps):
+        x = step_fn(i, t, x, _dummy_model(x, t))
+    return x
+
+
+@pytest.mark.parametrize("over,want_sum,want_mean", _DDIM_KATS)
+def test_ddim_full_loop_matches_diffusers_known_answers(over, want_sum, want_mean):
+    cfg = dict(_KAT_CFG, **over)
+    o = R.DDIMSchedulerRef(**cfg)
+    o.set_timesteps(10)
+    x = _ddim_loop(lambda i, t, x, eps: o.step(eps, t, x, eta=0.0), o.timesteps.tolist())
+    assert abs(float(x.abs().sum()) - want_sum) < 2e-3 and abs(float(x.abs().mean()) - want_mean) < 1e-4
+    # the product: host coefficient table + the kernel's elementwise update (restated by _apply above)
+    p = S.DDIMScheduler(prediction_type="epsilon", **cfg)
+    p.set_timesteps(10)
+    assert p.timesteps.tolist() == o.timesteps.tolist() == list(range(900, -1, -100))
+    coefs = p.step_coefficients(eta=0.0)
+    y = _ddim_loop(lambda i, t, x, eps: _apply(coefs[i], x, eps, torch.zeros_like(x)), p.timesteps.tolist())
+    assert abs(float(y.abs().sum()) - want_sum) < 2e-3 and abs(float(y.abs().mean()) - want_mean) < 1e-4
+
+
+def test_ddpm_full_loop_matches_diffusers_known_answers():
+    want_sum, want_mean = _DDPM_KAT
+
+    def run(step_fn):
+        g = torch.manual_seed(0)                      # upstream: generator = torch.manual_seed(0)
+        x = _dummy_sample_deter()
+        for i, t in enumerate(reversed(range(1000))):
+            eps = _dummy_model(x, t)
+            z = torch.randn(eps.shape, generator=g)   # upstream draws a variance_noise at every step, t = 0 included
+            x = step_fn(i, t, x, eps, z)
+        return x
+
+    o = R.DDPMSchedulerRef(**_KAT_CFG)                # num_inference_steps unset: prev_t = t - 1
+    x = run(lambda i, t, x, eps, z: o.step(eps, t, x, variance_noise=z))
+    assert abs(float(x.abs().sum()) - want_sum) < 2e-3 and abs(float(x.abs().mean()) - want_mean) < 1e-4
+    p = S.DDPMScheduler(prediction_type="epsilon", **_KAT_CFG)
+    p.set_timesteps(1000)
+    coefs = p.step_coefficients()
+    y = run(lambda i, t, x, eps, z: _apply(coefs[i], x, eps, z))
+    assert abs(float(y.abs().sum()) - want_sum) < 2e-3 and abs(float(y.abs().mean()) - want_mean) < 1e-4
+
+
+def test_variances_match_diffusers_known_answers():
+    """DDIMSchedulerTest.test_variance (`_get_variance(t, prev_t)`) and DDPMSchedulerTest.test_variance
+    (`_get_variance(t)`, fixed_small), tolerance 1e-5 as upstream."""
+    o = R.DDIMSchedulerRef(**_KAT_CFG)
+    ac = o.alphas_cumprod
+
+    def ddim_var(t, p):
+        return float(((1 - ac[p]) / (1 - ac[t])) * (1 - ac[t] / ac[p]))
+
+    for t, p, want in ((0, 0, 0.0), (420, 400, 0.14771), (980, 960, 0.32460), (487, 486, 0.00979), (999, 998, 0.02)):
+        assert abs(ddim_var(t, p) - want) < 1e-5, (t, p)
+    # the product's k_noise is sqrt(variance): DDPM at t = 487 / 999 (t = 0 adds no noise), DDIM eta = 1 at 980 -> 960
+    p = S.DDPMScheduler(prediction_type="epsilon", **_KAT_CFG)
+    p.set_timesteps(1000)
+    cf = {int(c.timestep): c for c in p.step_coefficients()}
+    assert abs(cf[487].k_noise ** 2 - 0.00979) < 1e-5 and abs(cf[999].k_noise ** 2 - 0.02) < 1e-5 and cf[0].k_noise == 0.0
+    d = S.DDIMScheduler(prediction_type="epsilon", **_KAT_CFG)
+    d.set_timesteps(50)
+    cd = {int(c.timestep): c for c in d.step_coefficients(eta=1.0)}
+    assert abs(cd[980].k_noise ** 2 - 0.32460) < 1e-5 and abs(cd[420].k_noise ** 2 - 0.14771) < 1e-5
