@@ -330,3 +330,23 @@ def test_two_successive_batches_each_get_their_own_condition():
     crm.invalidate()
     m.denoiser.invalidate()
     fresh.denoiser.invalidate()
+
+
+def test_update_kernel_reproduces_diffusers_known_answers(raw):
+    """The CUDA update kernel (`hd_sampler_update`), driven step by step through the full loops of diffusers' own
+    scheduler tests (tests/schedulers/test_scheduler_ddim.py / test_scheduler_ddpm.py `test_full_loop_no_noise`; fixtures
+    and harness in tests/util.py, validated on CPU by tests/test_schedulers.py): 10 DDIM steps and all 1000 ancestral
+    DDPM steps with `torch.manual_seed(0)` noise must land on upstream's asserted checksums, at upstream's tolerances."""
+    from util import KAT_CFG, KAT_DDIM, KAT_DDPM, kat_ddim_loop, kat_ddpm_loop
+    p = S.DDIMScheduler(prediction_type="epsilon", **KAT_CFG)
+    p.set_timesteps(10)
+    c = p.step_coefficients(eta=0.0)
+    s, m, _ = kat_ddim_loop(lambda i, x, eps: _update(raw, x, eps, c, i), p.timesteps.tolist())
+    print(f"DDIM-10 through the kernel: sum |x| {s:.4f} (diffusers {KAT_DDIM[0]}), mean {m:.6f} ({KAT_DDIM[1]})")
+    assert abs(s - KAT_DDIM[0]) < 1e-2 and abs(m - KAT_DDIM[1]) < 1e-3
+    q = S.DDPMScheduler(prediction_type="epsilon", **KAT_CFG)
+    q.set_timesteps(1000)
+    d = q.step_coefficients()
+    s, m, _ = kat_ddpm_loop(lambda i, x, eps, z: _update(raw, x, eps, d, i, noise=z.cuda()))
+    print(f"DDPM-1000 through the kernel: sum |x| {s:.4f} (diffusers {KAT_DDPM[0]}), mean {m:.6f} ({KAT_DDPM[1]})")
+    assert abs(s - KAT_DDPM[0]) < 1e-2 and abs(m - KAT_DDPM[1]) < 1e-3

@@ -236,3 +236,20 @@ def test_variances_match_diffusers_known_answers():
     d.set_timesteps(50)
     cd = {int(c.timestep): c for c in d.step_coefficients(eta=1.0)}
     assert abs(cd[980].k_noise ** 2 - 0.32460) < 1e-5 and abs(cd[420].k_noise ** 2 - 0.14771) < 1e-5
+
+
+def test_known_answer_loops_on_the_kernel_shape():
+    """The harness the GPU test `test_update_kernel_reproduces_diffusers_known_answers` drives through the CUDA update
+    kernel, run here with the kernel's arithmetic restated (`_apply`): one padded (1,4,16,16) face, flattened in logical
+    order, reproduces the same known answers, and the padding stays 0."""
+    from util import KAT_CFG, KAT_DDIM, KAT_DDPM, kat_ddim_loop, kat_ddpm_loop
+    p = S.DDIMScheduler(prediction_type="epsilon", **KAT_CFG)
+    p.set_timesteps(10)
+    c = p.step_coefficients(eta=0.0)
+    s, m, pad = kat_ddim_loop(lambda i, x, eps: _apply(c[i], x, eps, torch.zeros_like(x)), p.timesteps.tolist())
+    assert abs(s - KAT_DDIM[0]) < 2e-3 and abs(m - KAT_DDIM[1]) < 1e-4 and pad == 0.0
+    q = S.DDPMScheduler(prediction_type="epsilon", **KAT_CFG)
+    q.set_timesteps(1000)
+    d = q.step_coefficients()
+    s, m, pad = kat_ddpm_loop(lambda i, x, eps, z: _apply(d[i], x, eps, z))
+    assert abs(s - KAT_DDPM[0]) < 2e-3 and abs(m - KAT_DDPM[1]) < 1e-4 and pad == 0.0   # the noise is zero-padded too

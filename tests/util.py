@@ -83,3 +83,45 @@ def hca_shapes(d):
     out["fused_mlp.0.bias"] = torch.empty(d)
     bn("fused_mlp.1.", d)
     return out
+
+
+# ---- diffusers' scheduler known-answer loops on the update kernel's own tensor shape -----------------------------
+# The fixtures of huggingface/diffusers tests/schedulers (see tests/test_schedulers.py) are (4,3,8,8) = 768 values; the
+# update kernel works on whole faces of 4*16*16 = 1024 values.  The update is elementwise, so the 768 values ride in the
+# head of one (1,4,16,16) face and the 256 padding values stay exactly 0 (x = 0, eps = 0 * t / (t + 1) = 0).
+KAT_CFG = dict(num_train_timesteps=1000, beta_start=1e-4, beta_end=0.02, beta_schedule="linear", clip_sample=True)
+KAT_DDIM = (172.0067, 0.223967)    # DDIMSchedulerTest.test_full_loop_no_noise: sum |x|, mean |x|
+KAT_DDPM = (258.9606, 0.3372)      # DDPMSchedulerTest.test_full_loop_no_noise
+
+
+def kat_sample():
+    b, c, h, w = 4, 3, 8, 8
+    n = b * c * h * w
+    return (torch.arange(n).reshape(c, h, w, b) / n).permute(3, 0, 1, 2)
+
+
+def _as_face(v):
+    out = torch.zeros(1024, dtype=torch.float32)
+    out[:768] = v.reshape(-1)
+    return out.reshape(1, 4, 16, 16)
+
+
+def kat_ddim_loop(step, timesteps):
+    """step(i, x_face, eps_face) -> x_face for step index i; returns (sum |x|, mean |x|, padding max |x|)."""
+    x = _as_face(kat_sample())
+    for i, t in enumerate(timesteps):
+        x = step(i, x, x * t / (t + 1))
+    v = x.reshape(-1)
+    return float(v[:768].abs().sum()), float(v[:768].abs().mean()), float(v[768:].abs().max())
+
+
+def kat_ddpm_loop(step):
+    """step(i, x_face, eps_face, z_face) for i = 0..999 (t = 999 - i); noise as upstream: torch.manual_seed(0),
+    one (4,3,8,8) draw per step, t = 0 included."""
+    g = torch.manual_seed(0)
+    x = _as_face(kat_sample())
+    for i, t in enumerate(reversed(range(1000))):
+        z = _as_face(torch.randn((4, 3, 8, 8), generator=g))
+        x = step(i, x, x * t / (t + 1), z)
+    v = x.reshape(-1)
+    return float(v[:768].abs().sum()), float(v[:768].abs().mean()), float(v[768:].abs().max())
